@@ -1,0 +1,877 @@
+// C-ABI of libclair3b200.so (see include/clair3_b200.h): model lifetime, strict state_dict ingestion, weight folding /
+// packing, per-stream workspaces and the forward orchestration of both precisions.  No CPU fallback anywhere.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "c3b_internal.h"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+void c3b_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *c3b_last_error(void) { return g_err; }
+extern "C" const char *c3b_version(void) { return "clair3_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------ helpers
+uint16_t c3b_f2bf(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);                                            // round to nearest even
+    return (uint16_t)(u >> 16);
+}
+
+namespace {
+
+struct Blob {
+    std::vector<uint8_t> data;
+    size_t add(const void *src, size_t bytes) {
+        size_t off = (data.size() + 255) / 256 * 256;
+        data.resize(off + bytes);
+        if (src) memcpy(data.data() + off, src, bytes);
+        return off;
+    }
+};
+
+const char *kConvNames[9][2] = {
+    {"conv1.conv", "conv1.bn"},
+    {"res_block1.0.conv1", "res_block1.0.bn1"},
+    {"res_block1.0.conv2", "res_block1.0.bn2"},
+    {"conv3.conv", "conv3.bn"},
+    {"res_block2.0.conv1", "res_block2.0.bn1"},
+    {"res_block2.0.conv2", "res_block2.0.bn2"},
+    {"conv5.conv", "conv5.bn"},
+    {"res_block3.0.conv1", "res_block3.0.bn1"},
+    {"res_block3.0.conv2", "res_block3.0.bn2"},
+};
+const int kConvCout[9] = {64, 64, 64, 128, 128, 128, 256, 256, 256};
+const int kConvStride[9] = {2, 1, 1, 2, 1, 1, 2, 1, 1};
+const char *kHeadNames[4][2] = {{"L5_1", "Y_gt21_logits"},
+                                {"L5_2", "Y_genotype_logits"},
+                                {"L5_3", "Y_indel_length_logits_1"},
+                                {"L5_4", "Y_indel_length_logits_2"}};
+const int kHeadDims[4] = {21, 3, 33, 33};
+
+int conv_cin(const c3b_model *m, int i) { return i == 0 ? m->channels : kConvCout[i - 1]; }
+
+void expect(c3b_model *m, const std::string &key, std::vector<int64_t> shape) {
+    m->expected.push_back(key);
+    m->expected_shape[key] = shape;
+}
+
+void build_expected(c3b_model *m) {
+    if (m->kind == C3B_PILEUP) {
+        const int hid[2] = {C3B_H1, C3B_H2};
+        const int inp[2] = {m->channels, 2 * C3B_H1};
+        for (int l = 0; l < 2; ++l)
+            for (int d = 0; d < 2; ++d) {
+                const std::string sfx = d ? "_l0_reverse" : "_l0";
+                const std::string base = std::string("LSTM") + char('1' + l) + ".";
+                expect(m, base + "weight_ih" + sfx, {4 * hid[l], inp[l]});
+                expect(m, base + "weight_hh" + sfx, {4 * hid[l], hid[l]});
+                expect(m, base + "bias_ih" + sfx, {4 * hid[l]});
+                expect(m, base + "bias_hh" + sfx, {4 * hid[l]});
+            }
+    } else {
+        for (int i = 0; i < 9; ++i) {
+            const std::string c = kConvNames[i][0], b = kConvNames[i][1];
+            expect(m, c + ".weight", {kConvCout[i], conv_cin(m, i), 3, 3});
+            expect(m, c + ".bias", {kConvCout[i]});
+            expect(m, b + ".weight", {kConvCout[i]});
+            expect(m, b + ".bias", {kConvCout[i]});
+            expect(m, b + ".running_mean", {kConvCout[i]});
+            expect(m, b + ".running_var", {kConvCout[i]});
+            expect(m, b + ".num_batches_tracked", {});
+        }
+    }
+    expect(m, "L4.weight", {m->d4, m->l4_in});
+    expect(m, "L4.bias", {m->d4});
+    for (int h = 0; h < m->nheads; ++h) {
+        expect(m, std::string(kHeadNames[h][0]) + ".weight", {128, m->d4});
+        expect(m, std::string(kHeadNames[h][0]) + ".bias", {128});
+        expect(m, std::string(kHeadNames[h][1]) + ".weight", {kHeadDims[h], 128});
+        expect(m, std::string(kHeadNames[h][1]) + ".bias", {kHeadDims[h]});
+    }
+}
+
+const std::vector<float> &P(const c3b_model *m, const std::string &k) { return m->params.at(k).data; }
+
+// UMMA SWIZZLE_NONE K-major operand image of a [rows][k] matrix: [chunk][rowblock][8 kgroups][rb rows][8] bf16.
+// get(row, k) supplies the (already folded / permuted) element; out-of-range k is zero.
+template <typename F>
+std::vector<uint16_t> pack_igemm(int rows, int kgroups, int rb, F get) {
+    const int nchunks = (kgroups + 7) / 8;
+    const int nrb = rows / rb;
+    std::vector<uint16_t> img((size_t)nchunks * nrb * 8 * rb * 8, 0);
+    for (int c = 0; c < nchunks; ++c)
+        for (int b = 0; b < nrb; ++b)
+            for (int kg = 0; kg < 8; ++kg) {
+                const int g = c * 8 + kg;
+                if (g >= kgroups) continue;
+                for (int r = 0; r < rb; ++r)
+                    for (int e = 0; e < 8; ++e)
+                        img[((((size_t)c * nrb + b) * 8 + kg) * rb + r) * 8 + e] = c3b_f2bf(get(b * rb + r, g * 8 + e));
+            }
+    return img;
+}
+
+// torch gate-row index for LSTM2's permuted row R in [0,640): blocks 0..3 = gate m, units 0..127; block 4 = [i f g o] x units 128..159
+int lstm2_torch_row(int r640) {
+    const int blk = r640 / 128, r = r640 % 128;
+    if (blk < 4) return blk * C3B_H2 + r;
+    return (r / 32) * C3B_H2 + 128 + (r % 32);
+}
+
+struct Tap {
+    const void *ptr;
+    int fmt;        // 0 f32, 1 bf16
+    int layout;     // 0 [B][...] row-major with `inner` elements per site; 1 time-major [33][bp][inner]
+    int64_t inner;
+    int bp;
+};
+
+}  // namespace
+
+struct WorkspaceTaps {
+    std::map<std::string, Tap> taps;
+};
+static std::map<const Workspace *, WorkspaceTaps> g_taps;   // debug only
+
+// ------------------------------------------------------------------------------------------------ create / params
+extern "C" int c3b_create(c3b_model **out, int kind, int channels, int add_indel_length, int device_ordinal) {
+    if (!out) { c3b_set_error("c3b_create: null out"); return 1; }
+    *out = nullptr;
+    if (kind != C3B_PILEUP && kind != C3B_FULL_ALIGNMENT) { c3b_set_error("c3b_create: bad kind %d", kind); return 1; }
+    if (kind == C3B_PILEUP && (channels < 1 || channels > 32)) { c3b_set_error("pileup channels must be in [1,32], got %d", channels); return 1; }
+    if (kind == C3B_FULL_ALIGNMENT && (channels < 1 || channels > 16)) { c3b_set_error("full-alignment channels must be in [1,16], got %d", channels); return 1; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        c3b_set_error("no CUDA device: %s (clair3_b200 has no CPU fallback)", cudaGetErrorString(e));
+        return 2;
+    }
+    if (device_ordinal < 0 || device_ordinal >= ndev) { c3b_set_error("bad device ordinal %d", device_ordinal); return 1; }
+    cudaDeviceProp prop;
+    C3B_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+    if (prop.major != 10) {
+        c3b_set_error("device %d is sm_%d%d; this library contains only sm_100a code", device_ordinal, prop.major, prop.minor);
+        return 2;
+    }
+    C3B_CUDA(cudaSetDevice(device_ordinal));
+    c3b_model *m = new c3b_model();
+    m->kind = kind;
+    m->channels = channels;
+    m->add_indel = add_indel_length ? 1 : 0;
+    m->device = device_ordinal;
+    m->nheads = add_indel_length ? 4 : 2;
+    m->out_dim = add_indel_length ? 90 : 24;
+    m->d4 = kind == C3B_PILEUP ? 128 : 256;
+    m->l4_in = kind == C3B_PILEUP ? 2 * C3B_H2 * C3B_T : 3584;
+    m->sm_count = prop.multiProcessorCount;
+    build_expected(m);
+    *out = m;
+    return 0;
+}
+
+extern "C" int c3b_set_param(c3b_model *m, const char *key, const void *host_data, int dtype, const int64_t *shape, int ndim) {
+    if (!m || !key) { c3b_set_error("c3b_set_param: null argument"); return 1; }
+    auto it = m->expected_shape.find(key);
+    if (it == m->expected_shape.end()) { c3b_set_error("Unexpected key in state_dict: \"%s\"", key); return 1; }
+    const std::vector<int64_t> &want = it->second;
+    bool ok = (int)want.size() == ndim;
+    for (int i = 0; ok && i < ndim; ++i) ok = want[i] == shape[i];
+    if (!ok) {
+        std::string got = "[", exp = "[";
+        for (int i = 0; i < ndim; ++i) got += std::to_string(shape[i]) + (i + 1 < ndim ? "," : "");
+        for (size_t i = 0; i < want.size(); ++i) exp += std::to_string(want[i]) + (i + 1 < want.size() ? "," : "");
+        c3b_set_error("size mismatch for %s: checkpoint %s], model %s]", key, got.c_str(), exp.c_str());
+        return 1;
+    }
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) n *= shape[i];
+    HostParam hp;
+    hp.shape.assign(shape, shape + ndim);
+    hp.data.resize((size_t)n);
+    if (dtype == C3B_DT_F32) {
+        if (n && !host_data) { c3b_set_error("c3b_set_param: null data"); return 1; }
+        memcpy(hp.data.data(), host_data, (size_t)n * 4);
+    } else if (dtype == C3B_DT_I64) {
+        for (int64_t i = 0; i < n; ++i) hp.data[i] = (float)((const int64_t *)host_data)[i];
+    } else {
+        c3b_set_error("c3b_set_param: parameters must be float32 (or int64 counters), got dtype %d for %s", dtype, key);
+        return 1;
+    }
+    m->params[key] = std::move(hp);
+    m->finalized = false;
+    return 0;
+}
+
+extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
+    if (!m || !name) { c3b_set_error("c3b_set_option: null argument"); return 1; }
+    if (!strcmp(name, "precision")) {
+        if (value != C3B_PREC_BF16_TC && value != C3B_PREC_FP32) { c3b_set_error("bad precision %d", value); return 1; }
+        m->precision = value;
+    } else if (!strcmp(name, "chunk_sites")) {
+        if (value < 0) { c3b_set_error("bad chunk_sites %d", value); return 1; }
+        m->chunk_sites = value;
+    } else if (!strcmp(name, "lstm_tile")) {
+        if (value != 0 && value != 16 && value != 32 && value != 64) { c3b_set_error("bad lstm_tile %d", value); return 1; }
+        m->lstm_tile = value;
+    } else {
+        c3b_set_error("unknown option \"%s\"", name);
+        return 1;
+    }
+    return 0;
+}
+
+extern "C" int c3b_out_dim(const c3b_model *m) { return m ? m->out_dim : -1; }
+extern "C" int64_t c3b_launch_count(const c3b_model *m) { return m ? m->launches : -1; }
+
+// ------------------------------------------------------------------------------------------------ finalize
+static int finalize_impl(c3b_model *m) {
+    for (const std::string &k : m->expected)
+        if (!m->params.count(k)) { c3b_set_error("Missing key in state_dict: \"%s\"", k.c_str()); return 1; }
+    C3B_CUDA(cudaSetDevice(m->device));
+
+    Blob blob, fb;
+    struct Fix { size_t off; const void **dst; bool f32blob; };
+    std::vector<Fix> fixes;
+    auto put = [&](Blob &b, const void *src, size_t bytes, const void **dst, bool f32b) {
+        fixes.push_back({b.add(src, bytes), dst, f32b});
+    };
+
+    // ---- dense heads (fp32, shared by both precisions): transposed for coalesced reads
+    m->heads = HeadsParams();
+    m->heads.nheads = m->nheads;
+    m->heads.d4 = m->d4;
+    m->heads.out_dim = m->out_dim;
+    put(blob, P(m, "L4.bias").data(), (size_t)m->d4 * 4, (const void **)&m->heads.b4, false);
+    int off = 0;
+    for (int h = 0; h < m->nheads; ++h) {
+        const std::vector<float> &w5 = P(m, std::string(kHeadNames[h][0]) + ".weight");   // [128][d4]
+        const std::vector<float> &wy = P(m, std::string(kHeadNames[h][1]) + ".weight");   // [n][128]
+        const int n = kHeadDims[h];
+        std::vector<float> w5t((size_t)m->d4 * 128), wyt((size_t)128 * n);
+        for (int j = 0; j < 128; ++j)
+            for (int k = 0; k < m->d4; ++k) w5t[(size_t)k * 128 + j] = w5[(size_t)j * m->d4 + k];
+        for (int o = 0; o < n; ++o)
+            for (int j = 0; j < 128; ++j) wyt[(size_t)j * n + o] = wy[(size_t)o * 128 + j];
+        put(blob, w5t.data(), w5t.size() * 4, (const void **)&m->heads.h[h].w5t, false);
+        put(blob, P(m, std::string(kHeadNames[h][0]) + ".bias").data(), 128 * 4, (const void **)&m->heads.h[h].b5, false);
+        put(blob, wyt.data(), wyt.size() * 4, (const void **)&m->heads.h[h].wyt, false);
+        put(blob, P(m, std::string(kHeadNames[h][1]) + ".bias").data(), (size_t)n * 4, (const void **)&m->heads.h[h].by, false);
+        m->heads.h[h].n = n;
+        m->heads.h[h].out_off = off;
+        off += n;
+    }
+
+    // ---- L4: fp32 transposed (debug) + tensor-core image (swapped orientation: 128-row blocks)
+    {
+        const std::vector<float> &w4 = P(m, "L4.weight");   // [d4][l4_in]
+        std::vector<float> w4t((size_t)m->l4_in * m->d4);
+        for (int o = 0; o < m->d4; ++o)
+            for (int k = 0; k < m->l4_in; ++k) w4t[(size_t)k * m->d4 + o] = w4[(size_t)o * m->l4_in + k];
+        put(fb, w4t.data(), w4t.size() * 4, (const void **)&m->l4_f32_t, true);
+        const int kg = m->l4_in / 8;
+        const int l4_in = m->l4_in;
+        std::vector<uint16_t> img = pack_igemm(m->d4, kg, 128, [&](int r, int k) { return w4[(size_t)r * l4_in + k]; });
+        m->l4_tc = IgemmW();
+        m->l4_tc.n = m->d4;
+        m->l4_tc.kgroups = kg;
+        m->l4_tc.nchunks = (kg + 7) / 8;
+        m->l4_tc.bias = nullptr;
+        put(blob, img.data(), img.size() * 2, (const void **)&m->l4_tc.w_img, false);
+    }
+
+    if (m->kind == C3B_PILEUP) {
+        const int hid[2] = {C3B_H1, C3B_H2};
+        const int inp[2] = {m->channels, 2 * C3B_H1};
+        // fp32 debug weights: transposed [K][4H], summed bias
+        for (int l = 0; l < 2; ++l)
+            for (int d = 0; d < 2; ++d) {
+                const std::string sfx = d ? "_l0_reverse" : "_l0";
+                const std::string base = std::string("LSTM") + char('1' + l) + ".";
+                const std::vector<float> &wih = P(m, base + "weight_ih" + sfx), &whh = P(m, base + "weight_hh" + sfx);
+                const std::vector<float> &bih = P(m, base + "bias_ih" + sfx), &bhh = P(m, base + "bias_hh" + sfx);
+                const int H = hid[l], I = inp[l], G = 4 * H;
+                std::vector<float> wih_t((size_t)I * G), whh_t((size_t)H * G), bias(G);
+                for (int r = 0; r < G; ++r) {
+                    for (int k = 0; k < I; ++k) wih_t[(size_t)k * G + r] = wih[(size_t)r * I + k];
+                    for (int k = 0; k < H; ++k) whh_t[(size_t)k * G + r] = whh[(size_t)r * H + k];
+                    bias[r] = bih[r] + bhh[r];
+                }
+                put(fb, wih_t.data(), wih_t.size() * 4, (const void **)&m->lstm_f32[l][d].wih_t, true);
+                put(fb, whh_t.data(), whh_t.size() * 4, (const void **)&m->lstm_f32[l][d].whh_t, true);
+                put(fb, bias.data(), bias.size() * 4, (const void **)&m->lstm_f32[l][d].bias, true);
+            }
+        // tensor-core LSTM1 image: [dir][4 blocks][20 kgroups][128][8]; K = [x(32: 18 real) ; h(128)]
+        {
+            std::vector<uint16_t> img((size_t)2 * 4 * 20 * 128 * 8, 0);
+            std::vector<float> bias((size_t)2 * 512);
+            for (int d = 0; d < 2; ++d) {
+                const std::string sfx = d ? "_l0_reverse" : "_l0";
+                const std::vector<float> &wih = P(m, "LSTM1.weight_ih" + sfx), &whh = P(m, "LSTM1.weight_hh" + sfx);
+                const std::vector<float> &bih = P(m, "LSTM1.bias_ih" + sfx), &bhh = P(m, "LSTM1.bias_hh" + sfx);
+                const int I = m->channels;
+                for (int blk = 0; blk < 4; ++blk)
+                    for (int r = 0; r < 128; ++r) {
+                        const int row = blk * 128 + r;
+                        bias[(size_t)d * 512 + row] = bih[row] + bhh[row];
+                        for (int k = 0; k < 160; ++k) {
+                            float v = 0.f;
+                            if (k < 32) { if (k < I) v = wih[(size_t)row * I + k]; }
+                            else v = whh[(size_t)row * 128 + (k - 32)];
+                            img[((((size_t)d * 4 + blk) * 20 + k / 8) * 128 + r) * 8 + k % 8] = c3b_f2bf(v);
+                        }
+                    }
+            }
+            put(blob, img.data(), img.size() * 2, (const void **)&m->lstm_tc[0][0].w_img, false);
+            put(blob, bias.data(), bias.size() * 4, (const void **)&m->lstm_tc[0][0].bias, false);
+        }
+        // tensor-core LSTM2: recurrent image [dir][5 blocks][20][128][8] (permuted rows) + input projection GEMM (1280 rows)
+        {
+            std::vector<uint16_t> img((size_t)2 * 5 * 20 * 128 * 8, 0);
+            std::vector<float> pbias(1280);
+            const std::vector<float> *wih_d[2];
+            for (int d = 0; d < 2; ++d) {
+                const std::string sfx = d ? "_l0_reverse" : "_l0";
+                const std::vector<float> &whh = P(m, "LSTM2.weight_hh" + sfx);
+                const std::vector<float> &bih = P(m, "LSTM2.bias_ih" + sfx), &bhh = P(m, "LSTM2.bias_hh" + sfx);
+                wih_d[d] = &P(m, "LSTM2.weight_ih" + sfx);
+                for (int R = 0; R < 640; ++R) {
+                    const int row = lstm2_torch_row(R);
+                    pbias[(size_t)d * 640 + R] = bih[row] + bhh[row];
+                    for (int k = 0; k < 160; ++k)
+                        img[((((size_t)d * 5 + R / 128) * 20 + k / 8) * 128 + R % 128) * 8 + k % 8] =
+                            c3b_f2bf(whh[(size_t)row * 160 + k]);
+                }
+            }
+            put(blob, img.data(), img.size() * 2, (const void **)&m->lstm_tc[1][0].w_img, false);
+            m->lstm_tc[1][0].bias = nullptr;
+            std::vector<uint16_t> pimg = pack_igemm(1280, 32, 128, [&](int R, int k) {
+                const int d = R / 640;
+                return (*wih_d[d])[(size_t)lstm2_torch_row(R % 640) * 256 + k];
+            });
+            m->proj2 = IgemmW();
+            m->proj2.n = 1280;
+            m->proj2.kgroups = 32;
+            m->proj2.nchunks = 4;
+            put(blob, pimg.data(), pimg.size() * 2, (const void **)&m->proj2.w_img, false);
+            put(blob, pbias.data(), pbias.size() * 4, (const void **)&m->proj2.bias, false);
+        }
+    } else {
+        for (int i = 0; i < 9; ++i) {
+            const std::string c = kConvNames[i][0], b = kConvNames[i][1];
+            const std::vector<float> &w = P(m, c + ".weight"), &cb = P(m, c + ".bias");
+            const std::vector<float> &g = P(m, b + ".weight"), &be = P(m, b + ".bias");
+            const std::vector<float> &mu = P(m, b + ".running_mean"), &var = P(m, b + ".running_var");
+            const int cout = kConvCout[i], cin = conv_cin(m, i);
+            const float in_scale = (i == 0) ? 1.0f / 100.0f : 1.0f;      // x.float()/NORMALIZE_NUM (clair3/model.py:378)
+            std::vector<float> wf((size_t)9 * cin * cout), bf(cout);
+            for (int co = 0; co < cout; ++co) {
+                const float s = g[co] / sqrtf(var[co] + 1e-3f);           // BatchNorm2d(eps=1e-3), clair3/model.py:192
+                bf[co] = (cb[co] - mu[co]) * s + be[co];
+                for (int ci = 0; ci < cin; ++ci)
+                    for (int t = 0; t < 9; ++t)
+                        wf[((size_t)t * cin + ci) * cout + co] = w[((size_t)co * cin + ci) * 9 + t] * s * in_scale;
+            }
+            m->conv_f32[i].cin = cin;
+            m->conv_f32[i].cout = cout;
+            m->conv_f32[i].stride = kConvStride[i];
+            put(fb, wf.data(), wf.size() * 4, (const void **)&m->conv_f32[i].w, true);
+            put(fb, bf.data(), bf.size() * 4, (const void **)&m->conv_f32[i].bias, true);
+            // tensor-core image: k = tap*cin_pad + ci, cin_pad = 8|16 for conv1
+            const int cin_pad = (i == 0) ? ((cin + 7) / 8 * 8) : cin;
+            const int kg = 9 * cin_pad / 8;
+            std::vector<uint16_t> img = pack_igemm(cout, kg, cout, [&](int co, int k) {
+                const int t = k / cin_pad, ci = k % cin_pad;
+                return ci < cin ? wf[((size_t)t * cin + ci) * cout + co] : 0.f;
+            });
+            m->conv_tc[i] = IgemmW();
+            m->conv_tc[i].n = cout;
+            m->conv_tc[i].kgroups = kg;
+            m->conv_tc[i].nchunks = (kg + 7) / 8;
+            put(blob, img.data(), img.size() * 2, (const void **)&m->conv_tc[i].w_img, false);
+            put(blob, bf.data(), bf.size() * 4, (const void **)&m->conv_tc[i].bias, false);
+        }
+    }
+
+    if (m->blob) { cudaFree(m->blob); m->blob = nullptr; }
+    if (m->f32blob) { cudaFree(m->f32blob); m->f32blob = nullptr; }
+    m->blob_bytes = (blob.data.size() + 255) / 256 * 256;
+    m->f32blob_bytes = (fb.data.size() + 255) / 256 * 256;
+    C3B_CUDA(cudaMalloc(&m->blob, m->blob_bytes));
+    C3B_CUDA(cudaMalloc(&m->f32blob, m->f32blob_bytes));
+    C3B_CUDA(cudaMemcpy(m->blob, blob.data.data(), blob.data.size(), cudaMemcpyHostToDevice));
+    C3B_CUDA(cudaMemcpy(m->f32blob, fb.data.data(), fb.data.size(), cudaMemcpyHostToDevice));
+    for (const Fix &f : fixes) *f.dst = (f.f32blob ? m->f32blob : m->blob) + f.off;
+    m->lstm_tc[0][1] = m->lstm_tc[0][0];
+    m->lstm_tc[1][1] = m->lstm_tc[1][0];
+    m->finalized = true;
+    return 0;
+}
+
+extern "C" int c3b_finalize(c3b_model *m) {
+    if (!m) { c3b_set_error("c3b_finalize: null model"); return 1; }
+    try {
+        return finalize_impl(m);
+    } catch (const std::exception &e) {
+        c3b_set_error("c3b_finalize: %s", e.what());
+        return 1;
+    }
+}
+
+extern "C" int c3b_weight_blob(c3b_model *m, void **device_ptr, size_t *bytes) {
+    if (!m || !m->finalized) { c3b_set_error("c3b_weight_blob: model not finalized"); return 1; }
+    if (device_ptr) *device_ptr = m->blob;
+    if (bytes) *bytes = m->blob_bytes;
+    return 0;
+}
+
+extern "C" int c3b_bcast_weights(c3b_model *m, void *nccl_comm, int root, void *cuda_stream) {
+    if (!m || !m->finalized) { c3b_set_error("c3b_bcast_weights: model not finalized"); return 1; }
+    typedef int (*bcast_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    static bcast_fn fn = nullptr;
+    if (!fn) {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { c3b_set_error("c3b_bcast_weights: cannot dlopen libnccl: %s", dlerror()); return 1; }
+        fn = (bcast_fn)dlsym(h, "ncclBroadcast");
+        if (!fn) { c3b_set_error("c3b_bcast_weights: ncclBroadcast not found"); return 1; }
+    }
+    C3B_CUDA(cudaSetDevice(m->device));
+    const int rc = fn(m->blob, m->blob, m->blob_bytes, /*ncclUint8*/ 1, root, nccl_comm, (cudaStream_t)cuda_stream);
+    if (rc != 0) { c3b_set_error("ncclBroadcast failed with %d", rc); return 1; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ workspaces
+static int64_t round128(int64_t b) { return (b + 127) / 128 * 128; }
+static int conv_out(int v) { return (v - 1) / 2 + 1; }   // 3x3, stride 2, pad 1
+
+static size_t ws_bytes_needed(const c3b_model *m, int64_t sites, int depth) {
+    const int64_t bp = round128(sites);
+    size_t total = 0;
+    auto al = [&](size_t b) { total += (b + 255) / 256 * 256; };
+    if (m->kind == C3B_PILEUP) {
+        if (m->precision == C3B_PREC_FP32) {
+            al((size_t)sites * C3B_T * m->channels * 4);
+            al((size_t)sites * C3B_T * 256 * 4);
+            al((size_t)sites * C3B_T * 320 * 4);
+        } else {
+            al((size_t)C3B_T * bp * 32 * 2);
+            al((size_t)C3B_T * bp * 256 * 2);
+            al((size_t)C3B_T * bp * 1280 * 2);
+            al((size_t)bp * C3B_T * 320 * 2);
+        }
+        al((size_t)bp * 128 * 4);
+    } else {
+        const int h1 = conv_out(depth), w1 = conv_out(33), h2 = conv_out(h1), w2 = conv_out(w1), h3 = conv_out(h2), w3 = conv_out(w2);
+        const size_t es = m->precision == C3B_PREC_FP32 ? 4 : 2;
+        const int cpad = m->precision == C3B_PREC_FP32 ? m->channels : (m->channels + 7) / 8 * 8;
+        al((size_t)sites * depth * 33 * cpad * es);
+        for (int i = 0; i < 3; ++i) al((size_t)sites * h1 * w1 * 64 * es);
+        for (int i = 0; i < 3; ++i) al((size_t)sites * h2 * w2 * 128 * es);
+        for (int i = 0; i < 3; ++i) al((size_t)sites * h3 * w3 * 256 * es);
+        al((size_t)sites * 3584 * es);
+        al((size_t)bp * 256 * 4);
+    }
+    return total + 4096;
+}
+
+static Workspace *get_workspace(c3b_model *m, cudaStream_t stream) {
+    for (Workspace *w : m->ws)
+        if (w->stream == stream) return w;
+    if (m->ws.size() >= 64) { c3b_set_error("too many distinct streams on one model"); return nullptr; }
+    Workspace *w = new Workspace();
+    w->stream = stream;
+    m->ws.push_back(w);
+    return w;
+}
+
+static int ensure_dev(void **p, size_t *have, size_t need) {
+    if (*have >= need) return 0;
+    if (*p) C3B_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *have = 0;
+    C3B_CUDA(cudaMalloc(p, need));
+    *have = need;
+    return 0;
+}
+
+struct Carver {
+    char *base;
+    size_t off = 0;
+    template <typename T>
+    T *take(size_t bytes) {
+        T *p = reinterpret_cast<T *>(base + off);
+        off += (bytes + 255) / 256 * 256;
+        return p;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ forward passes
+static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x_dtype, int64_t n, float *y, bool tap,
+                                cudaStream_t s) {
+    Carver cv{w->dev};
+    const int64_t bp = round128(n);
+    WorkspaceTaps &wt = g_taps[w];
+    if (m->precision == C3B_PREC_FP32) {
+        float *xf = cv.take<float>((size_t)n * C3B_T * m->channels * 4);
+        float *l1 = cv.take<float>((size_t)n * C3B_T * 256 * 4);
+        float *l2 = cv.take<float>((size_t)n * C3B_T * 320 * 4);
+        float *z4 = cv.take<float>((size_t)bp * 128 * 4);
+        if (c3b_launch_ingest_pileup_f32(x, x_dtype, xf, n * C3B_T * m->channels, s)) return 1;
+        if (c3b_launch_lstm_f32(xf, m->lstm_f32[0][0], m->lstm_f32[0][1], l1, n, m->channels, C3B_H1, s)) return 1;
+        if (c3b_launch_lstm_f32(l1, m->lstm_f32[1][0], m->lstm_f32[1][1], l2, n, 256, C3B_H2, s)) return 1;
+        if (c3b_launch_dense_f32(l2, m->l4_f32_t, z4, n, m->l4_in, 128, s)) return 1;
+        if (c3b_launch_heads(z4, m->heads, y, n, s)) return 1;
+        m->launches += 5;
+        if (tap) {
+            wt.taps["lstm1"] = {l1, 0, 0, (int64_t)C3B_T * 256, 0};
+            wt.taps["lstm2"] = {l2, 0, 0, (int64_t)C3B_T * 320, 0};
+            wt.taps["l4_pre"] = {z4, 0, 0, 128, 0};
+        }
+        return 0;
+    }
+    TcPileupBuffers b;
+    b.xs = cv.take<__nv_bfloat16>((size_t)C3B_T * bp * 32 * 2);
+    b.h1 = cv.take<__nv_bfloat16>((size_t)C3B_T * bp * 256 * 2);
+    b.pg = cv.take<__half>((size_t)C3B_T * bp * 1280 * 2);
+    b.h2 = cv.take<__nv_bfloat16>((size_t)bp * C3B_T * 320 * 2);
+    b.z4 = cv.take<float>((size_t)bp * 128 * 4);
+    int tile1 = m->lstm_tile, tile2 = m->lstm_tile;
+    if (tile1 == 0) {
+        // enough CTAs to cover the SMs: 2 directions x bp / tile
+        tile1 = (2 * bp / 64 >= m->sm_count) ? 64 : (2 * bp / 32 >= m->sm_count) ? 32 : 16;
+        tile2 = tile1;
+    }
+    if (tile2 > 32) tile2 = 32;
+    if (c3b_launch_ingest_pileup_tc(x, x_dtype, m->channels, b.xs, n, s)) return 1;
+    m->launches += 1;
+    if (c3b_launch_lstm1_tc(m, b, n, tile1, s)) return 1;
+    IgemmArgs pa = {};
+    pa.a = b.h1;
+    pa.m = (int64_t)C3B_T * bp;
+    pa.taps = 1;
+    pa.hin = (int)bp;          // pre-gate geometry (padded batch, LSTM2 tile) rides in hin / win
+    pa.win = tile2;
+    pa.cin = 256;
+    pa.lda = 256;
+    pa.w = m->proj2;
+    pa.out = b.pg;
+    pa.epilogue = IGEMM_EPI_F16_BIAS;
+    if (c3b_launch_igemm(m, pa, s)) return 1;
+    if (c3b_launch_lstm2_tc(m, b, n, tile2, s)) return 1;
+    C3B_CUDA(cudaMemsetAsync(b.z4, 0, (size_t)bp * 128 * 4, s));
+    IgemmArgs la = {};
+    la.a = b.h2;
+    la.m = n;
+    la.taps = 1;
+    la.cin = m->l4_in;
+    la.lda = m->l4_in;
+    la.w = m->l4_tc;
+    la.out = b.z4;
+    la.ldo = 128;
+    la.epilogue = IGEMM_EPI_F32_ATOMIC;
+    la.ksplit = 11;
+    if (c3b_launch_igemm(m, la, s)) return 1;
+    if (c3b_launch_heads(b.z4, m->heads, y, n, s)) return 1;
+    m->launches += 1;
+    if (tap) {
+        wt.taps["lstm1"] = {b.h1, 1, 1, 256, (int)bp};
+        wt.taps["lstm2"] = {b.h2, 1, 0, (int64_t)C3B_T * 320, 0};
+        wt.taps["l4_pre"] = {b.z4, 0, 0, 128, 0};
+    }
+    return 0;
+}
+
+static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dtype, int64_t n, int depth, float *y, bool tap,
+                            cudaStream_t s) {
+    Carver cv{w->dev};
+    const int64_t bp = round128(n);
+    WorkspaceTaps &wt = g_taps[w];
+    int hh[4] = {depth, 0, 0, 0}, ww[4] = {33, 0, 0, 0};
+    for (int i = 1; i < 4; ++i) { hh[i] = conv_out(hh[i - 1]); ww[i] = conv_out(ww[i - 1]); }
+    const int chans[4] = {m->channels, 64, 128, 256};
+    const bool f32 = m->precision == C3B_PREC_FP32;
+    const size_t es = f32 ? 4 : 2;
+    const int cpad = f32 ? m->channels : (m->channels + 7) / 8 * 8;
+    char *xin = cv.take<char>((size_t)n * depth * 33 * cpad * es);
+    char *act[3][3];
+    for (int l = 0; l < 3; ++l)
+        for (int i = 0; i < 3; ++i) act[l][i] = cv.take<char>((size_t)n * hh[l + 1] * ww[l + 1] * chans[l + 1] * es);
+    char *sp = cv.take<char>((size_t)n * 3584 * es);
+    float *z4 = cv.take<float>((size_t)bp * 256 * 4);
+    const char *tapname[3][2] = {{"conv1", "res_block1"}, {"conv3", "res_block2"}, {"conv5", "res_block3"}};
+
+    if (f32) {
+        if (c3b_launch_ingest_fa_f32(x, x_dtype, (float *)xin, n * depth * 33 * m->channels, s)) return 1;
+        const float *cur = (const float *)xin;
+        for (int l = 0; l < 3; ++l) {
+            float *a0 = (float *)act[l][0], *a1 = (float *)act[l][1], *a2 = (float *)act[l][2];
+            if (c3b_launch_conv_f32(cur, m->conv_f32[3 * l], nullptr, a0, n, hh[l], ww[l], hh[l + 1], ww[l + 1], s)) return 1;
+            if (c3b_launch_conv_f32(a0, m->conv_f32[3 * l + 1], nullptr, a1, n, hh[l + 1], ww[l + 1], hh[l + 1], ww[l + 1], s)) return 1;
+            if (c3b_launch_conv_f32(a1, m->conv_f32[3 * l + 2], a0, a2, n, hh[l + 1], ww[l + 1], hh[l + 1], ww[l + 1], s)) return 1;
+            cur = a2;
+        }
+        if (c3b_launch_spp_f32(cur, (float *)sp, n, hh[3], ww[3], 256, s)) return 1;
+        if (c3b_launch_dense_f32((float *)sp, m->l4_f32_t, z4, n, 3584, 256, s)) return 1;
+        if (c3b_launch_heads(z4, m->heads, y, n, s)) return 1;
+        m->launches += 13;
+    } else {
+        if (c3b_launch_ingest_fa_tc(x, x_dtype, m->channels, cpad, (__nv_bfloat16 *)xin, n * depth * 33, s)) return 1;
+        const __nv_bfloat16 *cur = (const __nv_bfloat16 *)xin;
+        int cur_c = cpad;
+        for (int l = 0; l < 3; ++l) {
+            __nv_bfloat16 *a0 = (__nv_bfloat16 *)act[l][0], *a1 = (__nv_bfloat16 *)act[l][1], *a2 = (__nv_bfloat16 *)act[l][2];
+            const int co = chans[l + 1];
+            IgemmArgs ca = {};
+            ca.taps = 9;
+            ca.epilogue = IGEMM_EPI_BF16_BIAS_RELU;
+            ca.relu = 1;
+            ca.ldo = co;
+            ca.hout = hh[l + 1];
+            ca.wout = ww[l + 1];
+            ca.m = n * hh[l + 1] * ww[l + 1];
+            // strided stem conv
+            ca.a = cur; ca.hin = hh[l]; ca.win = ww[l]; ca.cin = cur_c; ca.stride = 2;
+            ca.w = m->conv_tc[3 * l]; ca.out = a0; ca.residual = nullptr;
+            if (c3b_launch_igemm(m, ca, s)) return 1;
+            // residual block
+            ca.a = a0; ca.hin = hh[l + 1]; ca.win = ww[l + 1]; ca.cin = co; ca.stride = 1;
+            ca.w = m->conv_tc[3 * l + 1]; ca.out = a1; ca.residual = nullptr;
+            if (c3b_launch_igemm(m, ca, s)) return 1;
+            ca.a = a1; ca.w = m->conv_tc[3 * l + 2]; ca.out = a2; ca.residual = a0;
+            if (c3b_launch_igemm(m, ca, s)) return 1;
+            cur = a2;
+            cur_c = co;
+        }
+        if (c3b_launch_spp_tc(cur, (__nv_bfloat16 *)sp, n, hh[3], ww[3], 256, s)) return 1;
+        C3B_CUDA(cudaMemsetAsync(z4, 0, (size_t)bp * 256 * 4, s));
+        IgemmArgs la = {};
+        la.a = (const __nv_bfloat16 *)sp;
+        la.m = n;
+        la.taps = 1;
+        la.cin = 3584;
+        la.lda = 3584;
+        la.w = m->l4_tc;
+        la.out = z4;
+        la.ldo = 256;
+        la.epilogue = IGEMM_EPI_F32_ATOMIC;
+        la.ksplit = 8;
+        if (c3b_launch_igemm(m, la, s)) return 1;
+        if (c3b_launch_heads(z4, m->heads, y, n, s)) return 1;
+        m->launches += 3;
+    }
+    if (tap) {
+        const int fmt = f32 ? 0 : 1;
+        for (int l = 0; l < 3; ++l) {
+            const int64_t inner = (int64_t)hh[l + 1] * ww[l + 1] * chans[l + 1];
+            wt.taps[tapname[l][0]] = {act[l][0], fmt, 0, inner, 0};
+            wt.taps[tapname[l][1]] = {act[l][2], fmt, 0, inner, 0};
+        }
+        wt.taps["spp"] = {sp, fmt, 0, 3584, 0};
+        wt.taps["l4_pre"] = {z4, 0, 0, 256, 0};
+    }
+    return 0;
+}
+
+extern "C" int c3b_forward(c3b_model *m, const void *x, int x_dtype, int x_on_device, int64_t batch, int depth, float *y,
+                           int y_on_device, void *cuda_stream) {
+    if (!m) { c3b_set_error("c3b_forward: null model"); return 1; }
+    if (!m->finalized) { c3b_set_error("c3b_forward: load_state_dict/c3b_finalize has not completed"); return 1; }
+    if (batch < 0) { c3b_set_error("c3b_forward: negative batch"); return 1; }
+    if (batch == 0) return 0;
+    if (!x || !y) { c3b_set_error("c3b_forward: null buffer"); return 1; }
+    size_t esz;
+    switch (x_dtype) {
+        case C3B_DT_I8: esz = 1; break;
+        case C3B_DT_I32: esz = 4; break;
+        case C3B_DT_F32: esz = 4; break;
+        default: c3b_set_error("c3b_forward: unsupported input dtype %d", x_dtype); return 1;
+    }
+    if (m->kind == C3B_FULL_ALIGNMENT) {
+        if (depth < 8 || depth > 512) { c3b_set_error("c3b_forward: bad full-alignment depth %d", depth); return 1; }
+        int h = depth, w = 33;
+        for (int i = 0; i < 3; ++i) { h = conv_out(h); w = conv_out(w); }
+        for (int p = 1; p <= 3; ++p) {
+            const int wh = (h + p - 1) / p, ww = (w + p - 1) / p;
+            if ((h + wh - 1) / wh != p || (w + ww - 1) / ww != p) {
+                c3b_set_error("depth %d gives a %dx%d feature map whose pyramid pooling does not yield 3584 features", depth, h, w);
+                return 1;
+            }
+        }
+    } else {
+        depth = 0;
+    }
+    C3B_CUDA(cudaSetDevice(m->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    Workspace *w = get_workspace(m, s);
+    if (!w) return 1;
+    const size_t site_elems = m->kind == C3B_PILEUP ? (size_t)C3B_T * m->channels : (size_t)depth * 33 * m->channels;
+    int64_t chunk = m->chunk_sites > 0 ? m->chunk_sites : (m->kind == C3B_PILEUP ? 1024 : 256);
+    if (chunk > batch) chunk = batch;
+
+    const size_t need = ws_bytes_needed(m, chunk, depth);
+    if (w->dev_bytes < need) {
+        C3B_CUDA(cudaStreamSynchronize(s));
+        if (ensure_dev((void **)&w->dev, &w->dev_bytes, need)) return 1;
+    }
+    const void *xd = x;
+    float *yd = y;
+    if (!x_on_device) {
+        if (w->dev_x_bytes < batch * site_elems * esz) C3B_CUDA(cudaStreamSynchronize(s));
+        if (ensure_dev(&w->dev_x, &w->dev_x_bytes, batch * site_elems * esz)) return 1;
+        C3B_CUDA(cudaMemcpyAsync(w->dev_x, x, batch * site_elems * esz, cudaMemcpyHostToDevice, s));
+        xd = w->dev_x;
+    }
+    if (!y_on_device) {
+        if (w->dev_y_bytes < (size_t)batch * m->out_dim * 4) C3B_CUDA(cudaStreamSynchronize(s));
+        if (ensure_dev((void **)&w->dev_y, &w->dev_y_bytes, (size_t)batch * m->out_dim * 4)) return 1;
+        yd = w->dev_y;
+    }
+    g_taps[w].taps.clear();
+    for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
+        const int64_t n = std::min(chunk, batch - b0);
+        const void *xc = (const char *)xd + (size_t)b0 * site_elems * esz;
+        float *yc = yd + (size_t)b0 * m->out_dim;
+        int rc = m->kind == C3B_PILEUP ? forward_pileup_chunk(m, w, xc, x_dtype, n, yc, b0 == 0, s)
+                                       : forward_fa_chunk(m, w, xc, x_dtype, n, depth, yc, b0 == 0, s);
+        if (rc) return rc;
+    }
+    m->last_batch = std::min(chunk, batch);
+    m->last_depth = depth;
+    if (!y_on_device) C3B_CUDA(cudaMemcpyAsync(y, yd, (size_t)batch * m->out_dim * 4, cudaMemcpyDeviceToHost, s));
+    if (!x_on_device || !y_on_device) {
+        C3B_CUDA(cudaStreamSynchronize(s));
+        C3B_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ taps (debug)
+extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int64_t *count_inout) {
+    if (!m || !name || !count_inout) { c3b_set_error("c3b_get_tap: null argument"); return 1; }
+    C3B_CUDA(cudaSetDevice(m->device));
+    for (Workspace *w : m->ws) {
+        auto git = g_taps.find(w);
+        if (git == g_taps.end()) continue;
+        auto it = git->second.taps.find(name);
+        if (it == git->second.taps.end()) continue;
+        const Tap &t = it->second;
+        const int64_t n = m->last_batch;
+        const int64_t count = n * t.inner;
+        if (*count_inout < count || !host_out) { *count_inout = count; c3b_set_error("c3b_get_tap: buffer too small"); return 1; }
+        C3B_CUDA(cudaStreamSynchronize(w->stream));
+        const int64_t rows = t.layout == 1 ? (int64_t)C3B_T * t.bp : n;
+        const int64_t src_count = t.layout == 1 ? rows * t.inner : count;
+        std::vector<float> tmp((size_t)src_count);
+        if (t.fmt == 0) {
+            C3B_CUDA(cudaMemcpy(tmp.data(), t.ptr, (size_t)src_count * 4, cudaMemcpyDeviceToHost));
+        } else {
+            std::vector<uint16_t> raw((size_t)src_count);
+            C3B_CUDA(cudaMemcpy(raw.data(), t.ptr, (size_t)src_count * 2, cudaMemcpyDeviceToHost));
+            for (int64_t i = 0; i < src_count; ++i) {
+                uint32_t u = (uint32_t)raw[i] << 16;
+                memcpy(&tmp[i], &u, 4);
+            }
+        }
+        if (t.layout == 1) {   // [33][bp][inner] -> [n][33][inner]
+            for (int64_t b = 0; b < n; ++b)
+                for (int tt = 0; tt < C3B_T; ++tt)
+                    memcpy(host_out + (b * C3B_T + tt) * t.inner, tmp.data() + ((int64_t)tt * t.bp + b) * t.inner, (size_t)t.inner * 4);
+            *count_inout = n * C3B_T * t.inner;
+        } else {
+            memcpy(host_out, tmp.data(), (size_t)count * 4);
+            *count_inout = count;
+        }
+        return 0;
+    }
+    c3b_set_error("c3b_get_tap: no tap named \"%s\" (run a forward first)", name);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel unit-test hooks
+// Exercise the tcgen05 implicit-GEMM kernel on caller-provided matrices (tests/test_igemm.py); not part of the drop-in API.
+extern "C" int c3b_debug_gemm(c3b_model *m, int swapped, int64_t M, int N, int K, const float *a, const float *wmat,
+                              const float *bias, int relu, int ksplit, float *out) {
+    if (!m) { c3b_set_error("c3b_debug_gemm: null model"); return 1; }
+    if (K % 8) { c3b_set_error("c3b_debug_gemm: K must be a multiple of 8"); return 1; }
+    C3B_CUDA(cudaSetDevice(m->device));
+    std::vector<uint16_t> ab((size_t)M * K);
+    for (size_t i = 0; i < ab.size(); ++i) ab[i] = c3b_f2bf(a[i]);
+    const int rb = swapped ? 128 : N;
+    std::vector<uint16_t> img = pack_igemm(N, K / 8, rb, [&](int r, int k) { return wmat[(size_t)r * K + k]; });
+    void *da = nullptr, *dw = nullptr, *db = nullptr, *dout = nullptr;
+    C3B_CUDA(cudaMalloc(&da, ab.size() * 2));
+    C3B_CUDA(cudaMalloc(&dw, img.size() * 2));
+    C3B_CUDA(cudaMalloc(&db, (size_t)N * 4));
+    const size_t out_bytes = (size_t)M * N * (swapped ? 4 : 2);
+    C3B_CUDA(cudaMalloc(&dout, out_bytes));
+    C3B_CUDA(cudaMemcpy(da, ab.data(), ab.size() * 2, cudaMemcpyHostToDevice));
+    C3B_CUDA(cudaMemcpy(dw, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    std::vector<float> zb((size_t)N, 0.f);
+    C3B_CUDA(cudaMemcpy(db, bias ? bias : zb.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
+    C3B_CUDA(cudaMemset(dout, 0, out_bytes));
+    IgemmArgs ga = {};
+    ga.a = (const __nv_bfloat16 *)da;
+    ga.m = M;
+    ga.taps = 1;
+    ga.cin = K;
+    ga.lda = K;
+    ga.w.w_img = (const __nv_bfloat16 *)dw;
+    ga.w.bias = (const float *)db;
+    ga.w.n = N;
+    ga.w.kgroups = K / 8;
+    ga.w.nchunks = (K / 8 + 7) / 8;
+    ga.out = dout;
+    ga.ldo = N;
+    ga.relu = relu;
+    ga.epilogue = swapped ? IGEMM_EPI_F32_ATOMIC : IGEMM_EPI_BF16_BIAS_RELU;
+    ga.ksplit = ksplit;
+    int rc = c3b_launch_igemm(m, ga, 0);
+    if (!rc) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { c3b_set_error("igemm kernel failed: %s", cudaGetErrorString(e)); rc = 1; }
+    }
+    if (!rc) {
+        if (swapped) {
+            C3B_CUDA(cudaMemcpy(out, dout, out_bytes, cudaMemcpyDeviceToHost));
+        } else {
+            std::vector<uint16_t> raw((size_t)M * N);
+            C3B_CUDA(cudaMemcpy(raw.data(), dout, out_bytes, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < raw.size(); ++i) {
+                uint32_t u = (uint32_t)raw[i] << 16;
+                memcpy(&out[i], &u, 4);
+            }
+        }
+    }
+    cudaFree(da); cudaFree(dw); cudaFree(db); cudaFree(dout);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ destroy
+extern "C" void c3b_destroy(c3b_model *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    for (Workspace *w : m->ws) {
+        g_taps.erase(w);
+        if (w->dev) cudaFree(w->dev);
+        if (w->dev_x) cudaFree(w->dev_x);
+        if (w->dev_y) cudaFree(w->dev_y);
+        delete w;
+    }
+    if (m->blob) cudaFree(m->blob);
+    if (m->f32blob) cudaFree(m->f32blob);
+    delete m;
+}

@@ -1,0 +1,192 @@
+// Internal declarations shared by the C-ABI translation unit and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/clair3_b200.h"
+
+#define C3B_T 33            // positions per site (shared/param_p.py:34-35)
+#define C3B_H1 128          // LSTM1 hidden (clair3/model.py:46)
+#define C3B_H2 160          // LSTM2 hidden (clair3/model.py:47)
+#define C3B_MAX_HEADS 4
+
+void c3b_set_error(const char *fmt, ...);
+
+#define C3B_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            c3b_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+struct HostParam {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+// One dense head: L5_k (D4 -> 128) then Y_k (128 -> n).  fp32, transposed for coalesced reads.
+struct HeadWeights {
+    const float *w5t;   // [D4][128]
+    const float *b5;    // [128]
+    const float *wyt;   // [128][n]
+    const float *by;    // [n]
+    int n;
+    int out_off;
+};
+
+struct HeadsParams {
+    HeadWeights h[C3B_MAX_HEADS];
+    const float *b4;    // [D4]
+    int nheads;
+    int d4;
+    int out_dim;
+};
+
+// ---- fp32 debug path weights (device pointers) ----
+struct LstmF32 {
+    const float *wih_t;  // [I][4H]
+    const float *whh_t;  // [H][4H]
+    const float *bias;   // [4H] = b_ih + b_hh
+};
+struct ConvF32 {
+    const float *w;      // [9][Cin][Cout]  (BN folded; conv1 also carries 1/100)
+    const float *bias;   // [Cout]          (BN folded)
+    int cin, cout, stride;
+};
+
+// ---- tensor-core path packed operands (device pointers into the weight blob) ----
+struct LstmTC {
+    const __nv_bfloat16 *w_img;   // UMMA A-operand image: [nblk][K/8][128 rows][8] bf16, rows permuted (see lstm_tc.cu)
+    const float *bias;            // [nblk*128] permuted, b_ih + b_hh (LSTM1 only; LSTM2's bias rides in the projection)
+};
+struct IgemmW {
+    const __nv_bfloat16 *w_img;   // UMMA B-operand image per k-chunk: [nchunks][8 kgroups][N rows][8] bf16
+    const float *bias;            // [N]
+    int n;                        // output columns (Cout / gate rows / dense units)
+    int kgroups;                  // K/8 (16-byte k-groups), real
+    int nchunks;                  // ceil(kgroups/8)
+};
+
+struct ConvGeom {
+    int hin, win, cin, hout, wout, cout, stride;
+};
+
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    bool in_use = false;
+    int64_t cap_sites = 0;
+    int depth = 0;
+    // generic device scratch, carved by the forward pass
+    char *dev = nullptr;
+    size_t dev_bytes = 0;
+    // staging for host-side callers
+    void *pin_x = nullptr;
+    size_t pin_x_bytes = 0;
+    float *pin_y = nullptr;
+    size_t pin_y_bytes = 0;
+    void *dev_x = nullptr;
+    size_t dev_x_bytes = 0;
+    float *dev_y = nullptr;
+    size_t dev_y_bytes = 0;
+    // named regions of the last forward (for taps)
+    std::map<std::string, std::pair<void *, int64_t>> taps;
+};
+
+struct c3b_model {
+    int kind = 0, channels = 0, add_indel = 0, device = 0;
+    int nheads = 2, out_dim = 24, d4 = 128, l4_in = 0;
+    int precision = C3B_PREC_BF16_TC;
+    int chunk_sites = 0;
+    int lstm_tile = 0;
+    int sm_count = 148;
+    bool finalized = false;
+    std::map<std::string, HostParam> params;
+    std::vector<std::string> expected;
+    std::map<std::string, std::vector<int64_t>> expected_shape;
+
+    // device weights
+    char *blob = nullptr;        // tensor-core images + shared fp32 head weights (broadcast unit)
+    size_t blob_bytes = 0;
+    char *f32blob = nullptr;     // fp32 debug path weights
+    size_t f32blob_bytes = 0;
+
+    HeadsParams heads;
+    // fp32 path
+    LstmF32 lstm_f32[2][2];
+    const float *l4_f32_t = nullptr;   // [l4_in][d4]
+    ConvF32 conv_f32[9];
+    // tc path
+    LstmTC lstm_tc[2][2];
+    IgemmW proj2;                      // LSTM2 input projection, both directions: N = 1280
+    IgemmW l4_tc;
+    IgemmW conv_tc[9];
+
+    std::vector<Workspace *> ws;
+    int64_t launches = 0;
+    int last_depth = 0;
+    int64_t last_batch = 0;
+};
+
+// conv order used everywhere: 0 conv1, 1 rb1.conv1, 2 rb1.conv2, 3 conv3, 4 rb2.conv1, 5 rb2.conv2, 6 conv5, 7 rb3.conv1, 8 rb3.conv2
+
+// ---- kernels_common.cu ----
+int c3b_launch_ingest_pileup_f32(const void *x, int dtype, float *out, int64_t n_elems, cudaStream_t s);
+int c3b_launch_ingest_fa_f32(const void *x, int dtype, float *out, int64_t n_elems, cudaStream_t s);
+int c3b_launch_heads(const float *z4, const HeadsParams &hp, float *out, int64_t batch, cudaStream_t s);
+
+// ---- kernels_fp32.cu ----
+int c3b_launch_lstm_f32(const float *x, const LstmF32 &fwd, const LstmF32 &bwd, float *out, int64_t batch, int in_dim,
+                        int hidden, cudaStream_t s);
+int c3b_launch_dense_f32(const float *x, const float *w_t, float *out, int64_t batch, int k, int n, cudaStream_t s);
+int c3b_launch_conv_f32(const float *x, const ConvF32 &w, const float *residual, float *out, int64_t batch, int hin,
+                        int win, int hout, int wout, cudaStream_t s);
+int c3b_launch_spp_f32(const float *x, float *out, int64_t batch, int h, int w, int c, cudaStream_t s);
+
+// ---- tensor-core path (lstm_tc.cu / igemm_tc.cu) ----
+struct TcPileupBuffers {
+    __nv_bfloat16 *xs;     // [33][B][32] bf16, time-major, channels zero-padded 18 -> 32
+    __nv_bfloat16 *h1;     // [33][B][256] bf16, time-major
+    __half *pg;            // [33*B][1280] fp16 pre-gates of LSTM2 (bias included), permuted gate columns
+    __nv_bfloat16 *h2;     // [B][33][320] bf16, batch-major (flatten order of clair3/model.py:135)
+    float *z4;             // [B][128] fp32, L4 pre-activation without bias (split-K accumulated)
+};
+int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, __nv_bfloat16 *xs, int64_t batch, cudaStream_t s);
+int c3b_launch_lstm1_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t batch, int tile, cudaStream_t s);
+int c3b_launch_lstm2_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t batch, int tile, cudaStream_t s);
+
+// Generic implicit GEMM on tcgen05:  D[M x N] = A[M x K] * W[N x K]^T with fused epilogues.
+enum IgemmEpilogue {
+    IGEMM_EPI_BF16_BIAS_RELU = 0,   // bf16 NHWC store, + bias, optional residual add, ReLU      (convs)
+    IGEMM_EPI_F16_BIAS = 1,         // fp16 row-major store, + bias                              (LSTM2 pre-gates)
+    IGEMM_EPI_F32_ATOMIC = 2,       // fp32 atomicAdd into [M][N] (split-K)                      (L4)
+};
+struct IgemmArgs {
+    const __nv_bfloat16 *a;   // activations
+    int64_t m;                // GEMM rows (pixels / positions / sites)
+    // row addressing: conv mode (taps = 9) or plain (taps = 1)
+    int taps;                 // 1 or 9
+    int hin, win, cin;        // conv input geometry (NHWC); plain: cin = K, hin = win = 1
+    int hout, wout, stride;   // conv output geometry
+    int64_t lda;              // plain mode: row stride in elements
+    IgemmW w;
+    void *out;                // bf16 / f16 / f32
+    int64_t ldo;              // output row stride in elements
+    const __nv_bfloat16 *residual;   // optional (same layout as out, bf16)
+    int relu;
+    int epilogue;
+    int ksplit;               // >1: split K chunks across blockIdx.y (atomic epilogue only)
+};
+int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s);
+
+int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, __nv_bfloat16 *out, int64_t n_pix, cudaStream_t s);
+int c3b_launch_spp_tc(const __nv_bfloat16 *x, __nv_bfloat16 *out, int64_t batch, int h, int w, int c, cudaStream_t s);
+
+// host-side packing helpers (c3b_pack.cu)
+uint16_t c3b_f2bf(float f);

@@ -1,0 +1,72 @@
+// Small memory-bound kernels around the tensor-core convolution stack of Clair3_F:
+//  * ingest: int8 NHWC read image [B,D,33,C] -> bf16 [B,D,33,Cpad] (Cpad = 8 or 16); the 1/100 normalisation of
+//    clair3/model.py:378 is folded into conv1's weights, and int8 values are exact in bf16.
+//  * spp: 3-level spatial pyramid max pool (clair3/model.py:250-279) on the bf16 NHWC res_block3 output.
+#include "c3b_internal.h"
+
+namespace {
+
+template <typename T>
+__global__ void ingest_fa_tc_kernel(const T *__restrict__ x, __nv_bfloat16 *__restrict__ out, int64_t n_pix, int channels,
+                                    int cpad) {
+    const int groups = cpad / 8;
+    const int64_t total = n_pix * groups;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = idx / groups;
+        const int g = (int)(idx - pix * groups);
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int ch = g * 8 + i;
+            v[i] = __float2bfloat16_rn(ch < channels ? (float)x[pix * channels + ch] : 0.f);
+        }
+        *reinterpret_cast<uint4 *>(out + idx * 8) = *reinterpret_cast<const uint4 *>(v);
+    }
+}
+
+__global__ void spp_tc_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ out, int h, int w, int c) {
+    const int64_t b = blockIdx.x;
+    const int cells = 14;
+    for (int i = threadIdx.x; i < cells * c; i += blockDim.x) {
+        const int cell = i / c, ch = i - cell * c;
+        int p, idx;
+        if (cell < 9) { p = 3; idx = cell; }
+        else if (cell < 13) { p = 2; idx = cell - 9; }
+        else { p = 1; idx = 0; }
+        const int wh = (h + p - 1) / p, ww = (w + p - 1) / p;
+        const int oh = (h + wh - 1) / wh, ow = (w + ww - 1) / ww;
+        const int ph = max((oh - 1) * wh + wh - h, 0), pw = max((ow - 1) * ww + ww - w, 0);
+        const int pt = ph / 2, pl = pw / 2;
+        const int oi = idx / ow, oj = idx - oi * ow;
+        const int h0 = oi * wh - pt, w0 = oj * ww - pl;
+        float m = 0.f;                       // inputs are post-ReLU: zero padding == floor at 0
+        for (int hh = max(h0, 0); hh < min(h0 + wh, h); ++hh)
+            for (int wv = max(w0, 0); wv < min(w0 + ww, w); ++wv)
+                m = fmaxf(m, __bfloat162float(x[((b * h + hh) * w + wv) * c + ch]));
+        out[b * (cells * c) + i] = __float2bfloat16_rn(m);
+    }
+}
+
+}  // namespace
+
+int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, __nv_bfloat16 *out, int64_t n_pix,
+                            cudaStream_t s) {
+    if (n_pix == 0) return 0;
+    const int64_t total = n_pix * (cpad / 8);
+    const int blocks = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
+    switch (dtype) {
+        case C3B_DT_I8: ingest_fa_tc_kernel<int8_t><<<blocks, 256, 0, s>>>((const int8_t *)x, out, n_pix, channels, cpad); break;
+        case C3B_DT_I32: ingest_fa_tc_kernel<int32_t><<<blocks, 256, 0, s>>>((const int32_t *)x, out, n_pix, channels, cpad); break;
+        case C3B_DT_F32: ingest_fa_tc_kernel<float><<<blocks, 256, 0, s>>>((const float *)x, out, n_pix, channels, cpad); break;
+        default: c3b_set_error("unsupported input dtype %d", dtype); return 1;
+    }
+    C3B_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int c3b_launch_spp_tc(const __nv_bfloat16 *x, __nv_bfloat16 *out, int64_t batch, int h, int w, int c, cudaStream_t s) {
+    if (batch == 0) return 0;
+    spp_tc_kernel<<<(unsigned)batch, 256, 0, s>>>(x, out, h, w, c);
+    C3B_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,111 @@
+// Kernels shared by both precisions: input ingest (dtype -> float) and the dense multi-task heads
+// (SELU(L4) -> SELU(L5_k) -> SELU(Y_k) -> softmax, clair3/model.py:136-159 and 391-411), all fp32 on CUDA cores.
+#include "c3b_internal.h"
+
+namespace {
+
+constexpr float kSeluAlpha = 1.6732632423543772f;
+constexpr float kSeluScale = 1.0507009873554805f;
+
+__device__ __forceinline__ float selu(float x) {
+    return kSeluScale * (x > 0.f ? x : kSeluAlpha * expm1f(x));
+}
+
+template <typename T>
+__global__ void ingest_f32_kernel(const T *__restrict__ x, float *__restrict__ out, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = (float)x[i];
+}
+
+constexpr int HEADS_G = 8;        // sites per block
+constexpr int HEADS_THREADS = 128;
+
+// z4: [B][D4] L4 pre-activation WITHOUT bias.  One block handles HEADS_G sites so head weights are read once per 8 sites.
+__global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__restrict__ z4, HeadsParams hp,
+                                                              float *__restrict__ out, int64_t batch) {
+    extern __shared__ float smem[];
+    const int d4 = hp.d4;
+    float *a = smem;                         // [G][d4]
+    float *l5 = a + HEADS_G * d4;            // [G][128]
+    float *yv = l5 + HEADS_G * 128;          // [G][36]
+    const int tid = threadIdx.x;
+    const int64_t b0 = (int64_t)blockIdx.x * HEADS_G;
+    const int g_n = (int)min((int64_t)HEADS_G, batch - b0);
+
+    for (int i = tid; i < HEADS_G * d4; i += HEADS_THREADS) {
+        int g = i / d4, k = i - g * d4;
+        a[i] = (g < g_n) ? selu(z4[(b0 + g) * d4 + k] + hp.b4[k]) : 0.f;
+    }
+    __syncthreads();
+
+    for (int h = 0; h < hp.nheads; ++h) {
+        const HeadWeights hw = hp.h[h];
+        float acc[HEADS_G];
+        const float bias = hw.b5[tid];
+#pragma unroll
+        for (int g = 0; g < HEADS_G; ++g) acc[g] = bias;
+        for (int k = 0; k < d4; ++k) {
+            const float w = hw.w5t[k * 128 + tid];
+#pragma unroll
+            for (int g = 0; g < HEADS_G; ++g) acc[g] = fmaf(a[g * d4 + k], w, acc[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < HEADS_G; ++g) l5[g * 128 + tid] = selu(acc[g]);
+        __syncthreads();
+        for (int i = tid; i < HEADS_G * hw.n; i += HEADS_THREADS) {
+            int g = i / hw.n, o = i - g * hw.n;
+            float s = hw.by[o];
+            for (int j = 0; j < 128; ++j) s = fmaf(l5[g * 128 + j], hw.wyt[j * hw.n + o], s);
+            yv[g * 36 + o] = selu(s);
+        }
+        __syncthreads();
+        if (tid < g_n) {
+            const float *v = yv + tid * 36;
+            float mx = v[0];
+            for (int o = 1; o < hw.n; ++o) mx = fmaxf(mx, v[o]);
+            float sum = 0.f;
+            for (int o = 0; o < hw.n; ++o) sum += expf(v[o] - mx);
+            const float inv = 1.f / sum;
+            float *dst = out + (b0 + tid) * hp.out_dim + hw.out_off;
+            for (int o = 0; o < hw.n; ++o) dst[o] = expf(v[o] - mx) * inv;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+int launch_ingest(const void *x, float *out, int64_t n, cudaStream_t s) {
+    if (n == 0) return 0;
+    int blocks = (int)min((int64_t)4096, (n + 255) / 256);
+    ingest_f32_kernel<T><<<blocks, 256, 0, s>>>((const T *)x, out, n);
+    C3B_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ingest_any(const void *x, int dtype, float *out, int64_t n, cudaStream_t s) {
+    switch (dtype) {
+        case C3B_DT_I8: return launch_ingest<int8_t>(x, out, n, s);
+        case C3B_DT_I32: return launch_ingest<int32_t>(x, out, n, s);
+        case C3B_DT_F32: return launch_ingest<float>(x, out, n, s);
+        default: c3b_set_error("unsupported input dtype %d", dtype); return 1;
+    }
+}
+
+}  // namespace
+
+int c3b_launch_ingest_pileup_f32(const void *x, int dtype, float *out, int64_t n, cudaStream_t s) {
+    return ingest_any(x, dtype, out, n, s);
+}
+int c3b_launch_ingest_fa_f32(const void *x, int dtype, float *out, int64_t n, cudaStream_t s) {
+    return ingest_any(x, dtype, out, n, s);
+}
+
+int c3b_launch_heads(const float *z4, const HeadsParams &hp, float *out, int64_t batch, cudaStream_t s) {
+    if (batch == 0) return 0;
+    size_t smem = sizeof(float) * (HEADS_G * hp.d4 + HEADS_G * 128 + HEADS_G * 36);
+    int blocks = (int)((batch + HEADS_G - 1) / HEADS_G);
+    heads_kernel<<<blocks, HEADS_THREADS, smem, s>>>(z4, hp, out, batch);
+    C3B_CUDA(cudaGetLastError());
+    return 0;
+}

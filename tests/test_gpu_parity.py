@@ -1,0 +1,207 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Everything goes through the C-ABI
+(``libclair3b200.so`` via cffi); the checker is the oracle / the golden vectors minted from the reference.
+
+Tolerances (stated):
+  * fp32 debug kernels vs the fp32 reference:   max |dp| <= 1e-4 on probabilities, taps rel-L2 <= 1e-4
+  * bf16 tensor-core kernels vs the fp32 reference: max |dp| <= 2e-2, mean |dp| <= 2e-3, taps rel-L2 <= 2e-2,
+    >= 99% arg-max agreement per head.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_FA, GOLDEN_PILEUP, golden_case
+
+pytestmark = pytest.mark.gpu
+
+FP32, TC = 1, 0
+HEAD_SLICES = [(0, 21), (21, 24), (24, 57), (57, 90)]
+
+
+def _relerr(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def _model(meta, sd, precision, **opts):
+    from clair3_b200.model import Clair3_F, Clair3_P
+    cls = Clair3_P if meta["kind"] == "pileup" else Clair3_F
+    ch = 18 if meta["kind"] == "pileup" else meta["channels"]
+    m = cls(add_indel_length=meta["add_indel_length"], predict=True, input_channels=ch)
+    m.set_option("precision", precision)
+    for k, v in opts.items():
+        m.set_option(k, v)
+    m.to(torch.device("cuda"))
+    m.eval()
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    return m
+
+
+def _check_probs(y, ref, max_tol, mean_tol, argmax_frac):
+    assert y.shape == ref.shape
+    assert np.isfinite(y).all()
+    d = np.abs(y - ref)
+    assert d.max() <= max_tol, "max |dp| %.3e" % d.max()
+    assert d.mean() <= mean_tol, "mean |dp| %.3e" % d.mean()
+    for lo, hi in HEAD_SLICES:
+        if hi <= y.shape[1]:
+            assert np.allclose(y[:, lo:hi].sum(1), 1.0, atol=1e-4)
+            agree = (y[:, lo:hi].argmax(1) == ref[:, lo:hi].argmax(1)).mean()
+            assert agree >= argmax_frac, "argmax agreement %.3f" % agree
+
+
+@pytest.mark.parametrize("name", GOLDEN_PILEUP + GOLDEN_FA)
+def test_fp32_kernels_match_reference(name):
+    z, meta, sd, x = golden_case(name)
+    m = _model(meta, sd, FP32)
+    y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    _check_probs(y, z["y"], 1e-4, 1e-5, 1.0)
+    for tap in ("lstm1", "lstm2", "spp", "l4_pre"):
+        if "tap_" + tap in z.files:
+            got = m.tap(tap).reshape(x.shape[0], -1)
+            want = z["tap_" + tap]
+            if tap == "l4_pre":       # library tap excludes the L4 bias
+                got = got + sd["L4.bias"][None, :]
+            n = want.shape[0]
+            assert _relerr(got[:n].reshape(want.shape), want) < 1e-4, tap
+
+
+@pytest.mark.parametrize("name", GOLDEN_PILEUP + GOLDEN_FA)
+def test_tensor_core_kernels_match_reference(name):
+    z, meta, sd, x = golden_case(name)
+    m = _model(meta, sd, TC)
+    y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    for tap in ("lstm1", "lstm2", "spp", "l4_pre"):
+        if "tap_" + tap in z.files:
+            got = m.tap(tap).reshape(x.shape[0], -1)
+            want = z["tap_" + tap]
+            if tap == "l4_pre":
+                got = got + sd["L4.bias"][None, :]
+            n = want.shape[0]
+            assert _relerr(got[:n].reshape(want.shape), want) < 2e-2, tap
+    _check_probs(y, z["y"], 2e-2, 2e-3, 0.99)
+
+
+def test_tensor_core_conv_taps_match_reference():
+    z, meta, sd, x = golden_case("f8")
+    m = _model(meta, sd, TC)
+    m(torch.from_numpy(x).cuda())
+    for tap in ("conv1", "res_block1", "conv3", "res_block2", "conv5", "res_block3"):
+        want = z["tap_" + tap]                         # [1,C,H,W]
+        got = m.tap(tap).reshape(x.shape[0], want.shape[2], want.shape[3], want.shape[1])[:1].transpose(0, 3, 1, 2)
+        assert _relerr(got, want) < 2e-2, tap
+
+
+@pytest.mark.parametrize("swapped,M,N,K,ksplit", [
+    (0, 128, 64, 64, 1), (0, 300, 64, 72, 1), (0, 1000, 128, 576, 1), (0, 257, 256, 1152, 1), (0, 130, 16, 16, 1),
+    (1, 128, 128, 64, 1), (1, 200, 256, 256, 1), (1, 77, 128, 1064, 3), (1, 1024, 128, 10560, 11),
+])
+def test_igemm_kernel_against_numpy(swapped, M, N, K, ksplit):
+    from clair3_b200._ffi import check, ffi, lib
+    r = np.random.default_rng(M + N + K)
+    a = r.standard_normal((M, K)).astype(np.float32)
+    w = (r.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = r.standard_normal(N).astype(np.float32)
+    out = np.zeros((M, N), dtype=np.float32)
+    h = ffi.new("c3b_model **")
+    check(lib().c3b_create(h, 0, 18, 0, 0))
+    try:
+        check(lib().c3b_debug_gemm(h[0], swapped, M, N, K, ffi.cast("float *", a.ctypes.data),
+                                   ffi.cast("float *", w.ctypes.data), ffi.cast("float *", bias.ctypes.data), 1, ksplit,
+                                   ffi.cast("float *", out.ctypes.data)))
+    finally:
+        lib().c3b_destroy(h[0])
+    a16 = torch.from_numpy(a).bfloat16().float().numpy().astype(np.float64)
+    w16 = torch.from_numpy(w).bfloat16().float().numpy().astype(np.float64)
+    ref = a16 @ w16.T
+    if not swapped:
+        ref = np.maximum(ref + bias, 0)
+        tol = 2e-2                      # output is bf16-rounded
+    else:
+        tol = 1e-3
+    assert np.abs(out - ref).max() <= tol * max(1.0, np.abs(ref).max())
+
+
+def test_ragged_empty_and_host_buffers():
+    z, meta, sd, x = golden_case("p24")
+    m = _model(meta, sd, TC)
+    full = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    # host in / host out (the _torch_predict shape: numpy in, numpy out)
+    y_host = m(torch.from_numpy(x))
+    assert y_host.device.type == "cpu"
+    assert np.abs(y_host.numpy() - full).max() < 1e-6
+    # ragged batches: any B >= 1, every site independent of its batch neighbours
+    for b in (1, 7, 33):
+        yb = m(torch.from_numpy(x[:b]).cuda()).cpu().numpy()
+        assert np.abs(yb - full[:b]).max() < 1e-6
+    assert m(torch.from_numpy(x[:0]).cuda()).shape == (0, 24)
+    # chunked internal passes give the same answer
+    m.set_option("chunk_sites", 16)
+    assert np.abs(m(torch.from_numpy(x).cuda()).cpu().numpy() - full).max() < 1e-6
+
+
+def test_lstm_tiles_agree():
+    z, meta, sd, x = golden_case("p24")
+    outs = []
+    for tile in (16, 32, 64):
+        m = _model(meta, sd, TC, lstm_tile=tile)
+        outs.append(m(torch.from_numpy(x).cuda()).cpu().numpy())
+    assert np.abs(outs[0] - outs[1]).max() < 1e-5 and np.abs(outs[0] - outs[2]).max() < 1e-5
+
+
+def test_input_dtypes_agree():
+    z, meta, sd, x = golden_case("p24_int8")
+    m = _model(meta, sd, TC)
+    y8 = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    y32 = m(torch.from_numpy(x.astype(np.int32)).cuda()).cpu().numpy()
+    yf = m(torch.from_numpy(x.astype(np.float32)).cuda()).cpu().numpy()
+    assert np.array_equal(y8, y32) and np.array_equal(y8, yf)
+
+
+def test_strict_state_dict_errors():
+    from clair3_b200._ffi import C3BError
+    z, meta, sd, x = golden_case("p24")
+    bad = dict(sd)
+    bad.pop("L4.bias")
+    with pytest.raises(C3BError, match="Missing key"):
+        _model(meta, bad, TC)
+    bad = dict(sd)
+    bad["nonsense.weight"] = np.zeros(3, dtype=np.float32)
+    with pytest.raises(C3BError, match="Unexpected key"):
+        _model(meta, bad, TC)
+    bad = dict(sd)
+    bad["L4.weight"] = np.zeros((128, 10), dtype=np.float32)
+    with pytest.raises(C3BError, match="size mismatch"):
+        _model(meta, bad, TC)
+
+
+def test_large_batch_properties():
+    """BASELINE.json full sizes through size-independent properties: rows are probability vectors, every site is
+    independent of its batch neighbours (permutation equivariance), and the fp32 and bf16 paths agree."""
+    from clair3_b200 import synth
+    sd = synth.pileup_state_dict(False, seed=11)
+    x = synth.pileup_inputs(1024, seed=11)
+    meta = dict(kind="pileup", add_indel_length=False)
+    m = _model(meta, sd, TC)
+    y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.isfinite(y).all() and np.allclose(y[:, :21].sum(1), 1, atol=1e-4) and np.allclose(y[:, 21:].sum(1), 1, atol=1e-4)
+    perm = np.random.default_rng(0).permutation(1024)
+    yp = m(torch.from_numpy(x[perm]).cuda()).cpu().numpy()
+    assert np.abs(yp - y[perm]).max() < 1e-6
+    m32 = _model(meta, sd, FP32)
+    y32 = m32(torch.from_numpy(x[:256]).cuda()).cpu().numpy()
+    assert np.abs(y[:256] - y32).max() < 2e-2
+
+    sdf = synth.fa_state_dict(True, channels=8, seed=12)
+    xf = synth.fa_inputs(256, depth=89, channels=8, seed=12)
+    metaf = dict(kind="fa", add_indel_length=True, channels=8)
+    mf = _model(metaf, sdf, TC)
+    yf = mf(torch.from_numpy(xf).cuda()).cpu().numpy()
+    assert np.isfinite(yf).all()
+    for lo, hi in HEAD_SLICES:
+        assert np.allclose(yf[:, lo:hi].sum(1), 1, atol=1e-4)
+    permf = np.random.default_rng(1).permutation(256)
+    ypf = mf(torch.from_numpy(xf[permf]).cuda()).cpu().numpy()
+    assert np.abs(ypf - yf[permf]).max() < 1e-6
+    # all-zero rows beyond read depth (calloc'ed tensors): an all-zero site must still give finite probabilities
+    z0 = mf(torch.zeros((4, 89, 33, 8), dtype=torch.int8).cuda()).cpu().numpy()
+    assert np.isfinite(z0).all()

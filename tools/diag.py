@@ -1,0 +1,115 @@
+"""GPU diagnostics: per-case, per-tap error report for both precisions (prints, never asserts).
+
+    python tools/diag.py fp32|tc|igemm [case ...]
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from conftest import GOLDEN_FA, GOLDEN_PILEUP, golden_case  # noqa: E402
+
+
+def relerr(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def run_case(name, precision, opts):
+    from clair3_b200.model import Clair3_F, Clair3_P
+    z, meta, sd, x = golden_case(name)
+    cls = Clair3_P if meta["kind"] == "pileup" else Clair3_F
+    ch = 18 if meta["kind"] == "pileup" else meta["channels"]
+    m = cls(add_indel_length=meta["add_indel_length"], predict=True, input_channels=ch)
+    m.set_option("precision", precision)
+    for k, v in opts.items():
+        m.set_option(k, v)
+    m.to(torch.device("cuda"))
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    t0 = time.time()
+    y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    dt = time.time() - t0
+    d = np.abs(y - z["y"])
+    print(f"[{name}] prec={precision} opts={opts} out max|dp|={d.max():.3e} mean|dp|={d.mean():.3e} "
+          f"finite={np.isfinite(y).all()} ({dt*1e3:.1f} ms first call)", flush=True)
+    for tap in ("lstm1", "lstm2", "conv1", "res_block1", "conv3", "res_block2", "conv5", "res_block3", "spp", "l4_pre"):
+        key = "tap_" + tap
+        if key not in z.files:
+            continue
+        want = z[key]
+        try:
+            got = m.tap(tap)
+        except Exception as e:  # noqa: BLE001
+            print(f"    tap {tap}: unavailable ({e})")
+            continue
+        if tap in ("conv1", "res_block1", "conv3", "res_block2", "conv5", "res_block3"):
+            got = got.reshape(x.shape[0], want.shape[2], want.shape[3], want.shape[1])[:1].transpose(0, 3, 1, 2)
+        else:
+            got = got.reshape(x.shape[0], -1)
+            if tap == "l4_pre":
+                got = got + sd["L4.bias"][None, :]
+            got = got[:want.shape[0]].reshape(want.shape)
+        print(f"    tap {tap:11s} rel-L2 {relerr(got, want):.3e}  max|d| {np.abs(got - want).max():.3e}  "
+              f"(|ref| max {np.abs(want).max():.2f})", flush=True)
+
+
+def run_igemm():
+    from clair3_b200._ffi import check, ffi, lib
+    shapes = [(0, 128, 64, 64, 1), (0, 128, 16, 16, 1), (0, 300, 64, 72, 1), (0, 1000, 128, 576, 1), (0, 257, 256, 1152, 1),
+              (1, 128, 128, 64, 1), (1, 200, 256, 256, 1), (1, 77, 128, 1064, 3), (1, 1024, 128, 10560, 11)]
+    for swapped, M, N, K, ks in shapes:
+        r = np.random.default_rng(M + N + K)
+        a = r.standard_normal((M, K)).astype(np.float32)
+        w = (r.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+        bias = r.standard_normal(N).astype(np.float32)
+        out = np.zeros((M, N), dtype=np.float32)
+        h = ffi.new("c3b_model **")
+        check(lib().c3b_create(h, 0, 18, 0, 0))
+        try:
+            check(lib().c3b_debug_gemm(h[0], swapped, M, N, K, ffi.cast("float *", a.ctypes.data),
+                                       ffi.cast("float *", w.ctypes.data), ffi.cast("float *", bias.ctypes.data), 0, ks,
+                                       ffi.cast("float *", out.ctypes.data)))
+        except Exception as e:  # noqa: BLE001
+            print(f"igemm swapped={swapped} M={M} N={N} K={K}: ERROR {e}", flush=True)
+            continue
+        finally:
+            lib().c3b_destroy(h[0])
+        a16 = torch.from_numpy(a).bfloat16().float().numpy().astype(np.float64)
+        w16 = torch.from_numpy(w).bfloat16().float().numpy().astype(np.float64)
+        ref = a16 @ w16.T + (0 if swapped else bias)
+        err = np.abs(out - ref)
+        print(f"igemm swapped={swapped} M={M} N={N} K={K} ks={ks}: max err {err.max():.3e} (|ref| max {np.abs(ref).max():.2f}) "
+              f"rel {relerr(out, ref):.3e}", flush=True)
+        if err.max() > 0.1:
+            # help localise layout bugs: error by row block / column block
+            rb = err.reshape(-1, N)[:128].max(axis=1)
+            cb = err[:128].max(axis=0)
+            print("    row err (first 16):", np.round(rb[:16], 2), " col err (first 16):", np.round(cb[:16], 2))
+            print("    out[0,:8]", np.round(out[0, :8], 3), " ref[0,:8]", np.round(ref[0, :8], 3))
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1]
+    cases = sys.argv[2:] or (GOLDEN_PILEUP + GOLDEN_FA)
+    opts = {}
+    cases2 = []
+    for c in cases:
+        if "=" in c:
+            k, v = c.split("=")
+            opts[k] = int(v)
+        else:
+            cases2.append(c)
+    cases = cases2 or (GOLDEN_PILEUP + GOLDEN_FA)
+    if mode == "igemm":
+        run_igemm()
+    else:
+        for c in cases:
+            try:
+                run_case(c, 1 if mode == "fp32" else 0, opts)
+            except Exception as e:  # noqa: BLE001
+                print(f"[{c}] ERROR: {e}", flush=True)
