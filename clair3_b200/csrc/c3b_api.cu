@@ -223,6 +223,13 @@ extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
     } else if (!strcmp(name, "chunk_sites")) {
         if (value < 0) { c3b_set_error("bad chunk_sites %d", value); return 1; }
         m->chunk_sites = value;
+    } else if (!strcmp(name, "profile")) {
+        m->profile = value ? 1 : 0;
+        m->prof_total.clear();
+        for (Workspace *w : m->ws) {
+            for (auto &r : w->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+            w->prof.clear();
+        }
     } else if (!strcmp(name, "lstm_tile")) {
         if (value != 0 && value != 16 && value != 32 && value != 64) { c3b_set_error("bad lstm_tile %d", value); return 1; }
         m->lstm_tile = value;
@@ -519,6 +526,49 @@ struct Carver {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ profiling
+struct ProfScope {
+    c3b_model *m; Workspace *w; cudaStream_t s; cudaEvent_t e0 = nullptr, e1 = nullptr; const char *name;
+    ProfScope(c3b_model *m_, Workspace *w_, cudaStream_t s_, const char *name_) : m(m_), w(w_), s(s_), name(name_) {
+        if (m->profile) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, s);
+        }
+    }
+    ~ProfScope() {
+        if (m->profile) {
+            cudaEventRecord(e1, s);
+            w->prof.push_back({name, e0, e1});
+        }
+    }
+};
+#define PROF(name) ProfScope _prof_scope(m, w, s, name)
+
+extern "C" int c3b_get_profile(c3b_model *m, const char *kernel, double *total_ms, int64_t *launches) {
+    if (!m || !kernel) { c3b_set_error("c3b_get_profile: null argument"); return 1; }
+    C3B_CUDA(cudaSetDevice(m->device));
+    for (Workspace *w : m->ws) {
+        if (w->prof.empty()) continue;
+        C3B_CUDA(cudaStreamSynchronize(w->stream));
+        for (auto &r : w->prof) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+                auto &t = m->prof_total[r.name];
+                t.first += ms;
+                t.second += 1;
+            }
+            cudaEventDestroy(r.e0);
+            cudaEventDestroy(r.e1);
+        }
+        w->prof.clear();
+    }
+    auto it = m->prof_total.find(kernel);
+    if (total_ms) *total_ms = it == m->prof_total.end() ? 0.0 : it->second.first;
+    if (launches) *launches = it == m->prof_total.end() ? 0 : it->second.second;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ forward passes
 static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x_dtype, int64_t n, float *y, bool tap,
                                 cudaStream_t s) {
@@ -556,9 +606,9 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
         tile2 = tile1;
     }
     if (tile2 > 32) tile2 = 32;
-    if (c3b_launch_ingest_pileup_tc(x, x_dtype, m->channels, b.xs, n, s)) return 1;
+    { PROF("ingest"); if (c3b_launch_ingest_pileup_tc(x, x_dtype, m->channels, b.xs, n, s)) return 1; }
     m->launches += 1;
-    if (c3b_launch_lstm1_tc(m, b, n, tile1, s)) return 1;
+    { PROF("lstm1"); if (c3b_launch_lstm1_tc(m, b, n, tile1, s)) return 1; }
     IgemmArgs pa = {};
     pa.a = b.h1;
     pa.m = (int64_t)C3B_T * bp;
@@ -570,8 +620,8 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
     pa.w = m->proj2;
     pa.out = b.pg;
     pa.epilogue = IGEMM_EPI_F16_BIAS;
-    if (c3b_launch_igemm(m, pa, s)) return 1;
-    if (c3b_launch_lstm2_tc(m, b, n, tile2, s)) return 1;
+    { PROF("proj2"); if (c3b_launch_igemm(m, pa, s)) return 1; }
+    { PROF("lstm2"); if (c3b_launch_lstm2_tc(m, b, n, tile2, s)) return 1; }
     C3B_CUDA(cudaMemsetAsync(b.z4, 0, (size_t)bp * 128 * 4, s));
     IgemmArgs la = {};
     la.a = b.h2;
@@ -584,8 +634,8 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
     la.ldo = 128;
     la.epilogue = IGEMM_EPI_F32_ATOMIC;
     la.ksplit = 11;
-    if (c3b_launch_igemm(m, la, s)) return 1;
-    if (c3b_launch_heads(b.z4, m->heads, y, n, s)) return 1;
+    { PROF("l4"); if (c3b_launch_igemm(m, la, s)) return 1; }
+    { PROF("heads"); if (c3b_launch_heads(b.z4, m->heads, y, n, s)) return 1; }
     m->launches += 1;
     if (tap) {
         wt.taps["lstm1"] = {b.h1, 1, 1, 256, (int)bp};
@@ -629,7 +679,7 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
         if (c3b_launch_heads(z4, m->heads, y, n, s)) return 1;
         m->launches += 13;
     } else {
-        if (c3b_launch_ingest_fa_tc(x, x_dtype, m->channels, cpad, (__nv_bfloat16 *)xin, n * depth * 33, s)) return 1;
+        { PROF("ingest"); if (c3b_launch_ingest_fa_tc(x, x_dtype, m->channels, cpad, (__nv_bfloat16 *)xin, n * depth * 33, s)) return 1; }
         const __nv_bfloat16 *cur = (const __nv_bfloat16 *)xin;
         int cur_c = cpad;
         for (int l = 0; l < 3; ++l) {
@@ -646,17 +696,18 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
             // strided stem conv
             ca.a = cur; ca.hin = hh[l]; ca.win = ww[l]; ca.cin = cur_c; ca.stride = 2;
             ca.w = m->conv_tc[3 * l]; ca.out = a0; ca.residual = nullptr;
-            if (c3b_launch_igemm(m, ca, s)) return 1;
+            static const char *cn[9] = {"conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv8"};
+            { PROF(cn[3 * l]); if (c3b_launch_igemm(m, ca, s)) return 1; }
             // residual block
             ca.a = a0; ca.hin = hh[l + 1]; ca.win = ww[l + 1]; ca.cin = co; ca.stride = 1;
             ca.w = m->conv_tc[3 * l + 1]; ca.out = a1; ca.residual = nullptr;
-            if (c3b_launch_igemm(m, ca, s)) return 1;
+            { PROF(cn[3 * l + 1]); if (c3b_launch_igemm(m, ca, s)) return 1; }
             ca.a = a1; ca.w = m->conv_tc[3 * l + 2]; ca.out = a2; ca.residual = a0;
-            if (c3b_launch_igemm(m, ca, s)) return 1;
+            { PROF(cn[3 * l + 2]); if (c3b_launch_igemm(m, ca, s)) return 1; }
             cur = a2;
             cur_c = co;
         }
-        if (c3b_launch_spp_tc(cur, (__nv_bfloat16 *)sp, n, hh[3], ww[3], 256, s)) return 1;
+        { PROF("spp"); if (c3b_launch_spp_tc(cur, (__nv_bfloat16 *)sp, n, hh[3], ww[3], 256, s)) return 1; }
         C3B_CUDA(cudaMemsetAsync(z4, 0, (size_t)bp * 256 * 4, s));
         IgemmArgs la = {};
         la.a = (const __nv_bfloat16 *)sp;
@@ -669,8 +720,8 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
         la.ldo = 256;
         la.epilogue = IGEMM_EPI_F32_ATOMIC;
         la.ksplit = 8;
-        if (c3b_launch_igemm(m, la, s)) return 1;
-        if (c3b_launch_heads(z4, m->heads, y, n, s)) return 1;
+        { PROF("l4"); if (c3b_launch_igemm(m, la, s)) return 1; }
+        { PROF("heads"); if (c3b_launch_heads(z4, m->heads, y, n, s)) return 1; }
         m->launches += 3;
     }
     if (tap) {
@@ -770,7 +821,7 @@ extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int6
         if (it == git->second.taps.end()) continue;
         const Tap &t = it->second;
         const int64_t n = m->last_batch;
-        const int64_t count = n * t.inner;
+        const int64_t count = n * t.inner * (t.layout == 1 ? C3B_T : 1);
         if (*count_inout < count || !host_out) { *count_inout = count; c3b_set_error("c3b_get_tap: buffer too small"); return 1; }
         C3B_CUDA(cudaStreamSynchronize(w->stream));
         const int64_t rows = t.layout == 1 ? (int64_t)C3B_T * t.bp : n;
@@ -866,6 +917,7 @@ extern "C" void c3b_destroy(c3b_model *m) {
     cudaSetDevice(m->device);
     for (Workspace *w : m->ws) {
         g_taps.erase(w);
+        for (auto &r : w->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
         if (w->dev) cudaFree(w->dev);
         if (w->dev_x) cudaFree(w->dev_x);
         if (w->dev_y) cudaFree(w->dev_y);

@@ -95,8 +95,9 @@ struct Workspace {
     size_t dev_x_bytes = 0;
     float *dev_y = nullptr;
     size_t dev_y_bytes = 0;
-    // named regions of the last forward (for taps)
-    std::map<std::string, std::pair<void *, int64_t>> taps;
+    // per-kernel CUDA-event pairs recorded while option "profile" is on (resolved lazily by c3b_get_profile)
+    struct ProfRec { const char *name; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof;
 };
 
 struct c3b_model {
@@ -105,6 +106,8 @@ struct c3b_model {
     int precision = C3B_PREC_BF16_TC;
     int chunk_sites = 0;
     int lstm_tile = 0;
+    int profile = 0;
+    std::map<std::string, std::pair<double, int64_t>> prof_total;   // name -> (ms, launches)
     int sm_count = 148;
     bool finalized = false;
     std::map<std::string, HostParam> params;

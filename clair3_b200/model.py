@@ -97,13 +97,14 @@ class _C3BModule:
         L = lib()
         for key, t in sd.items():
             if t.dtype == torch.int64:
-                arr = np.ascontiguousarray(t.numpy())
+                arr = t.contiguous().numpy()
                 dt = K["C3B_DT_I64"]
             else:
-                arr = np.ascontiguousarray(t.to(torch.float32).numpy())
+                arr = t.to(torch.float32).contiguous().numpy()
                 dt = K["C3B_DT_F32"]
-            shape = ffi.new("int64_t[]", list(arr.shape) or [0])
-            check(L.c3b_set_param(self._handle, key.encode(), ffi.cast("void *", arr.ctypes.data), dt, shape, arr.ndim))
+            dims = list(t.shape)                         # 0-d tensors (num_batches_tracked) keep ndim = 0
+            shape = ffi.new("int64_t[]", dims or [0])
+            check(L.c3b_set_param(self._handle, key.encode(), ffi.cast("void *", arr.ctypes.data), dt, shape, len(dims)))
         check(L.c3b_finalize(self._handle))
 
     @property

@@ -60,7 +60,8 @@ int c3b_set_param(c3b_model *m, const char *key, const void *host_data, int dtyp
  * packs bf16 UMMA operand images and uploads them once. */
 int c3b_finalize(c3b_model *m);
 
-/* name: "precision" (C3B_PREC_*), "chunk_sites" (sites per internal pass), "lstm_tile" (batch columns per LSTM CTA: 16|32|64, 0 = auto). */
+/* name: "precision" (C3B_PREC_*), "chunk_sites" (sites per internal pass), "lstm_tile" (batch columns per LSTM CTA: 16|32|64, 0 = auto),
+ * "profile" (1: bracket every kernel launch with CUDA events on its stream and accumulate per-kernel time; setting it resets the totals). */
 int c3b_set_option(c3b_model *m, const char *name, int value);
 
 /* Replaces Y = m(X) (clair3/model.py:130-161 / 377-416) including the H2D/D2H of _torch_predict
@@ -87,6 +88,10 @@ int c3b_bcast_weights(c3b_model *m, void *nccl_comm, int root, void *cuda_stream
  * as float32.  names: pileup "lstm1"[B,33,256] "lstm2"[B,33,320] "l4_pre"[B,128]; full-alignment "conv1" "res_block1"
  * "conv3" "res_block2" "conv5" "res_block3" (NHWC) "spp"[B,3584] "l4_pre"[B,256].  *count_inout: capacity in / elements out. */
 int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int64_t *count_inout);
+
+/* Per-kernel device time accumulated while option "profile" is on.  kernel names: pileup "ingest" "lstm1" "proj2" "lstm2"
+ * "l4" "heads"; full-alignment "ingest" "conv0".."conv8" "spp" "l4" "heads".  Synchronises the streams it recorded on. */
+int c3b_get_profile(c3b_model *m, const char *kernel, double *total_ms, int64_t *launches);
 
 /* Number of this library's kernels launched on behalf of m so far (bench.py's gpu_launches). */
 int64_t c3b_launch_count(const c3b_model *m);
