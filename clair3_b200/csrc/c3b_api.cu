@@ -22,12 +22,44 @@ extern "C" const char *c3b_last_error(void) { return g_err; }
 extern "C" const char *c3b_version(void) { return "clair3_b200 0.1 (sm_100a)"; }
 
 // ------------------------------------------------------------------------------------------------ helpers
-uint16_t c3b_f2bf(float f) {
+uint16_t c3b_f2op(float f) {
+    // fp32 -> fp16 bits, round-to-nearest-even, saturating to +-65504 (NaN preserved)
     uint32_t u;
     memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
-    u += 0x7fffu + ((u >> 16) & 1u);                                            // round to nearest even
-    return (uint16_t)(u >> 16);
+    const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+    const uint32_t a = u & 0x7fffffffu;
+    if (a > 0x7f800000u) return sign | 0x7e00;                 // NaN
+    if (a >= 0x477ff000u) return sign | 0x7bff;                // >= 65520 rounds past max -> saturate
+    if (a < 0x33000001u) return sign;                          // < 2^-25 -> 0
+    int e = (int)(a >> 23) - 127;
+    uint32_t man = (a & 0x7fffffu) | 0x800000u;
+    int shift;
+    uint32_t he;
+    if (e < -14) { shift = 13 + (-14 - e); he = 0; }           // subnormal half
+    else { shift = 13; he = (uint32_t)(e + 15); }
+    uint32_t hm = man >> shift;
+    const uint32_t rem = man & ((1u << shift) - 1), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (hm & 1u))) hm++;
+    uint32_t out;
+    if (he == 0) out = hm;                                     // may carry into exponent 1: bit pattern is still right
+    else out = ((he << 10) + (hm - 0x400u));                   // hm includes the implicit bit; carry propagates into he
+    return sign | (uint16_t)out;
+}
+float c3b_op2f(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t e = (h >> 10) & 0x1f, m = h & 0x3ff, u;
+    if (e == 0) {
+        if (m == 0) u = sign;
+        else {
+            int sh = 0;
+            while (!(m & 0x400u)) { m <<= 1; ++sh; }
+            u = sign | ((uint32_t)(127 - 15 - sh + 1) << 23) | ((m & 0x3ffu) << 13);
+        }
+    } else if (e == 31) u = sign | 0x7f800000u | (m << 13);
+    else u = sign | ((e + 112) << 23) | (m << 13);
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
 }
 
 namespace {
@@ -119,7 +151,7 @@ std::vector<uint16_t> pack_igemm(int rows, int kgroups, int rb, F get) {
                 if (g >= kgroups) continue;
                 for (int r = 0; r < rb; ++r)
                     for (int e = 0; e < 8; ++e)
-                        img[((((size_t)c * nrb + b) * 8 + kg) * rb + r) * 8 + e] = c3b_f2bf(get(b * rb + r, g * 8 + e));
+                        img[((((size_t)c * nrb + b) * 8 + kg) * rb + r) * 8 + e] = c3b_f2op(get(b * rb + r, g * 8 + e));
             }
     return img;
 }
@@ -230,6 +262,15 @@ extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
             for (auto &r : w->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
             w->prof.clear();
         }
+    } else if (!strcmp(name, "lstm_trace")) {
+        if (value && !m->lstm_trace) {
+            C3B_CUDA(cudaSetDevice(m->device));
+            C3B_CUDA(cudaMalloc(&m->lstm_trace, sizeof(long long) * 2 * C3B_T * 4));
+            C3B_CUDA(cudaMemset(m->lstm_trace, 0, sizeof(long long) * 2 * C3B_T * 4));
+        } else if (!value && m->lstm_trace) {
+            cudaFree(m->lstm_trace);
+            m->lstm_trace = nullptr;
+        }
     } else if (!strcmp(name, "lstm_tile")) {
         if (value != 0 && value != 16 && value != 32 && value != 64) { c3b_set_error("bad lstm_tile %d", value); return 1; }
         m->lstm_tile = value;
@@ -337,7 +378,7 @@ static int finalize_impl(c3b_model *m) {
                             float v = 0.f;
                             if (k < 32) { if (k < I) v = wih[(size_t)row * I + k]; }
                             else v = whh[(size_t)row * 128 + (k - 32)];
-                            img[((((size_t)d * 4 + blk) * 20 + k / 8) * 128 + r) * 8 + k % 8] = c3b_f2bf(v);
+                            img[((((size_t)d * 4 + blk) * 20 + k / 8) * 128 + r) * 8 + k % 8] = c3b_f2op(v);
                         }
                     }
             }
@@ -359,7 +400,7 @@ static int finalize_impl(c3b_model *m) {
                     pbias[(size_t)d * 640 + R] = bih[row] + bhh[row];
                     for (int k = 0; k < 160; ++k)
                         img[((((size_t)d * 5 + R / 128) * 20 + k / 8) * 128 + R % 128) * 8 + k % 8] =
-                            c3b_f2bf(whh[(size_t)row * 160 + k]);
+                            c3b_f2op(whh[(size_t)row * 160 + k]);
                 }
             }
             put(blob, img.data(), img.size() * 2, (const void **)&m->lstm_tc[1][0].w_img, false);
@@ -594,10 +635,10 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
         return 0;
     }
     TcPileupBuffers b;
-    b.xs = cv.take<__nv_bfloat16>((size_t)C3B_T * bp * 32 * 2);
-    b.h1 = cv.take<__nv_bfloat16>((size_t)C3B_T * bp * 256 * 2);
+    b.xs = cv.take<op_t>((size_t)C3B_T * bp * 32 * 2);
+    b.h1 = cv.take<op_t>((size_t)C3B_T * bp * 256 * 2);
     b.pg = cv.take<__half>((size_t)C3B_T * bp * 1280 * 2);
-    b.h2 = cv.take<__nv_bfloat16>((size_t)bp * C3B_T * 320 * 2);
+    b.h2 = cv.take<op_t>((size_t)bp * C3B_T * 320 * 2);
     b.z4 = cv.take<float>((size_t)bp * 128 * 4);
     int tile1 = m->lstm_tile, tile2 = m->lstm_tile;
     if (tile1 == 0) {
@@ -679,11 +720,11 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
         if (c3b_launch_heads(z4, m->heads, y, n, s)) return 1;
         m->launches += 13;
     } else {
-        { PROF("ingest"); if (c3b_launch_ingest_fa_tc(x, x_dtype, m->channels, cpad, (__nv_bfloat16 *)xin, n * depth * 33, s)) return 1; }
-        const __nv_bfloat16 *cur = (const __nv_bfloat16 *)xin;
+        { PROF("ingest"); if (c3b_launch_ingest_fa_tc(x, x_dtype, m->channels, cpad, (op_t *)xin, n * depth * 33, s)) return 1; }
+        const op_t *cur = (const op_t *)xin;
         int cur_c = cpad;
         for (int l = 0; l < 3; ++l) {
-            __nv_bfloat16 *a0 = (__nv_bfloat16 *)act[l][0], *a1 = (__nv_bfloat16 *)act[l][1], *a2 = (__nv_bfloat16 *)act[l][2];
+            op_t *a0 = (op_t *)act[l][0], *a1 = (op_t *)act[l][1], *a2 = (op_t *)act[l][2];
             const int co = chans[l + 1];
             IgemmArgs ca = {};
             ca.taps = 9;
@@ -707,10 +748,10 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
             cur = a2;
             cur_c = co;
         }
-        { PROF("spp"); if (c3b_launch_spp_tc(cur, (__nv_bfloat16 *)sp, n, hh[3], ww[3], 256, s)) return 1; }
+        { PROF("spp"); if (c3b_launch_spp_tc(cur, (op_t *)sp, n, hh[3], ww[3], 256, s)) return 1; }
         C3B_CUDA(cudaMemsetAsync(z4, 0, (size_t)bp * 256 * 4, s));
         IgemmArgs la = {};
-        la.a = (const __nv_bfloat16 *)sp;
+        la.a = (const op_t *)sp;
         la.m = n;
         la.taps = 1;
         la.cin = 3584;
@@ -832,10 +873,7 @@ extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int6
         } else {
             std::vector<uint16_t> raw((size_t)src_count);
             C3B_CUDA(cudaMemcpy(raw.data(), t.ptr, (size_t)src_count * 2, cudaMemcpyDeviceToHost));
-            for (int64_t i = 0; i < src_count; ++i) {
-                uint32_t u = (uint32_t)raw[i] << 16;
-                memcpy(&tmp[i], &u, 4);
-            }
+            for (int64_t i = 0; i < src_count; ++i) tmp[i] = c3b_op2f(raw[i]);
         }
         if (t.layout == 1) {   // [33][bp][inner] -> [n][33][inner]
             for (int64_t b = 0; b < n; ++b)
@@ -852,6 +890,14 @@ extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int6
     return 1;
 }
 
+extern "C" int c3b_debug_lstm_trace(c3b_model *m, int64_t *out264) {
+    if (!m || !m->lstm_trace || !out264) { c3b_set_error("c3b_debug_lstm_trace: option lstm_trace is off"); return 1; }
+    C3B_CUDA(cudaSetDevice(m->device));
+    C3B_CUDA(cudaDeviceSynchronize());
+    C3B_CUDA(cudaMemcpy(out264, m->lstm_trace, sizeof(long long) * 2 * C3B_T * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ kernel unit-test hooks
 // Exercise the tcgen05 implicit-GEMM kernel on caller-provided matrices (tests/test_igemm.py); not part of the drop-in API.
 extern "C" int c3b_debug_gemm(c3b_model *m, int swapped, int64_t M, int N, int K, const float *a, const float *wmat,
@@ -860,7 +906,7 @@ extern "C" int c3b_debug_gemm(c3b_model *m, int swapped, int64_t M, int N, int K
     if (K % 8) { c3b_set_error("c3b_debug_gemm: K must be a multiple of 8"); return 1; }
     C3B_CUDA(cudaSetDevice(m->device));
     std::vector<uint16_t> ab((size_t)M * K);
-    for (size_t i = 0; i < ab.size(); ++i) ab[i] = c3b_f2bf(a[i]);
+    for (size_t i = 0; i < ab.size(); ++i) ab[i] = c3b_f2op(a[i]);
     const int rb = swapped ? 128 : N;
     std::vector<uint16_t> img = pack_igemm(N, K / 8, rb, [&](int r, int k) { return wmat[(size_t)r * K + k]; });
     void *da = nullptr, *dw = nullptr, *db = nullptr, *dout = nullptr;
@@ -875,12 +921,12 @@ extern "C" int c3b_debug_gemm(c3b_model *m, int swapped, int64_t M, int N, int K
     C3B_CUDA(cudaMemcpy(db, bias ? bias : zb.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
     C3B_CUDA(cudaMemset(dout, 0, out_bytes));
     IgemmArgs ga = {};
-    ga.a = (const __nv_bfloat16 *)da;
+    ga.a = (const op_t *)da;
     ga.m = M;
     ga.taps = 1;
     ga.cin = K;
     ga.lda = K;
-    ga.w.w_img = (const __nv_bfloat16 *)dw;
+    ga.w.w_img = (const op_t *)dw;
     ga.w.bias = (const float *)db;
     ga.w.n = N;
     ga.w.kgroups = K / 8;
@@ -901,10 +947,7 @@ extern "C" int c3b_debug_gemm(c3b_model *m, int swapped, int64_t M, int N, int K
         } else {
             std::vector<uint16_t> raw((size_t)M * N);
             C3B_CUDA(cudaMemcpy(raw.data(), dout, out_bytes, cudaMemcpyDeviceToHost));
-            for (size_t i = 0; i < raw.size(); ++i) {
-                uint32_t u = (uint32_t)raw[i] << 16;
-                memcpy(&out[i], &u, 4);
-            }
+            for (size_t i = 0; i < raw.size(); ++i) out[i] = c3b_op2f(raw[i]);
         }
     }
     cudaFree(da); cudaFree(dw); cudaFree(db); cudaFree(dout);
@@ -925,5 +968,6 @@ extern "C" void c3b_destroy(c3b_model *m) {
     }
     if (m->blob) cudaFree(m->blob);
     if (m->f32blob) cudaFree(m->f32blob);
+    if (m->lstm_trace) cudaFree(m->lstm_trace);
     delete m;
 }

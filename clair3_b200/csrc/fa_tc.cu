@@ -7,24 +7,24 @@
 namespace {
 
 template <typename T>
-__global__ void ingest_fa_tc_kernel(const T *__restrict__ x, __nv_bfloat16 *__restrict__ out, int64_t n_pix, int channels,
+__global__ void ingest_fa_tc_kernel(const T *__restrict__ x, op_t *__restrict__ out, int64_t n_pix, int channels,
                                     int cpad) {
     const int groups = cpad / 8;
     const int64_t total = n_pix * groups;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t pix = idx / groups;
         const int g = (int)(idx - pix * groups);
-        __align__(16) __nv_bfloat16 v[8];
+        __align__(16) op_t v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int ch = g * 8 + i;
-            v[i] = __float2bfloat16_rn(ch < channels ? (float)x[pix * channels + ch] : 0.f);
+            v[i] = f2op(ch < channels ? (float)x[pix * channels + ch] : 0.f);
         }
         *reinterpret_cast<uint4 *>(out + idx * 8) = *reinterpret_cast<const uint4 *>(v);
     }
 }
 
-__global__ void spp_tc_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ out, int h, int w, int c) {
+__global__ void spp_tc_kernel(const op_t *__restrict__ x, op_t *__restrict__ out, int h, int w, int c) {
     const int64_t b = blockIdx.x;
     const int cells = 14;
     for (int i = threadIdx.x; i < cells * c; i += blockDim.x) {
@@ -42,14 +42,14 @@ __global__ void spp_tc_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16
         float m = 0.f;                       // inputs are post-ReLU: zero padding == floor at 0
         for (int hh = max(h0, 0); hh < min(h0 + wh, h); ++hh)
             for (int wv = max(w0, 0); wv < min(w0 + ww, w); ++wv)
-                m = fmaxf(m, __bfloat162float(x[((b * h + hh) * w + wv) * c + ch]));
-        out[b * (cells * c) + i] = __float2bfloat16_rn(m);
+                m = fmaxf(m, op2f(x[((b * h + hh) * w + wv) * c + ch]));
+        out[b * (cells * c) + i] = f2op(m);
     }
 }
 
 }  // namespace
 
-int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, __nv_bfloat16 *out, int64_t n_pix,
+int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, op_t *out, int64_t n_pix,
                             cudaStream_t s) {
     if (n_pix == 0) return 0;
     const int64_t total = n_pix * (cpad / 8);
@@ -64,7 +64,7 @@ int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, __
     return 0;
 }
 
-int c3b_launch_spp_tc(const __nv_bfloat16 *x, __nv_bfloat16 *out, int64_t batch, int h, int w, int c, cudaStream_t s) {
+int c3b_launch_spp_tc(const op_t *x, op_t *out, int64_t batch, int h, int w, int c, cudaStream_t s) {
     if (batch == 0) return 0;
     spp_tc_kernel<<<(unsigned)batch, 256, 0, s>>>(x, out, h, w, c);
     C3B_CUDA(cudaGetLastError());

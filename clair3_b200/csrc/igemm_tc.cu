@@ -33,11 +33,11 @@ constexpr int kLag = 2;            // cp.async groups in flight per producer thr
 constexpr int kMaxStages = 8;
 
 struct IgemmDev {
-    const __nv_bfloat16 *act;
-    const __nv_bfloat16 *w_img;
+    const op_t *act;
+    const op_t *w_img;
     const float *bias;
     void *out;
-    const __nv_bfloat16 *residual;
+    const op_t *residual;
     int64_t m_valid;       // valid activation rows (pixels / positions / sites)
     int64_t lda;           // plain mode row stride (elements)
     int64_t ldo;           // output row stride (elements)
@@ -74,7 +74,7 @@ __device__ __forceinline__ SmemLayout make_layout(const IgemmDev &p) {
 
 template <bool SWAP, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t full_bar[kMaxStages];
     __shared__ uint64_t empty_bar[kMaxStages];
     __shared__ uint64_t tmem_full_bar[2];
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
     } else if (warp == 8) {
         // ===================================================== MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)ncols);
+            const uint32_t idesc = ptx::umma_idesc_f16(128, (uint32_t)ncols);
             const uint32_t lbo_act = (uint32_t)p.act_rows * 16u;
             const uint32_t lbo_w = (uint32_t)p.w_rows * 16u;
             int it = 0;
@@ -230,9 +230,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                             ptx::umma_desc_nosw(stage + L.act_bytes + (uint32_t)k * 2u * lbo_w, lbo_w, 128u);
                         const uint32_t accum = (c > c_begin || k > 0) ? 1u : 0u;
                         if (SWAP)
-                            ptx::umma_bf16(d_tmem, w_desc, act_desc, idesc, accum);
+                            ptx::umma_f16(d_tmem, w_desc, act_desc, idesc, accum);
                         else
-                            ptx::umma_bf16(d_tmem, act_desc, w_desc, idesc, accum);
+                            ptx::umma_f16(d_tmem, act_desc, w_desc, idesc, accum);
                     }
                     ptx::umma_commit(&empty_bar[s]);
                 }
@@ -256,8 +256,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                 // thread = pixel row, columns = output channels
                 const int64_t pix = (int64_t)at * 128 + r;
                 const bool ok = pix < p.m_valid;
-                __nv_bfloat16 *orow = (__nv_bfloat16 *)p.out + pix * p.ldo;
-                const __nv_bfloat16 *rrow = p.residual ? p.residual + pix * p.ldo : nullptr;
+                op_t *orow = (op_t *)p.out + pix * p.ldo;
+                const op_t *rrow = p.residual ? p.residual + pix * p.ldo : nullptr;
                 for (int j0 = 0; j0 < ncols; j0 += 16) {
                     float v[16];
                     ptx::tmem_ld16(taddr + (uint32_t)j0, v);
@@ -270,13 +270,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                         }
                         uint4 pk[2];
                         uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
-                        const __nv_bfloat162 *rp = reinterpret_cast<const __nv_bfloat162 *>(res);
+                        const op2_t *rp = reinterpret_cast<const op2_t *>(res);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             float a = v[2 * i] + bias_s[j0 + 2 * i];
                             float b = v[2 * i + 1] + bias_s[j0 + 2 * i + 1];
                             if (rrow) {
-                                const float2 rf = __bfloat1622float2(rp[i]);
+                                const float2 rf = op22f2(rp[i]);
                                 a += rf.x;
                                 b += rf.y;
                             }
@@ -284,7 +284,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                                 a = fmaxf(a, 0.f);
                                 b = fmaxf(b, 0.f);
                             }
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                            a = op_clamp(a);
+                            b = op_clamp(b);
+                            op2_t h2 = f2op2(a, b);
                             pw[i] = *reinterpret_cast<uint32_t *>(&h2);
                         }
                         *reinterpret_cast<uint4 *>(orow + j0) = pk[0];
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                         uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            __half2 h2 = __floats2half2_rn(v[2 * i] + bias, v[2 * i + 1] + bias);
+                            __half2 h2 = __floats2half2_rn(op_clamp(v[2 * i] + bias), op_clamp(v[2 * i + 1] + bias));
                             pw[i] = *reinterpret_cast<uint32_t *>(&h2);
                         }
                         __half *dst = (__half *)p.out + off;

@@ -19,58 +19,71 @@ __global__ void ingest_f32_kernel(const T *__restrict__ x, float *__restrict__ o
 }
 
 constexpr int HEADS_G = 8;        // sites per block
-constexpr int HEADS_THREADS = 128;
+constexpr int HEADS_THREADS = 256;
 
-// z4: [B][D4] L4 pre-activation WITHOUT bias.  One block handles HEADS_G sites so head weights are read once per 8 sites.
+// z4: [B][D4] L4 pre-activation WITHOUT bias.  One block = HEADS_G sites x all heads; thread (t/128, t%128) owns one L5
+// unit of one head (two heads in flight, four heads in two passes), weights are read once per block through the
+// read-only path, activations broadcast from shared memory.
 __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__restrict__ z4, HeadsParams hp,
                                                               float *__restrict__ out, int64_t batch) {
     extern __shared__ float smem[];
     const int d4 = hp.d4;
-    float *a = smem;                         // [G][d4]
-    float *l5 = a + HEADS_G * d4;            // [G][128]
-    float *yv = l5 + HEADS_G * 128;          // [G][36]
+    float *a = smem;                                   // [G][d4]
+    float *l5 = a + HEADS_G * d4;                      // [nheads][G][128]
+    float *yv = l5 + C3B_MAX_HEADS * HEADS_G * 128;    // [G][96]
     const int tid = threadIdx.x;
     const int64_t b0 = (int64_t)blockIdx.x * HEADS_G;
     const int g_n = (int)min((int64_t)HEADS_G, batch - b0);
 
     for (int i = tid; i < HEADS_G * d4; i += HEADS_THREADS) {
-        int g = i / d4, k = i - g * d4;
-        a[i] = (g < g_n) ? selu(z4[(b0 + g) * d4 + k] + hp.b4[k]) : 0.f;
+        const int g = i / d4, k = i - g * d4;
+        a[i] = (g < g_n) ? selu(z4[(b0 + g) * d4 + k] + __ldg(hp.b4 + k)) : 0.f;
     }
     __syncthreads();
 
-    for (int h = 0; h < hp.nheads; ++h) {
-        const HeadWeights hw = hp.h[h];
+    const int j = tid & 127;
+    for (int h = tid >> 7; h < hp.nheads; h += 2) {
+        const float *__restrict__ w = hp.h[h].w5t + j;
         float acc[HEADS_G];
-        const float bias = hw.b5[tid];
+        const float bias = __ldg(hp.h[h].b5 + j);
 #pragma unroll
         for (int g = 0; g < HEADS_G; ++g) acc[g] = bias;
+#pragma unroll 8
         for (int k = 0; k < d4; ++k) {
-            const float w = hw.w5t[k * 128 + tid];
+            const float wv = __ldg(w + (size_t)k * 128);
 #pragma unroll
-            for (int g = 0; g < HEADS_G; ++g) acc[g] = fmaf(a[g * d4 + k], w, acc[g]);
+            for (int g = 0; g < HEADS_G; ++g) acc[g] = fmaf(a[g * d4 + k], wv, acc[g]);
         }
 #pragma unroll
-        for (int g = 0; g < HEADS_G; ++g) l5[g * 128 + tid] = selu(acc[g]);
-        __syncthreads();
-        for (int i = tid; i < HEADS_G * hw.n; i += HEADS_THREADS) {
-            int g = i / hw.n, o = i - g * hw.n;
-            float s = hw.by[o];
-            for (int j = 0; j < 128; ++j) s = fmaf(l5[g * 128 + j], hw.wyt[j * hw.n + o], s);
-            yv[g * 36 + o] = selu(s);
-        }
-        __syncthreads();
-        if (tid < g_n) {
-            const float *v = yv + tid * 36;
-            float mx = v[0];
-            for (int o = 1; o < hw.n; ++o) mx = fmaxf(mx, v[o]);
-            float sum = 0.f;
-            for (int o = 0; o < hw.n; ++o) sum += expf(v[o] - mx);
-            const float inv = 1.f / sum;
-            float *dst = out + (b0 + tid) * hp.out_dim + hw.out_off;
-            for (int o = 0; o < hw.n; ++o) dst[o] = expf(v[o] - mx) * inv;
-        }
-        __syncthreads();
+        for (int g = 0; g < HEADS_G; ++g) l5[(h * HEADS_G + g) * 128 + j] = selu(acc[g]);
+    }
+    __syncthreads();
+
+    for (int i = tid; i < HEADS_G * hp.out_dim; i += HEADS_THREADS) {
+        const int g = i / hp.out_dim, o = i - g * hp.out_dim;
+        int h = 0;
+        while (h + 1 < hp.nheads && o >= hp.h[h + 1].out_off) ++h;
+        const int n = hp.h[h].n, oo = o - hp.h[h].out_off;
+        const float *__restrict__ wy = hp.h[h].wyt + oo;
+        const float *lv = l5 + (h * HEADS_G + g) * 128;
+        float s = __ldg(hp.h[h].by + oo);
+#pragma unroll 8
+        for (int jj = 0; jj < 128; ++jj) s = fmaf(lv[jj], __ldg(wy + jj * n), s);
+        yv[g * 96 + o] = selu(s);
+    }
+    __syncthreads();
+
+    if (tid < g_n * hp.nheads) {
+        const int g = tid / hp.nheads, h = tid - g * hp.nheads;
+        const int n = hp.h[h].n, off = hp.h[h].out_off;
+        const float *v = yv + g * 96 + off;
+        float mx = v[0];
+        for (int o = 1; o < n; ++o) mx = fmaxf(mx, v[o]);
+        float sum = 0.f;
+        for (int o = 0; o < n; ++o) sum += expf(v[o] - mx);
+        const float inv = 1.f / sum;
+        float *dst = out + (b0 + g) * hp.out_dim + off;
+        for (int o = 0; o < n; ++o) dst[o] = expf(v[o] - mx) * inv;
     }
 }
 
@@ -103,7 +116,7 @@ int c3b_launch_ingest_fa_f32(const void *x, int dtype, float *out, int64_t n, cu
 
 int c3b_launch_heads(const float *z4, const HeadsParams &hp, float *out, int64_t batch, cudaStream_t s) {
     if (batch == 0) return 0;
-    size_t smem = sizeof(float) * (HEADS_G * hp.d4 + HEADS_G * 128 + HEADS_G * 36);
+    size_t smem = sizeof(float) * (HEADS_G * hp.d4 + C3B_MAX_HEADS * HEADS_G * 128 + HEADS_G * 96);
     int blocks = (int)((batch + HEADS_G - 1) / HEADS_G);
     heads_kernel<<<blocks, HEADS_THREADS, smem, s>>>(z4, hp, out, batch);
     C3B_CUDA(cudaGetLastError());

@@ -28,12 +28,13 @@ constexpr int kThreads = 128;
 constexpr int kBlkBytes = 20 * 128 * 16;       // one 128-row x K=160 weight block: [K/8][128][8] bf16
 
 struct LstmDev {
-    const __nv_bfloat16 *w_img;    // [dir][NBLK][20][128][8]
+    const op_t *w_img;    // [dir][NBLK][20][128][8]
     const float *bias;             // [dir][NBLK*128] (LSTM1)
-    const __nv_bfloat16 *xs;       // LSTM1 input  [33][Bp][32]
+    const op_t *xs;       // LSTM1 input  [33][Bp][32]
     const __half *pg;              // LSTM2 pre-gates pgT[dir][33][Bp/NB][5][128][NB]
-    __nv_bfloat16 *hout;           // LSTM1: h1[33][Bp][256]; LSTM2: h2[Bp][33][320]
+    op_t *hout;           // LSTM1: h1[33][Bp][256]; LSTM2: h2[Bp][33][320]
     int bp;                        // padded batch
+    long long *trace;              // optional [33][4] clock64 stamps of CTA (0,0) thread 0 (debug option "lstm_trace")
 };
 
 template <int NB>
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
     constexpr uint32_t TCOLS = (NBLK * NB <= 32) ? 32 : (NBLK * NB <= 64) ? 64 : (NBLK * NB <= 128) ? 128
                                : (NBLK * NB <= 256) ? 256 : 512;
 
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t w_bar, acc_bar;
     __shared__ uint32_t tmem_base_smem;
     uint8_t *w_smem = smem;
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
 #pragma unroll
     for (int i = 0; i < (LAYER2 ? NB / 4 : 1); ++i) c_tail[i] = 0.f;
 
-    const uint32_t idesc = ptx::umma_idesc_bf16(128, NB);
+    const uint32_t idesc = ptx::umma_idesc_f16(128, NB);
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int ntl = p.bp / NB;
 
@@ -142,6 +143,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncthreads();                                                    // S1: operands of this step are in place
+        const bool tr = p.trace != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+        if (tr) p.trace[step * 4 + 0] = clock64();
         if (tid == 0) {
             if (step == 0) ptx::mbar_wait(&w_bar, 0);
             ptx::tc_fence_after();
@@ -151,18 +154,19 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
                 for (int ks = 0; ks < K / 16; ++ks) {
                     const uint64_t a_desc = ptx::umma_desc_nosw(w_addr + m * kBlkBytes + ks * 2 * 2048, 2048, 128);
                     const uint64_t b_desc = ptx::umma_desc_nosw(b_addr + ks * 2 * LBO_B, LBO_B, 128);
-                    ptx::umma_bf16(tmem_base + m * NB, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
+                    ptx::umma_f16(tmem_base + m * NB, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
                 }
             }
             ptx::umma_commit(&acc_bar);
         }
+        if (tr) p.trace[step * 4 + 1] = clock64();
 
         // while the MMAs run: ship h_{t_prev} (still in the operand buffer) to global memory
         if (step > 0) {
             for (int idx = tid; idx < NB * (H / 8); idx += kThreads) {
                 const int n = idx / (H / 8), kgh = idx % (H / 8);
                 const uint4 v = *reinterpret_cast<const uint4 *>(b_smem + (KX / 8 + kgh) * LBO_B + n * 16);
-                __nv_bfloat16 *dst = LAYER2 ? p.hout + ((size_t)(b0 + n) * C3B_T + t_prev) * 320 + dir * 160 + kgh * 8
+                op_t *dst = LAYER2 ? p.hout + ((size_t)(b0 + n) * C3B_T + t_prev) * 320 + dir * 160 + kgh * 8
                                             : p.hout + ((size_t)t_prev * p.bp + b0 + n) * 256 + dir * 128 + kgh * 8;
                 *reinterpret_cast<uint4 *>(dst) = v;
             }
@@ -180,6 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
 
         ptx::mbar_wait(&acc_bar, (uint32_t)step & 1u);
         ptx::tc_fence_after();
+        if (tr) p.trace[step * 4 + 2] = clock64();
         __syncthreads();                                                    // S2: everyone is done reading h_{t_prev}
 
         if (LAYER2) {
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
             uint8_t *dst = b_smem + (kcol >> 3) * LBO_B + (kcol & 7) * 2;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<__nv_bfloat16 *>(dst + (j * 8 + i) * 16) = __float2bfloat16_rn(h[i]);
+                *reinterpret_cast<op_t *>(dst + (j * 8 + i) * 16) = f2op(h[i]);
         }
 
         if (LAYER2) {
@@ -253,11 +258,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
                 c_tail[k] = fmaf(fv, c_tail[k], iv * gv);
                 const float hv = ov * ptx::tanh_approx(c_tail[k]);
                 const uint32_t kcol = 128 + lane;
-                *reinterpret_cast<__nv_bfloat16 *>(b_smem + (kcol >> 3) * LBO_B + n * 16 + (kcol & 7) * 2) =
-                    __float2bfloat16_rn(hv);
+                *reinterpret_cast<op_t *>(b_smem + (kcol >> 3) * LBO_B + n * 16 + (kcol & 7) * 2) =
+                    f2op(hv);
             }
         }
         t_prev = t;
+        if (tr) p.trace[step * 4 + 3] = clock64();
     }
 
     // last h
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
     for (int idx = tid; idx < NB * (H / 8); idx += kThreads) {
         const int n = idx / (H / 8), kgh = idx % (H / 8);
         const uint4 v = *reinterpret_cast<const uint4 *>(b_smem + (KX / 8 + kgh) * LBO_B + n * 16);
-        __nv_bfloat16 *dst = LAYER2 ? p.hout + ((size_t)(b0 + n) * C3B_T + t_prev) * 320 + dir * 160 + kgh * 8
+        op_t *dst = LAYER2 ? p.hout + ((size_t)(b0 + n) * C3B_T + t_prev) * 320 + dir * 160 + kgh * 8
                                     : p.hout + ((size_t)t_prev * p.bp + b0 + n) * 256 + dir * 128 + kgh * 8;
         *reinterpret_cast<uint4 *>(dst) = v;
     }
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
 }
 
 template <typename T>
-__global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, __nv_bfloat16 *__restrict__ xs, int64_t batch, int bp,
+__global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, op_t *__restrict__ xs, int64_t batch, int bp,
                                         int channels) {
     // one thread per 8-channel group of xs[t][b][32]
     const int64_t total = (int64_t)C3B_T * bp * 4;
@@ -287,13 +293,13 @@ __global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, __nv_bfloat16 *
         const int64_t tb = idx >> 2;
         const int b = (int)(tb % bp);
         const int t = (int)(tb / bp);
-        __align__(16) __nv_bfloat16 v[8];
+        __align__(16) op_t v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int ch = kg * 8 + i;
             float f = 0.f;
             if (b < batch && ch < channels) f = (float)x[((int64_t)b * C3B_T + t) * channels + ch];
-            v[i] = __float2bfloat16_rn(f);
+            v[i] = f2op(f);
         }
         *reinterpret_cast<uint4 *>(xs + idx * 8) = *reinterpret_cast<const uint4 *>(v);
     }
@@ -313,7 +319,7 @@ int launch_lstm(const LstmDev &p, cudaStream_t s) {
 
 }  // namespace
 
-int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, __nv_bfloat16 *xs, int64_t batch, cudaStream_t s) {
+int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, op_t *xs, int64_t batch, cudaStream_t s) {
     const int bp = (int)((batch + 127) / 128 * 128);
     const int64_t total = (int64_t)C3B_T * bp * 4;
     const int blocks = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
@@ -333,6 +339,7 @@ int c3b_launch_lstm1_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t ba
     p.bias = m->lstm_tc[0][0].bias;
     p.xs = b.xs;
     p.hout = b.h1;
+    p.trace = m->lstm_trace ? m->lstm_trace : nullptr;
     p.bp = (int)((batch + 127) / 128 * 128);
     const_cast<c3b_model *>(m)->launches++;
     switch (tile) {
@@ -349,6 +356,7 @@ int c3b_launch_lstm2_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t ba
     p.w_img = m->lstm_tc[1][0].w_img;
     p.pg = b.pg;
     p.hout = b.h2;
+    p.trace = m->lstm_trace ? m->lstm_trace + C3B_T * 4 : nullptr;
     p.bp = (int)((batch + 127) / 128 * 128);
     const_cast<c3b_model *>(m)->launches++;
     switch (tile) {

@@ -69,8 +69,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {     // one full w
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32, single CTA.  One thread issues.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, fp16 x fp16 -> fp32, single CTA.  One thread issues.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -118,11 +118,11 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t 
     d |= (uint64_t)1 << 46;
     return d;
 }
-// Instruction descriptor for kind::f16: bf16 A/B (K-major both), fp32 accumulate, dense.
-// Bits: [4,6) D fmt = 1 (f32), [7,10) A fmt = 1 (bf16), [10,13) B fmt = 1 (bf16), [15] A major = 0 (K), [16] B major = 0 (K),
-// [17,23) N>>3, [24,29) M>>4.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+// Instruction descriptor for kind::f16: fp16 A/B (K-major both), fp32 accumulate, dense.
+// Bits: [4,6) D fmt = 1 (f32), [7,10) A fmt = 0 (f16; 1 = bf16), [10,13) B fmt = 0 (f16), [15] A major = 0 (K),
+// [16] B major = 0 (K), [17,23) N>>3, [24,29) M>>4.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 __device__ __forceinline__ float tanh_approx(float x) {

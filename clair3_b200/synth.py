@@ -87,7 +87,7 @@ def fa_state_dict(add_indel_length=True, channels=8, seed=0):
     for prefix in ("conv1.", "res_block1.", "conv3.", "res_block2.", "conv5.", "res_block3."):
         order += [k for k in sd if k.startswith(prefix)]
     sd = {k: sd[k] for k in order}
-    sd["L4.weight"] = _normal(r, (256, 3584), 2.0 / np.sqrt(3584))
+    sd["L4.weight"] = _normal(r, (256, 3584), 0.35 / np.sqrt(3584))
     sd["L4.bias"] = _normal(r, (256,), 0.1)
     heads = [("L5_1", "Y_gt21_logits", 21), ("L5_2", "Y_genotype_logits", 3)]
     if add_indel_length:

@@ -60,7 +60,7 @@ int c3b_set_param(c3b_model *m, const char *key, const void *host_data, int dtyp
  * packs bf16 UMMA operand images and uploads them once. */
 int c3b_finalize(c3b_model *m);
 
-/* name: "precision" (C3B_PREC_*), "chunk_sites" (sites per internal pass), "lstm_tile" (batch columns per LSTM CTA: 16|32|64, 0 = auto),
+/* name: "precision" (C3B_PREC_*), "chunk_sites" (sites per internal pass), "lstm_tile" (batch columns per LSTM CTA: 16|32|64, 0 = auto), "lstm_trace" (debug clock stamps),
  * "profile" (1: bracket every kernel launch with CUDA events on its stream and accumulate per-kernel time; setting it resets the totals). */
 int c3b_set_option(c3b_model *m, const char *name, int value);
 
@@ -102,6 +102,10 @@ int64_t c3b_launch_count(const c3b_model *m);
  * (N % 128 == 0 when swapped). */
 int c3b_debug_gemm(c3b_model *m, int swapped, int64_t M, int N, int K, const float *a, const float *w, const float *bias,
                    int relu, int ksplit, float *out);
+
+/* Kernel timing hook: with option "lstm_trace" on, CTA (0,0) of each LSTM kernel stamps clock64 at four points of every
+ * step (operands ready, MMAs issued, accumulator ready, epilogue done); copies [2 layers][33 steps][4] stamps out. */
+int c3b_debug_lstm_trace(c3b_model *m, int64_t *out264);
 
 void c3b_destroy(c3b_model *m);
 

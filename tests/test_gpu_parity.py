@@ -3,7 +3,7 @@
 
 Tolerances (stated):
   * fp32 debug kernels vs the fp32 reference:   max |dp| <= 1e-4 on probabilities, taps rel-L2 <= 1e-4
-  * bf16 tensor-core kernels vs the fp32 reference: max |dp| <= 2e-2, mean |dp| <= 2e-3, taps rel-L2 <= 2e-2,
+  * fp16-operand tensor-core kernels vs the fp32 reference: max |dp| <= 2e-2, mean |dp| <= 2e-3, taps rel-L2 <= 2e-2,
     >= 99% arg-max agreement per head.
 """
 import numpy as np
@@ -110,12 +110,12 @@ def test_igemm_kernel_against_numpy(swapped, M, N, K, ksplit):
                                    ffi.cast("float *", out.ctypes.data)))
     finally:
         lib().c3b_destroy(h[0])
-    a16 = torch.from_numpy(a).bfloat16().float().numpy().astype(np.float64)
-    w16 = torch.from_numpy(w).bfloat16().float().numpy().astype(np.float64)
+    a16 = torch.from_numpy(a).half().float().numpy().astype(np.float64)
+    w16 = torch.from_numpy(w).half().float().numpy().astype(np.float64)
     ref = a16 @ w16.T
     if not swapped:
         ref = np.maximum(ref + bias, 0)
-        tol = 2e-2                      # output is bf16-rounded
+        tol = 2e-3                      # output is fp16-rounded
     else:
         tol = 1e-3
     assert np.abs(out - ref).max() <= tol * max(1.0, np.abs(ref).max())
@@ -128,15 +128,15 @@ def test_ragged_empty_and_host_buffers():
     # host in / host out (the _torch_predict shape: numpy in, numpy out)
     y_host = m(torch.from_numpy(x))
     assert y_host.device.type == "cpu"
-    assert np.abs(y_host.numpy() - full).max() < 1e-6
+    assert np.abs(y_host.numpy() - full).max() < 1e-5
     # ragged batches: any B >= 1, every site independent of its batch neighbours
     for b in (1, 7, 33):
         yb = m(torch.from_numpy(x[:b]).cuda()).cpu().numpy()
-        assert np.abs(yb - full[:b]).max() < 1e-6
+        assert np.abs(yb - full[:b]).max() < 1e-5
     assert m(torch.from_numpy(x[:0]).cuda()).shape == (0, 24)
     # chunked internal passes give the same answer
     m.set_option("chunk_sites", 16)
-    assert np.abs(m(torch.from_numpy(x).cuda()).cpu().numpy() - full).max() < 1e-6
+    assert np.abs(m(torch.from_numpy(x).cuda()).cpu().numpy() - full).max() < 1e-5
 
 
 def test_lstm_tiles_agree():
@@ -186,7 +186,7 @@ def test_large_batch_properties():
     assert np.isfinite(y).all() and np.allclose(y[:, :21].sum(1), 1, atol=1e-4) and np.allclose(y[:, 21:].sum(1), 1, atol=1e-4)
     perm = np.random.default_rng(0).permutation(1024)
     yp = m(torch.from_numpy(x[perm]).cuda()).cpu().numpy()
-    assert np.abs(yp - y[perm]).max() < 1e-6
+    assert np.abs(yp - y[perm]).max() < 1e-5
     m32 = _model(meta, sd, FP32)
     y32 = m32(torch.from_numpy(x[:256]).cuda()).cpu().numpy()
     assert np.abs(y[:256] - y32).max() < 2e-2
@@ -201,7 +201,7 @@ def test_large_batch_properties():
         assert np.allclose(yf[:, lo:hi].sum(1), 1, atol=1e-4)
     permf = np.random.default_rng(1).permutation(256)
     ypf = mf(torch.from_numpy(xf[permf]).cuda()).cpu().numpy()
-    assert np.abs(ypf - yf[permf]).max() < 1e-6
+    assert np.abs(ypf - yf[permf]).max() < 1e-5
     # all-zero rows beyond read depth (calloc'ed tensors): an all-zero site must still give finite probabilities
     z0 = mf(torch.zeros((4, 89, 33, 8), dtype=torch.int8).cuda()).cpu().numpy()
     assert np.isfinite(z0).all()

@@ -79,8 +79,8 @@ def run_igemm():
             continue
         finally:
             lib().c3b_destroy(h[0])
-        a16 = torch.from_numpy(a).bfloat16().float().numpy().astype(np.float64)
-        w16 = torch.from_numpy(w).bfloat16().float().numpy().astype(np.float64)
+        a16 = torch.from_numpy(a).half().float().numpy().astype(np.float64)
+        w16 = torch.from_numpy(w).half().float().numpy().astype(np.float64)
         ref = a16 @ w16.T + (0 if swapped else bias)
         err = np.abs(out - ref)
         print(f"igemm swapped={swapped} M={M} N={N} K={K} ks={ks}: max err {err.max():.3e} (|ref| max {np.abs(ref).max():.2f}) "
@@ -91,6 +91,36 @@ def run_igemm():
             cb = err[:128].max(axis=0)
             print("    row err (first 16):", np.round(rb[:16], 2), " col err (first 16):", np.round(cb[:16], 2))
             print("    out[0,:8]", np.round(out[0, :8], 3), " ref[0,:8]", np.round(ref[0, :8], 3))
+
+
+def run_trace(opts):
+    """Per-step cycle breakdown of the persistent LSTM kernels (CTA 0, thread 0)."""
+    from clair3_b200 import synth
+    from clair3_b200._ffi import check, ffi, lib
+    from clair3_b200.model import Clair3_P
+    sd = synth.pileup_state_dict(False, seed=0)
+    x = synth.pileup_inputs(1024, seed=0)
+    for tile in ([opts["lstm_tile"]] if "lstm_tile" in opts else [16, 32, 64]):
+        m = Clair3_P(add_indel_length=False, predict=True, input_channels=18)
+        m.set_option("lstm_tile", tile)
+        m.set_option("lstm_trace", 1)
+        m.to(torch.device("cuda"))
+        m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+        xd = torch.from_numpy(x).cuda()
+        for _ in range(3):
+            m(xd)
+        buf = np.zeros(2 * 33 * 4, dtype=np.int64)
+        check(lib().c3b_debug_lstm_trace(m._handle, ffi.cast("int64_t *", buf.ctypes.data)))
+        tr = buf.reshape(2, 33, 4)
+        for layer in range(2):
+            t = tr[layer]
+            issue = (t[:, 1] - t[:, 0])[2:].mean()
+            mma_wait = (t[:, 2] - t[:, 1])[2:].mean()
+            epi = (t[:, 3] - t[:, 2])[2:].mean()
+            gap = (t[1:, 0] - t[:-1, 3])[2:].mean()
+            total = (t[-1, 3] - t[0, 0]) / 33.0
+            print(f"tile {tile} LSTM{layer+1}: per step {total:.0f} cyc = issue {issue:.0f} + wait-for-accumulator {mma_wait:.0f} "
+                  f"+ epilogue {epi:.0f} + stage/sync gap {gap:.0f}", flush=True)
 
 
 if __name__ == "__main__":
@@ -107,6 +137,8 @@ if __name__ == "__main__":
     cases = cases2 or (GOLDEN_PILEUP + GOLDEN_FA)
     if mode == "igemm":
         run_igemm()
+    elif mode == "trace":
+        run_trace(opts)
     else:
         for c in cases:
             try:
