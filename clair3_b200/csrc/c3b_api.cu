@@ -373,12 +373,14 @@ static int finalize_impl(c3b_model *m) {
                 for (int blk = 0; blk < 4; ++blk)
                     for (int r = 0; r < 128; ++r) {
                         const int row = blk * 128 + r;
-                        bias[(size_t)d * 512 + row] = bih[row] + bhh[row];
+                        // sigmoid gates (i,f,o) are pre-halved: sigma(x) = 0.5*tanh(x/2)+0.5 costs one MUFU + one FMA
+                        const float gs = (blk == 2) ? 1.0f : 0.5f;
+                        bias[(size_t)d * 512 + row] = (bih[row] + bhh[row]) * gs;
                         for (int k = 0; k < 160; ++k) {
                             float v = 0.f;
                             if (k < 32) { if (k < I) v = wih[(size_t)row * I + k]; }
                             else v = whh[(size_t)row * 128 + (k - 32)];
-                            img[((((size_t)d * 4 + blk) * 20 + k / 8) * 128 + r) * 8 + k % 8] = c3b_f2op(v);
+                            img[((((size_t)d * 4 + blk) * 20 + k / 8) * 128 + r) * 8 + k % 8] = c3b_f2op(v * gs);
                         }
                     }
             }
@@ -397,17 +399,19 @@ static int finalize_impl(c3b_model *m) {
                 wih_d[d] = &P(m, "LSTM2.weight_ih" + sfx);
                 for (int R = 0; R < 640; ++R) {
                     const int row = lstm2_torch_row(R);
-                    pbias[(size_t)d * 640 + R] = bih[row] + bhh[row];
+                    const float gs = (row / C3B_H2 == 2) ? 1.0f : 0.5f;      // pre-halved sigmoid gates
+                    pbias[(size_t)d * 640 + R] = (bih[row] + bhh[row]) * gs;
                     for (int k = 0; k < 160; ++k)
                         img[((((size_t)d * 5 + R / 128) * 20 + k / 8) * 128 + R % 128) * 8 + k % 8] =
-                            c3b_f2op(whh[(size_t)row * 160 + k]);
+                            c3b_f2op(whh[(size_t)row * 160 + k] * gs);
                 }
             }
             put(blob, img.data(), img.size() * 2, (const void **)&m->lstm_tc[1][0].w_img, false);
             m->lstm_tc[1][0].bias = nullptr;
             std::vector<uint16_t> pimg = pack_igemm(1280, 32, 128, [&](int R, int k) {
                 const int d = R / 640;
-                return (*wih_d[d])[(size_t)lstm2_torch_row(R % 640) * 256 + k];
+                const int row = lstm2_torch_row(R % 640);
+                return (*wih_d[d])[(size_t)row * 256 + k] * ((row / C3B_H2 == 2) ? 1.0f : 0.5f);
             });
             m->proj2 = IgemmW();
             m->proj2.n = 1280;

@@ -1,27 +1,31 @@
 // Implicit GEMM on 5th-gen tensor cores (tcgen05, accumulators in TMEM) with fused epilogues.
 //
-//   D[rows x cols] = ACT[act_rows x K] * W[w_rows x K]^T      bf16 operands, fp32 accumulate
+//   D[rows x cols] = ACT[act_rows x K] * W[w_rows x K]^T      fp16 operands, fp32 accumulate
 //
 // Used for (a) the 3x3 convolutions of Clair3_F (clair3/model.py:183-235; BatchNorm folded, bias+ReLU(+residual)
-// epilogue, NHWC bf16 in/out), (b) the LSTM2 input projection of Clair3_P (the W_ih half of nn.LSTM's gate GEMM,
+// epilogue, NHWC fp16 in/out), (b) the LSTM2 input projection of Clair3_P (the W_ih half of nn.LSTM's gate GEMM,
 // clair3/model.py:102-107) and (c) the L4 dense layers (clair3/model.py:110,344) as split-K.
 //
 // Operand staging (no tensor maps): weights are pre-packed on the host into the exact shared-memory image of a
-// SWIZZLE_NONE K-major UMMA operand, one contiguous piece per (k-chunk, row-block), and land in shared memory with a
-// single cp.async.bulk (TMA engine) per stage.  Activation tiles are gathered by 128 producer threads with 16-byte
-// cp.async (zero-fill for conv padding / ragged rows) straight into the same canonical layout: element (row,k) lives at
-// (k/8)*LBO + row*16 + (k%8)*2 bytes, i.e. LBO = rows*16, SBO = 128.
+// SWIZZLE_NONE K-major UMMA operand, one contiguous piece per (k-chunk, row-block), and land in shared memory with
+// cp.async.bulk (TMA engine).  When the CTA's whole weight slab fits (LSTM2 projection: 256 rows x K=256 = 128 KB; conv1,
+// res_block1, conv3) it is loaded ONCE per CTA and stays resident ("W-stationary"); otherwise one piece rides in every
+// pipeline stage.  Activation tiles are gathered by 128 producer threads with 16-byte cp.async (zero-fill for conv
+// padding / ragged rows) straight into the same canonical layout: element (row,k) lives at (k/8)*LBO + row*16 + (k%8)*2
+// bytes, i.e. LBO = rows*16, SBO = 128.
 //
 // Two orientations share the pipeline:
 //   standard (SWAP=false): A = activation tile (M = 128 pixels -> TMEM lanes), B = weights (N = Cout <= 256 columns).
 //                          A thread of the epilogue owns one pixel and writes its Cout channels contiguously.
-//   swapped  (SWAP=true) : A = 128 weight rows (-> TMEM lanes), B = activation tile (N = positions / sites).
-//                          A thread owns one output unit and a run of consecutive positions: the layout the persistent
-//                          LSTM kernel wants its pre-gates in, and coalesced split-K atomics for L4.
+//   swapped  (SWAP=true) : A = 128 weight rows (-> TMEM lanes), B = activation tile (N = positions / sites); a CTA tile
+//                          may cover two 128-row blocks (two accumulators per tile) so every activation byte fetched
+//                          from L2 feeds 256 weight rows.  A thread owns one output unit and a run of consecutive
+//                          positions: the layout the persistent LSTM kernel wants its pre-gates in, and coalesced
+//                          split-K atomics for L4.
 //
-// Roles (288 threads): warps 0-3 activation producers (+ thread 0 issues the weight bulk copy), warps 4-7 epilogue
+// Roles (288 threads): warps 0-3 activation producers (+ thread 0 issues weight bulk copies), warps 4-7 epilogue
 // (TMEM lane quadrant = warp % 4), warp 8 allocates TMEM and its lane 0 issues tcgen05.mma.  Persistent over tiles with
-// two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+// two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "c3b_internal.h"
 #include "ptx.cuh"
 
@@ -46,31 +50,50 @@ struct IgemmDev {
     int cpk_shift;         // log2(cin/8) in conv mode
     int kgroups;           // real K/8
     int nchunks;           // total k-chunks
-    int act_rows;          // activation rows per tile (standard: 128)
-    int w_rows;            // weight rows per tile (standard: N, swapped: 128)
-    int n_rowblocks;       // weight row blocks (standard: 1)
+    int act_rows;          // activation rows per tile (128)
+    int w_rows;            // weight rows per piece (standard: N, swapped: 128)
+    int n_rowblocks;       // weight row blocks in the image (standard: 1)
+    int wb;                // row blocks per CTA tile (1; 2 for the swapped resident mode)
+    int w_resident;        // 1: the CTA's weight slab is loaded once and stays in shared memory
     int n_act_tiles;
     int ksplit;
     int chunks_per_split;
     int stages;
     int relu;
-    // swapped / pre-gate epilogue geometry
-    int pg_bp;             // padded batch (multiple of 128)
-    int pg_nbl;            // LSTM tile (batch columns per LSTM CTA)
-    int n_total;           // total W rows (for bias indexing / atomic ld)
+    int pg_bp;             // pre-gate epilogue: padded batch (multiple of 128)
+    int pg_nbl;            //                    LSTM tile (batch columns per LSTM CTA)
 };
 
-struct SmemLayout {
-    uint32_t act_bytes, w_bytes, stage_bytes;
+// Tile walk shared by the three roles.  Streaming mode: tile = ((at * n_rowblocks) + rb) * ksplit + ks over a flat grid.
+// Resident mode: the CTA is pinned to row-block group blockIdx.x % n_rg and strides over activation tiles.
+struct TileWalk {
+    int n_rg, at, at_step, tile, num_tiles;
+    __device__ TileWalk(const IgemmDev &p) {
+        n_rg = p.n_rowblocks / p.wb;
+        num_tiles = p.n_act_tiles * p.n_rowblocks * p.ksplit;
+        tile = blockIdx.x;
+        at = blockIdx.x / n_rg;
+        at_step = gridDim.x / n_rg;
+    }
+    __device__ bool valid(const IgemmDev &p) const { return p.w_resident ? at < p.n_act_tiles : tile < num_tiles; }
+    __device__ void next(const IgemmDev &p) {
+        if (p.w_resident) at += at_step; else tile += gridDim.x;
+    }
+    __device__ void decode(const IgemmDev &p, int &act_tile, int &rb0, int &c_begin, int &c_end) const {
+        if (p.w_resident) {
+            act_tile = at;
+            rb0 = (blockIdx.x % n_rg) * p.wb;
+            c_begin = 0;
+            c_end = p.nchunks;
+        } else {
+            const int ks = tile % p.ksplit;
+            rb0 = (tile / p.ksplit) % p.n_rowblocks;
+            act_tile = tile / (p.ksplit * p.n_rowblocks);
+            c_begin = ks * p.chunks_per_split;
+            c_end = min(p.nchunks, c_begin + p.chunks_per_split);
+        }
+    }
 };
-
-__device__ __forceinline__ SmemLayout make_layout(const IgemmDev &p) {
-    SmemLayout l;
-    l.act_bytes = (uint32_t)p.act_rows * 16u * 8u;
-    l.w_bytes = (uint32_t)p.w_rows * 16u * 8u;
-    l.stage_bytes = l.act_bytes + l.w_bytes;
-    return l;
-}
 
 template <bool SWAP, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
@@ -79,26 +102,33 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
     __shared__ uint64_t empty_bar[kMaxStages];
     __shared__ uint64_t tmem_full_bar[2];
     __shared__ uint64_t tmem_empty_bar[2];
+    __shared__ uint64_t w_bar;
     __shared__ uint32_t tmem_base_smem;
     __shared__ float bias_s[SWAP ? 1 : 256];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const SmemLayout L = make_layout(p);
     const int S = p.stages;
-    const int num_tiles = p.n_act_tiles * p.n_rowblocks * p.ksplit;
+    const uint32_t act_bytes = (uint32_t)p.act_rows * 128u;
+    const uint32_t w_bytes = (uint32_t)p.w_rows * 128u;
+    const uint32_t w_res_bytes = p.w_resident ? (uint32_t)p.wb * p.nchunks * w_bytes : 0u;
+    const uint32_t stage_bytes = act_bytes + (p.w_resident ? 0u : w_bytes);
     const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint32_t stages_base = smem_base + w_res_bytes;
+    const int ncols = SWAP ? p.act_rows : p.w_rows;     // accumulator columns per row block
+    const int acc_stride = p.wb * ncols;                // TMEM columns per accumulator stage (<= 256)
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            ptx::mbar_init(&full_bar[s], kProducerThreads + 1);
+            ptx::mbar_init(&full_bar[s], kProducerThreads + (p.w_resident ? 0 : 1));
             ptx::mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full_bar[a], 1);
             ptx::mbar_init(&tmem_empty_bar[a], 128);
         }
+        ptx::mbar_init(&w_bar, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 8) ptx::tmem_alloc<512>(&tmem_base_smem);
@@ -109,80 +139,71 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
-    const int ncols = SWAP ? p.act_rows : p.w_rows;     // accumulator columns
 
     if (warp < 4) {
-        // ===================================================== activation producers (+ weight bulk copy)
-        int it = 0;                      // global chunk iteration counter of this CTA (ring position)
+        // ===================================================== activation producers (+ weight bulk copies)
+        if (p.w_resident && tid == 0) {
+            const int rb0 = (blockIdx.x % (p.n_rowblocks / p.wb)) * p.wb;
+            ptx::mbar_arrive_expect_tx(&w_bar, w_res_bytes);
+            for (int c = 0; c < p.nchunks; ++c)
+                for (int b = 0; b < p.wb; ++b)
+                    ptx::bulk_g2s(smem_base + (uint32_t)(c * p.wb + b) * w_bytes,
+                                  (const char *)p.w_img + ((size_t)c * p.n_rowblocks + rb0 + b) * w_bytes, w_bytes, &w_bar);
+        }
+        int it = 0;                      // chunk iteration counter of this CTA (ring position)
         int pending[kLag];               // stages issued but not yet published
         int npending = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int ks = tile % p.ksplit;
-            const int rb = (tile / p.ksplit) % p.n_rowblocks;
-            const int at = tile / (p.ksplit * p.n_rowblocks);
-            const int c_begin = ks * p.chunks_per_split;
-            const int c_end = min(p.nchunks, c_begin + p.chunks_per_split);
-            // per-thread row state (up to 2 rows when act_rows = 256)
-            const char *row_base[2];
-            int hi0[2], wi0[2];
-            bool row_ok[2];
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int row = tid + rr * 128;
-                const int64_t g = (int64_t)at * p.act_rows + row;
-                row_ok[rr] = (row < p.act_rows) && (g < p.m_valid);
-                hi0[rr] = wi0[rr] = 0;
-                row_base[rr] = (const char *)p.act;
-                if (row_ok[rr]) {
-                    if (p.taps == 1) {
-                        row_base[rr] = (const char *)(p.act + g * p.lda);
-                    } else {
-                        const int wo = (int)(g % p.wout);
-                        const int ho = (int)((g / p.wout) % p.hout);
-                        const int64_t b = g / ((int64_t)p.wout * p.hout);
-                        hi0[rr] = ho * p.stride - 1;
-                        wi0[rr] = wo * p.stride - 1;
-                        row_base[rr] = (const char *)(p.act + b * (int64_t)p.hin * p.win * p.cin);
-                    }
+        for (TileWalk tw(p); tw.valid(p); tw.next(p)) {
+            int at, rb0, c_begin, c_end;
+            tw.decode(p, at, rb0, c_begin, c_end);
+            const int64_t g = (int64_t)at * p.act_rows + tid;
+            const bool row_ok = g < p.m_valid;
+            int hi0 = 0, wi0 = 0;
+            const char *row_base = (const char *)p.act;
+            if (row_ok) {
+                if (p.taps == 1) {
+                    row_base = (const char *)(p.act + g * p.lda);
+                } else {
+                    const int wo = (int)(g % p.wout);
+                    const int ho = (int)((g / p.wout) % p.hout);
+                    const int64_t b = g / ((int64_t)p.wout * p.hout);
+                    hi0 = ho * p.stride - 1;
+                    wi0 = wo * p.stride - 1;
+                    row_base = (const char *)(p.act + b * (int64_t)p.hin * p.win * p.cin);
                 }
             }
             for (int c = c_begin; c < c_end; ++c, ++it) {
                 const int s = it % S;
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
                 ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-                const uint32_t stage = smem_base + (uint32_t)s * L.stage_bytes;
-                if (tid == 0) {
-                    ptx::mbar_arrive_expect_tx(&full_bar[s], L.w_bytes);
-                    const char *src = (const char *)p.w_img + ((size_t)c * p.n_rowblocks + rb) * L.w_bytes;
-                    ptx::bulk_g2s(stage + L.act_bytes, src, L.w_bytes, &full_bar[s]);
+                const uint32_t stage = stages_base + (uint32_t)s * stage_bytes;
+                if (!p.w_resident && tid == 0) {
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], w_bytes);
+                    const char *src = (const char *)p.w_img + ((size_t)c * p.n_rowblocks + rb0) * w_bytes;
+                    ptx::bulk_g2s(stage + act_bytes, src, w_bytes, &full_bar[s]);
                 }
+                const uint32_t dst_row = stage + (uint32_t)tid * 16u;
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int row = tid + rr * 128;
-                    if (row >= p.act_rows) break;
-                    const uint32_t dst_row = stage + (uint32_t)row * 16u;
-#pragma unroll
-                    for (int kg = 0; kg < 8; ++kg) {
-                        const int g = c * 8 + kg;
-                        const char *src = (const char *)p.act;
-                        uint32_t nbytes = 0;
-                        if (row_ok[rr] && g < p.kgroups) {
-                            if (p.taps == 1) {
-                                src = row_base[rr] + (size_t)g * 16;
+                for (int kg = 0; kg < 8; ++kg) {
+                    const int gk = c * 8 + kg;
+                    const char *src = (const char *)p.act;
+                    uint32_t nbytes = 0;
+                    if (row_ok && gk < p.kgroups) {
+                        if (p.taps == 1) {
+                            src = row_base + (size_t)gk * 16;
+                            nbytes = 16;
+                        } else {
+                            const int tap = gk >> p.cpk_shift;
+                            const int c8 = gk - (tap << p.cpk_shift);
+                            const int hi = hi0 + tap / 3;
+                            const int wi = wi0 + tap % 3;
+                            if (hi >= 0 && hi < p.hin && wi >= 0 && wi < p.win) {
+                                src = row_base + ((size_t)(hi * p.win + wi) * p.cin + c8 * 8) * 2;
                                 nbytes = 16;
-                            } else {
-                                const int tap = g >> p.cpk_shift;
-                                const int c8 = g - (tap << p.cpk_shift);
-                                const int hi = hi0[rr] + tap / 3;
-                                const int wi = wi0[rr] + tap % 3;
-                                if (hi >= 0 && hi < p.hin && wi >= 0 && wi < p.win) {
-                                    src = row_base[rr] + ((size_t)(hi * p.win + wi) * p.cin + c8 * 8) * 2;
-                                    nbytes = 16;
-                                }
                             }
                         }
-                        ptx::cp_async16(dst_row + (uint32_t)kg * (uint32_t)p.act_rows * 16u, src, nbytes);
                     }
+                    ptx::cp_async16(dst_row + (uint32_t)kg * (uint32_t)p.act_rows * 16u, src, nbytes);
                 }
                 ptx::cp_async_commit();
                 if (npending == kLag) {
@@ -207,32 +228,34 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
             const uint32_t lbo_w = (uint32_t)p.w_rows * 16u;
             int it = 0;
             int tcount = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-                const int ks = tile % p.ksplit;
-                const int c_begin = ks * p.chunks_per_split;
-                const int c_end = min(p.nchunks, c_begin + p.chunks_per_split);
+            if (p.w_resident) ptx::mbar_wait(&w_bar, 0);
+            for (TileWalk tw(p); tw.valid(p); tw.next(p), ++tcount) {
+                int at, rb0, c_begin, c_end;
+                tw.decode(p, at, rb0, c_begin, c_end);
                 const int acc = tcount & 1;
                 const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
                 ptx::mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
                 for (int c = c_begin; c < c_end; ++c, ++it) {
                     const int s = it % S;
                     const uint32_t ph = (uint32_t)(it / S) & 1u;
                     ptx::mbar_wait(&full_bar[s], ph);
                     ptx::tc_fence_after();
-                    const uint32_t stage = smem_base + (uint32_t)s * L.stage_bytes;
+                    const uint32_t stage = stages_base + (uint32_t)s * stage_bytes;
                     const int kgs = min(8, p.kgroups - c * 8);
                     const int ksteps = (kgs + 1) >> 1;
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint64_t act_desc = ptx::umma_desc_nosw(stage + (uint32_t)k * 2u * lbo_act, lbo_act, 128u);
-                        const uint64_t w_desc =
-                            ptx::umma_desc_nosw(stage + L.act_bytes + (uint32_t)k * 2u * lbo_w, lbo_w, 128u);
-                        const uint32_t accum = (c > c_begin || k > 0) ? 1u : 0u;
-                        if (SWAP)
-                            ptx::umma_f16(d_tmem, w_desc, act_desc, idesc, accum);
-                        else
-                            ptx::umma_f16(d_tmem, act_desc, w_desc, idesc, accum);
+                    for (int b = 0; b < p.wb; ++b) {
+                        const uint32_t w_addr = p.w_resident ? smem_base + (uint32_t)(c * p.wb + b) * w_bytes : stage + act_bytes;
+                        for (int k = 0; k < ksteps; ++k) {
+                            const uint64_t act_desc = ptx::umma_desc_nosw(stage + (uint32_t)k * 2u * lbo_act, lbo_act, 128u);
+                            const uint64_t w_desc = ptx::umma_desc_nosw(w_addr + (uint32_t)k * 2u * lbo_w, lbo_w, 128u);
+                            const uint32_t accum = (c > c_begin || k > 0) ? 1u : 0u;
+                            if (SWAP)
+                                ptx::umma_f16(d_tmem + (uint32_t)(b * ncols), w_desc, act_desc, idesc, accum);
+                            else
+                                ptx::umma_f16(d_tmem, act_desc, w_desc, idesc, accum);
+                        }
                     }
                     ptx::umma_commit(&empty_bar[s]);
                 }
@@ -244,14 +267,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
         const int q = warp & 3;                       // TMEM lane quadrant
         const int r = q * 32 + lane;                  // lane / row within the tile
         int tcount = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-            const int rb = (tile / p.ksplit) % p.n_rowblocks;
-            const int at = tile / (p.ksplit * p.n_rowblocks);
+        for (TileWalk tw(p); tw.valid(p); tw.next(p), ++tcount) {
+            int at, rb0, c_begin, c_end;
+            tw.decode(p, at, rb0, c_begin, c_end);
             const int acc = tcount & 1;
             const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
             ptx::mbar_wait(&tmem_full_bar[acc], acc_ph);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
             if (!SWAP) {
                 // thread = pixel row, columns = output channels
                 const int64_t pix = (int64_t)at * 128 + r;
@@ -284,9 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                                 a = fmaxf(a, 0.f);
                                 b = fmaxf(b, 0.f);
                             }
-                            a = op_clamp(a);
-                            b = op_clamp(b);
-                            op2_t h2 = f2op2(a, b);
+                            op2_t h2 = f2op2(op_clamp(a), op_clamp(b));
                             pw[i] = *reinterpret_cast<uint32_t *>(&h2);
                         }
                         *reinterpret_cast<uint4 *>(orow + j0) = pk[0];
@@ -295,44 +316,47 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                 }
             } else {
                 // thread = weight row (output unit), columns = positions
-                const int R = rb * 128 + r;
-                const float bias = (p.bias && EPI != IGEMM_EPI_F32_ATOMIC) ? p.bias[R] : 0.f;
                 const int64_t pos0 = (int64_t)at * p.act_rows;
-                if (EPI == IGEMM_EPI_F16_BIAS) {
-                    // pre-gate layout pgT[dir][t][b/NBL][blk][r][b%NBL]  (see lstm_tc.cu)
-                    const int dir = R / 640, blk = (R % 640) >> 7;
-                    const int t = (int)(pos0 / p.pg_bp);
-                    const int bb0 = (int)(pos0 % p.pg_bp);
-                    const int ntl = p.pg_bp / p.pg_nbl;
-                    for (int j0 = 0; j0 < ncols; j0 += 16) {
-                        float v[16];
-                        ptx::tmem_ld16(taddr + (uint32_t)j0, v);
-                        ptx::tmem_ld_wait();
-                        const int b = bb0 + j0;
-                        const size_t off =
-                            ((((size_t)(dir * C3B_T + t) * ntl + b / p.pg_nbl) * 5 + blk) * 128 + r) * p.pg_nbl +
-                            (b % p.pg_nbl);
-                        uint4 pk[2];
-                        uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
+                for (int b = 0; b < p.wb; ++b) {
+                    const int R = (rb0 + b) * 128 + r;
+                    const uint32_t tb = taddr + (uint32_t)(b * ncols);
+                    if (EPI == IGEMM_EPI_F16_BIAS) {
+                        // pre-gate layout pgT[dir][t][b/NBL][blk][r][b%NBL]  (see lstm_tc.cu)
+                        const float bias = p.bias ? p.bias[R] : 0.f;
+                        const int dir = R / 640, blk = (R % 640) >> 7;
+                        const int t = (int)(pos0 / p.pg_bp);
+                        const int bb0 = (int)(pos0 % p.pg_bp);
+                        const int ntl = p.pg_bp / p.pg_nbl;
+                        for (int j0 = 0; j0 < ncols; j0 += 16) {
+                            float v[16];
+                            ptx::tmem_ld16(tb + (uint32_t)j0, v);
+                            ptx::tmem_ld_wait();
+                            const int bb = bb0 + j0;
+                            const size_t off =
+                                ((((size_t)(dir * C3B_T + t) * ntl + bb / p.pg_nbl) * 5 + blk) * 128 + r) * p.pg_nbl +
+                                (bb % p.pg_nbl);
+                            uint4 pk[2];
+                            uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            __half2 h2 = __floats2half2_rn(op_clamp(v[2 * i] + bias), op_clamp(v[2 * i + 1] + bias));
-                            pw[i] = *reinterpret_cast<uint32_t *>(&h2);
+                            for (int i = 0; i < 8; ++i) {
+                                __half2 h2 = __floats2half2_rn(op_clamp(v[2 * i] + bias), op_clamp(v[2 * i + 1] + bias));
+                                pw[i] = *reinterpret_cast<uint32_t *>(&h2);
+                            }
+                            __half *dst = (__half *)p.out + off;
+                            *reinterpret_cast<uint4 *>(dst) = pk[0];
+                            *reinterpret_cast<uint4 *>(dst + 8) = pk[1];
                         }
-                        __half *dst = (__half *)p.out + off;
-                        *reinterpret_cast<uint4 *>(dst) = pk[0];
-                        *reinterpret_cast<uint4 *>(dst + 8) = pk[1];
-                    }
-                } else {
-                    float *outp = (float *)p.out;
-                    for (int j0 = 0; j0 < ncols; j0 += 16) {
-                        float v[16];
-                        ptx::tmem_ld16(taddr + (uint32_t)j0, v);
-                        ptx::tmem_ld_wait();
+                    } else {
+                        float *outp = (float *)p.out;
+                        for (int j0 = 0; j0 < ncols; j0 += 16) {
+                            float v[16];
+                            ptx::tmem_ld16(tb + (uint32_t)j0, v);
+                            ptx::tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int64_t pos = pos0 + j0 + i;
-                            if (pos < p.m_valid) atomicAdd(outp + pos * p.ldo + R, v[i]);
+                            for (int i = 0; i < 16; ++i) {
+                                const int64_t pos = pos0 + j0 + i;
+                                if (pos < p.m_valid) atomicAdd(outp + pos * p.ldo + R, v[i]);
+                            }
                         }
                     }
                 }
@@ -358,11 +382,7 @@ int ilog2(int v) {
 template <bool SWAP, int EPI>
 int launch(const IgemmDev &p, int grid, size_t smem, cudaStream_t s) {
     auto kern = igemm_kernel<SWAP, EPI>;
-    static bool configured = false;
-    if (!configured) {
-        C3B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        configured = true;
-    }
+    C3B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     kern<<<grid, kThreads, smem, s>>>(p);
     C3B_CUDA(cudaGetLastError());
     return 0;
@@ -387,17 +407,16 @@ int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s) {
     p.kgroups = a.w.kgroups;
     p.nchunks = a.w.nchunks;
     p.relu = a.relu;
-    p.n_total = a.w.n;
+    p.act_rows = 128;
+    p.wb = 1;
     const bool swap = (a.epilogue != IGEMM_EPI_BF16_BIAS_RELU);
     if (!swap) {
         if (a.w.n % 16 || a.w.n > 256 || a.w.n < 16) { c3b_set_error("igemm: bad N %d", a.w.n); return 1; }
-        p.act_rows = 128;
         p.w_rows = a.w.n;
         p.n_rowblocks = 1;
         p.ksplit = 1;
     } else {
         if (a.w.n % 128) { c3b_set_error("igemm(swap): weight rows %d not a multiple of 128", a.w.n); return 1; }
-        p.act_rows = 128;
         p.w_rows = 128;
         p.n_rowblocks = a.w.n / 128;
         p.ksplit = a.ksplit > 0 ? a.ksplit : 1;
@@ -405,19 +424,45 @@ int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s) {
     p.n_act_tiles = (int)((a.m + p.act_rows - 1) / p.act_rows);
     p.chunks_per_split = (p.nchunks + p.ksplit - 1) / p.ksplit;
     p.ksplit = (p.nchunks + p.chunks_per_split - 1) / p.chunks_per_split;   // drop empty splits
-    const size_t stage_bytes = (size_t)(p.act_rows + p.w_rows) * 128;
-    int stages = (int)((200 * 1024) / stage_bytes);
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < kLag + 1) { c3b_set_error("igemm: tile too large for the shared-memory pipeline"); return 1; }
-    p.stages = stages;
-    const size_t smem = stage_bytes * stages + 1024;
-    const int num_tiles = p.n_act_tiles * p.n_rowblocks * p.ksplit;
-    const int grid = num_tiles < m->sm_count ? num_tiles : m->sm_count;
+
+    const size_t budget = 216 * 1024;
+    const size_t act_bytes = (size_t)p.act_rows * 128, w_bytes = (size_t)p.w_rows * 128;
+    // W-stationary when the slab fits beside >= 4 activation stages (and there are enough tiles to amortise the load)
+    if (p.ksplit == 1) {
+        int wb = (swap && p.n_rowblocks % 2 == 0 && 2 * p.act_rows <= 256) ? 2 : 1;
+        for (; wb >= 1; --wb) {
+            const size_t slab = (size_t)wb * p.nchunks * w_bytes;
+            if (slab + 4 * act_bytes <= budget && p.n_act_tiles >= 2 * (m->sm_count / (p.n_rowblocks / wb))) {
+                p.w_resident = 1;
+                p.wb = wb;
+                break;
+            }
+        }
+    }
+    int grid;
+    size_t smem;
+    if (p.w_resident) {
+        const size_t slab = (size_t)p.wb * p.nchunks * w_bytes;
+        int stages = (int)((budget - slab) / act_bytes);
+        p.stages = stages > kMaxStages ? kMaxStages : stages;
+        smem = slab + act_bytes * p.stages + 256;
+        const int n_rg = p.n_rowblocks / p.wb;
+        int per = m->sm_count / n_rg;
+        if (per > p.n_act_tiles) per = p.n_act_tiles;
+        grid = n_rg * per;
+    } else {
+        const size_t stage_bytes = act_bytes + w_bytes;
+        int stages = (int)(budget / stage_bytes);
+        p.stages = stages > kMaxStages ? kMaxStages : stages;
+        smem = stage_bytes * p.stages + 256;
+        const int num_tiles = p.n_act_tiles * p.n_rowblocks * p.ksplit;
+        grid = num_tiles < m->sm_count ? num_tiles : m->sm_count;
+    }
+    if (p.stages < kLag + 1) { c3b_set_error("igemm: tile too large for the shared-memory pipeline"); return 1; }
     const_cast<c3b_model *>(m)->launches++;
     switch (a.epilogue) {
         case IGEMM_EPI_BF16_BIAS_RELU: return launch<false, IGEMM_EPI_BF16_BIAS_RELU>(p, grid, smem, s);
         case IGEMM_EPI_F16_BIAS: {
-            // pre-gate geometry rides in lda-independent fields
             p.pg_bp = (int)a.hin;     // caller passes padded batch / LSTM tile through hin / win in plain mode
             p.pg_nbl = (int)a.win;
             if (p.pg_bp % 128 || p.pg_nbl % 16) { c3b_set_error("igemm: bad pre-gate geometry"); return 1; }

@@ -42,10 +42,10 @@ __device__ __forceinline__ void lstm_cell8(const float *gi, const float *gf, con
                                            float *h) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const float iv = ptx::sigmoid_approx(gi[i]);
-        const float fv = ptx::sigmoid_approx(gf[i]);
+        const float iv = ptx::sigmoid_prehalved(gi[i]);
+        const float fv = ptx::sigmoid_prehalved(gf[i]);
         const float gv = ptx::tanh_approx(gg[i]);
-        const float ov = ptx::sigmoid_approx(go[i]);
+        const float ov = ptx::sigmoid_prehalved(go[i]);
         c[i] = fmaf(fv, c[i], iv * gv);
         h[i] = ov * ptx::tanh_approx(c[i]);
     }
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float x = v[i] + pgf[i];
-                    const float a = (warp == 2) ? ptx::tanh_approx(x) : ptx::sigmoid_approx(x);
+                    const float a = (warp == 2) ? ptx::tanh_approx(x) : ptx::sigmoid_prehalved(x);
                     xch[(j * 8 + i) * 128 + tid] = a;
                 }
             }

@@ -1,0 +1,125 @@
+// Micro-probes of tcgen05 behaviour on this part (diagnostics, tools/diag.py probe): (1) numerics of an MMA whose A
+// operand lives in TMEM ("TS" form) under the assumed layout lane = row, one 32-bit column = two consecutive K elements;
+// (2) cycles per MMA for back-to-back issue with A from shared memory (SS) and from TMEM (TS) at several N.
+#include "c3b_internal.h"
+#include "ptx.cuh"
+
+namespace {
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// a: [128][16] fp16 row-major, b: [n][16] fp16 row-major, d: [128][n] fp32.  timing[0..]: cycles for `reps` back-to-back MMAs.
+__global__ void __launch_bounds__(128, 1) probe_kernel(const __half *a, const __half *b, float *d, int n, int reps,
+                                                       long long *timing) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint8_t *a_smem = smem;                 // [2 kgroups][128][8]  (LBO = 2048)
+    uint8_t *b_smem = smem + 4096;          // [2 kgroups][n][8]    (LBO = n*16)
+    if (tid == 0) { ptx::mbar_init(&bar, 1); ptx::fence_barrier_init(); }
+    if (warp == 0) ptx::tmem_alloc<512>(&tmem_base_smem);
+    // stage A (smem image) and B
+    for (int i = tid; i < 128 * 2; i += 128) {
+        const int row = i >> 1, kg = i & 1;
+        *reinterpret_cast<uint4 *>(a_smem + kg * 2048 + row * 16) = *reinterpret_cast<const uint4 *>(a + row * 16 + kg * 8);
+    }
+    for (int i = tid; i < n * 2; i += 128) {
+        const int row = i >> 1, kg = i & 1;
+        *reinterpret_cast<uint4 *>(b_smem + kg * n * 16 + row * 16) = *reinterpret_cast<const uint4 *>(b + row * 16 + kg * 8);
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t lane_t = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // A into TMEM columns [256, 264): thread = row, 8 x 32-bit = 16 fp16 of its row
+    {
+        uint32_t r[8];
+        const uint4 v0 = *reinterpret_cast<const uint4 *>(a + tid * 16);
+        const uint4 v1 = *reinterpret_cast<const uint4 *>(a + tid * 16 + 8);
+        r[0] = v0.x; r[1] = v0.y; r[2] = v0.z; r[3] = v0.w; r[4] = v1.x; r[5] = v1.y; r[6] = v1.z; r[7] = v1.w;
+        tmem_st8(lane_t + 256, r);
+        tmem_st_wait();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t idesc = ptx::umma_idesc_f16(128, (uint32_t)n);
+    const uint64_t a_desc = ptx::umma_desc_nosw(ptx::smem_u32(a_smem), 2048, 128);
+    const uint64_t b_desc = ptx::umma_desc_nosw(ptx::smem_u32(b_smem), (uint32_t)n * 16u, 128);
+    uint32_t phase = 0;
+    // ---- numerics: D_ts at columns [0,n), D_ss at columns [n, 2n) is skipped (SS is validated by the igemm tests)
+    if (tid == 0) {
+        umma_f16_ts(tmem_base, tmem_base + 256, b_desc, idesc, 0);
+        ptx::umma_commit(&bar);
+    }
+    ptx::mbar_wait(&bar, phase); phase ^= 1;
+    ptx::tc_fence_after();
+    for (int j0 = 0; j0 < n; j0 += 8) {
+        float v[8];
+        ptx::tmem_ld8(lane_t + j0, v);
+        ptx::tmem_ld_wait();
+        for (int i = 0; i < 8; ++i) d[tid * n + j0 + i] = v[i];
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    // ---- timing: reps back-to-back MMAs (accumulating), SS then TS
+    for (int mode = 0; mode < 2; ++mode) {
+        long long t0 = 0;
+        if (tid == 0) {
+            t0 = clock64();
+            for (int i = 0; i < reps; ++i) {
+                if (mode == 0) ptx::umma_f16(tmem_base, a_desc, b_desc, idesc, 1);
+                else umma_f16_ts(tmem_base, tmem_base + 256, b_desc, idesc, 1);
+            }
+            ptx::umma_commit(&bar);
+            timing[mode * 2 + 0] = clock64() - t0;          // issue time
+        }
+        ptx::mbar_wait(&bar, phase); phase ^= 1;
+        if (tid == 0) timing[mode * 2 + 1] = clock64() - t0;  // completion time
+        ptx::tc_fence_after();
+        __syncthreads();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc<512>(tmem_base); }
+}
+
+}  // namespace
+
+// out_d: [128][n] fp32 (TS-form result), timing4: {SS issue, SS done, TS issue, TS done} cycles for `reps` MMAs
+extern "C" int c3b_debug_ts_probe(const float *a, const float *b, int n, int reps, float *out_d, int64_t *timing4) {
+    if (n % 16 || n < 16 || n > 256) { c3b_set_error("probe: bad n"); return 1; }
+    std::vector<uint16_t> ah(128 * 16), bh((size_t)n * 16);
+    for (size_t i = 0; i < ah.size(); ++i) ah[i] = c3b_f2op(a[i]);
+    for (size_t i = 0; i < bh.size(); ++i) bh[i] = c3b_f2op(b[i]);
+    void *da, *db, *dd, *dt;
+    C3B_CUDA(cudaMalloc(&da, ah.size() * 2));
+    C3B_CUDA(cudaMalloc(&db, bh.size() * 2));
+    C3B_CUDA(cudaMalloc(&dd, (size_t)128 * n * 4));
+    C3B_CUDA(cudaMalloc(&dt, 4 * 8));
+    C3B_CUDA(cudaMemcpy(da, ah.data(), ah.size() * 2, cudaMemcpyHostToDevice));
+    C3B_CUDA(cudaMemcpy(db, bh.data(), bh.size() * 2, cudaMemcpyHostToDevice));
+    probe_kernel<<<1, 128, 4096 + n * 32 + 128>>>((const __half *)da, (const __half *)db, (float *)dd, n, reps, (long long *)dt);
+    C3B_CUDA(cudaGetLastError());
+    C3B_CUDA(cudaDeviceSynchronize());
+    C3B_CUDA(cudaMemcpy(out_d, dd, (size_t)128 * n * 4, cudaMemcpyDeviceToHost));
+    C3B_CUDA(cudaMemcpy(timing4, dt, 32, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dd); cudaFree(dt);
+    return 0;
+}

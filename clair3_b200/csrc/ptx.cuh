@@ -130,6 +130,7 @@ __device__ __forceinline__ float tanh_approx(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float sigmoid_approx(float x) { return fmaf(tanh_approx(0.5f * x), 0.5f, 0.5f); }
+// sigmoid of a PRE-HALVED argument: sigma(2*xh) = 0.5*tanh(xh) + 0.5
+__device__ __forceinline__ float sigmoid_prehalved(float xh) { return fmaf(tanh_approx(xh), 0.5f, 0.5f); }
 
 }  // namespace ptx

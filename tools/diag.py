@@ -61,7 +61,8 @@ def run_case(name, precision, opts):
 def run_igemm():
     from clair3_b200._ffi import check, ffi, lib
     shapes = [(0, 128, 64, 64, 1), (0, 128, 16, 16, 1), (0, 300, 64, 72, 1), (0, 1000, 128, 576, 1), (0, 257, 256, 1152, 1),
-              (1, 128, 128, 64, 1), (1, 200, 256, 256, 1), (1, 77, 128, 1064, 3), (1, 1024, 128, 10560, 11)]
+              (1, 128, 128, 64, 1), (1, 200, 256, 256, 1), (1, 77, 128, 1064, 3), (1, 1024, 128, 10560, 11),
+              (0, 40000, 64, 576, 1), (1, 40000, 256, 256, 1), (1, 20000, 128, 72, 1)]
     for swapped, M, N, K, ks in shapes:
         r = np.random.default_rng(M + N + K)
         a = r.standard_normal((M, K)).astype(np.float32)
@@ -91,6 +92,22 @@ def run_igemm():
             cb = err[:128].max(axis=0)
             print("    row err (first 16):", np.round(rb[:16], 2), " col err (first 16):", np.round(cb[:16], 2))
             print("    out[0,:8]", np.round(out[0, :8], 3), " ref[0,:8]", np.round(ref[0, :8], 3))
+
+
+def run_probe():
+    from clair3_b200._ffi import check, ffi, lib
+    r = np.random.default_rng(0)
+    for n in (16, 32, 64, 128, 256):
+        a = r.standard_normal((128, 16)).astype(np.float32)
+        b = r.standard_normal((n, 16)).astype(np.float32)
+        d = np.zeros((128, n), dtype=np.float32)
+        tm = np.zeros(4, dtype=np.int64)
+        reps = 64
+        check(lib().c3b_debug_ts_probe(ffi.cast("float *", a.ctypes.data), ffi.cast("float *", b.ctypes.data), n, reps,
+                                       ffi.cast("float *", d.ctypes.data), ffi.cast("int64_t *", tm.ctypes.data)))
+        ref = a.astype(np.float16).astype(np.float64) @ b.astype(np.float16).astype(np.float64).T
+        print(f"probe N={n}: TS-form max err {np.abs(d - ref).max():.3e} (|ref| max {np.abs(ref).max():.2f});  per MMA: "
+              f"SS issue {tm[0]/reps:.1f} done {tm[1]/reps:.1f} cyc | TS issue {tm[2]/reps:.1f} done {tm[3]/reps:.1f} cyc", flush=True)
 
 
 def run_trace(opts):
@@ -137,6 +154,8 @@ if __name__ == "__main__":
     cases = cases2 or (GOLDEN_PILEUP + GOLDEN_FA)
     if mode == "igemm":
         run_igemm()
+    elif mode == "probe":
+        run_probe()
     elif mode == "trace":
         run_trace(opts)
     else:
