@@ -24,26 +24,26 @@ __global__ void ingest_fa_tc_kernel(const T *__restrict__ x, op_t *__restrict__ 
     }
 }
 
+// grid (B, 14 pyramid cells), block = channels: every thread reduces one window of one channel (coalesced over channels).
 __global__ void spp_tc_kernel(const op_t *__restrict__ x, op_t *__restrict__ out, int h, int w, int c) {
     const int64_t b = blockIdx.x;
-    const int cells = 14;
-    for (int i = threadIdx.x; i < cells * c; i += blockDim.x) {
-        const int cell = i / c, ch = i - cell * c;
-        int p, idx;
-        if (cell < 9) { p = 3; idx = cell; }
-        else if (cell < 13) { p = 2; idx = cell - 9; }
-        else { p = 1; idx = 0; }
-        const int wh = (h + p - 1) / p, ww = (w + p - 1) / p;
-        const int oh = (h + wh - 1) / wh, ow = (w + ww - 1) / ww;
-        const int ph = max((oh - 1) * wh + wh - h, 0), pw = max((ow - 1) * ww + ww - w, 0);
-        const int pt = ph / 2, pl = pw / 2;
-        const int oi = idx / ow, oj = idx - oi * ow;
-        const int h0 = oi * wh - pt, w0 = oj * ww - pl;
+    const int cell = blockIdx.y;
+    int p, idx;
+    if (cell < 9) { p = 3; idx = cell; }
+    else if (cell < 13) { p = 2; idx = cell - 9; }
+    else { p = 1; idx = 0; }
+    const int wh = (h + p - 1) / p, ww = (w + p - 1) / p;
+    const int oh = (h + wh - 1) / wh, ow = (w + ww - 1) / ww;
+    const int ph = max((oh - 1) * wh + wh - h, 0), pw = max((ow - 1) * ww + ww - w, 0);
+    const int pt = ph / 2, pl = pw / 2;
+    const int oi = idx / ow, oj = idx - oi * ow;
+    const int h0 = max(oi * wh - pt, 0), h1 = min(oi * wh - pt + wh, h);
+    const int w0 = max(oj * ww - pl, 0), w1 = min(oj * ww - pl + ww, w);
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
         float m = 0.f;                       // inputs are post-ReLU: zero padding == floor at 0
-        for (int hh = max(h0, 0); hh < min(h0 + wh, h); ++hh)
-            for (int wv = max(w0, 0); wv < min(w0 + ww, w); ++wv)
-                m = fmaxf(m, op2f(x[((b * h + hh) * w + wv) * c + ch]));
-        out[b * (cells * c) + i] = f2op(m);
+        for (int hh = h0; hh < h1; ++hh)
+            for (int wv = w0; wv < w1; ++wv) m = fmaxf(m, op2f(x[((b * h + hh) * w + wv) * c + ch]));
+        out[b * (14 * c) + cell * c + ch] = f2op(m);
     }
 }
 
@@ -66,7 +66,7 @@ int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, op
 
 int c3b_launch_spp_tc(const op_t *x, op_t *out, int64_t batch, int h, int w, int c, cudaStream_t s) {
     if (batch == 0) return 0;
-    spp_tc_kernel<<<(unsigned)batch, 256, 0, s>>>(x, out, h, w, c);
+    spp_tc_kernel<<<dim3((unsigned)batch, 14), 256, 0, s>>>(x, out, h, w, c);
     C3B_CUDA(cudaGetLastError());
     return 0;
 }

@@ -221,36 +221,36 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
         ptx::fence_proxy_async_smem();
         for (int i = 0; i < npending; ++i) ptx::mbar_arrive(&full_bar[pending[i]]);
     } else if (warp == 8) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = ptx::umma_idesc_f16(128, (uint32_t)ncols);
-            const uint32_t lbo_act = (uint32_t)p.act_rows * 16u;
-            const uint32_t lbo_w = (uint32_t)p.w_rows * 16u;
-            int it = 0;
-            int tcount = 0;
-            if (p.w_resident) ptx::mbar_wait(&w_bar, 0);
-            for (TileWalk tw(p); tw.valid(p); tw.next(p), ++tcount) {
-                int at, rb0, c_begin, c_end;
-                tw.decode(p, at, rb0, c_begin, c_end);
-                const int acc = tcount & 1;
-                const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
-                ptx::mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);
+        // ===================================================== MMA issuer (whole warp walks the tiles, one elected lane issues)
+        const uint32_t idesc = ptx::umma_idesc_f16(128, (uint32_t)ncols);
+        const uint32_t lbo_act = (uint32_t)p.act_rows * 16u;
+        const uint32_t lbo_w = (uint32_t)p.w_rows * 16u;
+        int it = 0;
+        int tcount = 0;
+        if (p.w_resident) ptx::mbar_wait(&w_bar, 0);
+        for (TileWalk tw(p); tw.valid(p); tw.next(p), ++tcount) {
+            int at, rb0, c_begin, c_end;
+            tw.decode(p, at, rb0, c_begin, c_end);
+            const int acc = tcount & 1;
+            const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+            ptx::mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+            for (int c = c_begin; c < c_end; ++c, ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                ptx::mbar_wait(&full_bar[s], ph);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
-                for (int c = c_begin; c < c_end; ++c, ++it) {
-                    const int s = it % S;
-                    const uint32_t ph = (uint32_t)(it / S) & 1u;
-                    ptx::mbar_wait(&full_bar[s], ph);
-                    ptx::tc_fence_after();
-                    const uint32_t stage = stages_base + (uint32_t)s * stage_bytes;
-                    const int kgs = min(8, p.kgroups - c * 8);
-                    const int ksteps = (kgs + 1) >> 1;
-                    for (int b = 0; b < p.wb; ++b) {
-                        const uint32_t w_addr = p.w_resident ? smem_base + (uint32_t)(c * p.wb + b) * w_bytes : stage + act_bytes;
-                        for (int k = 0; k < ksteps; ++k) {
-                            const uint64_t act_desc = ptx::umma_desc_nosw(stage + (uint32_t)k * 2u * lbo_act, lbo_act, 128u);
+                const uint32_t stage = stages_base + (uint32_t)s * stage_bytes;
+                const int kgs = min(8, p.kgroups - c * 8);
+                const int ksteps = (kgs + 1) >> 1;
+                if (ptx::elect_one()) {
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t act_desc = ptx::umma_desc_nosw(stage + (uint32_t)k * 2u * lbo_act, lbo_act, 128u);
+                        const uint32_t accum = (c > c_begin || k > 0) ? 1u : 0u;
+                        for (int b = 0; b < p.wb; ++b) {
+                            const uint32_t w_addr = p.w_resident ? smem_base + (uint32_t)(c * p.wb + b) * w_bytes : stage + act_bytes;
                             const uint64_t w_desc = ptx::umma_desc_nosw(w_addr + (uint32_t)k * 2u * lbo_w, lbo_w, 128u);
-                            const uint32_t accum = (c > c_begin || k > 0) ? 1u : 0u;
                             if (SWAP)
                                 ptx::umma_f16(d_tmem + (uint32_t)(b * ncols), w_desc, act_desc, idesc, accum);
                             else
@@ -258,8 +258,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                         }
                     }
                     ptx::umma_commit(&empty_bar[s]);
+                    if (c + 1 == c_end) ptx::umma_commit(&tmem_full_bar[acc]);
                 }
-                ptx::umma_commit(&tmem_full_bar[acc]);
+                __syncwarp();
             }
         }
     } else {

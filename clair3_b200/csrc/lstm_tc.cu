@@ -24,7 +24,8 @@
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 128;            // epilogue threads (one per TMEM lane); warp 4 issues the MMAs
+constexpr int kBlockThreads = 160;
 constexpr int kBlkBytes = 20 * 128 * 16;       // one 128-row x K=160 weight block: [K/8][128][8] bf16
 
 struct LstmDev {
@@ -62,7 +63,7 @@ __device__ __forceinline__ void unpack_half8(const uint4 &v, float *f) {
 }
 
 template <int NB, bool LAYER2>
-__global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
+__global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev p) {
     constexpr int H = LAYER2 ? 160 : 128;
     constexpr int KX = LAYER2 ? 0 : 32;
     constexpr int K = KX + H;                       // 160 for both layers
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
                                : (NBLK * NB <= 256) ? 256 : 512;
 
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t w_bar, acc_bar;
+    __shared__ uint64_t w_bar, acc_bar, ready_bar;
     __shared__ uint32_t tmem_base_smem;
     uint8_t *w_smem = smem;
     uint8_t *b_smem = smem + NBLK * kBlkBytes;
@@ -92,10 +93,11 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
     if (tid == 0) {
         ptx::mbar_init(&w_bar, 1);
         ptx::mbar_init(&acc_bar, 1);
+        ptx::mbar_init(&ready_bar, kThreads);
         ptx::fence_barrier_init();
     }
-    if (warp == 0) ptx::tmem_alloc<TCOLS>(&tmem_base_smem);
-    for (uint32_t i = tid * 16; i < B_BYTES; i += kThreads * 16) *reinterpret_cast<uint4 *>(b_smem + i) = make_uint4(0, 0, 0, 0);
+    if (warp == 4) ptx::tmem_alloc<TCOLS>(&tmem_base_smem);
+    for (uint32_t i = tid * 16; i < B_BYTES; i += kBlockThreads * 16) *reinterpret_cast<uint4 *>(b_smem + i) = make_uint4(0, 0, 0, 0);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -106,6 +108,34 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
         const char *src = reinterpret_cast<const char *>(p.w_img) + (size_t)dir * NBLK * kBlkBytes;
 #pragma unroll
         for (int m = 0; m < NBLK; ++m) ptx::bulk_g2s(w_addr + m * kBlkBytes, src + (size_t)m * kBlkBytes, kBlkBytes, &w_bar);
+    }
+
+    const uint32_t idesc = ptx::umma_idesc_f16(128, NB);
+    if (warp == 4) {
+        // ===================================================== MMA warp: wait for [x_t ; h_{t-1}], issue the step's gate GEMM
+        ptx::mbar_wait(&w_bar, 0);
+        for (int step = 0; step < C3B_T; ++step) {
+            ptx::mbar_wait(&ready_bar, (uint32_t)step & 1u);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < K / 16; ++ks) {
+                    const uint64_t b_desc = ptx::umma_desc_nosw(b_addr + ks * 2 * LBO_B, LBO_B, 128);
+#pragma unroll
+                    for (int m = 0; m < NBLK; ++m) {
+                        const uint64_t a_desc = ptx::umma_desc_nosw(w_addr + m * kBlkBytes + ks * 2 * 2048, 2048, 128);
+                        ptx::umma_f16(tmem_base + m * NB, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
+                    }
+                }
+                ptx::umma_commit(&acc_bar);
+            }
+            __syncwarp();
+        }
+        ptx::tc_fence_before();
+        __syncthreads();                      // matches the epilogue threads' final barrier
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<TCOLS>(tmem_base);
+        return;
     }
 
     float bias_i = 0.f, bias_f = 0.f, bias_g = 0.f, bias_o = 0.f;
@@ -124,7 +154,6 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
 #pragma unroll
     for (int i = 0; i < (LAYER2 ? NB / 4 : 1); ++i) c_tail[i] = 0.f;
 
-    const uint32_t idesc = ptx::umma_idesc_f16(128, NB);
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int ntl = p.bp / NB;
 
@@ -142,23 +171,9 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
         }
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
-        __syncthreads();                                                    // S1: operands of this step are in place
+        ptx::mbar_arrive(&ready_bar);                                       // S1: this thread's operands / TMEM reads are done
         const bool tr = p.trace != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
         if (tr) p.trace[step * 4 + 0] = clock64();
-        if (tid == 0) {
-            if (step == 0) ptx::mbar_wait(&w_bar, 0);
-            ptx::tc_fence_after();
-#pragma unroll 1
-            for (int m = 0; m < NBLK; ++m) {
-#pragma unroll
-                for (int ks = 0; ks < K / 16; ++ks) {
-                    const uint64_t a_desc = ptx::umma_desc_nosw(w_addr + m * kBlkBytes + ks * 2 * 2048, 2048, 128);
-                    const uint64_t b_desc = ptx::umma_desc_nosw(b_addr + ks * 2 * LBO_B, LBO_B, 128);
-                    ptx::umma_f16(tmem_base + m * NB, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
-                }
-            }
-            ptx::umma_commit(&acc_bar);
-        }
         if (tr) p.trace[step * 4 + 1] = clock64();
 
         // while the MMAs run: ship h_{t_prev} (still in the operand buffer) to global memory
@@ -185,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
         ptx::mbar_wait(&acc_bar, (uint32_t)step & 1u);
         ptx::tc_fence_after();
         if (tr) p.trace[step * 4 + 2] = clock64();
-        __syncthreads();                                                    // S2: everyone is done reading h_{t_prev}
+        ptx::named_bar_sync(1, kThreads);                                   // S2: everyone is done reading h_{t_prev}
 
         if (LAYER2) {
             // tail block (units 128..159): warp w holds gate w; activate and publish to the exchange buffer
@@ -202,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
                     xch[(j * 8 + i) * 128 + tid] = a;
                 }
             }
-            __syncthreads();
+            ptx::named_bar_sync(1, kThreads);
         }
 
         // main blocks: thread = hidden unit `tid`, 8 sites at a time
@@ -267,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
     }
 
     // last h
-    __syncthreads();
+    ptx::named_bar_sync(1, kThreads);
     for (int idx = tid; idx < NB * (H / 8); idx += kThreads) {
         const int n = idx / (H / 8), kgh = idx % (H / 8);
         const uint4 v = *reinterpret_cast<const uint4 *>(b_smem + (KX / 8 + kgh) * LBO_B + n * 16);
@@ -277,10 +292,6 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_tc_kernel(const LstmDev p) {
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
-        ptx::tc_fence_after();
-        ptx::tmem_dealloc<TCOLS>(tmem_base);
-    }
 }
 
 template <typename T>
@@ -312,7 +323,7 @@ int launch_lstm(const LstmDev &p, cudaStream_t s) {
     auto kern = lstm_tc_kernel<NB, LAYER2>;
     C3B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(p.bp / NB, 2);
-    kern<<<grid, kThreads, smem, s>>>(p);
+    kern<<<grid, kBlockThreads, smem, s>>>(p);
     C3B_CUDA(cudaGetLastError());
     return 0;
 }

@@ -79,13 +79,18 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __half *a, const __
     __syncthreads();
     ptx::tc_fence_after();
     // ---- timing: reps back-to-back MMAs (accumulating), SS then TS
-    for (int mode = 0; mode < 2; ++mode) {
+    // modes: 0 SS same accumulator, 1 TS same accumulator, 2 SS round-robin over 4 accumulators (n <= 64),
+    //        3 SS round-robin over 2 accumulators (n <= 128), 4 TS round-robin over 4 accumulators (n <= 32)
+    for (int mode = 0; mode < 5; ++mode) {
         long long t0 = 0;
         if (tid == 0) {
             t0 = clock64();
             for (int i = 0; i < reps; ++i) {
                 if (mode == 0) ptx::umma_f16(tmem_base, a_desc, b_desc, idesc, 1);
-                else umma_f16_ts(tmem_base, tmem_base + 256, b_desc, idesc, 1);
+                else if (mode == 1) umma_f16_ts(tmem_base, tmem_base + 256, b_desc, idesc, 1);
+                else if (mode == 2) ptx::umma_f16(tmem_base + (uint32_t)((i & 3) * (n <= 64 ? n : 0)), a_desc, b_desc, idesc, 1);
+                else if (mode == 3) ptx::umma_f16(tmem_base + (uint32_t)((i & 1) * (n <= 128 ? n : 0)), a_desc, b_desc, idesc, 1);
+                else umma_f16_ts(tmem_base + (uint32_t)((i & 3) * (n <= 32 ? n : 0)), tmem_base + 256, b_desc, idesc, 1);
             }
             ptx::umma_commit(&bar);
             timing[mode * 2 + 0] = clock64() - t0;          // issue time
@@ -102,7 +107,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __half *a, const __
 
 }  // namespace
 
-// out_d: [128][n] fp32 (TS-form result), timing4: {SS issue, SS done, TS issue, TS done} cycles for `reps` MMAs
+// out_d: [128][n] fp32 (TS-form result), timing4: 5 modes x {issue, done} cycles for `reps` MMAs
 extern "C" int c3b_debug_ts_probe(const float *a, const float *b, int n, int reps, float *out_d, int64_t *timing4) {
     if (n % 16 || n < 16 || n > 256) { c3b_set_error("probe: bad n"); return 1; }
     std::vector<uint16_t> ah(128 * 16), bh((size_t)n * 16);
@@ -112,14 +117,14 @@ extern "C" int c3b_debug_ts_probe(const float *a, const float *b, int n, int rep
     C3B_CUDA(cudaMalloc(&da, ah.size() * 2));
     C3B_CUDA(cudaMalloc(&db, bh.size() * 2));
     C3B_CUDA(cudaMalloc(&dd, (size_t)128 * n * 4));
-    C3B_CUDA(cudaMalloc(&dt, 4 * 8));
+    C3B_CUDA(cudaMalloc(&dt, 10 * 8));
     C3B_CUDA(cudaMemcpy(da, ah.data(), ah.size() * 2, cudaMemcpyHostToDevice));
     C3B_CUDA(cudaMemcpy(db, bh.data(), bh.size() * 2, cudaMemcpyHostToDevice));
     probe_kernel<<<1, 128, 4096 + n * 32 + 128>>>((const __half *)da, (const __half *)db, (float *)dd, n, reps, (long long *)dt);
     C3B_CUDA(cudaGetLastError());
     C3B_CUDA(cudaDeviceSynchronize());
     C3B_CUDA(cudaMemcpy(out_d, dd, (size_t)128 * n * 4, cudaMemcpyDeviceToHost));
-    C3B_CUDA(cudaMemcpy(timing4, dt, 32, cudaMemcpyDeviceToHost));
+    C3B_CUDA(cudaMemcpy(timing4, dt, 80, cudaMemcpyDeviceToHost));
     cudaFree(da); cudaFree(db); cudaFree(dd); cudaFree(dt);
     return 0;
 }

@@ -105,6 +105,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One lane of a fully-converged warp (the canonical way to issue tcgen05.mma: the compiler keeps the issue loop on the
+// uniform datapath instead of wrapping every UTCHMMA in an ELECT/branch loop as it does under `if (lane == 0)`).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// Named barrier among `nthreads` threads (id 1..15; 0 is __syncthreads).
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave") canonical layout: 8x8 (16-byte-row) core
 // matrices stored as 128 contiguous bytes; LBO = byte distance between the two core matrices adjacent in K,

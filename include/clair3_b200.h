@@ -109,7 +109,7 @@ int c3b_debug_lstm_trace(c3b_model *m, int64_t *out264);
 
 /* Hardware probe (tools/diag.py probe): one tcgen05.mma with its A operand in TMEM (checks the assumed layout) and the
  * cycles of `reps` back-to-back MMAs with A from shared memory vs TMEM.  a[128][16], b[n][16] -> out_d[128][n]. */
-int c3b_debug_ts_probe(const float *a, const float *b, int n, int reps, float *out_d, int64_t *timing4);
+int c3b_debug_ts_probe(const float *a, const float *b, int n, int reps, float *out_d, int64_t *timing10);
 
 void c3b_destroy(c3b_model *m);
 

@@ -101,13 +101,14 @@ def run_probe():
         a = r.standard_normal((128, 16)).astype(np.float32)
         b = r.standard_normal((n, 16)).astype(np.float32)
         d = np.zeros((128, n), dtype=np.float32)
-        tm = np.zeros(4, dtype=np.int64)
+        tm = np.zeros(10, dtype=np.int64)
         reps = 64
         check(lib().c3b_debug_ts_probe(ffi.cast("float *", a.ctypes.data), ffi.cast("float *", b.ctypes.data), n, reps,
                                        ffi.cast("float *", d.ctypes.data), ffi.cast("int64_t *", tm.ctypes.data)))
         ref = a.astype(np.float16).astype(np.float64) @ b.astype(np.float16).astype(np.float64).T
         print(f"probe N={n}: TS-form max err {np.abs(d - ref).max():.3e} (|ref| max {np.abs(ref).max():.2f});  per MMA: "
-              f"SS issue {tm[0]/reps:.1f} done {tm[1]/reps:.1f} cyc | TS issue {tm[2]/reps:.1f} done {tm[3]/reps:.1f} cyc", flush=True)
+              f"SS {tm[1]/reps:.1f} | TS {tm[3]/reps:.1f} | SS 4-acc round-robin {tm[5]/reps:.1f} | SS 2-acc {tm[7]/reps:.1f} | "
+              f"TS 4-acc {tm[9]/reps:.1f} cycles (issue-only: {tm[0]/reps:.1f}/{tm[2]/reps:.1f}/{tm[4]/reps:.1f}/{tm[6]/reps:.1f}/{tm[8]/reps:.1f})", flush=True)
 
 
 def run_trace(opts):

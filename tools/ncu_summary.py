@@ -1,0 +1,45 @@
+"""Summarise an `ncu --page raw --csv` export into the few metrics DESIGN.md / bench.py cite.
+
+    ncu -i gpurun_out/X.ncu-rep --page raw --csv > X_raw.csv ; python tools/ncu_summary.py X_raw.csv > profiles/X.md
+"""
+import csv
+import sys
+
+KEYS = [
+    ("gpu__time_duration.sum", "duration"),
+    ("launch__grid_size", "grid"),
+    ("launch__registers_per_thread", "registers/thread"),
+    ("sm__cycles_elapsed.max", "SM cycles elapsed"),
+    ("dram__bytes_read.sum", "DRAM read"),
+    ("dram__bytes_write.sum", "DRAM write"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % of peak"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe (math) active % of active cycles"),
+    ("sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active", "tensor-core unit busy % (incl. operand fetch)"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem->TC operand wavefronts % of peak"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU (MUFU) pipe % of active"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput % of peak"),
+    ("lts__t_bytes.sum", "L2 bytes"),
+]
+
+
+def main(path):
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    print("| kernel | " + " | ".join(k[1] for k in KEYS) + " |")
+    print("|---|" + "---|" * len(KEYS))
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]].replace("<unnamed>::", "").replace("void ", "")
+        cells = []
+        for key, _ in KEYS:
+            if key in idx:
+                cells.append("%s %s" % (r[idx[key]], units[idx[key]]))
+            else:
+                cells.append("n/a")
+        print("| `%s` | " % name + " | ".join(cells) + " |")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
