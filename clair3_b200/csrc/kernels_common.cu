@@ -18,7 +18,7 @@ __global__ void ingest_f32_kernel(const T *__restrict__ x, float *__restrict__ o
     for (; i < n; i += stride) out[i] = (float)x[i];
 }
 
-constexpr int HEADS_G = 4;        // sites per block
+constexpr int HEADS_G = 8;        // sites per block
 constexpr int HEADS_THREADS = 256;
 
 // z4: [B][D4] L4 pre-activation WITHOUT bias.  One block = HEADS_G sites x all heads; thread (t/128, t%128) owns one L5

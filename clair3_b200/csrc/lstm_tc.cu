@@ -118,13 +118,17 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
             ptx::mbar_wait(&ready_bar, (uint32_t)step & 1u);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
-#pragma unroll
+                // rolled k loop: descriptors are re-derived from the loop counter on the uniform datapath every
+                // iteration (a fully unrolled loop makes ptxas hoist 60 descriptors into vector registers and pay
+                // R2UR moves in front of every UTCHMMA)
+#pragma unroll 1
                 for (int ks = 0; ks < K / 16; ++ks) {
                     const uint64_t b_desc = ptx::umma_desc_nosw(b_addr + ks * 2 * LBO_B, LBO_B, 128);
+                    const uint32_t acc = ks > 0 ? 1u : 0u;
 #pragma unroll
                     for (int m = 0; m < NBLK; ++m) {
                         const uint64_t a_desc = ptx::umma_desc_nosw(w_addr + m * kBlkBytes + ks * 2 * 2048, 2048, 128);
-                        ptx::umma_f16(tmem_base + m * NB, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
+                        ptx::umma_f16(tmem_base + m * NB, a_desc, b_desc, idesc, acc);
                     }
                 }
                 ptx::umma_commit(&acc_bar);
