@@ -262,6 +262,8 @@ extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
             for (auto &r : w->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
             w->prof.clear();
         }
+    } else if (!strcmp(name, "host_async")) {
+        m->host_async = value ? 1 : 0;
     } else if (!strcmp(name, "lstm_trace")) {
         if (value && !m->lstm_trace) {
             C3B_CUDA(cudaSetDevice(m->device));
@@ -644,10 +646,10 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
     b.pg = cv.take<__half>((size_t)C3B_T * bp * 1280 * 2);
     b.h2 = cv.take<op_t>((size_t)bp * C3B_T * 320 * 2);
     b.z4 = cv.take<float>((size_t)bp * 128 * 4);
+    // sub-tile width (sites per MMA column block); a CTA ping-pongs two sub-tiles -> 2 directions x bp / (2*tile) CTAs
     int tile1 = m->lstm_tile, tile2 = m->lstm_tile;
     if (tile1 == 0) {
-        // enough CTAs to cover the SMs: 2 directions x bp / tile
-        tile1 = (2 * bp / 64 >= m->sm_count) ? 64 : (2 * bp / 32 >= m->sm_count) ? 32 : 16;
+        tile1 = (bp / 64 >= m->sm_count) ? 64 : (bp / 32 >= m->sm_count) ? 32 : 16;
         tile2 = tile1;
     }
     if (tile2 > 32) tile2 = 32;
@@ -848,7 +850,7 @@ extern "C" int c3b_forward(c3b_model *m, const void *x, int x_dtype, int x_on_de
     m->last_batch = std::min(chunk, batch);
     m->last_depth = depth;
     if (!y_on_device) C3B_CUDA(cudaMemcpyAsync(y, yd, (size_t)batch * m->out_dim * 4, cudaMemcpyDeviceToHost, s));
-    if (!x_on_device || !y_on_device) {
+    if ((!x_on_device || !y_on_device) && !m->host_async) {
         C3B_CUDA(cudaStreamSynchronize(s));
         C3B_CUDA(cudaGetLastError());
     }

@@ -27,13 +27,15 @@
 // (TMEM lane quadrant = warp % 4), warp 8 allocates TMEM and its lane 0 issues tcgen05.mma.  Persistent over tiles with
 // two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "c3b_internal.h"
+#include <limits.h>
+
 #include "ptx.cuh"
 
 namespace {
 
 constexpr int kThreads = 288;
 constexpr int kProducerThreads = 128;
-constexpr int kLag = 2;            // cp.async groups in flight per producer thread before the oldest is published
+constexpr int kLag = 3;            // cp.async groups in flight per producer thread before the oldest is published
 constexpr int kMaxStages = 8;
 
 struct IgemmDev {
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const int S = p.stages;
-    const uint32_t act_bytes = (uint32_t)p.act_rows * 128u;
+    const uint32_t act_bytes = (uint32_t)(p.act_rows + 1) * 128u;      // 8 k-groups x (rows + 1 pad) x 16 B
     const uint32_t w_bytes = (uint32_t)p.w_rows * 128u;
     const uint32_t w_res_bytes = p.w_resident ? (uint32_t)p.wb * p.nchunks * w_bytes : 0u;
     const uint32_t stage_bytes = act_bytes + (p.w_resident ? 0u : w_bytes);
@@ -150,26 +152,34 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                     ptx::bulk_g2s(smem_base + (uint32_t)(c * p.wb + b) * w_bytes,
                                   (const char *)p.w_img + ((size_t)c * p.n_rowblocks + rb0 + b) * w_bytes, w_bytes, &w_bar);
         }
+        // Thread -> (k-group kgl = tid & 7, rows (tid >> 3) + 16 j): one warp-level cp.async covers 4 rows x 128
+        // contiguous bytes of the activation matrix (fully coalesced); the padded LBO keeps the smem side conflict-free.
+        const int kgl = tid & 7;
+        const int rsub = tid >> 3;
+        const uint32_t lbo_act = (uint32_t)(p.act_rows + 1) * 16u;
         int it = 0;                      // chunk iteration counter of this CTA (ring position)
-        int pending[kLag];               // stages issued but not yet published
-        int npending = 0;
+        int pend0 = -1, pend1 = -1, pend2 = -1;   // stages issued but not yet published (oldest first)
         for (TileWalk tw(p); tw.valid(p); tw.next(p)) {
             int at, rb0, c_begin, c_end;
             tw.decode(p, at, rb0, c_begin, c_end);
-            const int64_t g = (int64_t)at * p.act_rows + tid;
-            const bool row_ok = g < p.m_valid;
-            int hi0 = 0, wi0 = 0;
-            const char *row_base = (const char *)p.act;
-            if (row_ok) {
-                if (p.taps == 1) {
-                    row_base = (const char *)(p.act + g * p.lda);
-                } else {
-                    const int wo = (int)(g % p.wout);
-                    const int ho = (int)((g / p.wout) % p.hout);
-                    const int64_t b = g / ((int64_t)p.wout * p.hout);
-                    hi0 = ho * p.stride - 1;
-                    wi0 = wo * p.stride - 1;
-                    row_base = (const char *)(p.act + b * (int64_t)p.hin * p.win * p.cin);
+            const char *row_base[8];
+            int hw0[8];                  // (hi0 << 16) | (wi0 & 0xffff), or INT_MIN for an invalid row
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t g = (int64_t)at * p.act_rows + rsub + 16 * j;
+                row_base[j] = (const char *)p.act;
+                hw0[j] = INT_MIN;
+                if (g < p.m_valid) {
+                    if (p.taps == 1) {
+                        row_base[j] = (const char *)(p.act + g * p.lda);
+                        hw0[j] = 0;
+                    } else {
+                        const int wo = (int)(g % p.wout);
+                        const int ho = (int)((g / p.wout) % p.hout);
+                        const int64_t b = g / ((int64_t)p.wout * p.hout);
+                        row_base[j] = (const char *)(p.act + b * (int64_t)p.hin * p.win * p.cin);
+                        hw0[j] = ((ho * p.stride - 1) << 16) | ((wo * p.stride - 1) & 0xffff);
+                    }
                 }
             }
             for (int c = c_begin; c < c_end; ++c, ++it) {
@@ -182,48 +192,57 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                     const char *src = (const char *)p.w_img + ((size_t)c * p.n_rowblocks + rb0) * w_bytes;
                     ptx::bulk_g2s(stage + act_bytes, src, w_bytes, &full_bar[s]);
                 }
-                const uint32_t dst_row = stage + (uint32_t)tid * 16u;
+                const int gk = c * 8 + kgl;
+                const bool k_ok = gk < p.kgroups;
+                int dh = 0, dw = 0;
+                size_t koff = (size_t)gk * 16;                   // plain mode: byte offset inside the row
+                if (p.taps != 1) {
+                    const int tap = gk >> p.cpk_shift;
+                    const int c8 = gk - (tap << p.cpk_shift);
+                    dh = tap / 3;
+                    dw = tap - dh * 3;
+                    koff = (size_t)c8 * 16;
+                }
+                const uint32_t dst0 = stage + (uint32_t)kgl * lbo_act + (uint32_t)rsub * 16u;
 #pragma unroll
-                for (int kg = 0; kg < 8; ++kg) {
-                    const int gk = c * 8 + kg;
+                for (int j = 0; j < 8; ++j) {
                     const char *src = (const char *)p.act;
                     uint32_t nbytes = 0;
-                    if (row_ok && gk < p.kgroups) {
+                    if (k_ok && hw0[j] != INT_MIN) {
                         if (p.taps == 1) {
-                            src = row_base + (size_t)gk * 16;
+                            src = row_base[j] + koff;
                             nbytes = 16;
                         } else {
-                            const int tap = gk >> p.cpk_shift;
-                            const int c8 = gk - (tap << p.cpk_shift);
-                            const int hi = hi0 + tap / 3;
-                            const int wi = wi0 + tap % 3;
+                            const int hi = (hw0[j] >> 16) + dh;
+                            const int wi = (int)(short)(hw0[j] & 0xffff) + dw;
                             if (hi >= 0 && hi < p.hin && wi >= 0 && wi < p.win) {
-                                src = row_base + ((size_t)(hi * p.win + wi) * p.cin + c8 * 8) * 2;
+                                src = row_base[j] + ((size_t)(hi * p.win + wi) * p.cin) * 2 + koff;
                                 nbytes = 16;
                             }
                         }
                     }
-                    ptx::cp_async16(dst_row + (uint32_t)kg * (uint32_t)p.act_rows * 16u, src, nbytes);
+                    ptx::cp_async16(dst0 + (uint32_t)j * 256u, src, nbytes);
                 }
                 ptx::cp_async_commit();
-                if (npending == kLag) {
+                if (pend2 >= 0) {                                // kLag groups already in flight: publish the oldest
                     ptx::cp_async_wait<kLag>();
                     ptx::fence_proxy_async_smem();
-                    ptx::mbar_arrive(&full_bar[pending[0]]);
-#pragma unroll
-                    for (int i = 0; i + 1 < kLag; ++i) pending[i] = pending[i + 1];
-                    --npending;
+                    ptx::mbar_arrive(&full_bar[pend2]);
                 }
-                pending[npending++] = s;
+                pend2 = pend1;
+                pend1 = pend0;
+                pend0 = s;
             }
         }
         ptx::cp_async_wait<0>();
         ptx::fence_proxy_async_smem();
-        for (int i = 0; i < npending; ++i) ptx::mbar_arrive(&full_bar[pending[i]]);
+        if (pend2 >= 0) ptx::mbar_arrive(&full_bar[pend2]);
+        if (pend1 >= 0) ptx::mbar_arrive(&full_bar[pend1]);
+        if (pend0 >= 0) ptx::mbar_arrive(&full_bar[pend0]);
     } else if (warp == 8) {
         // ===================================================== MMA issuer (whole warp walks the tiles, one elected lane issues)
         const uint32_t idesc = ptx::umma_idesc_f16(128, (uint32_t)ncols);
-        const uint32_t lbo_act = (uint32_t)p.act_rows * 16u;
+        const uint32_t lbo_act = (uint32_t)(p.act_rows + 1) * 16u;
         const uint32_t lbo_w = (uint32_t)p.w_rows * 16u;
         int it = 0;
         int tcount = 0;
@@ -328,14 +347,18 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                         const int t = (int)(pos0 / p.pg_bp);
                         const int bb0 = (int)(pos0 % p.pg_bp);
                         const int ntl = p.pg_bp / p.pg_nbl;
+                        // the tile's 128 positions span 128/NBL consecutive sub-tiles of one time step
+                        const size_t row_off = ((size_t)(dir * C3B_T + t) * ntl + bb0 / p.pg_nbl) * 5 * 128 * p.pg_nbl +
+                                               ((size_t)blk * 128 + r) * p.pg_nbl;
+                        const size_t st_stride = (size_t)5 * 128 * p.pg_nbl;
+                        int st_i = 0, in_st = 0;
                         for (int j0 = 0; j0 < ncols; j0 += 16) {
                             float v[16];
                             ptx::tmem_ld16(tb + (uint32_t)j0, v);
                             ptx::tmem_ld_wait();
-                            const int bb = bb0 + j0;
-                            const size_t off =
-                                ((((size_t)(dir * C3B_T + t) * ntl + bb / p.pg_nbl) * 5 + blk) * 128 + r) * p.pg_nbl +
-                                (bb % p.pg_nbl);
+                            const size_t off = row_off + (size_t)st_i * st_stride + in_st;
+                            in_st += 16;
+                            if (in_st == p.pg_nbl) { in_st = 0; ++st_i; }
                             uint4 pk[2];
                             uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
 #pragma unroll
@@ -427,13 +450,13 @@ int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s) {
     p.ksplit = (p.nchunks + p.chunks_per_split - 1) / p.chunks_per_split;   // drop empty splits
 
     const size_t budget = 216 * 1024;
-    const size_t act_bytes = (size_t)p.act_rows * 128, w_bytes = (size_t)p.w_rows * 128;
+    const size_t act_bytes = (size_t)(p.act_rows + 1) * 128, w_bytes = (size_t)p.w_rows * 128;
     // W-stationary when the slab fits beside >= 4 activation stages (and there are enough tiles to amortise the load)
     if (p.ksplit == 1) {
         int wb = (swap && p.n_rowblocks % 2 == 0 && 2 * p.act_rows <= 256) ? 2 : 1;
         for (; wb >= 1; --wb) {
             const size_t slab = (size_t)wb * p.nchunks * w_bytes;
-            if (slab + 4 * act_bytes <= budget && p.n_act_tiles >= 2 * (m->sm_count / (p.n_rowblocks / wb))) {
+            if (slab + 5 * act_bytes <= budget && p.n_act_tiles >= 2 * (m->sm_count / (p.n_rowblocks / wb))) {
                 p.w_resident = 1;
                 p.wb = wb;
                 break;

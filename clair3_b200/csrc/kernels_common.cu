@@ -35,9 +35,10 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
     const int64_t b0 = (int64_t)blockIdx.x * HEADS_G;
     const int g_n = (int)min((int64_t)HEADS_G, batch - b0);
 
+    // a is stored [k][G] so the L5 loop reads the 8 sites of one k with two 16-byte broadcast loads
     for (int i = tid; i < HEADS_G * d4; i += HEADS_THREADS) {
         const int g = i / d4, k = i - g * d4;
-        a[i] = (g < g_n) ? selu(z4[(b0 + g) * d4 + k] + __ldg(hp.b4 + k)) : 0.f;
+        a[k * HEADS_G + g] = (g < g_n) ? selu(z4[(b0 + g) * d4 + k] + __ldg(hp.b4 + k)) : 0.f;
     }
     __syncthreads();
 
@@ -48,11 +49,20 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
         const float bias = __ldg(hp.h[h].b5 + j);
 #pragma unroll
         for (int g = 0; g < HEADS_G; ++g) acc[g] = bias;
+        static_assert(HEADS_G == 8, "two float4 per k");
 #pragma unroll 8
         for (int k = 0; k < d4; ++k) {
             const float wv = __ldg(w + (size_t)k * 128);
-#pragma unroll
-            for (int g = 0; g < HEADS_G; ++g) acc[g] = fmaf(a[g * d4 + k], wv, acc[g]);
+            const float4 a0 = *reinterpret_cast<const float4 *>(a + k * HEADS_G);
+            const float4 a1 = *reinterpret_cast<const float4 *>(a + k * HEADS_G + 4);
+            acc[0] = fmaf(a0.x, wv, acc[0]);
+            acc[1] = fmaf(a0.y, wv, acc[1]);
+            acc[2] = fmaf(a0.z, wv, acc[2]);
+            acc[3] = fmaf(a0.w, wv, acc[3]);
+            acc[4] = fmaf(a1.x, wv, acc[4]);
+            acc[5] = fmaf(a1.y, wv, acc[5]);
+            acc[6] = fmaf(a1.z, wv, acc[6]);
+            acc[7] = fmaf(a1.w, wv, acc[7]);
         }
 #pragma unroll
         for (int g = 0; g < HEADS_G; ++g) l5[(h * HEADS_G + g) * 128 + j] = selu(acc[g]);

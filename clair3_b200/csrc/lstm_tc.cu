@@ -2,21 +2,25 @@
 // clair3/model.py:96-107,132-133; torch nn.LSTM semantics: gate rows i,f,g,o, h0 = c0 = 0, the reverse direction
 // walks t = 32..0 and both directions are concatenated per time step).
 //
-// One CTA owns (a tile of NB candidate sites) x (one direction) for all 33 steps.  The gate GEMM is issued "swapped":
-// the recurrent weight matrix is the UMMA A operand (gate rows -> the 128 TMEM lanes, one 128-row block per gate), the
-// activations [x_t ; h_{t-1}] of the NB sites are the B operand (sites -> TMEM columns).  So
-//   * the whole weight matrix stays resident in shared memory for the 33 steps (160 KB LSTM1, 200 KB LSTM2), loaded
-//     once per CTA by cp.async.bulk (TMA engine) from a host-packed SWIZZLE_NONE K-major image;
-//   * epilogue thread r owns hidden unit r: it reads its i,f,g,o pre-activations for every site of the tile from four
+// One CTA owns (two sub-tiles of NB candidate sites) x (one direction) for all 33 steps.  The gate GEMM is issued
+// "swapped": the recurrent weight matrix is the UMMA A operand (gate rows -> the 128 TMEM lanes, one 128-row block per
+// gate), the activations [x_t ; h_{t-1}] of a sub-tile's NB sites are the B operand (sites -> TMEM columns).  So
+//   * the whole weight matrix stays on chip for the 33 steps (160 KB LSTM1; LSTM2: 160 KB in shared memory + its fifth
+//     row block as a TMEM-resident A operand), loaded once per CTA from a host-packed SWIZZLE_NONE K-major image;
+//   * epilogue thread r owns hidden unit r: it reads its i,f,g,o pre-activations for every site of the sub-tile from four
 //     TMEM column ranges of its own lane, keeps the cell state c[NB] in fp32 registers for the whole sequence, and writes
-//     h_t (bf16) back into the B-operand buffer for step t+1 - no cross-thread exchange, no grid-wide sync;
-//   * small NB (16/32/64) gives 2*B/NB CTAs, enough to fill 148 SMs at a 1024-site batch.
+//     h_t (fp16) back into the B-operand buffer for step t+1 - no cross-thread exchange, no grid-wide sync;
+//   * the two sub-tiles ping-pong: while warpgroup 0 runs the sigma/tanh/cell epilogue of sub-tile 0 (MUFU-bound), the
+//     MMA warp issues the gate GEMM of sub-tile 1, and vice versa, so the tensor pipe and the MUFU pipe overlap.
+//     Measured on B200: a 128xNx16 tcgen05.mma costs ~44 cycles for any N <= 64 (65 at N=128, 128 at N=256), so the
+//     per-step tensor time is fixed (40-50 MMAs) and wide sub-tiles amortise it.
 //
 // LSTM1 (H=128, x has 18 channels zero-padded to 32): K = 32 + 128, the x projection is fused into the same MMAs, bias
 // added in the epilogue.  LSTM2 (H=160, input 256): the input projection W_ih*h1 (+bias) is a separate big GEMM
-// (igemm_tc.cu) that leaves fp16 pre-gates in the thread-friendly layout pgT[dir][t][tile][blk][row][NB]; this kernel
-// keeps only W_hh resident (K = 160).  Units 0..127 are lane-aligned in row blocks 0..3; units 128..159 live in a fifth
+// (igemm_tc.cu) that leaves fp16 pre-gates in the thread-friendly layout pgT[dir][t][subtile][blk][row][NB]; this kernel
+// keeps only W_hh on chip (K = 160).  Units 0..127 are lane-aligned in row blocks 0..3; units 128..159 live in a fifth
 // block laid out [i(32) f(32) g(32) o(32)] whose activated gates cross warps through a small shared-memory exchange.
+// The sigmoid gates' rows are pre-halved on the host so sigma(x) = 0.5*tanh(x/2)+0.5 is one MUFU + one FMA.
 //
 // h_t leaves the CTA as 16-byte chunks copied from the operand buffer while the next step's MMAs run.
 #include "c3b_internal.h"
@@ -24,21 +28,20 @@
 
 namespace {
 
-constexpr int kThreads = 128;            // epilogue threads (one per TMEM lane); warp 4 issues the MMAs
-constexpr int kBlockThreads = 160;
-constexpr int kBlkBytes = 20 * 128 * 16;       // one 128-row x K=160 weight block: [K/8][128][8] bf16
+constexpr int kWgThreads = 128;                // one epilogue warpgroup = one thread per TMEM lane
+constexpr int kBlockThreads = 288;             // 2 epilogue warpgroups + the MMA warp
+constexpr int kBlkBytes = 20 * 128 * 16;       // one 128-row x K=160 weight block: [K/8][128][8] fp16
 
 struct LstmDev {
-    const op_t *w_img;    // [dir][NBLK][20][128][8]
+    const op_t *w_img;             // [dir][NBLK][20][128][8]
     const float *bias;             // [dir][NBLK*128] (LSTM1)
-    const op_t *xs;       // LSTM1 input  [33][Bp][32]
+    const op_t *xs;                // LSTM1 input  [33][Bp][32]
     const __half *pg;              // LSTM2 pre-gates pgT[dir][33][Bp/NB][5][128][NB]
-    op_t *hout;           // LSTM1: h1[33][Bp][256]; LSTM2: h2[Bp][33][320]
+    op_t *hout;                    // LSTM1: h1[33][Bp][256]; LSTM2: h2[Bp][33][320]
     int bp;                        // padded batch
     long long *trace;              // optional [33][4] clock64 stamps of CTA (0,0) thread 0 (debug option "lstm_trace")
 };
 
-template <int NB>
 __device__ __forceinline__ void lstm_cell8(const float *gi, const float *gf, const float *gg, const float *go, float *c,
                                            float *h) {
 #pragma unroll
@@ -68,72 +71,82 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
     constexpr int KX = LAYER2 ? 0 : 32;
     constexpr int K = KX + H;                       // 160 for both layers
     static_assert(K == 160, "weight block image assumes K = 160");
-    constexpr int NBLK = LAYER2 ? 5 : 4;
-    constexpr uint32_t LBO_B = (NB + 1) * 16;        // padded: conflict-free h stores
+    constexpr int NBLK = LAYER2 ? 5 : 4;            // accumulator row blocks
+    constexpr int NBLK_S = 4;                       // row blocks whose weights live in shared memory
+    constexpr uint32_t LBO_B = (NB + 1) * 16;       // padded: conflict-free h stores
     constexpr uint32_t B_BYTES = (K / 8) * LBO_B;
-    constexpr uint32_t TCOLS = (NBLK * NB <= 32) ? 32 : (NBLK * NB <= 64) ? 64 : (NBLK * NB <= 128) ? 128
-                               : (NBLK * NB <= 256) ? 256 : 512;
+    constexpr uint32_t ACC_COLS = 2 * NBLK * NB;    // two sub-tiles
+    constexpr uint32_t WT_COLS = LAYER2 ? 80 : 0;   // LSTM2 tail block weights as a TMEM A operand (K=160 -> 80 columns)
+    constexpr uint32_t NEED = ACC_COLS + WT_COLS;
+    constexpr uint32_t TCOLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
+    static_assert(NEED <= 512, "TMEM budget");
 
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t w_bar, acc_bar, ready_bar;
+    __shared__ uint64_t w_bar, acc_bar[2], ready_bar[2];
     __shared__ uint32_t tmem_base_smem;
     uint8_t *w_smem = smem;
-    uint8_t *b_smem = smem + NBLK * kBlkBytes;
-    float *xch = reinterpret_cast<float *>(b_smem + B_BYTES);     // LAYER2 only: [NB][128]
+    uint8_t *b_smem0 = smem + NBLK_S * kBlkBytes;
+    float *xch0 = reinterpret_cast<float *>(b_smem0 + 2 * B_BYTES);     // LAYER2 only: [2][NB][128]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const int tile = blockIdx.x;
     const int dir = blockIdx.y;
-    const int b0 = tile * NB;
     const uint32_t w_addr = ptx::smem_u32(w_smem);
-    const uint32_t b_addr = ptx::smem_u32(b_smem);
+    const uint32_t b_addr0 = ptx::smem_u32(b_smem0);
 
     if (tid == 0) {
         ptx::mbar_init(&w_bar, 1);
-        ptx::mbar_init(&acc_bar, 1);
-        ptx::mbar_init(&ready_bar, kThreads);
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&acc_bar[s], 1);
+            ptx::mbar_init(&ready_bar[s], kWgThreads);
+        }
         ptx::fence_barrier_init();
     }
-    if (warp == 4) ptx::tmem_alloc<TCOLS>(&tmem_base_smem);
-    for (uint32_t i = tid * 16; i < B_BYTES; i += kBlockThreads * 16) *reinterpret_cast<uint4 *>(b_smem + i) = make_uint4(0, 0, 0, 0);
+    if (warp == 8) ptx::tmem_alloc<TCOLS>(&tmem_base_smem);
+    for (uint32_t i = tid * 16; i < 2 * B_BYTES; i += kBlockThreads * 16)
+        *reinterpret_cast<uint4 *>(b_smem0 + i) = make_uint4(0, 0, 0, 0);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
     if (tid == 0) {
-        ptx::mbar_arrive_expect_tx(&w_bar, NBLK * kBlkBytes);
+        ptx::mbar_arrive_expect_tx(&w_bar, NBLK_S * kBlkBytes);
         const char *src = reinterpret_cast<const char *>(p.w_img) + (size_t)dir * NBLK * kBlkBytes;
 #pragma unroll
-        for (int m = 0; m < NBLK; ++m) ptx::bulk_g2s(w_addr + m * kBlkBytes, src + (size_t)m * kBlkBytes, kBlkBytes, &w_bar);
+        for (int m = 0; m < NBLK_S; ++m) ptx::bulk_g2s(w_addr + m * kBlkBytes, src + (size_t)m * kBlkBytes, kBlkBytes, &w_bar);
     }
 
     const uint32_t idesc = ptx::umma_idesc_f16(128, NB);
-    if (warp == 4) {
-        // ===================================================== MMA warp: wait for [x_t ; h_{t-1}], issue the step's gate GEMM
+    if (warp == 8) {
+        // ===================================================== MMA warp: alternate between the two sub-tiles
         ptx::mbar_wait(&w_bar, 0);
         for (int step = 0; step < C3B_T; ++step) {
-            ptx::mbar_wait(&ready_bar, (uint32_t)step & 1u);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-                // rolled k loop: descriptors are re-derived from the loop counter on the uniform datapath every
-                // iteration (a fully unrolled loop makes ptxas hoist 60 descriptors into vector registers and pay
-                // R2UR moves in front of every UTCHMMA)
 #pragma unroll 1
-                for (int ks = 0; ks < K / 16; ++ks) {
-                    const uint64_t b_desc = ptx::umma_desc_nosw(b_addr + ks * 2 * LBO_B, LBO_B, 128);
-                    const uint32_t acc = ks > 0 ? 1u : 0u;
+            for (int s = 0; s < 2; ++s) {
+                ptx::mbar_wait(&ready_bar[s], (uint32_t)step & 1u);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint32_t d0 = tmem_base + (uint32_t)(s * NBLK * NB);
+                    const uint32_t bs = b_addr0 + (uint32_t)s * B_BYTES;
+                    // rolled k loop: descriptors are re-derived from the loop counter on the uniform datapath (a fully
+                    // unrolled loop makes ptxas hoist every descriptor into vector registers and pay R2UR moves)
+#pragma unroll 1
+                    for (int ks = 0; ks < K / 16; ++ks) {
+                        const uint64_t b_desc = ptx::umma_desc_nosw(bs + ks * 2 * LBO_B, LBO_B, 128);
+                        const uint32_t acc = ks > 0 ? 1u : 0u;
 #pragma unroll
-                    for (int m = 0; m < NBLK; ++m) {
-                        const uint64_t a_desc = ptx::umma_desc_nosw(w_addr + m * kBlkBytes + ks * 2 * 2048, 2048, 128);
-                        ptx::umma_f16(tmem_base + m * NB, a_desc, b_desc, idesc, acc);
+                        for (int m = 0; m < NBLK_S; ++m) {
+                            const uint64_t a_desc = ptx::umma_desc_nosw(w_addr + m * kBlkBytes + ks * 2 * 2048, 2048, 128);
+                            ptx::umma_f16(d0 + m * NB, a_desc, b_desc, idesc, acc);
+                        }
+                        if (LAYER2) ptx::umma_f16_ts(d0 + 4 * NB, tmem_base + ACC_COLS + ks * 8, b_desc, idesc, acc);
                     }
+                    ptx::umma_commit(&acc_bar[s]);
                 }
-                ptx::umma_commit(&acc_bar);
+                __syncwarp();
             }
-            __syncwarp();
         }
         ptx::tc_fence_before();
         __syncthreads();                      // matches the epilogue threads' final barrier
@@ -142,13 +155,38 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
         return;
     }
 
+    // ========================================================= epilogue warpgroup `sub` (0 or 1)
+    const int sub = warp >> 2;
+    const int q = warp & 3;                         // TMEM lane quadrant
+    const int wt = tid & 127;                       // thread index in the warpgroup = TMEM lane = hidden unit
+    const int subtile = blockIdx.x * 2 + sub;       // index of this NB-site sub-tile in the padded batch
+    const int b0 = subtile * NB;
+    uint8_t *b_smem = b_smem0 + sub * B_BYTES;
+    float *xch = xch0 + sub * NB * 128;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * NBLK * NB);
+    const int ntl = p.bp / NB;
+    const uint32_t bar_id = 1 + sub;
+
+    if (LAYER2 && sub == 0) {
+        // tail-block weights (units 128..159) -> TMEM columns [ACC_COLS, ACC_COLS+80): thread = row, 16 halves per k-step
+        const op_t *wt_img = p.w_img + ((size_t)dir * NBLK + 4) * (kBlkBytes / 2);
+#pragma unroll 1
+        for (int ks = 0; ks < K / 16; ++ks) {
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(wt_img + ((size_t)(2 * ks) * 128 + wt) * 8);
+            const uint4 v1 = *reinterpret_cast<const uint4 *>(wt_img + ((size_t)(2 * ks + 1) * 128 + wt) * 8);
+            uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            ptx::tmem_st8(tmem_base + ((uint32_t)(q * 32) << 16) + ACC_COLS + ks * 8, r);
+        }
+        ptx::tmem_st_wait();
+    }
+
     float bias_i = 0.f, bias_f = 0.f, bias_g = 0.f, bias_o = 0.f;
     if (!LAYER2) {
         const float *bp = p.bias + dir * (NBLK * 128);
-        bias_i = bp[tid];
-        bias_f = bp[128 + tid];
-        bias_g = bp[256 + tid];
-        bias_o = bp[384 + tid];
+        bias_i = bp[wt];
+        bias_f = bp[128 + wt];
+        bias_g = bp[256 + wt];
+        bias_o = bp[384 + wt];
     }
 
     float c[NB];
@@ -158,16 +196,13 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
 #pragma unroll
     for (int i = 0; i < (LAYER2 ? NB / 4 : 1); ++i) c_tail[i] = 0.f;
 
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const int ntl = p.bp / NB;
-
     int t_prev = 0;
     for (int step = 0; step < C3B_T; ++step) {
         const int t = dir ? (C3B_T - 1 - step) : step;
 
         if (!LAYER2) {
             // stage x_t: xs[t][b0+n][0..31] -> operand k-groups 0..3
-            for (int idx = tid; idx < NB * 4; idx += kThreads) {
+            for (int idx = wt; idx < NB * 4; idx += kWgThreads) {
                 const int n = idx >> 2, kg = idx & 3;
                 const uint4 v = *reinterpret_cast<const uint4 *>(p.xs + ((size_t)t * p.bp + b0 + n) * 32 + kg * 8);
                 *reinterpret_cast<uint4 *>(b_smem + kg * LBO_B + n * 16) = v;
@@ -175,25 +210,25 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
         }
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&ready_bar);                                       // S1: this thread's operands / TMEM reads are done
+        ptx::mbar_arrive(&ready_bar[sub]);                                  // S1: this thread's operands / TMEM reads are done
         const bool tr = p.trace != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
         if (tr) p.trace[step * 4 + 0] = clock64();
         if (tr) p.trace[step * 4 + 1] = clock64();
 
         // while the MMAs run: ship h_{t_prev} (still in the operand buffer) to global memory
         if (step > 0) {
-            for (int idx = tid; idx < NB * (H / 8); idx += kThreads) {
+            for (int idx = wt; idx < NB * (H / 8); idx += kWgThreads) {
                 const int n = idx / (H / 8), kgh = idx % (H / 8);
                 const uint4 v = *reinterpret_cast<const uint4 *>(b_smem + (KX / 8 + kgh) * LBO_B + n * 16);
                 op_t *dst = LAYER2 ? p.hout + ((size_t)(b0 + n) * C3B_T + t_prev) * 320 + dir * 160 + kgh * 8
-                                            : p.hout + ((size_t)t_prev * p.bp + b0 + n) * 256 + dir * 128 + kgh * 8;
+                                   : p.hout + ((size_t)t_prev * p.bp + b0 + n) * 256 + dir * 128 + kgh * 8;
                 *reinterpret_cast<uint4 *>(dst) = v;
             }
         }
         // LSTM2: prefetch this step's pre-gates (fp16, NB contiguous values per (block,row))
         uint4 pgv[LAYER2 ? 5 : 1][LAYER2 ? NB / 8 : 1];
         if (LAYER2) {
-            const __half *pgp = p.pg + ((((size_t)(dir * C3B_T + t) * ntl + tile) * 5) * 128 + tid) * NB;
+            const __half *pgp = p.pg + ((((size_t)(dir * C3B_T + t) * ntl + subtile) * 5) * 128 + wt) * NB;
 #pragma unroll
             for (int m = 0; m < 5; ++m)
 #pragma unroll
@@ -201,13 +236,13 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
                     pgv[m][j] = *reinterpret_cast<const uint4 *>(pgp + (size_t)m * 128 * NB + j * 8);
         }
 
-        ptx::mbar_wait(&acc_bar, (uint32_t)step & 1u);
+        ptx::mbar_wait(&acc_bar[sub], (uint32_t)step & 1u);
         ptx::tc_fence_after();
         if (tr) p.trace[step * 4 + 2] = clock64();
-        ptx::named_bar_sync(1, kThreads);                                   // S2: everyone is done reading h_{t_prev}
+        ptx::named_bar_sync(bar_id, kWgThreads);                            // S2: the warpgroup is done reading h_{t_prev}
 
         if (LAYER2) {
-            // tail block (units 128..159): warp w holds gate w; activate and publish to the exchange buffer
+            // tail block (units 128..159): warp q holds gate q; activate and publish to the exchange buffer
 #pragma unroll
             for (int j = 0; j < NB / 8; ++j) {
                 float v[8], pgf[8];
@@ -217,14 +252,14 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float x = v[i] + pgf[i];
-                    const float a = (warp == 2) ? ptx::tanh_approx(x) : ptx::sigmoid_prehalved(x);
-                    xch[(j * 8 + i) * 128 + tid] = a;
+                    const float a = (q == 2) ? ptx::tanh_approx(x) : ptx::sigmoid_prehalved(x);
+                    xch[(j * 8 + i) * 128 + wt] = a;
                 }
             }
-            ptx::named_bar_sync(1, kThreads);
+            ptx::named_bar_sync(bar_id, kWgThreads);
         }
 
-        // main blocks: thread = hidden unit `tid`, 8 sites at a time
+        // main blocks: thread = hidden unit `wt`, 8 sites at a time
 #pragma unroll
         for (int j = 0; j < NB / 8; ++j) {
             float gi[8], gf[8], gg[8], go[8], h[8];
@@ -256,20 +291,19 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
                     go[i] += bias_o;
                 }
             }
-            lstm_cell8<NB>(gi, gf, gg, go, &c[j * 8], h);
-            // h[n][unit] -> operand buffer (bf16), element (n, k = KX + tid)
-            const uint32_t kcol = KX + tid;
+            lstm_cell8(gi, gf, gg, go, &c[j * 8], h);
+            // h[n][unit] -> operand buffer (fp16), element (n, k = KX + wt)
+            const uint32_t kcol = KX + wt;
             uint8_t *dst = b_smem + (kcol >> 3) * LBO_B + (kcol & 7) * 2;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<op_t *>(dst + (j * 8 + i) * 16) = f2op(h[i]);
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<op_t *>(dst + (j * 8 + i) * 16) = f2op(h[i]);
         }
 
         if (LAYER2) {
-            // tail cells: unit 128 + lane, sites n = warp + 4*k
+            // tail cells: unit 128 + lane, sites n = q + 4*k
 #pragma unroll
             for (int k = 0; k < NB / 4; ++k) {
-                const int n = warp + 4 * k;
+                const int n = q + 4 * k;
                 const float iv = xch[n * 128 + lane];
                 const float fv = xch[n * 128 + 32 + lane];
                 const float gv = xch[n * 128 + 64 + lane];
@@ -277,8 +311,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
                 c_tail[k] = fmaf(fv, c_tail[k], iv * gv);
                 const float hv = ov * ptx::tanh_approx(c_tail[k]);
                 const uint32_t kcol = 128 + lane;
-                *reinterpret_cast<op_t *>(b_smem + (kcol >> 3) * LBO_B + n * 16 + (kcol & 7) * 2) =
-                    f2op(hv);
+                *reinterpret_cast<op_t *>(b_smem + (kcol >> 3) * LBO_B + n * 16 + (kcol & 7) * 2) = f2op(hv);
             }
         }
         t_prev = t;
@@ -286,12 +319,12 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
     }
 
     // last h
-    ptx::named_bar_sync(1, kThreads);
-    for (int idx = tid; idx < NB * (H / 8); idx += kThreads) {
+    ptx::named_bar_sync(bar_id, kWgThreads);
+    for (int idx = wt; idx < NB * (H / 8); idx += kWgThreads) {
         const int n = idx / (H / 8), kgh = idx % (H / 8);
         const uint4 v = *reinterpret_cast<const uint4 *>(b_smem + (KX / 8 + kgh) * LBO_B + n * 16);
         op_t *dst = LAYER2 ? p.hout + ((size_t)(b0 + n) * C3B_T + t_prev) * 320 + dir * 160 + kgh * 8
-                                    : p.hout + ((size_t)t_prev * p.bp + b0 + n) * 256 + dir * 128 + kgh * 8;
+                           : p.hout + ((size_t)t_prev * p.bp + b0 + n) * 256 + dir * 128 + kgh * 8;
         *reinterpret_cast<uint4 *>(dst) = v;
     }
     ptx::tc_fence_before();
@@ -322,11 +355,10 @@ __global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, op_t *__restric
 
 template <int NB, bool LAYER2>
 int launch_lstm(const LstmDev &p, cudaStream_t s) {
-    constexpr int NBLK = LAYER2 ? 5 : 4;
-    const size_t smem = (size_t)NBLK * kBlkBytes + 20 * (NB + 1) * 16 + (LAYER2 ? (size_t)NB * 128 * 4 : 0);
+    const size_t smem = (size_t)4 * kBlkBytes + 2 * 20 * (NB + 1) * 16 + (LAYER2 ? (size_t)2 * NB * 128 * 4 : 0);
     auto kern = lstm_tc_kernel<NB, LAYER2>;
     C3B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(p.bp / NB, 2);
+    dim3 grid(p.bp / (2 * NB), 2);
     kern<<<grid, kBlockThreads, smem, s>>>(p);
     C3B_CUDA(cudaGetLastError());
     return 0;
@@ -348,6 +380,7 @@ int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, op_t *xs
     return 0;
 }
 
+// `tile` = sites per sub-tile (a CTA covers two sub-tiles).
 int c3b_launch_lstm1_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t batch, int tile, cudaStream_t s) {
     LstmDev p = {};
     p.w_img = m->lstm_tc[0][0].w_img;     // both directions are contiguous

@@ -6,20 +6,6 @@
 
 namespace {
 
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 // a: [128][16] fp16 row-major, b: [n][16] fp16 row-major, d: [128][n] fp32.  timing[0..]: cycles for `reps` back-to-back MMAs.
 __global__ void __launch_bounds__(128, 1) probe_kernel(const __half *a, const __half *b, float *d, int n, int reps,
                                                        long long *timing) {
@@ -52,8 +38,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __half *a, const __
         const uint4 v0 = *reinterpret_cast<const uint4 *>(a + tid * 16);
         const uint4 v1 = *reinterpret_cast<const uint4 *>(a + tid * 16 + 8);
         r[0] = v0.x; r[1] = v0.y; r[2] = v0.z; r[3] = v0.w; r[4] = v1.x; r[5] = v1.y; r[6] = v1.z; r[7] = v1.w;
-        tmem_st8(lane_t + 256, r);
-        tmem_st_wait();
+        ptx::tmem_st8(lane_t + 256, r);
+        ptx::tmem_st_wait();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -64,7 +50,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __half *a, const __
     uint32_t phase = 0;
     // ---- numerics: D_ts at columns [0,n), D_ss at columns [n, 2n) is skipped (SS is validated by the igemm tests)
     if (tid == 0) {
-        umma_f16_ts(tmem_base, tmem_base + 256, b_desc, idesc, 0);
+        ptx::umma_f16_ts(tmem_base, tmem_base + 256, b_desc, idesc, 0);
         ptx::umma_commit(&bar);
     }
     ptx::mbar_wait(&bar, phase); phase ^= 1;
@@ -87,10 +73,10 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __half *a, const __
             t0 = clock64();
             for (int i = 0; i < reps; ++i) {
                 if (mode == 0) ptx::umma_f16(tmem_base, a_desc, b_desc, idesc, 1);
-                else if (mode == 1) umma_f16_ts(tmem_base, tmem_base + 256, b_desc, idesc, 1);
+                else if (mode == 1) ptx::umma_f16_ts(tmem_base, tmem_base + 256, b_desc, idesc, 1);
                 else if (mode == 2) ptx::umma_f16(tmem_base + (uint32_t)((i & 3) * (n <= 64 ? n : 0)), a_desc, b_desc, idesc, 1);
                 else if (mode == 3) ptx::umma_f16(tmem_base + (uint32_t)((i & 1) * (n <= 128 ? n : 0)), a_desc, b_desc, idesc, 1);
-                else umma_f16_ts(tmem_base + (uint32_t)((i & 3) * (n <= 32 ? n : 0)), tmem_base + 256, b_desc, idesc, 1);
+                else ptx::umma_f16_ts(tmem_base + (uint32_t)((i & 3) * (n <= 32 ? n : 0)), tmem_base + 256, b_desc, idesc, 1);
             }
             ptx::umma_commit(&bar);
             timing[mode * 2 + 0] = clock64() - t0;          // issue time

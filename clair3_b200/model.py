@@ -138,6 +138,27 @@ class _C3BModule:
 
     __call__ = forward
 
+    def forward_async(self, x_host, y_host):
+        """Stream-ordered forward on PINNED host tensors (H2D -> kernels -> D2H on the current CUDA stream, no host
+        synchronisation): the double-buffered caller of SURVEY.md §8f N1.  The caller synchronises the stream before
+        reading ``y_host`` and must keep both tensors alive until then."""
+        if not (x_host.is_pinned() and y_host.is_pinned()):
+            raise C3BError("forward_async needs pinned host tensors")
+        if x_host.dtype not in _DT or not x_host.is_contiguous() or y_host.dtype != torch.float32:
+            raise C3BError("forward_async: x must be contiguous int8/int32/float32, y float32")
+        batch = x_host.shape[0]
+        depth = x_host.shape[1] if x_host.ndim == 4 else 0
+        if tuple(y_host.shape) != (batch, self.out_dim):
+            raise C3BError("forward_async: y must be [batch, %d]" % self.out_dim)
+        self.set_option("host_async", 1)
+        try:
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            check(lib().c3b_forward(self._handle, ffi.cast("void *", x_host.data_ptr()), _DT[x_host.dtype], 0, batch, depth,
+                                    ffi.cast("float *", y_host.data_ptr()), 0, ffi.cast("void *", stream)))
+        finally:
+            self.set_option("host_async", 0)
+        return y_host
+
     def _split(self, y):
         if self.predict:
             return y
