@@ -262,6 +262,8 @@ extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
             for (auto &r : w->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
             w->prof.clear();
         }
+    } else if (!strcmp(name, "lstm_mufu16")) {
+        m->lstm_mufu16 = value ? 1 : 0;
     } else if (!strcmp(name, "host_async")) {
         m->host_async = value ? 1 : 0;
     } else if (!strcmp(name, "lstm_trace")) {

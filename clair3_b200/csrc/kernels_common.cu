@@ -20,66 +20,105 @@ __global__ void ingest_f32_kernel(const T *__restrict__ x, float *__restrict__ o
 
 constexpr int HEADS_G = 8;        // sites per block
 constexpr int HEADS_THREADS = 256;
+constexpr int HEADS_KT = 32;      // k rows of an L5 weight tile staged in shared memory
 
-// z4: [B][D4] L4 pre-activation WITHOUT bias.  One block = HEADS_G sites x all heads; thread (t/128, t%128) owns one L5
-// unit of one head (two heads in flight, four heads in two passes), weights are read once per block through the
-// read-only path, activations broadcast from shared memory.
+__device__ __forceinline__ void heads_cp16(float *dst_smem, const float *src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+
+// z4: [B][D4] L4 pre-activation WITHOUT bias.  One block = HEADS_G sites x all heads.  L5: thread (t/128, t%128) owns one
+// unit of one head (two heads in flight, four heads in two passes); the [D4][128] weight matrix of each head streams through
+// shared memory in double-buffered 32-row tiles (16-byte cp.async, fully coalesced) so the FMA loop never waits on L2.
 __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__restrict__ z4, HeadsParams hp,
                                                               float *__restrict__ out, int64_t batch) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int d4 = hp.d4;
-    float *a = smem;                                   // [G][d4]
+    float *a = smem;                                   // [d4][G]
     float *l5 = a + HEADS_G * d4;                      // [nheads][G][128]
     float *yv = l5 + C3B_MAX_HEADS * HEADS_G * 128;    // [G][96]
+    float *wt = yv + HEADS_G * 96;                     // [2 stages][2 heads][HEADS_KT][128]
     const int tid = threadIdx.x;
     const int64_t b0 = (int64_t)blockIdx.x * HEADS_G;
     const int g_n = (int)min((int64_t)HEADS_G, batch - b0);
 
     // a is stored [k][G] so the L5 loop reads the 8 sites of one k with two 16-byte broadcast loads
     for (int i = tid; i < HEADS_G * d4; i += HEADS_THREADS) {
-        const int g = i / d4, k = i - g * d4;
-        a[k * HEADS_G + g] = (g < g_n) ? selu(z4[(b0 + g) * d4 + k] + __ldg(hp.b4 + k)) : 0.f;
+        const int k = i / HEADS_G, g = i - k * HEADS_G;
+        a[i] = (g < g_n) ? selu(z4[(b0 + g) * d4 + k] + __ldg(hp.b4 + k)) : 0.f;
     }
-    __syncthreads();
 
     const int j = tid & 127;
-    for (int h = tid >> 7; h < hp.nheads; h += 2) {
-        const float *__restrict__ w = hp.h[h].w5t + j;
+    const int hsel = tid >> 7;                         // which head of the in-flight pair this thread works on
+    const int ntiles = d4 / HEADS_KT;
+    for (int hp0 = 0; hp0 < hp.nheads; hp0 += 2) {
+        const float *w0 = hp.h[hp0].w5t, *w1 = hp.h[hp0 + 1].w5t;
+        // stage loader: 2 heads x 32 rows x 128 floats = 2048 float4, 8 per thread
+        auto load_tile = [&](int tile, int stage) {
+            float *dst = wt + stage * (2 * HEADS_KT * 128);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int idx = r * HEADS_THREADS + tid;        // float4 index
+                const int hh = idx >> 10, rem = idx & 1023;
+                const float *src = (hh ? w1 : w0) + (size_t)tile * HEADS_KT * 128 + rem * 4;
+                heads_cp16(dst + hh * (HEADS_KT * 128) + rem * 4, src);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
         float acc[HEADS_G];
-        const float bias = __ldg(hp.h[h].b5 + j);
+        const float bias = __ldg(hp.h[hp0 + hsel].b5 + j);
 #pragma unroll
         for (int g = 0; g < HEADS_G; ++g) acc[g] = bias;
-        static_assert(HEADS_G == 8, "two float4 per k");
+        load_tile(0, 0);
+        for (int t = 0; t < ntiles; ++t) {
+            if (t + 1 < ntiles) {
+                load_tile(t + 1, (t + 1) & 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();
+            const float *ws = wt + (t & 1) * (2 * HEADS_KT * 128) + hsel * (HEADS_KT * 128) + j;
+            const float *as = a + (size_t)t * HEADS_KT * HEADS_G;
 #pragma unroll 8
-        for (int k = 0; k < d4; ++k) {
-            const float wv = __ldg(w + (size_t)k * 128);
-            const float4 a0 = *reinterpret_cast<const float4 *>(a + k * HEADS_G);
-            const float4 a1 = *reinterpret_cast<const float4 *>(a + k * HEADS_G + 4);
-            acc[0] = fmaf(a0.x, wv, acc[0]);
-            acc[1] = fmaf(a0.y, wv, acc[1]);
-            acc[2] = fmaf(a0.z, wv, acc[2]);
-            acc[3] = fmaf(a0.w, wv, acc[3]);
-            acc[4] = fmaf(a1.x, wv, acc[4]);
-            acc[5] = fmaf(a1.y, wv, acc[5]);
-            acc[6] = fmaf(a1.z, wv, acc[6]);
-            acc[7] = fmaf(a1.w, wv, acc[7]);
+            for (int k = 0; k < HEADS_KT; ++k) {
+                const float wv = ws[k * 128];
+                const float4 a0 = *reinterpret_cast<const float4 *>(as + k * HEADS_G);
+                const float4 a1 = *reinterpret_cast<const float4 *>(as + k * HEADS_G + 4);
+                acc[0] = fmaf(a0.x, wv, acc[0]);
+                acc[1] = fmaf(a0.y, wv, acc[1]);
+                acc[2] = fmaf(a0.z, wv, acc[2]);
+                acc[3] = fmaf(a0.w, wv, acc[3]);
+                acc[4] = fmaf(a1.x, wv, acc[4]);
+                acc[5] = fmaf(a1.y, wv, acc[5]);
+                acc[6] = fmaf(a1.z, wv, acc[6]);
+                acc[7] = fmaf(a1.w, wv, acc[7]);
+            }
+            __syncthreads();
         }
 #pragma unroll
-        for (int g = 0; g < HEADS_G; ++g) l5[(h * HEADS_G + g) * 128 + j] = selu(acc[g]);
+        for (int g = 0; g < HEADS_G; ++g) l5[((hp0 + hsel) * HEADS_G + g) * 128 + j] = selu(acc[g]);
     }
     __syncthreads();
 
     for (int i = tid; i < HEADS_G * hp.out_dim; i += HEADS_THREADS) {
         const int g = i / hp.out_dim, o = i - g * hp.out_dim;
         int h = 0;
-        while (h + 1 < hp.nheads && o >= hp.h[h + 1].out_off) ++h;
+        if (hp.nheads > 1 && o >= hp.h[1].out_off) h = 1;
+        if (hp.nheads > 2 && o >= hp.h[2].out_off) h = 2;
+        if (hp.nheads > 3 && o >= hp.h[3].out_off) h = 3;
         const int n = hp.h[h].n, oo = o - hp.h[h].out_off;
         const float *__restrict__ wy = hp.h[h].wyt + oo;
         const float *lv = l5 + (h * HEADS_G + g) * 128;
-        float s = __ldg(hp.h[h].by + oo);
-#pragma unroll 8
-        for (int jj = 0; jj < 128; ++jj) s = fmaf(lv[jj], __ldg(wy + jj * n), s);
-        yv[g * 96 + o] = selu(s);
+        float s0 = __ldg(hp.h[h].by + oo), s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+        for (int jj = 0; jj < 128; jj += 4) {
+            s0 = fmaf(lv[jj], __ldg(wy + jj * n), s0);
+            s1 = fmaf(lv[jj + 1], __ldg(wy + (jj + 1) * n), s1);
+            s2 = fmaf(lv[jj + 2], __ldg(wy + (jj + 2) * n), s2);
+            s3 = fmaf(lv[jj + 3], __ldg(wy + (jj + 3) * n), s3);
+        }
+        yv[g * 96 + o] = selu((s0 + s1) + (s2 + s3));
     }
     __syncthreads();
 
@@ -126,8 +165,9 @@ int c3b_launch_ingest_fa_f32(const void *x, int dtype, float *out, int64_t n, cu
 
 int c3b_launch_heads(const float *z4, const HeadsParams &hp, float *out, int64_t batch, cudaStream_t s) {
     if (batch == 0) return 0;
-    size_t smem = sizeof(float) * (HEADS_G * hp.d4 + C3B_MAX_HEADS * HEADS_G * 128 + HEADS_G * 96);
+    size_t smem = sizeof(float) * (HEADS_G * hp.d4 + C3B_MAX_HEADS * HEADS_G * 128 + HEADS_G * 96 + 2 * 2 * HEADS_KT * 128);
     int blocks = (int)((batch + HEADS_G - 1) / HEADS_G);
+    C3B_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     heads_kernel<<<blocks, HEADS_THREADS, smem, s>>>(z4, hp, out, batch);
     C3B_CUDA(cudaGetLastError());
     return 0;

@@ -55,6 +55,31 @@ __device__ __forceinline__ void lstm_cell8(const float *gi, const float *gf, con
     }
 }
 
+// Packed variant: the four gate activations and tanh(c) of two neighbouring sites share one MUFU op each
+// (tanh.approx.f16x2), halving the MUFU work that bounds the epilogue; c, the products and h stay fp32.
+__device__ __forceinline__ __half2 tanh_h2(float a, float b) {
+    const __half2 x = __floats2half2_rn(a, b);
+    uint32_t r;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t *>(&x)));
+    return *reinterpret_cast<__half2 *>(&r);
+}
+__device__ __forceinline__ void lstm_cell8_h2(const float *gi, const float *gf, const float *gg, const float *go, float *c,
+                                              float *h) {
+    const __half2 half = __floats2half2_rn(0.5f, 0.5f);
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        const float2 iv = __half22float2(__hfma2(tanh_h2(gi[i], gi[i + 1]), half, half));
+        const float2 fv = __half22float2(__hfma2(tanh_h2(gf[i], gf[i + 1]), half, half));
+        const float2 gv = __half22float2(tanh_h2(gg[i], gg[i + 1]));
+        const float2 ov = __half22float2(__hfma2(tanh_h2(go[i], go[i + 1]), half, half));
+        c[i] = fmaf(fv.x, c[i], iv.x * gv.x);
+        c[i + 1] = fmaf(fv.y, c[i + 1], iv.y * gv.y);
+        const float2 tc = __half22float2(tanh_h2(c[i], c[i + 1]));
+        h[i] = ov.x * tc.x;
+        h[i + 1] = ov.y * tc.y;
+    }
+}
+
 __device__ __forceinline__ void unpack_half8(const uint4 &v, float *f) {
     const __half2 *hp = reinterpret_cast<const __half2 *>(&v);
 #pragma unroll
@@ -65,7 +90,7 @@ __device__ __forceinline__ void unpack_half8(const uint4 &v, float *f) {
     }
 }
 
-template <int NB, bool LAYER2>
+template <int NB, bool LAYER2, bool MUFU16>
 __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev p) {
     constexpr int H = LAYER2 ? 160 : 128;
     constexpr int KX = LAYER2 ? 0 : 32;
@@ -291,7 +316,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
                     go[i] += bias_o;
                 }
             }
-            lstm_cell8(gi, gf, gg, go, &c[j * 8], h);
+            if (MUFU16) lstm_cell8_h2(gi, gf, gg, go, &c[j * 8], h);
+            else lstm_cell8(gi, gf, gg, go, &c[j * 8], h);
             // h[n][unit] -> operand buffer (fp16), element (n, k = KX + wt)
             const uint32_t kcol = KX + wt;
             uint8_t *dst = b_smem + (kcol >> 3) * LBO_B + (kcol & 7) * 2;
@@ -353,15 +379,20 @@ __global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, op_t *__restric
     }
 }
 
-template <int NB, bool LAYER2>
-int launch_lstm(const LstmDev &p, cudaStream_t s) {
+template <int NB, bool LAYER2, bool MUFU16>
+int launch_lstm_impl(const LstmDev &p, cudaStream_t s) {
     const size_t smem = (size_t)4 * kBlkBytes + 2 * 20 * (NB + 1) * 16 + (LAYER2 ? (size_t)2 * NB * 128 * 4 : 0);
-    auto kern = lstm_tc_kernel<NB, LAYER2>;
+    auto kern = lstm_tc_kernel<NB, LAYER2, MUFU16>;
     C3B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(p.bp / (2 * NB), 2);
     kern<<<grid, kBlockThreads, smem, s>>>(p);
     C3B_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int NB, bool LAYER2>
+int launch_lstm(const LstmDev &p, bool mufu16, cudaStream_t s) {
+    return mufu16 ? launch_lstm_impl<NB, LAYER2, true>(p, s) : launch_lstm_impl<NB, LAYER2, false>(p, s);
 }
 
 }  // namespace
@@ -391,9 +422,9 @@ int c3b_launch_lstm1_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t ba
     p.bp = (int)((batch + 127) / 128 * 128);
     const_cast<c3b_model *>(m)->launches++;
     switch (tile) {
-        case 16: return launch_lstm<16, false>(p, s);
-        case 32: return launch_lstm<32, false>(p, s);
-        case 64: return launch_lstm<64, false>(p, s);
+        case 16: return launch_lstm<16, false>(p, m->lstm_mufu16 != 0, s);
+        case 32: return launch_lstm<32, false>(p, m->lstm_mufu16 != 0, s);
+        case 64: return launch_lstm<64, false>(p, m->lstm_mufu16 != 0, s);
     }
     c3b_set_error("lstm1: unsupported tile %d", tile);
     return 1;
@@ -408,8 +439,8 @@ int c3b_launch_lstm2_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t ba
     p.bp = (int)((batch + 127) / 128 * 128);
     const_cast<c3b_model *>(m)->launches++;
     switch (tile) {
-        case 16: return launch_lstm<16, true>(p, s);
-        case 32: return launch_lstm<32, true>(p, s);
+        case 16: return launch_lstm<16, true>(p, m->lstm_mufu16 != 0, s);
+        case 32: return launch_lstm<32, true>(p, m->lstm_mufu16 != 0, s);
     }
     c3b_set_error("lstm2: unsupported tile %d", tile);
     return 1;

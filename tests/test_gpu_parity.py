@@ -150,6 +150,30 @@ def test_lstm_tiles_agree():
     assert np.abs(outs[0] - outs[1]).max() < 1e-5 and np.abs(outs[0] - outs[2]).max() < 1e-5
 
 
+def test_fp32_mufu_variant_matches_reference():
+    """The packed tanh.approx.f16x2 gate path (default) and the fp32 tanh.approx path both meet the stated tolerance."""
+    z, meta, sd, x = golden_case("p24")
+    for flag in (0, 1):
+        m = _model(meta, sd, TC, lstm_mufu16=flag)
+        y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+        _check_probs(y, z["y"], 2e-2, 2e-3, 0.99)
+
+
+def test_forward_async_pinned_host_pipeline():
+    z, meta, sd, x = golden_case("p24")
+    m = _model(meta, sd, TC)
+    ref = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    xs = [torch.from_numpy(x).pin_memory() for _ in range(3)]
+    ys = [torch.empty((x.shape[0], 24), dtype=torch.float32).pin_memory() for _ in range(3)]
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    for i in range(6):
+        with torch.cuda.stream(streams[i % 3]):
+            m.forward_async(xs[i % 3], ys[i % 3])
+    torch.cuda.synchronize()
+    for y in ys:
+        assert np.abs(y.numpy() - ref).max() < 1e-5
+
+
 def test_input_dtypes_agree():
     z, meta, sd, x = golden_case("p24_int8")
     m = _model(meta, sd, TC)

@@ -122,6 +122,8 @@ def run_trace(opts):
         m = Clair3_P(add_indel_length=False, predict=True, input_channels=18)
         m.set_option("lstm_tile", tile)
         m.set_option("lstm_trace", 1)
+        if "lstm_mufu16" in opts:
+            m.set_option("lstm_mufu16", opts["lstm_mufu16"])
         m.to(torch.device("cuda"))
         m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
         xd = torch.from_numpy(x).cuda()
