@@ -122,7 +122,7 @@ struct c3b_model {
     int chunk_sites = 0;
     int lstm_tile = 0;
     int profile = 0;
-    int lstm_mufu16 = 1;               // 1: packed tanh.approx.f16x2 gate activations (default), 0: fp32 tanh.approx
+    int lstm_mufu16 = 0;               // 1: packed tanh.approx.f16x2 gate activations, 0 (default, faster: the epilogue is issue-bound): fp32 tanh.approx
     int host_async = 0;                // 1: host-buffer forwards stay stream-ordered (pinned buffers; caller synchronises)
     long long *lstm_trace = nullptr;   // device [2][33][4] clock stamps (debug option "lstm_trace")
     std::map<std::string, std::pair<double, int64_t>> prof_total;   // name -> (ms, launches)
