@@ -165,8 +165,9 @@ int lstm2_torch_row(int r640) {
 
 struct Tap {
     const void *ptr;
-    int fmt;        // 0 f32, 1 bf16
-    int layout;     // 0 [B][...] row-major with `inner` elements per site; 1 time-major [33][bp][inner]
+    int fmt;        // 0 f32, 1 fp16
+    int layout;     // 0 [B][inner] row-major; 2 k-group-planar [inner/8][bp][8] (row = site);
+                    // 3 k-group-planar time-major [inner/8][33*bp][8] (row = t*bp + site) -> [B][33][inner]
     int64_t inner;
     int bp;
 };
@@ -382,8 +383,10 @@ static int finalize_impl(c3b_model *m) {
                         bias[(size_t)d * 512 + row] = (bih[row] + bhh[row]) * gs;
                         for (int k = 0; k < 160; ++k) {
                             float v = 0.f;
-                            if (k < 32) { if (k < I) v = wih[(size_t)row * I + k]; }
-                            else v = whh[(size_t)row * 128 + (k - 32)];
+                            if (k < 32) {
+                                if (k < I) v = wih[(size_t)row * I + k];
+                                else if (k == I && I < 32) v = bih[row] + bhh[row];   // bias rides on a constant-1 input column
+                            } else v = whh[(size_t)row * 128 + (k - 32)];
                             img[((((size_t)d * 4 + blk) * 20 + k / 8) * 128 + r) * 8 + k % 8] = c3b_f2op(v * gs);
                         }
                     }
@@ -538,7 +541,7 @@ static size_t ws_bytes_needed(const c3b_model *m, int64_t sites, int depth) {
         for (int i = 0; i < 3; ++i) al((size_t)sites * h1 * w1 * 64 * es);
         for (int i = 0; i < 3; ++i) al((size_t)sites * h2 * w2 * 128 * es);
         for (int i = 0; i < 3; ++i) al((size_t)sites * h3 * w3 * 256 * es);
-        al((size_t)sites * 3584 * es);
+        al((size_t)bp * 3584 * es);
         al((size_t)bp * 256 * 4);
     }
     return total + 4096;
@@ -661,7 +664,8 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
     IgemmArgs pa = {};
     pa.a = b.h1;
     pa.m = (int64_t)C3B_T * bp;
-    pa.taps = 1;
+    pa.taps = 0;                // k-group-planar operand
+    pa.ld_rows = (int64_t)C3B_T * bp;
     pa.hin = (int)bp;          // pre-gate geometry (padded batch, LSTM2 tile) rides in hin / win
     pa.win = tile2;
     pa.cin = 256;
@@ -675,7 +679,8 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
     IgemmArgs la = {};
     la.a = b.h2;
     la.m = n;
-    la.taps = 1;
+    la.taps = 0;
+    la.ld_rows = bp;
     la.cin = m->l4_in;
     la.lda = m->l4_in;
     la.w = m->l4_tc;
@@ -687,8 +692,8 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
     { PROF("heads"); if (c3b_launch_heads(b.z4, m->heads, y, n, s)) return 1; }
     m->launches += 1;
     if (tap) {
-        wt.taps["lstm1"] = {b.h1, 1, 1, 256, (int)bp};
-        wt.taps["lstm2"] = {b.h2, 1, 0, (int64_t)C3B_T * 320, 0};
+        wt.taps["lstm1"] = {b.h1, 1, 3, 256, (int)bp};
+        wt.taps["lstm2"] = {b.h2, 1, 2, (int64_t)C3B_T * 320, (int)bp};
         wt.taps["l4_pre"] = {b.z4, 0, 0, 128, 0};
     }
     return 0;
@@ -709,7 +714,7 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
     char *act[3][3];
     for (int l = 0; l < 3; ++l)
         for (int i = 0; i < 3; ++i) act[l][i] = cv.take<char>((size_t)n * hh[l + 1] * ww[l + 1] * chans[l + 1] * es);
-    char *sp = cv.take<char>((size_t)n * 3584 * es);
+    char *sp = cv.take<char>((size_t)bp * 3584 * es);
     float *z4 = cv.take<float>((size_t)bp * 256 * 4);
     const char *tapname[3][2] = {{"conv1", "res_block1"}, {"conv3", "res_block2"}, {"conv5", "res_block3"}};
 
@@ -756,12 +761,13 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
             cur = a2;
             cur_c = co;
         }
-        { PROF("spp"); if (c3b_launch_spp_tc(cur, (op_t *)sp, n, hh[3], ww[3], 256, s)) return 1; }
+        { PROF("spp"); if (c3b_launch_spp_tc(cur, (op_t *)sp, n, hh[3], ww[3], 256, (int)bp, s)) return 1; }
         C3B_CUDA(cudaMemsetAsync(z4, 0, (size_t)bp * 256 * 4, s));
         IgemmArgs la = {};
         la.a = (const op_t *)sp;
         la.m = n;
-        la.taps = 1;
+        la.taps = 0;
+        la.ld_rows = bp;
         la.cin = 3584;
         la.lda = 3584;
         la.w = m->l4_tc;
@@ -780,7 +786,7 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
             wt.taps[tapname[l][0]] = {act[l][0], fmt, 0, inner, 0};
             wt.taps[tapname[l][1]] = {act[l][2], fmt, 0, inner, 0};
         }
-        wt.taps["spp"] = {sp, fmt, 0, 3584, 0};
+        wt.taps["spp"] = {sp, fmt, f32 ? 0 : 2, 3584, (int)bp};
         wt.taps["l4_pre"] = {z4, 0, 0, 256, 0};
     }
     return 0;
@@ -870,11 +876,11 @@ extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int6
         if (it == git->second.taps.end()) continue;
         const Tap &t = it->second;
         const int64_t n = m->last_batch;
-        const int64_t count = n * t.inner * (t.layout == 1 ? C3B_T : 1);
+        const int64_t per_site = t.inner * (t.layout == 3 ? C3B_T : 1);
+        const int64_t count = n * per_site;
         if (*count_inout < count || !host_out) { *count_inout = count; c3b_set_error("c3b_get_tap: buffer too small"); return 1; }
         C3B_CUDA(cudaStreamSynchronize(w->stream));
-        const int64_t rows = t.layout == 1 ? (int64_t)C3B_T * t.bp : n;
-        const int64_t src_count = t.layout == 1 ? rows * t.inner : count;
+        const int64_t src_count = t.layout == 0 ? count : t.inner * (int64_t)t.bp * (t.layout == 3 ? C3B_T : 1);
         std::vector<float> tmp((size_t)src_count);
         if (t.fmt == 0) {
             C3B_CUDA(cudaMemcpy(tmp.data(), t.ptr, (size_t)src_count * 4, cudaMemcpyDeviceToHost));
@@ -883,15 +889,20 @@ extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int6
             C3B_CUDA(cudaMemcpy(raw.data(), t.ptr, (size_t)src_count * 2, cudaMemcpyDeviceToHost));
             for (int64_t i = 0; i < src_count; ++i) tmp[i] = c3b_op2f(raw[i]);
         }
-        if (t.layout == 1) {   // [33][bp][inner] -> [n][33][inner]
+        if (t.layout == 0) {
+            memcpy(host_out, tmp.data(), (size_t)count * 4);
+        } else if (t.layout == 2) {        // [inner/8][bp][8] -> [n][inner]
+            for (int64_t b = 0; b < n; ++b)
+                for (int64_t k = 0; k < t.inner; ++k)
+                    host_out[b * t.inner + k] = tmp[((k >> 3) * t.bp + b) * 8 + (k & 7)];
+        } else {                           // [inner/8][33*bp][8] -> [n][33][inner]
+            const int64_t rows = (int64_t)C3B_T * t.bp;
             for (int64_t b = 0; b < n; ++b)
                 for (int tt = 0; tt < C3B_T; ++tt)
-                    memcpy(host_out + (b * C3B_T + tt) * t.inner, tmp.data() + ((int64_t)tt * t.bp + b) * t.inner, (size_t)t.inner * 4);
-            *count_inout = n * C3B_T * t.inner;
-        } else {
-            memcpy(host_out, tmp.data(), (size_t)count * 4);
-            *count_inout = count;
+                    for (int64_t k = 0; k < t.inner; ++k)
+                        host_out[(b * C3B_T + tt) * t.inner + k] = tmp[((k >> 3) * rows + (int64_t)tt * t.bp + b) * 8 + (k & 7)];
         }
+        *count_inout = count;
         return 0;
     }
     c3b_set_error("c3b_get_tap: no tap named \"%s\" (run a forward first)", name);
@@ -913,8 +924,15 @@ extern "C" int c3b_debug_gemm(c3b_model *m, int swapped, int64_t M, int N, int K
     if (!m) { c3b_set_error("c3b_debug_gemm: null model"); return 1; }
     if (K % 8) { c3b_set_error("c3b_debug_gemm: K must be a multiple of 8"); return 1; }
     C3B_CUDA(cudaSetDevice(m->device));
-    std::vector<uint16_t> ab((size_t)M * K);
-    for (size_t i = 0; i < ab.size(); ++i) ab[i] = c3b_f2op(a[i]);
+    // swapped orientation = the k-group-planar bulk-copy operand path ([K/8][Mp][8]); standard = row-major gather path
+    const int64_t Mp = (M + 127) / 128 * 128;
+    std::vector<uint16_t> ab(swapped ? (size_t)Mp * K : (size_t)M * K, 0);
+    if (swapped) {
+        for (int64_t r = 0; r < M; ++r)
+            for (int k = 0; k < K; ++k) ab[((size_t)(k >> 3) * Mp + r) * 8 + (k & 7)] = c3b_f2op(a[(size_t)r * K + k]);
+    } else {
+        for (size_t i = 0; i < ab.size(); ++i) ab[i] = c3b_f2op(a[i]);
+    }
     const int rb = swapped ? 128 : N;
     std::vector<uint16_t> img = pack_igemm(N, K / 8, rb, [&](int r, int k) { return wmat[(size_t)r * K + k]; });
     void *da = nullptr, *dw = nullptr, *db = nullptr, *dout = nullptr;
@@ -931,7 +949,8 @@ extern "C" int c3b_debug_gemm(c3b_model *m, int swapped, int64_t M, int N, int K
     IgemmArgs ga = {};
     ga.a = (const op_t *)da;
     ga.m = M;
-    ga.taps = 1;
+    ga.taps = swapped ? 0 : 1;
+    ga.ld_rows = Mp;
     ga.cin = K;
     ga.lda = K;
     ga.w.w_img = (const op_t *)dw;

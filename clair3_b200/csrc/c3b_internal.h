@@ -173,9 +173,9 @@ int c3b_launch_spp_f32(const float *x, float *out, int64_t batch, int h, int w, 
 // ---- tensor-core path (lstm_tc.cu / igemm_tc.cu) ----
 struct TcPileupBuffers {
     op_t *xs;     // [33][B][32] bf16, time-major, channels zero-padded 18 -> 32
-    op_t *h1;     // [33][B][256] bf16, time-major
+    op_t *h1;     // k-group-planar [32][33*Bp][8]: row = t*Bp + b, k = dir*128 + j  (projection GEMM operand)
     __half *pg;            // [33*B][1280] fp16 pre-gates of LSTM2 (bias included), permuted gate columns
-    op_t *h2;     // [B][33][320] bf16, batch-major (flatten order of clair3/model.py:135)
+    op_t *h2;     // k-group-planar [1320][Bp][8]: row = b, k = t*320 + dir*160 + j (flatten order of clair3/model.py:135)
     float *z4;             // [B][128] fp32, L4 pre-activation without bias (split-K accumulated)
 };
 int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, op_t *xs, int64_t batch, cudaStream_t s);
@@ -192,7 +192,8 @@ struct IgemmArgs {
     const op_t *a;   // activations
     int64_t m;                // GEMM rows (pixels / positions / sites)
     // row addressing: conv mode (taps = 9) or plain (taps = 1)
-    int taps;                 // 1 or 9
+    int taps;                 // 9 conv gather | 1 plain row-major gather | 0 plain k-group-planar [K/8][ld_rows][8]
+    int64_t ld_rows;          // planar: rows per k-group plane
     int hin, win, cin;        // conv input geometry (NHWC); plain: cin = K, hin = win = 1
     int hout, wout, stride;   // conv output geometry
     int64_t lda;              // plain mode: row stride in elements
@@ -207,5 +208,5 @@ struct IgemmArgs {
 int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s);
 
 int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, op_t *out, int64_t n_pix, cudaStream_t s);
-int c3b_launch_spp_tc(const op_t *x, op_t *out, int64_t batch, int h, int w, int c, cudaStream_t s);
+int c3b_launch_spp_tc(const op_t *x, op_t *out, int64_t batch, int h, int w, int c, int bp, cudaStream_t s);
 

@@ -25,7 +25,7 @@ __global__ void ingest_fa_tc_kernel(const T *__restrict__ x, op_t *__restrict__ 
 }
 
 // grid (B, 14 pyramid cells), block = channels: every thread reduces one window of one channel (coalesced over channels).
-__global__ void spp_tc_kernel(const op_t *__restrict__ x, op_t *__restrict__ out, int h, int w, int c) {
+__global__ void spp_tc_kernel(const op_t *__restrict__ x, op_t *__restrict__ out, int h, int w, int c, int bp) {
     const int64_t b = blockIdx.x;
     const int cell = blockIdx.y;
     int p, idx;
@@ -43,7 +43,9 @@ __global__ void spp_tc_kernel(const op_t *__restrict__ x, op_t *__restrict__ out
         float m = 0.f;                       // inputs are post-ReLU: zero padding == floor at 0
         for (int hh = h0; hh < h1; ++hh)
             for (int wv = w0; wv < w1; ++wv) m = fmaxf(m, op2f(x[((b * h + hh) * w + wv) * c + ch]));
-        out[b * (14 * c) + cell * c + ch] = f2op(m);
+        // k-group-planar [3584/8][bp][8]: feature f = cell*c + ch (the reference's flatten order), operand of the L4 GEMM
+        const int f = cell * c + ch;
+        out[((size_t)(f >> 3) * bp + b) * 8 + (f & 7)] = f2op(m);
     }
 }
 
@@ -64,9 +66,9 @@ int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, op
     return 0;
 }
 
-int c3b_launch_spp_tc(const op_t *x, op_t *out, int64_t batch, int h, int w, int c, cudaStream_t s) {
+int c3b_launch_spp_tc(const op_t *x, op_t *out, int64_t batch, int h, int w, int c, int bp, cudaStream_t s) {
     if (batch == 0) return 0;
-    spp_tc_kernel<<<dim3((unsigned)batch, 14), 256, 0, s>>>(x, out, h, w, c);
+    spp_tc_kernel<<<dim3((unsigned)batch, 14), 256, 0, s>>>(x, out, h, w, c, bp);
     C3B_CUDA(cudaGetLastError());
     return 0;
 }

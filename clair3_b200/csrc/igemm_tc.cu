@@ -47,7 +47,8 @@ struct IgemmDev {
     int64_t m_valid;       // valid activation rows (pixels / positions / sites)
     int64_t lda;           // plain mode row stride (elements)
     int64_t ldo;           // output row stride (elements)
-    int taps;              // 1 plain, 9 conv
+    int taps;              // 9 conv gather, 1 plain row-major gather, 0 plain k-group-planar ([K/8][ld_rows][8]) via bulk copies
+    int64_t ld_rows;       // planar mode: rows per k-group plane
     int hin, win, cin, hout, wout, stride;
     int cpk_shift;         // log2(cin/8) in conv mode
     int kgroups;           // real K/8
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            ptx::mbar_init(&full_bar[s], kProducerThreads + (p.w_resident ? 0 : 1));
+            ptx::mbar_init(&full_bar[s], p.taps == 0 ? 1 : kProducerThreads + (p.w_resident ? 0 : 1));
             ptx::mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -152,6 +153,33 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                     ptx::bulk_g2s(smem_base + (uint32_t)(c * p.wb + b) * w_bytes,
                                   (const char *)p.w_img + ((size_t)c * p.n_rowblocks + rb0 + b) * w_bytes, w_bytes, &w_bar);
         }
+        if (p.taps == 0) {
+            // k-group-planar activations: a tile's chunk is 8 contiguous 2 KB runs -> 8 cp.async.bulk by one thread
+            // (TMA engine, async proxy: no per-thread gathers, no proxy fences), completion by mbarrier tx-count.
+            if (tid == 0) {
+                const uint32_t lbo_a = (uint32_t)(p.act_rows + 1) * 16u;
+                int it = 0;
+                for (TileWalk tw(p); tw.valid(p); tw.next(p)) {
+                    int at, rb0, c_begin, c_end;
+                    tw.decode(p, at, rb0, c_begin, c_end);
+                    for (int c = c_begin; c < c_end; ++c, ++it) {
+                        const int s = it % S;
+                        const uint32_t ph = (uint32_t)(it / S) & 1u;
+                        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+                        const uint32_t stage = stages_base + (uint32_t)s * stage_bytes;
+                        const int kgs = min(8, p.kgroups - c * 8);
+                        ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)kgs * 2048u + (p.w_resident ? 0u : w_bytes));
+                        if (!p.w_resident)
+                            ptx::bulk_g2s(stage + act_bytes, (const char *)p.w_img + ((size_t)c * p.n_rowblocks + rb0) * w_bytes,
+                                          w_bytes, &full_bar[s]);
+                        for (int kg = 0; kg < kgs; ++kg)
+                            ptx::bulk_g2s(stage + (uint32_t)kg * lbo_a,
+                                          (const char *)p.act + ((size_t)(c * 8 + kg) * p.ld_rows + (size_t)at * 128) * 16, 2048u,
+                                          &full_bar[s]);
+                    }
+                }
+            }
+        } else {
         // Thread -> (k-group kgl = tid & 7, rows (tid >> 3) + 16 j): one warp-level cp.async covers 4 rows x 128
         // contiguous bytes of the activation matrix (fully coalesced); the padded LBO keeps the smem side conflict-free.
         const int kgl = tid & 7;
@@ -239,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
         if (pend2 >= 0) ptx::mbar_arrive(&full_bar[pend2]);
         if (pend1 >= 0) ptx::mbar_arrive(&full_bar[pend1]);
         if (pend0 >= 0) ptx::mbar_arrive(&full_bar[pend0]);
+        }   // gather producers
     } else if (warp == 8) {
         // ===================================================== MMA issuer (whole warp walks the tiles, one elected lane issues)
         const uint32_t idesc = ptx::umma_idesc_f16(128, (uint32_t)ncols);
@@ -426,6 +455,8 @@ int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s) {
     p.lda = a.lda;
     p.ldo = a.ldo;
     p.taps = a.taps;
+    p.ld_rows = a.ld_rows;
+    if (a.taps == 0 && (a.w.kgroups & 1)) { c3b_set_error("igemm(planar): K/8 must be even"); return 1; }
     p.hin = a.hin; p.win = a.win; p.cin = a.cin; p.hout = a.hout; p.wout = a.wout; p.stride = a.stride;
     p.cpk_shift = (a.taps == 9) ? ilog2(a.cin / 8) : 0;
     p.kgroups = a.w.kgroups;

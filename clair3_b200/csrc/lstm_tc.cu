@@ -37,7 +37,7 @@ struct LstmDev {
     const float *bias;             // [dir][NBLK*128] (LSTM1)
     const op_t *xs;                // LSTM1 input  [33][Bp][32]
     const __half *pg;              // LSTM2 pre-gates pgT[dir][33][Bp/NB][5][128][NB]
-    op_t *hout;                    // LSTM1: h1[33][Bp][256]; LSTM2: h2[Bp][33][320]
+    op_t *hout;                    // k-group-planar: LSTM1 h1p[32][33*Bp][8] (row t*Bp+b); LSTM2 h2p[1320][Bp][8] (k = t*320+dir*160+j)
     int bp;                        // padded batch
     long long *trace;              // optional [33][4] clock64 stamps of CTA (0,0) thread 0 (debug option "lstm_trace")
 };
@@ -205,8 +205,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
         ptx::tmem_st_wait();
     }
 
+    // LSTM1 with fewer than 32 input channels: the bias is column `channels` of the weight image (the ingest kernel
+    // writes a constant 1 there), so the epilogue adds nothing.
+    const bool BIAS_IN_GEMM = !LAYER2 && p.bias == nullptr;
     float bias_i = 0.f, bias_f = 0.f, bias_g = 0.f, bias_o = 0.f;
-    if (!LAYER2) {
+    if (!LAYER2 && !BIAS_IN_GEMM) {
         const float *bp = p.bias + dir * (NBLK * 128);
         bias_i = bp[wt];
         bias_f = bp[128 + wt];
@@ -243,10 +246,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
         // while the MMAs run: ship h_{t_prev} (still in the operand buffer) to global memory
         if (step > 0) {
             for (int idx = wt; idx < NB * (H / 8); idx += kWgThreads) {
-                const int n = idx / (H / 8), kgh = idx % (H / 8);
+                const int kgh = idx / NB, n = idx % NB;           // consecutive threads -> consecutive sites: 16 B x NB runs
                 const uint4 v = *reinterpret_cast<const uint4 *>(b_smem + (KX / 8 + kgh) * LBO_B + n * 16);
-                op_t *dst = LAYER2 ? p.hout + ((size_t)(b0 + n) * C3B_T + t_prev) * 320 + dir * 160 + kgh * 8
-                                   : p.hout + ((size_t)t_prev * p.bp + b0 + n) * 256 + dir * 128 + kgh * 8;
+                op_t *dst = LAYER2 ? p.hout + ((size_t)(t_prev * 40 + dir * 20 + kgh) * p.bp + b0 + n) * 8
+                                   : p.hout + ((size_t)(dir * 16 + kgh) * (C3B_T * (size_t)p.bp) + (size_t)t_prev * p.bp + b0 + n) * 8;
                 *reinterpret_cast<uint4 *>(dst) = v;
             }
         }
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
                 unpack_half8(pgv[3][j], pf);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) go[i] += pf[i];
-            } else {
+            } else if (!BIAS_IN_GEMM) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     gi[i] += bias_i;
@@ -347,10 +350,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
     // last h
     ptx::named_bar_sync(bar_id, kWgThreads);
     for (int idx = wt; idx < NB * (H / 8); idx += kWgThreads) {
-        const int n = idx / (H / 8), kgh = idx % (H / 8);
+        const int kgh = idx / NB, n = idx % NB;
         const uint4 v = *reinterpret_cast<const uint4 *>(b_smem + (KX / 8 + kgh) * LBO_B + n * 16);
-        op_t *dst = LAYER2 ? p.hout + ((size_t)(b0 + n) * C3B_T + t_prev) * 320 + dir * 160 + kgh * 8
-                           : p.hout + ((size_t)t_prev * p.bp + b0 + n) * 256 + dir * 128 + kgh * 8;
+        op_t *dst = LAYER2 ? p.hout + ((size_t)(t_prev * 40 + dir * 20 + kgh) * p.bp + b0 + n) * 8
+                           : p.hout + ((size_t)(dir * 16 + kgh) * (C3B_T * (size_t)p.bp) + (size_t)t_prev * p.bp + b0 + n) * 8;
         *reinterpret_cast<uint4 *>(dst) = v;
     }
     ptx::tc_fence_before();
@@ -371,7 +374,7 @@ __global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, op_t *__restric
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int ch = kg * 8 + i;
-            float f = 0.f;
+            float f = (ch == channels) ? 1.f : 0.f;          // constant-1 column: LSTM1's bias is folded into the gate GEMM
             if (b < batch && ch < channels) f = (float)x[((int64_t)b * C3B_T + t) * channels + ch];
             v[i] = f2op(f);
         }
@@ -415,7 +418,7 @@ int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, op_t *xs
 int c3b_launch_lstm1_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t batch, int tile, cudaStream_t s) {
     LstmDev p = {};
     p.w_img = m->lstm_tc[0][0].w_img;     // both directions are contiguous
-    p.bias = m->lstm_tc[0][0].bias;
+    p.bias = (m->channels < 32) ? nullptr : m->lstm_tc[0][0].bias;   // bias folded into the GEMM when a spare input column exists
     p.xs = b.xs;
     p.hout = b.h1;
     p.trace = m->lstm_trace ? m->lstm_trace : nullptr;

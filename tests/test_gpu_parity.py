@@ -93,9 +93,9 @@ def test_tensor_core_conv_taps_match_reference():
 
 @pytest.mark.parametrize("swapped,M,N,K,ksplit", [
     (0, 128, 64, 64, 1), (0, 300, 64, 72, 1), (0, 1000, 128, 576, 1), (0, 257, 256, 1152, 1), (0, 130, 16, 16, 1),
-    (1, 128, 128, 64, 1), (1, 200, 256, 256, 1), (1, 77, 128, 1064, 3), (1, 1024, 128, 10560, 11),
+    (1, 128, 128, 64, 1), (1, 200, 256, 256, 1), (1, 77, 128, 1072, 3), (1, 1024, 128, 10560, 11),
     # enough tiles for the W-stationary mode (weights resident in shared memory; two row blocks per CTA when swapped)
-    (0, 40000, 64, 576, 1), (1, 40000, 256, 256, 1), (1, 20000, 128, 72, 1),
+    (0, 40000, 64, 576, 1), (1, 40000, 256, 256, 1), (1, 20000, 128, 80, 1),
 ])
 def test_igemm_kernel_against_numpy(swapped, M, N, K, ksplit):
     from clair3_b200._ffi import check, ffi, lib

@@ -61,8 +61,8 @@ def run_case(name, precision, opts):
 def run_igemm():
     from clair3_b200._ffi import check, ffi, lib
     shapes = [(0, 128, 64, 64, 1), (0, 128, 16, 16, 1), (0, 300, 64, 72, 1), (0, 1000, 128, 576, 1), (0, 257, 256, 1152, 1),
-              (1, 128, 128, 64, 1), (1, 200, 256, 256, 1), (1, 77, 128, 1064, 3), (1, 1024, 128, 10560, 11),
-              (0, 40000, 64, 576, 1), (1, 40000, 256, 256, 1), (1, 20000, 128, 72, 1)]
+              (1, 128, 128, 64, 1), (1, 200, 256, 256, 1), (1, 77, 128, 1072, 3), (1, 1024, 128, 10560, 11),
+              (0, 40000, 64, 576, 1), (1, 40000, 256, 256, 1), (1, 20000, 128, 80, 1)]
     for swapped, M, N, K, ks in shapes:
         r = np.random.default_rng(M + N + K)
         a = r.standard_normal((M, K)).astype(np.float32)
