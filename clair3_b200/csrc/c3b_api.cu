@@ -168,8 +168,10 @@ struct Tap {
     int fmt;        // 0 f32, 1 fp16
     int layout;     // 0 [B][inner] row-major; 2 k-group-planar [inner/8][bp][8] (row = site);
                     // 3 k-group-planar time-major [inner/8][33*bp][8] (row = t*bp + site) -> [B][33][inner]
+                    // 4 zero-padded planar feature map [inner/8][geom.p][8] -> NHWC [B][h][w][inner]
     int64_t inner;
     int bp;
+    PlanarGeom geom;
 };
 
 }  // namespace
@@ -265,6 +267,8 @@ extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
         }
     } else if (!strcmp(name, "lstm_mufu16")) {
         m->lstm_mufu16 = value ? 1 : 0;
+    } else if (!strcmp(name, "tap_ws")) {
+        m->tap_ws = value;           // which stream workspace (creation order) c3b_get_tap reads; -1 = first that has the tap
     } else if (!strcmp(name, "host_async")) {
         m->host_async = value ? 1 : 0;
     } else if (!strcmp(name, "lstm_trace")) {
@@ -535,13 +539,22 @@ static size_t ws_bytes_needed(const c3b_model *m, int64_t sites, int depth) {
         al((size_t)bp * 128 * 4);
     } else {
         const int h1 = conv_out(depth), w1 = conv_out(33), h2 = conv_out(h1), w2 = conv_out(w1), h3 = conv_out(h2), w3 = conv_out(w2);
-        const size_t es = m->precision == C3B_PREC_FP32 ? 4 : 2;
-        const int cpad = m->precision == C3B_PREC_FP32 ? m->channels : (m->channels + 7) / 8 * 8;
-        al((size_t)sites * depth * 33 * cpad * es);
-        for (int i = 0; i < 3; ++i) al((size_t)sites * h1 * w1 * 64 * es);
-        for (int i = 0; i < 3; ++i) al((size_t)sites * h2 * w2 * 128 * es);
-        for (int i = 0; i < 3; ++i) al((size_t)sites * h3 * w3 * 256 * es);
-        al((size_t)bp * 3584 * es);
+        if (m->precision == C3B_PREC_FP32) {
+            al((size_t)sites * depth * 33 * m->channels * 4);
+            for (int i = 0; i < 3; ++i) al((size_t)sites * h1 * w1 * 64 * 4);
+            for (int i = 0; i < 3; ++i) al((size_t)sites * h2 * w2 * 128 * 4);
+            for (int i = 0; i < 3; ++i) al((size_t)sites * h3 * w3 * 256 * 4);
+            al((size_t)bp * 3584 * 4);
+        } else {
+            const int cpad = (m->channels + 7) / 8 * 8;
+            al((size_t)sites * depth * 33 * cpad * 2);
+            const int hh[3] = {h1, h2, h3}, ww[3] = {w1, w2, w3}, cc[3] = {64, 128, 256};
+            for (int l = 0; l < 3; ++l) {
+                const PlanarGeom g = c3b_planar_geom(sites, hh[l], ww[l]);
+                for (int i = 0; i < 3; ++i) al((size_t)(cc[l] / 8) * g.p * 16);
+            }
+            al((size_t)bp * 3584 * 2);
+        }
         al((size_t)bp * 256 * 4);
     }
     return total + 4096;
@@ -639,9 +652,9 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
         if (c3b_launch_heads(z4, m->heads, y, n, s)) return 1;
         m->launches += 5;
         if (tap) {
-            wt.taps["lstm1"] = {l1, 0, 0, (int64_t)C3B_T * 256, 0};
-            wt.taps["lstm2"] = {l2, 0, 0, (int64_t)C3B_T * 320, 0};
-            wt.taps["l4_pre"] = {z4, 0, 0, 128, 0};
+            wt.taps["lstm1"] = {l1, 0, 0, (int64_t)C3B_T * 256, 0, {}};
+            wt.taps["lstm2"] = {l2, 0, 0, (int64_t)C3B_T * 320, 0, {}};
+            wt.taps["l4_pre"] = {z4, 0, 0, 128, 0, {}};
         }
         return 0;
     }
@@ -692,9 +705,9 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
     { PROF("heads"); if (c3b_launch_heads(b.z4, m->heads, y, n, s)) return 1; }
     m->launches += 1;
     if (tap) {
-        wt.taps["lstm1"] = {b.h1, 1, 3, 256, (int)bp};
-        wt.taps["lstm2"] = {b.h2, 1, 2, (int64_t)C3B_T * 320, (int)bp};
-        wt.taps["l4_pre"] = {b.z4, 0, 0, 128, 0};
+        wt.taps["lstm1"] = {b.h1, 1, 3, 256, (int)bp, {}};
+        wt.taps["lstm2"] = {b.h2, 1, 2, (int64_t)C3B_T * 320, (int)bp, {}};
+        wt.taps["l4_pre"] = {b.z4, 0, 0, 128, 0, {}};
     }
     return 0;
 }
@@ -708,86 +721,118 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
     for (int i = 1; i < 4; ++i) { hh[i] = conv_out(hh[i - 1]); ww[i] = conv_out(ww[i - 1]); }
     const int chans[4] = {m->channels, 64, 128, 256};
     const bool f32 = m->precision == C3B_PREC_FP32;
-    const size_t es = f32 ? 4 : 2;
-    const int cpad = f32 ? m->channels : (m->channels + 7) / 8 * 8;
-    char *xin = cv.take<char>((size_t)n * depth * 33 * cpad * es);
-    char *act[3][3];
-    for (int l = 0; l < 3; ++l)
-        for (int i = 0; i < 3; ++i) act[l][i] = cv.take<char>((size_t)n * hh[l + 1] * ww[l + 1] * chans[l + 1] * es);
-    char *sp = cv.take<char>((size_t)bp * 3584 * es);
-    float *z4 = cv.take<float>((size_t)bp * 256 * 4);
     const char *tapname[3][2] = {{"conv1", "res_block1"}, {"conv3", "res_block2"}, {"conv5", "res_block3"}};
 
     if (f32) {
-        if (c3b_launch_ingest_fa_f32(x, x_dtype, (float *)xin, n * depth * 33 * m->channels, s)) return 1;
-        const float *cur = (const float *)xin;
+        float *xin = cv.take<float>((size_t)n * depth * 33 * m->channels * 4);
+        float *act[3][3];
+        for (int l = 0; l < 3; ++l)
+            for (int i = 0; i < 3; ++i) act[l][i] = cv.take<float>((size_t)n * hh[l + 1] * ww[l + 1] * chans[l + 1] * 4);
+        float *sp = cv.take<float>((size_t)bp * 3584 * 4);
+        float *z4 = cv.take<float>((size_t)bp * 256 * 4);
+        if (c3b_launch_ingest_fa_f32(x, x_dtype, xin, n * depth * 33 * m->channels, s)) return 1;
+        const float *cur = xin;
         for (int l = 0; l < 3; ++l) {
-            float *a0 = (float *)act[l][0], *a1 = (float *)act[l][1], *a2 = (float *)act[l][2];
+            float *a0 = act[l][0], *a1 = act[l][1], *a2 = act[l][2];
             if (c3b_launch_conv_f32(cur, m->conv_f32[3 * l], nullptr, a0, n, hh[l], ww[l], hh[l + 1], ww[l + 1], s)) return 1;
             if (c3b_launch_conv_f32(a0, m->conv_f32[3 * l + 1], nullptr, a1, n, hh[l + 1], ww[l + 1], hh[l + 1], ww[l + 1], s)) return 1;
             if (c3b_launch_conv_f32(a1, m->conv_f32[3 * l + 2], a0, a2, n, hh[l + 1], ww[l + 1], hh[l + 1], ww[l + 1], s)) return 1;
             cur = a2;
         }
-        if (c3b_launch_spp_f32(cur, (float *)sp, n, hh[3], ww[3], 256, s)) return 1;
-        if (c3b_launch_dense_f32((float *)sp, m->l4_f32_t, z4, n, 3584, 256, s)) return 1;
+        if (c3b_launch_spp_f32(cur, sp, n, hh[3], ww[3], 256, s)) return 1;
+        if (c3b_launch_dense_f32(sp, m->l4_f32_t, z4, n, 3584, 256, s)) return 1;
         if (c3b_launch_heads(z4, m->heads, y, n, s)) return 1;
         m->launches += 13;
-    } else {
-        { PROF("ingest"); if (c3b_launch_ingest_fa_tc(x, x_dtype, m->channels, cpad, (op_t *)xin, n * depth * 33, s)) return 1; }
-        const op_t *cur = (const op_t *)xin;
-        int cur_c = cpad;
-        for (int l = 0; l < 3; ++l) {
-            op_t *a0 = (op_t *)act[l][0], *a1 = (op_t *)act[l][1], *a2 = (op_t *)act[l][2];
-            const int co = chans[l + 1];
-            IgemmArgs ca = {};
-            ca.taps = 9;
-            ca.epilogue = IGEMM_EPI_BF16_BIAS_RELU;
-            ca.relu = 1;
-            ca.ldo = co;
-            ca.hout = hh[l + 1];
-            ca.wout = ww[l + 1];
-            ca.m = n * hh[l + 1] * ww[l + 1];
-            // strided stem conv
-            ca.a = cur; ca.hin = hh[l]; ca.win = ww[l]; ca.cin = cur_c; ca.stride = 2;
-            ca.w = m->conv_tc[3 * l]; ca.out = a0; ca.residual = nullptr;
-            static const char *cn[9] = {"conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv8"};
-            { PROF(cn[3 * l]); if (c3b_launch_igemm(m, ca, s)) return 1; }
-            // residual block
-            ca.a = a0; ca.hin = hh[l + 1]; ca.win = ww[l + 1]; ca.cin = co; ca.stride = 1;
-            ca.w = m->conv_tc[3 * l + 1]; ca.out = a1; ca.residual = nullptr;
-            { PROF(cn[3 * l + 1]); if (c3b_launch_igemm(m, ca, s)) return 1; }
-            ca.a = a1; ca.w = m->conv_tc[3 * l + 2]; ca.out = a2; ca.residual = a0;
-            { PROF(cn[3 * l + 2]); if (c3b_launch_igemm(m, ca, s)) return 1; }
-            cur = a2;
-            cur_c = co;
+        if (tap) {
+            for (int l = 0; l < 3; ++l) {
+                const int64_t inner = (int64_t)hh[l + 1] * ww[l + 1] * chans[l + 1];
+                wt.taps[tapname[l][0]] = {act[l][0], 0, 0, inner, 0, {}};
+                wt.taps[tapname[l][1]] = {act[l][2], 0, 0, inner, 0, {}};
+            }
+            wt.taps["spp"] = {sp, 0, 0, 3584, 0, {}};
+            wt.taps["l4_pre"] = {z4, 0, 0, 256, 0, {}};
         }
-        { PROF("spp"); if (c3b_launch_spp_tc(cur, (op_t *)sp, n, hh[3], ww[3], 256, (int)bp, s)) return 1; }
-        C3B_CUDA(cudaMemsetAsync(z4, 0, (size_t)bp * 256 * 4, s));
-        IgemmArgs la = {};
-        la.a = (const op_t *)sp;
-        la.m = n;
-        la.taps = 0;
-        la.ld_rows = bp;
-        la.cin = 3584;
-        la.lda = 3584;
-        la.w = m->l4_tc;
-        la.out = z4;
-        la.ldo = 256;
-        la.epilogue = IGEMM_EPI_F32_ATOMIC;
-        la.ksplit = 8;
-        { PROF("l4"); if (c3b_launch_igemm(m, la, s)) return 1; }
-        { PROF("heads"); if (c3b_launch_heads(z4, m->heads, y, n, s)) return 1; }
-        m->launches += 3;
+        return 0;
     }
+
+    // ---- tensor-core path: NHWC fp16 input, then zero-padded channel-group-planar feature maps (pconv_tc.cu)
+    const int cpad = (m->channels + 7) / 8 * 8;
+    op_t *xin = cv.take<op_t>((size_t)n * depth * 33 * cpad * 2);
+    PlanarGeom geo[3];
+    op_t *act[3][3];
+    const size_t planar_begin = cv.off;
+    for (int l = 0; l < 3; ++l) {
+        geo[l] = c3b_planar_geom(n, hh[l + 1], ww[l + 1]);
+        for (int i = 0; i < 3; ++i) act[l][i] = cv.take<op_t>((size_t)(chans[l + 1] / 8) * geo[l].p * 16);
+    }
+    const size_t planar_end = cv.off;
+    op_t *sp = cv.take<op_t>((size_t)bp * 3584 * 2);
+    float *z4 = cv.take<float>((size_t)bp * 256 * 4);
+    // borders / guards of the planar maps must be zero; convs rewrite borders with zeros and never touch guards, so one
+    // clear per (workspace, geometry) is enough
+    if (w->fa_zero_sites != n || w->fa_zero_depth != depth) {
+        C3B_CUDA(cudaMemsetAsync(w->dev + planar_begin, 0, planar_end - planar_begin, s));
+        w->fa_zero_sites = n;
+        w->fa_zero_depth = depth;
+    }
+    static const char *cn[9] = {"conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv8"};
+    { PROF("ingest"); if (c3b_launch_ingest_fa_tc(x, x_dtype, m->channels, cpad, xin, n * depth * 33, s)) return 1; }
+    m->launches += 1;
+    for (int l = 0; l < 3; ++l) {
+        op_t *a0 = act[l][0], *a1 = act[l][1], *a2 = act[l][2];
+        const int co = chans[l + 1];
+        // strided stem conv: gather implicit GEMM; reads NHWC (l = 0) or the previous level's planar map, writes planar
+        IgemmArgs ca = {};
+        ca.taps = 9;
+        ca.epilogue = IGEMM_EPI_BF16_BIAS_RELU;
+        ca.relu = 1;
+        ca.ldo = co;
+        ca.hout = hh[l + 1];
+        ca.wout = ww[l + 1];
+        ca.m = n * hh[l + 1] * ww[l + 1];
+        ca.hin = hh[l]; ca.win = ww[l]; ca.stride = 2;
+        ca.cin = l == 0 ? cpad : chans[l];
+        ca.a = l == 0 ? xin : act[l - 1][2];
+        ca.in_planar = l == 0 ? 0 : 1;
+        if (l > 0) ca.gin = geo[l - 1];
+        ca.out_planar = 1;
+        ca.gout = geo[l];
+        ca.w = m->conv_tc[3 * l];
+        ca.out = a0;
+        { PROF(cn[3 * l]); if (c3b_launch_igemm(m, ca, s)) return 1; }
+        // residual block: two shifted-view convolutions on the planar map
+        PconvArgs pa = {};
+        pa.geom = geo[l];
+        pa.c = co; pa.n = co; pa.relu = 1;
+        pa.in = a0; pa.out = a1; pa.residual = nullptr; pa.w = m->conv_tc[3 * l + 1];
+        { PROF(cn[3 * l + 1]); if (c3b_launch_pconv(m, pa, s)) return 1; }
+        pa.in = a1; pa.out = a2; pa.residual = a0; pa.w = m->conv_tc[3 * l + 2];
+        { PROF(cn[3 * l + 2]); if (c3b_launch_pconv(m, pa, s)) return 1; }
+    }
+    { PROF("spp"); if (c3b_launch_spp_tc(act[2][2], geo[2], sp, n, 256, (int)bp, s)) return 1; }
+    C3B_CUDA(cudaMemsetAsync(z4, 0, (size_t)bp * 256 * 4, s));
+    IgemmArgs la = {};
+    la.a = sp;
+    la.m = n;
+    la.taps = 0;
+    la.ld_rows = bp;
+    la.cin = 3584;
+    la.lda = 3584;
+    la.w = m->l4_tc;
+    la.out = z4;
+    la.ldo = 256;
+    la.epilogue = IGEMM_EPI_F32_ATOMIC;
+    la.ksplit = 8;
+    { PROF("l4"); if (c3b_launch_igemm(m, la, s)) return 1; }
+    { PROF("heads"); if (c3b_launch_heads(z4, m->heads, y, n, s)) return 1; }
+    m->launches += 3;
     if (tap) {
-        const int fmt = f32 ? 0 : 1;
         for (int l = 0; l < 3; ++l) {
-            const int64_t inner = (int64_t)hh[l + 1] * ww[l + 1] * chans[l + 1];
-            wt.taps[tapname[l][0]] = {act[l][0], fmt, 0, inner, 0};
-            wt.taps[tapname[l][1]] = {act[l][2], fmt, 0, inner, 0};
+            wt.taps[tapname[l][0]] = {act[l][0], 1, 4, chans[l + 1], 0, geo[l]};
+            wt.taps[tapname[l][1]] = {act[l][2], 1, 4, chans[l + 1], 0, geo[l]};
         }
-        wt.taps["spp"] = {sp, fmt, f32 ? 0 : 2, 3584, (int)bp};
-        wt.taps["l4_pre"] = {z4, 0, 0, 256, 0};
+        wt.taps["spp"] = {sp, 1, 2, 3584, (int)bp, {}};
+        wt.taps["l4_pre"] = {z4, 0, 0, 256, 0, {}};
     }
     return 0;
 }
@@ -869,18 +914,23 @@ extern "C" int c3b_forward(c3b_model *m, const void *x, int x_dtype, int x_on_de
 extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int64_t *count_inout) {
     if (!m || !name || !count_inout) { c3b_set_error("c3b_get_tap: null argument"); return 1; }
     C3B_CUDA(cudaSetDevice(m->device));
+    int wi = -1;
     for (Workspace *w : m->ws) {
+        ++wi;
+        if (m->tap_ws >= 0 && wi != m->tap_ws) continue;
         auto git = g_taps.find(w);
         if (git == g_taps.end()) continue;
         auto it = git->second.taps.find(name);
         if (it == git->second.taps.end()) continue;
         const Tap &t = it->second;
         const int64_t n = m->last_batch;
-        const int64_t per_site = t.inner * (t.layout == 3 ? C3B_T : 1);
+        const int64_t per_site = t.layout == 4 ? t.inner * t.geom.h * t.geom.w : t.inner * (t.layout == 3 ? C3B_T : 1);
         const int64_t count = n * per_site;
         if (*count_inout < count || !host_out) { *count_inout = count; c3b_set_error("c3b_get_tap: buffer too small"); return 1; }
         C3B_CUDA(cudaStreamSynchronize(w->stream));
-        const int64_t src_count = t.layout == 0 ? count : t.inner * (int64_t)t.bp * (t.layout == 3 ? C3B_T : 1);
+        const int64_t src_count = t.layout == 0 ? count
+                                  : t.layout == 4 ? (t.inner / 8) * t.geom.p * 8
+                                                  : t.inner * (int64_t)t.bp * (t.layout == 3 ? C3B_T : 1);
         std::vector<float> tmp((size_t)src_count);
         if (t.fmt == 0) {
             C3B_CUDA(cudaMemcpy(tmp.data(), t.ptr, (size_t)src_count * 4, cudaMemcpyDeviceToHost));
@@ -895,6 +945,14 @@ extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int6
             for (int64_t b = 0; b < n; ++b)
                 for (int64_t k = 0; k < t.inner; ++k)
                     host_out[b * t.inner + k] = tmp[((k >> 3) * t.bp + b) * 8 + (k & 7)];
+        } else if (t.layout == 4) {        // planar padded -> NHWC
+            const PlanarGeom &g = t.geom;
+            for (int64_t b = 0; b < n; ++b)
+                for (int hh = 0; hh < g.h; ++hh)
+                    for (int wv = 0; wv < g.w; ++wv)
+                        for (int64_t k = 0; k < t.inner; ++k)
+                            host_out[((b * g.h + hh) * g.w + wv) * t.inner + k] =
+                                tmp[((k >> 3) * g.p + g.g + b * g.s + (int64_t)(hh + 1) * g.wp + (wv + 1)) * 8 + (k & 7)];
         } else {                           // [inner/8][33*bp][8] -> [n][33][inner]
             const int64_t rows = (int64_t)C3B_T * t.bp;
             for (int64_t b = 0; b < n; ++b)

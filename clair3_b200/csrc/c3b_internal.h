@@ -110,6 +110,8 @@ struct Workspace {
     size_t dev_x_bytes = 0;
     float *dev_y = nullptr;
     size_t dev_y_bytes = 0;
+    int64_t fa_zero_sites = -1;      // geometry for which the planar FA feature maps' borders / guards were last cleared
+    int fa_zero_depth = -1;
     // per-kernel CUDA-event pairs recorded while option "profile" is on (resolved lazily by c3b_get_profile)
     struct ProfRec { const char *name; cudaEvent_t e0, e1; };
     std::vector<ProfRec> prof;
@@ -123,6 +125,7 @@ struct c3b_model {
     int lstm_tile = 0;
     int profile = 0;
     int lstm_mufu16 = 0;               // 1: packed tanh.approx.f16x2 gate activations, 0 (default, faster: the epilogue is issue-bound): fp32 tanh.approx
+    int tap_ws = -1;                   // debug: workspace index c3b_get_tap reads
     int host_async = 0;                // 1: host-buffer forwards stay stream-ordered (pinned buffers; caller synchronises)
     long long *lstm_trace = nullptr;   // device [2][33][4] clock stamps (debug option "lstm_trace")
     std::map<std::string, std::pair<double, int64_t>> prof_total;   // name -> (ms, launches)
@@ -182,6 +185,29 @@ int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, op_t *xs
 int c3b_launch_lstm1_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t batch, int tile, cudaStream_t s);
 int c3b_launch_lstm2_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t batch, int tile, cudaStream_t s);
 
+// Zero-padded channel-group-planar feature map [C/8][p][8]: slot(b,h,w) = g + b*s + (h+1)*wp + (w+1)  (see pconv_tc.cu)
+struct PlanarGeom {
+    int h, w, wp, s, g;        // real dims, padded width (w+2), slots per site ((h+2)*wp), guard slots
+    int64_t t, p;              // data slots (B*s), plane pitch in slots (g + roundup(t,512) + g)
+};
+inline PlanarGeom c3b_planar_geom(int64_t batch, int h, int w) {
+    PlanarGeom g;
+    g.h = h; g.w = w; g.wp = w + 2; g.s = (h + 2) * (w + 2);
+    g.g = (g.wp + 1 + 7) / 8 * 8;
+    g.t = batch * g.s;
+    g.p = g.g + (g.t + 511) / 512 * 512 + g.g;
+    return g;
+}
+struct PconvArgs {
+    const op_t *in;            // planar padded, c channels
+    op_t *out;                 // planar padded, n channels, same geometry
+    const op_t *residual;      // optional, planar padded like out
+    IgemmW w;                  // per-chunk weight images (k = tap*c + ci)
+    PlanarGeom geom;
+    int c, n, relu;
+};
+int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s);
+
 // Generic implicit GEMM on tcgen05:  D[M x N] = A[M x K] * W[N x K]^T with fused epilogues.
 enum IgemmEpilogue {
     IGEMM_EPI_BF16_BIAS_RELU = 0,   // bf16 NHWC store, + bias, optional residual add, ReLU      (convs)
@@ -204,9 +230,13 @@ struct IgemmArgs {
     int relu;
     int epilogue;
     int ksplit;               // >1: split K chunks across blockIdx.y (atomic epilogue only)
+    // conv mode with planar padded tensors on either side (strided stem convs between pconv layers)
+    int in_planar, out_planar;
+    PlanarGeom gin, gout;
 };
 int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s);
 
+
 int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, op_t *out, int64_t n_pix, cudaStream_t s);
-int c3b_launch_spp_tc(const op_t *x, op_t *out, int64_t batch, int h, int w, int c, int bp, cudaStream_t s);
+int c3b_launch_spp_tc(const op_t *x, const PlanarGeom &g, op_t *out, int64_t batch, int c, int bp, cudaStream_t s);
 

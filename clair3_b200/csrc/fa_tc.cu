@@ -1,7 +1,7 @@
 // Small memory-bound kernels around the tensor-core convolution stack of Clair3_F:
 //  * ingest: int8 NHWC read image [B,D,33,C] -> bf16 [B,D,33,Cpad] (Cpad = 8 or 16); the 1/100 normalisation of
 //    clair3/model.py:378 is folded into conv1's weights, and int8 values are exact in bf16.
-//  * spp: 3-level spatial pyramid max pool (clair3/model.py:250-279) on the bf16 NHWC res_block3 output.
+//  * spp: 3-level spatial pyramid max pool (clair3/model.py:250-279) on the planar padded res_block3 output.
 #include "c3b_internal.h"
 
 namespace {
@@ -25,7 +25,8 @@ __global__ void ingest_fa_tc_kernel(const T *__restrict__ x, op_t *__restrict__ 
 }
 
 // grid (B, 14 pyramid cells), block = channels: every thread reduces one window of one channel (coalesced over channels).
-__global__ void spp_tc_kernel(const op_t *__restrict__ x, op_t *__restrict__ out, int h, int w, int c, int bp) {
+__global__ void spp_tc_kernel(const op_t *__restrict__ x, PlanarGeom pg, op_t *__restrict__ out, int c, int bp) {
+    const int h = pg.h, w = pg.w;
     const int64_t b = blockIdx.x;
     const int cell = blockIdx.y;
     int p, idx;
@@ -42,7 +43,8 @@ __global__ void spp_tc_kernel(const op_t *__restrict__ x, op_t *__restrict__ out
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
         float m = 0.f;                       // inputs are post-ReLU: zero padding == floor at 0
         for (int hh = h0; hh < h1; ++hh)
-            for (int wv = w0; wv < w1; ++wv) m = fmaxf(m, op2f(x[((b * h + hh) * w + wv) * c + ch]));
+            for (int wv = w0; wv < w1; ++wv)      // planar padded input [c/8][p][8]
+                m = fmaxf(m, op2f(x[((size_t)(ch >> 3) * pg.p + pg.g + b * pg.s + (hh + 1) * pg.wp + (wv + 1)) * 8 + (ch & 7)]));
         // k-group-planar [3584/8][bp][8]: feature f = cell*c + ch (the reference's flatten order), operand of the L4 GEMM
         const int f = cell * c + ch;
         out[((size_t)(f >> 3) * bp + b) * 8 + (f & 7)] = f2op(m);
@@ -66,9 +68,9 @@ int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, op
     return 0;
 }
 
-int c3b_launch_spp_tc(const op_t *x, op_t *out, int64_t batch, int h, int w, int c, int bp, cudaStream_t s) {
+int c3b_launch_spp_tc(const op_t *x, const PlanarGeom &g, op_t *out, int64_t batch, int c, int bp, cudaStream_t s) {
     if (batch == 0) return 0;
-    spp_tc_kernel<<<dim3((unsigned)batch, 14), 256, 0, s>>>(x, out, h, w, c, bp);
+    spp_tc_kernel<<<dim3((unsigned)batch, 14), 256, 0, s>>>(x, g, out, c, bp);
     C3B_CUDA(cudaGetLastError());
     return 0;
 }

@@ -63,6 +63,8 @@ struct IgemmDev {
     int chunks_per_split;
     int stages;
     int relu;
+    int in_planar, out_planar;   // conv mode: planar padded tensors (pconv_tc.cu) on the input / output side
+    PlanarGeom gin, gout;
     int pg_bp;             // pre-gate epilogue: padded batch (multiple of 128)
     int pg_nbl;            //                    LSTM tile (batch columns per LSTM CTA)
 };
@@ -205,8 +207,15 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                         const int wo = (int)(g % p.wout);
                         const int ho = (int)((g / p.wout) % p.hout);
                         const int64_t b = g / ((int64_t)p.wout * p.hout);
-                        row_base[j] = (const char *)(p.act + b * (int64_t)p.hin * p.win * p.cin);
-                        hw0[j] = ((ho * p.stride - 1) << 16) | ((wo * p.stride - 1) & 0xffff);
+                        if (p.in_planar) {
+                            // slot of padded input pixel (ho*stride + dh, wo*stride + dw) for dh = dw = 0; no bounds checks needed
+                            row_base[j] = (const char *)p.act +
+                                          ((size_t)p.gin.g + b * p.gin.s + (size_t)(ho * p.stride) * p.gin.wp + wo * p.stride) * 16;
+                            hw0[j] = 0;
+                        } else {
+                            row_base[j] = (const char *)(p.act + b * (int64_t)p.hin * p.win * p.cin);
+                            hw0[j] = ((ho * p.stride - 1) << 16) | ((wo * p.stride - 1) & 0xffff);
+                        }
                     }
                 }
             }
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                     const int c8 = gk - (tap << p.cpk_shift);
                     dh = tap / 3;
                     dw = tap - dh * 3;
-                    koff = (size_t)c8 * 16;
+                    koff = p.in_planar ? (size_t)c8 * p.gin.p * 16 : (size_t)c8 * 16;   // planar: channel group = plane
                 }
                 const uint32_t dst0 = stage + (uint32_t)kgl * lbo_act + (uint32_t)rsub * 16u;
 #pragma unroll
@@ -239,6 +248,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                     if (k_ok && hw0[j] != INT_MIN) {
                         if (p.taps == 1) {
                             src = row_base[j] + koff;
+                            nbytes = 16;
+                        } else if (p.in_planar) {
+                            src = row_base[j] + ((size_t)dh * p.gin.wp + dw) * 16 + koff;
                             nbytes = 16;
                         } else {
                             const int hi = (hw0[j] >> 16) + dh;
@@ -328,6 +340,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                 // thread = pixel row, columns = output channels
                 const int64_t pix = (int64_t)at * 128 + r;
                 const bool ok = pix < p.m_valid;
+                size_t pslot = 0;                                  // planar padded output: slot of this pixel
+                if (p.out_planar && ok) {
+                    const int wo = (int)(pix % p.wout);
+                    const int ho = (int)((pix / p.wout) % p.hout);
+                    const int64_t b = pix / ((int64_t)p.wout * p.hout);
+                    pslot = (size_t)p.gout.g + b * p.gout.s + (size_t)(ho + 1) * p.gout.wp + (wo + 1);
+                }
                 op_t *orow = (op_t *)p.out + pix * p.ldo;
                 const op_t *rrow = p.residual ? p.residual + pix * p.ldo : nullptr;
                 for (int j0 = 0; j0 < ncols; j0 += 16) {
@@ -359,8 +378,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                             op2_t h2 = f2op2(op_clamp(a), op_clamp(b));
                             pw[i] = *reinterpret_cast<uint32_t *>(&h2);
                         }
-                        *reinterpret_cast<uint4 *>(orow + j0) = pk[0];
-                        *reinterpret_cast<uint4 *>(orow + j0 + 8) = pk[1];
+                        if (p.out_planar) {
+                            op_t *o0 = (op_t *)p.out + ((size_t)(j0 >> 3) * p.gout.p + pslot) * 8;
+                            *reinterpret_cast<uint4 *>(o0) = pk[0];
+                            *reinterpret_cast<uint4 *>(o0 + (size_t)p.gout.p * 8) = pk[1];
+                        } else {
+                            *reinterpret_cast<uint4 *>(orow + j0) = pk[0];
+                            *reinterpret_cast<uint4 *>(orow + j0 + 8) = pk[1];
+                        }
                     }
                 }
             } else {
@@ -462,6 +487,7 @@ int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s) {
     p.kgroups = a.w.kgroups;
     p.nchunks = a.w.nchunks;
     p.relu = a.relu;
+    p.in_planar = a.in_planar; p.out_planar = a.out_planar; p.gin = a.gin; p.gout = a.gout;
     p.act_rows = 128;
     p.wb = 1;
     const bool swap = (a.epilogue != IGEMM_EPI_BF16_BIAS_RELU);

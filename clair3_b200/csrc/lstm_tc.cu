@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
         ptx::mbar_init(&w_bar, 1);
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&acc_bar[s], 1);
-            ptx::mbar_init(&ready_bar[s], kWgThreads);
+            ptx::mbar_init(&ready_bar[s], 1);
         }
         ptx::fence_barrier_init();
     }
@@ -238,7 +238,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
         }
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&ready_bar[sub]);                                  // S1: this thread's operands / TMEM reads are done
+        // S1: every thread of the warpgroup has written its h_t / x_t and finished its TMEM reads.  The barrier (not just
+        // per-thread mbarrier arrivals) matters: the copy-out below reads 16-byte chunks of h written by OTHER threads.
+        ptx::named_bar_sync(bar_id, kWgThreads);
+        if (wt == 0) ptx::mbar_arrive(&ready_bar[sub]);
         const bool tr = p.trace != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
         if (tr) p.trace[step * 4 + 0] = clock64();
         if (tr) p.trace[step * 4 + 1] = clock64();

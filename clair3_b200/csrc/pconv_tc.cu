@@ -1,0 +1,281 @@
+// Stride-1 3x3 convolution (the six residual-block convs of Clair3_F, 83 % of its FLOPs; clair3/model.py:200-235) as an
+// implicit GEMM over SHIFTED VIEWS of a shared-memory-resident, zero-padded, channel-group-planar feature map.
+//
+// Activation layout ("planar padded"): [C/8][P][8] fp16.  A site's H x W feature map is stored as its (H+2) x (W+2)
+// zero-bordered raster, sites back to back: slot g = b*S + (h+1)*Wp + (w+1), S = (H+2)*Wp, Wp = W+2, at plane offset G + g
+// (G guard slots of zeros at both ends).  With that layout
+//   * the input of a macro-tile (MT x 128 consecutive output slots plus a (Wp+1)-slot halo on each side) is C/8 CONTIGUOUS
+//     runs of memory: it lands in shared memory with C/8 cp.async.bulk (TMA engine, async proxy; no per-thread gathers,
+//     no im2col expansion, no proxy fences) in exactly the SWIZZLE_NONE K-major UMMA layout [k-group][slot][8];
+//   * the A operand of tap (dh,dw) is the SAME image viewed (dh-1)*Wp + (dw-1) slots later: only the descriptor's start
+//     address changes, so every input byte is fetched once per macro-tile and used by all nine taps;
+//   * border slots are computed like any other row and overwritten with zeros in the epilogue, so the output is again a
+//     valid planar padded tensor for the next convolution (and the residual add reads the same slot of its own input).
+// Weights: the host-packed per-chunk images of igemm_tc.cu ([tap*C/64 + kc][8 k-groups][N][8]); resident when they fit
+// (res_block1: 72 KB), otherwise streamed through a ring with each piece applied to MT accumulators.
+//
+// Roles (288 threads): warp 0 lane 0 issues all bulk copies, warp 8 issues tcgen05.mma (one elected lane), warps 4-7 run
+// the epilogue on their TMEM lane quadrant (bias + residual + ReLU + border mask, 16-byte coalesced planar stores).
+#include "c3b_internal.h"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int kThreads = 288;
+constexpr int kMaxWStages = 8;
+
+struct PconvDev {
+    const op_t *in;
+    const op_t *w_img;
+    const float *bias;
+    const op_t *residual;
+    op_t *out;
+    int C, N;
+    int H, W, Wp, S, G;
+    long long T, P;
+    int MT, n_macro, n_in;
+    int nchunks, cpt;
+    int w_resident, w_stages, img_bufs, acc_stages;
+    int relu;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
+    __shared__ uint64_t img_full[2], img_empty[2], tmem_full[2], tmem_empty[2], w_res_bar;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float bias_s[256];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const uint32_t w_bytes = (uint32_t)p.N * 128u;
+    const uint32_t img_bytes = (uint32_t)(p.C / 8) * (uint32_t)p.n_in * 16u;
+    const uint32_t lbo_img = (uint32_t)p.n_in * 16u;
+    const uint32_t lbo_w = (uint32_t)p.N * 16u;
+    const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint32_t w_region = p.w_resident ? (uint32_t)p.nchunks * w_bytes : (uint32_t)p.w_stages * w_bytes;
+    const uint32_t img_base = smem_base + w_region;
+
+    if (tid == 0) {
+        for (int s = 0; s < kMaxWStages; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&img_full[s], 1);
+            ptx::mbar_init(&img_empty[s], 1);
+            ptx::mbar_init(&tmem_full[s], 1);
+            ptx::mbar_init(&tmem_empty[s], 128);
+        }
+        ptx::mbar_init(&w_res_bar, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 8) ptx::tmem_alloc<512>(&tmem_base_smem);
+    for (int i = tid; i < p.N; i += kThreads) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================================================== loader (one thread): image chunks + weight pieces
+        if (lane == 0) {
+            if (p.w_resident) {
+                ptx::mbar_arrive_expect_tx(&w_res_bar, (uint32_t)p.nchunks * w_bytes);
+                for (int c = 0; c < p.nchunks; ++c)
+                    ptx::bulk_g2s(smem_base + (uint32_t)c * w_bytes, (const char *)p.w_img + (size_t)c * w_bytes, w_bytes, &w_res_bar);
+            }
+            auto load_img = [&](int macro, int li) {
+                const int buf = li % p.img_bufs;
+                const uint32_t ph = (uint32_t)(li / p.img_bufs) & 1u;
+                ptx::mbar_wait(&img_empty[buf], ph ^ 1u);
+                ptx::mbar_arrive_expect_tx(&img_full[buf], img_bytes);
+                const long long slot0 = (long long)p.G + 128LL * p.MT * macro - (p.Wp + 1);
+                const uint32_t dst = img_base + (uint32_t)buf * img_bytes;
+                for (int kg = 0; kg < p.C / 8; ++kg)
+                    ptx::bulk_g2s(dst + (uint32_t)kg * lbo_img, (const char *)p.in + ((size_t)kg * p.P + slot0) * 16, lbo_img,
+                                  &img_full[buf]);
+            };
+            int li = 0, wit = 0;
+            if ((int)blockIdx.x < p.n_macro) load_img(blockIdx.x, 0);
+            for (int macro = blockIdx.x; macro < p.n_macro; macro += gridDim.x, ++li) {
+                const int next = macro + gridDim.x;
+                if (p.img_bufs == 2 && next < p.n_macro) load_img(next, li + 1);      // prefetch while this tile computes
+                if (!p.w_resident) {
+                    for (int c = 0; c < p.nchunks; ++c, ++wit) {
+                        const int s = wit % p.w_stages;
+                        const uint32_t ph = (uint32_t)(wit / p.w_stages) & 1u;
+                        ptx::mbar_wait(&w_empty[s], ph ^ 1u);
+                        ptx::mbar_arrive_expect_tx(&w_full[s], w_bytes);
+                        ptx::bulk_g2s(smem_base + (uint32_t)s * w_bytes, (const char *)p.w_img + (size_t)c * w_bytes, w_bytes, &w_full[s]);
+                    }
+                }
+                if (p.img_bufs == 1 && next < p.n_macro) load_img(next, li + 1);      // single buffer: after this tile's MMAs
+            }
+        }
+    } else if (warp == 8) {
+        // ===================================================== MMA issuer
+        const uint32_t idesc = ptx::umma_idesc_f16(128, (uint32_t)p.N);
+        int li = 0, wit = 0;
+        if (p.w_resident) ptx::mbar_wait(&w_res_bar, 0);
+        for (int macro = blockIdx.x; macro < p.n_macro; macro += gridDim.x, ++li) {
+            const int buf = li % p.img_bufs;
+            const uint32_t iph = (uint32_t)(li / p.img_bufs) & 1u;
+            const int acc = li % p.acc_stages;
+            const uint32_t aph = (uint32_t)(li / p.acc_stages) & 1u;
+            ptx::mbar_wait(&img_full[buf], iph);
+            ptx::mbar_wait(&tmem_empty[acc], aph ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t img = img_base + (uint32_t)buf * img_bytes;
+            const uint32_t d0 = tmem_base + (uint32_t)(acc * p.MT * p.N);
+            for (int c = 0; c < p.nchunks; ++c) {
+                uint32_t w_addr = smem_base + (uint32_t)c * w_bytes;
+                int s = 0;
+                if (!p.w_resident) {
+                    s = wit % p.w_stages;
+                    ptx::mbar_wait(&w_full[s], (uint32_t)(wit / p.w_stages) & 1u);
+                    ptx::tc_fence_after();
+                    w_addr = smem_base + (uint32_t)s * w_bytes;
+                    ++wit;
+                }
+                if (ptx::elect_one()) {
+                    const int tap = c / p.cpt, kc = c - tap * p.cpt;
+                    const int dh = tap / 3, dw = tap - dh * 3;
+                    const int shift = (dh - 1) * p.Wp + (dw - 1) + (p.Wp + 1);      // >= 0: slot offset inside the chunk
+#pragma unroll 1
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t b_desc = ptx::umma_desc_nosw(w_addr + (uint32_t)ks * 2u * lbo_w, lbo_w, 128u);
+                        const uint32_t a0 = img + (uint32_t)(kc * 8 + ks * 2) * lbo_img + (uint32_t)shift * 16u;
+                        const uint32_t accum = (c > 0 || ks > 0) ? 1u : 0u;
+                        for (int ti = 0; ti < p.MT; ++ti) {
+                            const uint64_t a_desc = ptx::umma_desc_nosw(a0 + (uint32_t)ti * 2048u, lbo_img, 128u);
+                            ptx::umma_f16(d0 + (uint32_t)(ti * p.N), a_desc, b_desc, idesc, accum);
+                        }
+                    }
+                    if (!p.w_resident) ptx::umma_commit(&w_empty[s]);
+                    if (c + 1 == p.nchunks) {
+                        ptx::umma_commit(&tmem_full[acc]);
+                        ptx::umma_commit(&img_empty[buf]);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================== epilogue warps 4..7
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        int li = 0;
+        for (int macro = blockIdx.x; macro < p.n_macro; macro += gridDim.x, ++li) {
+            const int acc = li % p.acc_stages;
+            const uint32_t aph = (uint32_t)(li / p.acc_stages) & 1u;
+            ptx::mbar_wait(&tmem_full[acc], aph);
+            ptx::tc_fence_after();
+            for (int ti = 0; ti < p.MT; ++ti) {
+                const long long g = (128LL * p.MT) * macro + 128LL * ti + r;       // output slot
+                const bool in_data = g < p.T;
+                bool real = false;
+                if (in_data) {
+                    const int l = (int)(g % p.S);
+                    const int hh = l / p.Wp, ww = l - hh * p.Wp;
+                    real = hh >= 1 && hh <= p.H && ww >= 1 && ww <= p.W;
+                }
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.MT * p.N + ti * p.N);
+                for (int j0 = 0; j0 < p.N; j0 += 16) {
+                    float v[16];
+                    ptx::tmem_ld16(taddr + (uint32_t)j0, v);
+                    ptx::tmem_ld_wait();
+                    if (in_data) {
+                        const size_t o0 = ((size_t)(j0 >> 3) * p.P + p.G + g) * 8;
+                        const size_t o1 = o0 + (size_t)p.P * 8;
+                        uint4 pk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+                        if (real) {
+                            uint4 res[2];
+                            if (p.residual) {
+                                res[0] = *reinterpret_cast<const uint4 *>(p.residual + o0);
+                                res[1] = *reinterpret_cast<const uint4 *>(p.residual + o1);
+                            }
+                            uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
+                            const op2_t *rp = reinterpret_cast<const op2_t *>(res);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float a = v[2 * i] + bias_s[j0 + 2 * i];
+                                float b = v[2 * i + 1] + bias_s[j0 + 2 * i + 1];
+                                if (p.residual) {
+                                    const float2 rf = op22f2(rp[i]);
+                                    a += rf.x;
+                                    b += rf.y;
+                                }
+                                if (p.relu) {
+                                    a = fmaxf(a, 0.f);
+                                    b = fmaxf(b, 0.f);
+                                }
+                                op2_t h2 = f2op2(op_clamp(a), op_clamp(b));
+                                pw[i] = *reinterpret_cast<uint32_t *>(&h2);
+                            }
+                        }
+                        *reinterpret_cast<uint4 *>(p.out + o0) = pk[0];
+                        *reinterpret_cast<uint4 *>(p.out + o1) = pk[1];
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace
+
+int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
+    const PlanarGeom &g = a.geom;
+    if (a.c % 64 || a.n % 16 || a.n > 256 || a.n < 16) { c3b_set_error("pconv: unsupported channels %d -> %d", a.c, a.n); return 1; }
+    PconvDev p = {};
+    p.in = a.in; p.w_img = a.w.w_img; p.bias = a.w.bias; p.residual = a.residual; p.out = a.out;
+    p.C = a.c; p.N = a.n;
+    p.H = g.h; p.W = g.w; p.Wp = g.wp; p.S = g.s; p.G = g.g; p.T = g.t; p.P = g.p;
+    p.relu = a.relu;
+    p.nchunks = 9 * a.c / 64;
+    p.cpt = a.c / 64;
+    if (p.nchunks != a.w.nchunks) { c3b_set_error("pconv: weight image has %d chunks, expected %d", a.w.nchunks, p.nchunks); return 1; }
+    const size_t budget = 220 * 1024;
+    const size_t w_bytes = (size_t)a.n * 128;
+    // accumulators: MT tiles x N columns per stage
+    int mt = a.n <= 64 ? 4 : 2;
+    p.acc_stages = (mt * a.n * 2 <= 512) ? 2 : 1;
+    for (;; --mt) {
+        if (mt < 1) { c3b_set_error("pconv: feature map does not fit shared memory"); return 1; }
+        p.MT = mt;
+        p.n_in = 128 * mt + 2 * (g.wp + 1);
+        const size_t img_bytes = (size_t)(a.c / 8) * p.n_in * 16;
+        p.acc_stages = (mt * a.n * 2 <= 512) ? 2 : 1;
+        const size_t w_all = (size_t)p.nchunks * w_bytes;
+        if (w_all + 2 * img_bytes <= budget) { p.w_resident = 1; p.img_bufs = 2; p.w_stages = 0; break; }
+        if (2 * img_bytes + 2 * w_bytes <= budget) {
+            p.w_resident = 0; p.img_bufs = 2;
+            p.w_stages = (int)((budget - 2 * img_bytes) / w_bytes);
+            break;
+        }
+        if (img_bytes + 2 * w_bytes <= budget) {
+            p.w_resident = 0; p.img_bufs = 1;
+            p.w_stages = (int)((budget - img_bytes) / w_bytes);
+            break;
+        }
+    }
+    if (p.w_stages > kMaxWStages) p.w_stages = kMaxWStages;
+    const long long per_macro = 128LL * p.MT;
+    p.n_macro = (int)((g.t + per_macro - 1) / per_macro);
+    if ((long long)p.n_macro * per_macro + g.g > g.p - g.g + per_macro) { /* plane pitch covers the rounded-up slot range by construction */ }
+    const size_t img_bytes = (size_t)(a.c / 8) * p.n_in * 16;
+    const size_t smem = (p.w_resident ? (size_t)p.nchunks * w_bytes : (size_t)p.w_stages * w_bytes) + p.img_bufs * img_bytes + 256;
+    C3B_CUDA(cudaFuncSetAttribute(pconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    const int grid = p.n_macro < m->sm_count ? p.n_macro : m->sm_count;
+    const_cast<c3b_model *>(m)->launches++;
+    pconv_kernel<<<grid, kThreads, smem, s>>>(p);
+    C3B_CUDA(cudaGetLastError());
+    return 0;
+}

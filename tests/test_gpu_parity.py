@@ -174,6 +174,28 @@ def test_forward_async_pinned_host_pipeline():
         assert np.abs(y.numpy() - ref).max() < 1e-5
 
 
+@pytest.mark.parametrize("tile", [16, 64])
+def test_concurrent_streams_are_consistent(tile):
+    """Forwards of one model in flight on 8 CUDA streams (each with its own workspace) must equal the single-stream
+    result.  Regression test for a race found this way: an epilogue thread copied h_t chunks written by other threads
+    before they had been written (timing-dependent, only visible under memory contention)."""
+    from clair3_b200 import synth
+    sd = synth.pileup_state_dict(False, seed=0)
+    meta = dict(kind="pileup", add_indel_length=False)
+    m = _model(meta, sd, TC, lstm_tile=tile)
+    xd = [torch.from_numpy(synth.pileup_inputs(1024, seed=100 + i)).cuda() for i in range(8)]
+    ref = [m(x).cpu().numpy() for x in xd]
+    streams = [torch.cuda.Stream() for _ in range(8)]
+    for rep in range(4):
+        outs = [None] * 8
+        for i in range(8):
+            with torch.cuda.stream(streams[i]):
+                outs[i] = m(xd[i])
+        torch.cuda.synchronize()
+        for i in range(8):
+            assert np.abs(outs[i].cpu().numpy() - ref[i]).max() < 1e-4
+
+
 def test_input_dtypes_agree():
     z, meta, sd, x = golden_case("p24_int8")
     m = _model(meta, sd, TC)

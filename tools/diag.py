@@ -94,6 +94,53 @@ def run_igemm():
             print("    out[0,:8]", np.round(out[0, :8], 3), " ref[0,:8]", np.round(ref[0, :8], 3))
 
 
+def run_stress(opts):
+    """Concurrent-stream consistency: every pipelined forward must equal the single-stream result."""
+    from clair3_b200 import synth
+    from clair3_b200.model import Clair3_P
+    sd = synth.pileup_state_dict(False, seed=0)
+    xs = [synth.pileup_inputs(1024, seed=100 + i) for i in range(8)]
+    m = Clair3_P(add_indel_length=False, predict=True, input_channels=18)
+    for k, v in opts.items():
+        m.set_option(k, v)
+    m.to(torch.device("cuda"))
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    xd = [torch.from_numpy(x).cuda() for x in xs]
+    ref = [m(x).cpu().numpy() for x in xd]
+    again = [m(x).cpu().numpy() for x in xd]
+    print("single-stream repeatability max diff", max(float(np.abs(a - b).max()) for a, b in zip(ref, again)))
+    reftaps = {}
+    m.set_option("tap_ws", 0)
+    for j in range(8):
+        m(xd[j])
+        reftaps[j] = {t: m.tap(t).copy() for t in ("lstm1", "lstm2", "l4_pre")} if opts.get("precision", 0) == 0 or True else {}
+    streams = [torch.cuda.Stream() for _ in range(8)]
+    worst = 0.0
+    for rep in range(4):
+        outs = [None] * 8
+        for i in range(8):
+            with torch.cuda.stream(streams[i]):
+                outs[i] = m(xd[i])
+        torch.cuda.synchronize()
+        for i in range(8):
+            d = np.abs(outs[i].cpu().numpy() - ref[i])
+            worst = max(worst, float(d.max()))
+            if d.max() > 1e-4:
+                rows = np.where(d.max(1) > 1e-4)[0]
+                msg = f"rep {rep} stream {i}: out max diff {d.max():.3e} in {len(rows)} rows {rows[:10]}"
+                m.set_option("tap_ws", i + 1)          # workspace 0 belongs to the default stream
+                for t in ("lstm1", "lstm2", "l4_pre"):
+                    try:
+                        tv = m.tap(t)
+                        dd = np.abs(tv - reftaps[i][t]).reshape(1024, -1).max(1)
+                        bad = np.where(dd > 1e-3)[0]
+                        msg += f" | {t}: {len(bad)} bad rows {bad[:6]}"
+                    except Exception as e:  # noqa: BLE001
+                        msg += f" | {t}: {e}"
+                print(msg, flush=True)
+    print("multi-stream worst diff", worst, "opts", opts, flush=True)
+
+
 def run_probe():
     from clair3_b200._ffi import check, ffi, lib
     r = np.random.default_rng(0)
@@ -157,6 +204,8 @@ if __name__ == "__main__":
     cases = cases2 or (GOLDEN_PILEUP + GOLDEN_FA)
     if mode == "igemm":
         run_igemm()
+    elif mode == "stress":
+        run_stress(opts)
     elif mode == "probe":
         run_probe()
     elif mode == "trace":
