@@ -247,6 +247,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    args.warmup = max(args.warmup, args.streams)      # every stream's workspace exists before the timed region
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -172,6 +172,7 @@ struct Tap {
     int64_t inner;
     int bp;
     PlanarGeom geom;
+    int nsplit = 1;  // layout 5: [nsplit][bp][inner] split-K partial sums -> summed [B][inner]
 };
 
 }  // namespace
@@ -536,7 +537,7 @@ static size_t ws_bytes_needed(const c3b_model *m, int64_t sites, int depth) {
             al((size_t)C3B_T * bp * 1280 * 2);
             al((size_t)bp * C3B_T * 320 * 2);
         }
-        al((size_t)bp * 128 * 4);
+        al((size_t)16 * bp * 128 * 4);
     } else {
         const int h1 = conv_out(depth), w1 = conv_out(33), h2 = conv_out(h1), w2 = conv_out(w1), h3 = conv_out(h2), w3 = conv_out(w2);
         if (m->precision == C3B_PREC_FP32) {
@@ -555,7 +556,7 @@ static size_t ws_bytes_needed(const c3b_model *m, int64_t sites, int depth) {
             }
             al((size_t)bp * 3584 * 2);
         }
-        al((size_t)bp * 256 * 4);
+        al((size_t)16 * bp * 256 * 4);
     }
     return total + 4096;
 }
@@ -649,7 +650,7 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
         if (c3b_launch_lstm_f32(xf, m->lstm_f32[0][0], m->lstm_f32[0][1], l1, n, m->channels, C3B_H1, s)) return 1;
         if (c3b_launch_lstm_f32(l1, m->lstm_f32[1][0], m->lstm_f32[1][1], l2, n, 256, C3B_H2, s)) return 1;
         if (c3b_launch_dense_f32(l2, m->l4_f32_t, z4, n, m->l4_in, 128, s)) return 1;
-        if (c3b_launch_heads(z4, m->heads, y, n, s)) return 1;
+        if (c3b_launch_heads(z4, 1, 0, m->heads, y, n, s)) return 1;
         m->launches += 5;
         if (tap) {
             wt.taps["lstm1"] = {l1, 0, 0, (int64_t)C3B_T * 256, 0, {}};
@@ -663,7 +664,7 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
     b.h1 = cv.take<op_t>((size_t)C3B_T * bp * 256 * 2);
     b.pg = cv.take<__half>((size_t)C3B_T * bp * 1280 * 2);
     b.h2 = cv.take<op_t>((size_t)bp * C3B_T * 320 * 2);
-    b.z4 = cv.take<float>((size_t)bp * 128 * 4);
+    b.z4 = cv.take<float>((size_t)16 * bp * 128 * 4);
     // sub-tile width (sites per MMA column block); a CTA ping-pongs two sub-tiles -> 2 directions x bp / (2*tile) CTAs
     int tile1 = m->lstm_tile, tile2 = m->lstm_tile;
     if (tile1 == 0) {
@@ -688,7 +689,6 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
     pa.epilogue = IGEMM_EPI_F16_BIAS;
     { PROF("proj2"); if (c3b_launch_igemm(m, pa, s)) return 1; }
     { PROF("lstm2"); if (c3b_launch_lstm2_tc(m, b, n, tile2, s)) return 1; }
-    C3B_CUDA(cudaMemsetAsync(b.z4, 0, (size_t)bp * 128 * 4, s));
     IgemmArgs la = {};
     la.a = b.h2;
     la.m = n;
@@ -701,13 +701,15 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
     la.ldo = 128;
     la.epilogue = IGEMM_EPI_F32_ATOMIC;
     la.ksplit = 11;
+    la.split_stride = (int64_t)bp * 128;
+    const int ns_p = c3b_effective_ksplit(m->l4_tc.nchunks, la.ksplit);
     { PROF("l4"); if (c3b_launch_igemm(m, la, s)) return 1; }
-    { PROF("heads"); if (c3b_launch_heads(b.z4, m->heads, y, n, s)) return 1; }
+    { PROF("heads"); if (c3b_launch_heads(b.z4, ns_p, la.split_stride, m->heads, y, n, s)) return 1; }
     m->launches += 1;
     if (tap) {
         wt.taps["lstm1"] = {b.h1, 1, 3, 256, (int)bp, {}};
         wt.taps["lstm2"] = {b.h2, 1, 2, (int64_t)C3B_T * 320, (int)bp, {}};
-        wt.taps["l4_pre"] = {b.z4, 0, 0, 128, 0, {}};
+        wt.taps["l4_pre"] = {b.z4, 0, 5, 128, (int)bp, {}, ns_p};
     }
     return 0;
 }
@@ -741,7 +743,7 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
         }
         if (c3b_launch_spp_f32(cur, sp, n, hh[3], ww[3], 256, s)) return 1;
         if (c3b_launch_dense_f32(sp, m->l4_f32_t, z4, n, 3584, 256, s)) return 1;
-        if (c3b_launch_heads(z4, m->heads, y, n, s)) return 1;
+        if (c3b_launch_heads(z4, 1, 0, m->heads, y, n, s)) return 1;
         m->launches += 13;
         if (tap) {
             for (int l = 0; l < 3; ++l) {
@@ -767,7 +769,7 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
     }
     const size_t planar_end = cv.off;
     op_t *sp = cv.take<op_t>((size_t)bp * 3584 * 2);
-    float *z4 = cv.take<float>((size_t)bp * 256 * 4);
+    float *z4 = cv.take<float>((size_t)16 * bp * 256 * 4);
     // borders / guards of the planar maps must be zero; convs rewrite borders with zeros and never touch guards, so one
     // clear per (workspace, geometry) is enough
     if (w->fa_zero_sites != n || w->fa_zero_depth != depth) {
@@ -804,13 +806,14 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
         PconvArgs pa = {};
         pa.geom = geo[l];
         pa.c = co; pa.n = co; pa.relu = 1;
+        pa.trace = (m->lstm_trace && l == 0) ? m->lstm_trace : nullptr;   // debug: stamps of res_block1.conv1
         pa.in = a0; pa.out = a1; pa.residual = nullptr; pa.w = m->conv_tc[3 * l + 1];
         { PROF(cn[3 * l + 1]); if (c3b_launch_pconv(m, pa, s)) return 1; }
+        pa.trace = nullptr;
         pa.in = a1; pa.out = a2; pa.residual = a0; pa.w = m->conv_tc[3 * l + 2];
         { PROF(cn[3 * l + 2]); if (c3b_launch_pconv(m, pa, s)) return 1; }
     }
     { PROF("spp"); if (c3b_launch_spp_tc(act[2][2], geo[2], sp, n, 256, (int)bp, s)) return 1; }
-    C3B_CUDA(cudaMemsetAsync(z4, 0, (size_t)bp * 256 * 4, s));
     IgemmArgs la = {};
     la.a = sp;
     la.m = n;
@@ -823,8 +826,10 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
     la.ldo = 256;
     la.epilogue = IGEMM_EPI_F32_ATOMIC;
     la.ksplit = 8;
+    la.split_stride = (int64_t)bp * 256;
+    const int ns_f = c3b_effective_ksplit(m->l4_tc.nchunks, la.ksplit);
     { PROF("l4"); if (c3b_launch_igemm(m, la, s)) return 1; }
-    { PROF("heads"); if (c3b_launch_heads(z4, m->heads, y, n, s)) return 1; }
+    { PROF("heads"); if (c3b_launch_heads(z4, ns_f, la.split_stride, m->heads, y, n, s)) return 1; }
     m->launches += 3;
     if (tap) {
         for (int l = 0; l < 3; ++l) {
@@ -832,7 +837,7 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
             wt.taps[tapname[l][1]] = {act[l][2], 1, 4, chans[l + 1], 0, geo[l]};
         }
         wt.taps["spp"] = {sp, 1, 2, 3584, (int)bp, {}};
-        wt.taps["l4_pre"] = {z4, 0, 0, 256, 0, {}};
+        wt.taps["l4_pre"] = {z4, 0, 5, 256, (int)bp, {}, ns_f};
     }
     return 0;
 }
@@ -929,6 +934,7 @@ extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int6
         if (*count_inout < count || !host_out) { *count_inout = count; c3b_set_error("c3b_get_tap: buffer too small"); return 1; }
         C3B_CUDA(cudaStreamSynchronize(w->stream));
         const int64_t src_count = t.layout == 0 ? count
+                                  : t.layout == 5 ? (int64_t)t.nsplit * t.bp * t.inner
                                   : t.layout == 4 ? (t.inner / 8) * t.geom.p * 8
                                                   : t.inner * (int64_t)t.bp * (t.layout == 3 ? C3B_T : 1);
         std::vector<float> tmp((size_t)src_count);
@@ -941,6 +947,12 @@ extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int6
         }
         if (t.layout == 0) {
             memcpy(host_out, tmp.data(), (size_t)count * 4);
+        } else if (t.layout == 5) {        // sum the split-K partials
+            for (int64_t i = 0; i < count; ++i) {
+                float acc = 0.f;
+                for (int sp = 0; sp < t.nsplit; ++sp) acc += tmp[(size_t)sp * t.bp * t.inner + i];
+                host_out[i] = acc;
+            }
         } else if (t.layout == 2) {        // [inner/8][bp][8] -> [n][inner]
             for (int64_t b = 0; b < n; ++b)
                 for (int64_t k = 0; k < t.inner; ++k)
@@ -997,7 +1009,8 @@ extern "C" int c3b_debug_gemm(c3b_model *m, int swapped, int64_t M, int N, int K
     C3B_CUDA(cudaMalloc(&da, ab.size() * 2));
     C3B_CUDA(cudaMalloc(&dw, img.size() * 2));
     C3B_CUDA(cudaMalloc(&db, (size_t)N * 4));
-    const size_t out_bytes = (size_t)M * N * (swapped ? 4 : 2);
+    const int nsp = swapped ? c3b_effective_ksplit((K / 8 + 7) / 8, ksplit > 0 ? ksplit : 1) : 1;
+    const size_t out_bytes = swapped ? (size_t)nsp * M * N * 4 : (size_t)M * N * 2;
     C3B_CUDA(cudaMalloc(&dout, out_bytes));
     C3B_CUDA(cudaMemcpy(da, ab.data(), ab.size() * 2, cudaMemcpyHostToDevice));
     C3B_CUDA(cudaMemcpy(dw, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
@@ -1021,6 +1034,7 @@ extern "C" int c3b_debug_gemm(c3b_model *m, int swapped, int64_t M, int N, int K
     ga.relu = relu;
     ga.epilogue = swapped ? IGEMM_EPI_F32_ATOMIC : IGEMM_EPI_BF16_BIAS_RELU;
     ga.ksplit = ksplit;
+    ga.split_stride = (int64_t)M * N;
     int rc = c3b_launch_igemm(m, ga, 0);
     if (!rc) {
         cudaError_t e = cudaDeviceSynchronize();
@@ -1028,7 +1042,13 @@ extern "C" int c3b_debug_gemm(c3b_model *m, int swapped, int64_t M, int N, int K
     }
     if (!rc) {
         if (swapped) {
-            C3B_CUDA(cudaMemcpy(out, dout, out_bytes, cudaMemcpyDeviceToHost));
+            std::vector<float> part((size_t)nsp * M * N);
+            C3B_CUDA(cudaMemcpy(part.data(), dout, out_bytes, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < (size_t)M * N; ++i) {
+                float acc = 0.f;
+                for (int sp = 0; sp < nsp; ++sp) acc += part[(size_t)sp * M * N + i];
+                out[i] = acc;
+            }
         } else {
             std::vector<uint16_t> raw((size_t)M * N);
             C3B_CUDA(cudaMemcpy(raw.data(), dout, out_bytes, cudaMemcpyDeviceToHost));

@@ -27,6 +27,12 @@ __device__ __forceinline__ float op_clamp(float x) { return fminf(fmaxf(x, -6550
 __device__ __forceinline__ op_t f2op(float x) { return __float2half_rn(x); }
 __device__ __forceinline__ op2_t f2op2(float a, float b) { return __floats2half2_rn(a, b); }
 __device__ __forceinline__ float2 op22f2(op2_t v) { return __half22float2(v); }
+// two floats -> packed fp16 pair in ONE instruction, saturating at +-65504 instead of overflowing to inf
+__device__ __forceinline__ uint32_t f2op2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ float op2f(op_t v) { return __half2float(v); }
 #endif
 uint16_t c3b_f2op(float f);     // host: fp32 -> fp16 bits, round-to-nearest-even, saturating
@@ -163,7 +169,12 @@ struct c3b_model {
 // ---- kernels_common.cu ----
 int c3b_launch_ingest_pileup_f32(const void *x, int dtype, float *out, int64_t n_elems, cudaStream_t s);
 int c3b_launch_ingest_fa_f32(const void *x, int dtype, float *out, int64_t n_elems, cudaStream_t s);
-int c3b_launch_heads(const float *z4, const HeadsParams &hp, float *out, int64_t batch, cudaStream_t s);
+// z4: nsplit partial sums [nsplit][split_stride] of the L4 pre-activation (no bias); the kernel adds them
+int c3b_launch_heads(const float *z4, int nsplit, int64_t split_stride, const HeadsParams &hp, float *out, int64_t batch, cudaStream_t s);
+inline int c3b_effective_ksplit(int nchunks, int ksplit) {
+    const int cps = (nchunks + ksplit - 1) / ksplit;
+    return (nchunks + cps - 1) / cps;
+}
 
 // ---- kernels_fp32.cu ----
 int c3b_launch_lstm_f32(const float *x, const LstmF32 &fwd, const LstmF32 &bwd, float *out, int64_t batch, int in_dim,
@@ -205,6 +216,7 @@ struct PconvArgs {
     IgemmW w;                  // per-chunk weight images (k = tap*c + ci)
     PlanarGeom geom;
     int c, n, relu;
+    long long *trace;          // debug: clock stamps of CTA 0 (see pconv_tc.cu)
 };
 int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s);
 
@@ -212,7 +224,7 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s);
 enum IgemmEpilogue {
     IGEMM_EPI_BF16_BIAS_RELU = 0,   // bf16 NHWC store, + bias, optional residual add, ReLU      (convs)
     IGEMM_EPI_F16_BIAS = 1,         // fp16 row-major store, + bias                              (LSTM2 pre-gates)
-    IGEMM_EPI_F32_ATOMIC = 2,       // fp32 atomicAdd into [M][N] (split-K)                      (L4)
+    IGEMM_EPI_F32_ATOMIC = 2,       // fp32 split-K partial sums partial[ks][M][N] (plain stores; name kept)   (L4)
 };
 struct IgemmArgs {
     const op_t *a;   // activations
@@ -229,7 +241,8 @@ struct IgemmArgs {
     const op_t *residual;   // optional (same layout as out, bf16)
     int relu;
     int epilogue;
-    int ksplit;               // >1: split K chunks across blockIdx.y (atomic epilogue only)
+    int ksplit;               // >1: split the K chunks over `ksplit` CTAs per tile (partial-sum epilogue only)
+    int64_t split_stride;     // elements between the ks slices of the partial-sum output
     // conv mode with planar padded tensors on either side (strided stem convs between pconv layers)
     int in_planar, out_planar;
     PlanarGeom gin, gout;

@@ -24,30 +24,46 @@ __global__ void ingest_fa_tc_kernel(const T *__restrict__ x, op_t *__restrict__ 
     }
 }
 
-// grid (B, 14 pyramid cells), block = channels: every thread reduces one window of one channel (coalesced over channels).
+// One thread = one (pyramid cell, channel group of 8): 16-byte loads from the planar padded map, 8 running maxima,
+// one 16-byte store into the k-group-planar L4 operand.  grid = B, block = 14 * C/8 threads (448 for C = 256).
 __global__ void spp_tc_kernel(const op_t *__restrict__ x, PlanarGeom pg, op_t *__restrict__ out, int c, int bp) {
     const int h = pg.h, w = pg.w;
     const int64_t b = blockIdx.x;
-    const int cell = blockIdx.y;
-    int p, idx;
-    if (cell < 9) { p = 3; idx = cell; }
-    else if (cell < 13) { p = 2; idx = cell - 9; }
-    else { p = 1; idx = 0; }
-    const int wh = (h + p - 1) / p, ww = (w + p - 1) / p;
-    const int oh = (h + wh - 1) / wh, ow = (w + ww - 1) / ww;
-    const int ph = max((oh - 1) * wh + wh - h, 0), pw = max((ow - 1) * ww + ww - w, 0);
-    const int pt = ph / 2, pl = pw / 2;
-    const int oi = idx / ow, oj = idx - oi * ow;
-    const int h0 = max(oi * wh - pt, 0), h1 = min(oi * wh - pt + wh, h);
-    const int w0 = max(oj * ww - pl, 0), w1 = min(oj * ww - pl + ww, w);
-    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-        float m = 0.f;                       // inputs are post-ReLU: zero padding == floor at 0
+    const int ncg = c >> 3;
+    for (int i = threadIdx.x; i < 14 * ncg; i += blockDim.x) {
+        const int cell = i / ncg, cg = i - cell * ncg;
+        int p, idx;
+        if (cell < 9) { p = 3; idx = cell; }
+        else if (cell < 13) { p = 2; idx = cell - 9; }
+        else { p = 1; idx = 0; }
+        const int wh = (h + p - 1) / p, ww = (w + p - 1) / p;
+        const int oh = (h + wh - 1) / wh, ow = (w + ww - 1) / ww;
+        const int ph = max((oh - 1) * wh + wh - h, 0), pw = max((ow - 1) * ww + ww - w, 0);
+        const int pt = ph / 2, pl = pw / 2;
+        const int oi = idx / ow, oj = idx - oi * ow;
+        const int h0 = max(oi * wh - pt, 0), h1 = min(oi * wh - pt + wh, h);
+        const int w0 = max(oj * ww - pl, 0), w1 = min(oj * ww - pl + ww, w);
+        float m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = 0.f;              // inputs are post-ReLU: zero padding == floor at 0
+        const op_t *plane = x + ((size_t)cg * pg.p + pg.g + b * pg.s) * 8;
         for (int hh = h0; hh < h1; ++hh)
-            for (int wv = w0; wv < w1; ++wv)      // planar padded input [c/8][p][8]
-                m = fmaxf(m, op2f(x[((size_t)(ch >> 3) * pg.p + pg.g + b * pg.s + (hh + 1) * pg.wp + (wv + 1)) * 8 + (ch & 7)]));
-        // k-group-planar [3584/8][bp][8]: feature f = cell*c + ch (the reference's flatten order), operand of the L4 GEMM
-        const int f = cell * c + ch;
-        out[((size_t)(f >> 3) * bp + b) * 8 + (f & 7)] = f2op(m);
+            for (int wv = w0; wv < w1; ++wv) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(plane + ((size_t)(hh + 1) * pg.wp + (wv + 1)) * 8);
+                const op2_t *hp = reinterpret_cast<const op2_t *>(&v);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = op22f2(hp[k]);
+                    m[2 * k] = fmaxf(m[2 * k], f.x);
+                    m[2 * k + 1] = fmaxf(m[2 * k + 1], f.y);
+                }
+            }
+        // feature index f = cell*c + cg*8 + k (the reference's flatten order) -> k-group (f >> 3), planar [3584/8][bp][8]
+        uint4 o;
+        op2_t *oh2 = reinterpret_cast<op2_t *>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh2[k] = f2op2(m[2 * k], m[2 * k + 1]);
+        *reinterpret_cast<uint4 *>(out + ((size_t)(cell * ncg + cg) * bp + b) * 8) = o;
     }
 }
 
@@ -70,7 +86,7 @@ int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, op
 
 int c3b_launch_spp_tc(const op_t *x, const PlanarGeom &g, op_t *out, int64_t batch, int c, int bp, cudaStream_t s) {
     if (batch == 0) return 0;
-    spp_tc_kernel<<<dim3((unsigned)batch, 14), 256, 0, s>>>(x, g, out, c, bp);
+    spp_tc_kernel<<<(unsigned)batch, 448, 0, s>>>(x, g, out, c, bp);
     C3B_CUDA(cudaGetLastError());
     return 0;
 }

@@ -33,7 +33,7 @@
 
 namespace {
 
-constexpr int kThreads = 288;
+constexpr int kThreads = 320;       // warps 0-3 producers / 2nd epilogue group, 4-7 epilogue, 8 MMA, 9 bulk-copy loader
 constexpr int kProducerThreads = 128;
 constexpr int kLag = 3;            // cp.async groups in flight per producer thread before the oldest is published
 constexpr int kMaxStages = 8;
@@ -65,6 +65,7 @@ struct IgemmDev {
     int relu;
     int in_planar, out_planar;   // conv mode: planar padded tensors (pconv_tc.cu) on the input / output side
     PlanarGeom gin, gout;
+    int64_t split_stride;  // split-K partial epilogue: elements between ks slices
     int pg_bp;             // pre-gate epilogue: padded batch (multiple of 128)
     int pg_nbl;            //                    LSTM tile (batch columns per LSTM CTA)
 };
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full_bar[a], 1);
-            ptx::mbar_init(&tmem_empty_bar[a], 128);
+            ptx::mbar_init(&tmem_empty_bar[a], (SWAP && p.taps == 0) ? 256 : 128);
         }
         ptx::mbar_init(&w_bar, 1);
         ptx::fence_barrier_init();
@@ -145,20 +146,20 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp < 4) {
-        // ===================================================== activation producers (+ weight bulk copies)
-        if (p.w_resident && tid == 0) {
-            const int rb0 = (blockIdx.x % (p.n_rowblocks / p.wb)) * p.wb;
-            ptx::mbar_arrive_expect_tx(&w_bar, w_res_bytes);
-            for (int c = 0; c < p.nchunks; ++c)
-                for (int b = 0; b < p.wb; ++b)
-                    ptx::bulk_g2s(smem_base + (uint32_t)(c * p.wb + b) * w_bytes,
-                                  (const char *)p.w_img + ((size_t)c * p.n_rowblocks + rb0 + b) * w_bytes, w_bytes, &w_bar);
-        }
-        if (p.taps == 0) {
-            // k-group-planar activations: a tile's chunk is 8 contiguous 2 KB runs -> 8 cp.async.bulk by one thread
-            // (TMA engine, async proxy: no per-thread gathers, no proxy fences), completion by mbarrier tx-count.
-            if (tid == 0) {
+    const bool two_groups = SWAP && p.taps == 0;       // planar operands: warps 0-3 are free -> second epilogue warpgroup
+    if (warp == 9) {
+        // ===================================================== bulk-copy loader (one thread): resident weight slab and, for
+        // k-group-planar activations, every stage (8 contiguous 2 KB runs per chunk; TMA engine, async proxy, no fences)
+        if (lane == 0) {
+            if (p.w_resident) {
+                const int rbr = (blockIdx.x % (p.n_rowblocks / p.wb)) * p.wb;
+                ptx::mbar_arrive_expect_tx(&w_bar, w_res_bytes);
+                for (int c = 0; c < p.nchunks; ++c)
+                    for (int b = 0; b < p.wb; ++b)
+                        ptx::bulk_g2s(smem_base + (uint32_t)(c * p.wb + b) * w_bytes,
+                                      (const char *)p.w_img + ((size_t)c * p.n_rowblocks + rbr + b) * w_bytes, w_bytes, &w_bar);
+            }
+            if (p.taps == 0) {
                 const uint32_t lbo_a = (uint32_t)(p.act_rows + 1) * 16u;
                 int it = 0;
                 for (TileWalk tw(p); tw.valid(p); tw.next(p)) {
@@ -181,7 +182,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                     }
                 }
             }
-        } else {
+        }
+    } else if (warp < 4 && !two_groups) {
+        // ===================================================== activation producers (16-byte cp.async gathers)
+        {
         // Thread -> (k-group kgl = tid & 7, rows (tid >> 3) + 16 j): one warp-level cp.async covers 4 rows x 128
         // contiguous bytes of the activation matrix (fully coalesced); the padded LBO keeps the smem side conflict-free.
         const int kgl = tid & 7;
@@ -324,7 +328,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
             }
         }
     } else {
-        // ===================================================== epilogue warps 4..7
+        // ===================================================== epilogue warps 4..7 (+ warps 0..3 as a second group when the
+        // operands arrive by bulk copy): with two row blocks per tile each group takes one, otherwise half the columns
+        const int eg = warp < 4 ? 1 : 0;
         const int q = warp & 3;                       // TMEM lane quadrant
         const int r = q * 32 + lane;                  // lane / row within the tile
         int tcount = 0;
@@ -375,8 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                                 a = fmaxf(a, 0.f);
                                 b = fmaxf(b, 0.f);
                             }
-                            op2_t h2 = f2op2(op_clamp(a), op_clamp(b));
-                            pw[i] = *reinterpret_cast<uint32_t *>(&h2);
+                            pw[i] = f2op2_sat(a, b);
                         }
                         if (p.out_planar) {
                             op_t *o0 = (op_t *)p.out + ((size_t)(j0 >> 3) * p.gout.p + pslot) * 8;
@@ -391,7 +396,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
             } else {
                 // thread = weight row (output unit), columns = positions
                 const int64_t pos0 = (int64_t)at * p.act_rows;
-                for (int b = 0; b < p.wb; ++b) {
+                const int b_lo = (two_groups && p.wb == 2) ? eg : 0, b_hi = (two_groups && p.wb == 2) ? eg + 1 : p.wb;
+                const int j_lo = (two_groups && p.wb == 1) ? eg * (ncols / 2) : 0;
+                const int j_hi = (two_groups && p.wb == 1) ? j_lo + ncols / 2 : ncols;
+                for (int b = b_lo; b < b_hi; ++b) {
                     const int R = (rb0 + b) * 128 + r;
                     const uint32_t tb = taddr + (uint32_t)(b * ncols);
                     if (EPI == IGEMM_EPI_F16_BIAS) {
@@ -405,8 +413,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                         const size_t row_off = ((size_t)(dir * C3B_T + t) * ntl + bb0 / p.pg_nbl) * 5 * 128 * p.pg_nbl +
                                                ((size_t)blk * 128 + r) * p.pg_nbl;
                         const size_t st_stride = (size_t)5 * 128 * p.pg_nbl;
-                        int st_i = 0, in_st = 0;
-                        for (int j0 = 0; j0 < ncols; j0 += 16) {
+                        int st_i = j_lo / p.pg_nbl, in_st = j_lo % p.pg_nbl;
+                        for (int j0 = j_lo; j0 < j_hi; j0 += 16) {
                             float v[16];
                             ptx::tmem_ld16(tb + (uint32_t)j0, v);
                             ptx::tmem_ld_wait();
@@ -417,23 +425,25 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                             uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                __half2 h2 = __floats2half2_rn(op_clamp(v[2 * i] + bias), op_clamp(v[2 * i + 1] + bias));
-                                pw[i] = *reinterpret_cast<uint32_t *>(&h2);
+                                pw[i] = f2op2_sat(v[2 * i] + bias, v[2 * i + 1] + bias);
                             }
                             __half *dst = (__half *)p.out + off;
                             *reinterpret_cast<uint4 *>(dst) = pk[0];
                             *reinterpret_cast<uint4 *>(dst + 8) = pk[1];
                         }
                     } else {
-                        float *outp = (float *)p.out;
-                        for (int j0 = 0; j0 < ncols; j0 += 16) {
+                        // split-K partial sums: partial[ks][pos][R], plain stores (consecutive lanes = consecutive R: 128-byte
+                        // warp stores); the consumer (heads kernel) adds the ks slices - no atomics, no memset
+                        const int ks = p.w_resident ? 0 : (tw.tile % p.ksplit);
+                        float *outp = (float *)p.out + (size_t)ks * p.split_stride;
+                        for (int j0 = j_lo; j0 < j_hi; j0 += 16) {
                             float v[16];
                             ptx::tmem_ld16(tb + (uint32_t)j0, v);
                             ptx::tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
                                 const int64_t pos = pos0 + j0 + i;
-                                if (pos < p.m_valid) atomicAdd(outp + pos * p.ldo + R, v[i]);
+                                if (pos < p.m_valid) outp[pos * p.ldo + R] = v[i];
                             }
                         }
                     }
@@ -487,6 +497,7 @@ int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s) {
     p.kgroups = a.w.kgroups;
     p.nchunks = a.w.nchunks;
     p.relu = a.relu;
+    p.split_stride = a.split_stride;
     p.in_planar = a.in_planar; p.out_planar = a.out_planar; p.gin = a.gin; p.gout = a.gout;
     p.act_rows = 128;
     p.wb = 1;

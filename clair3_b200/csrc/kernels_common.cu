@@ -30,8 +30,8 @@ __device__ __forceinline__ void heads_cp16(float *dst_smem, const float *src) {
 // z4: [B][D4] L4 pre-activation WITHOUT bias.  One block = HEADS_G sites x all heads.  L5: thread (t/128, t%128) owns one
 // unit of one head (two heads in flight, four heads in two passes); the [D4][128] weight matrix of each head streams through
 // shared memory in double-buffered 32-row tiles (16-byte cp.async, fully coalesced) so the FMA loop never waits on L2.
-__global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__restrict__ z4, HeadsParams hp,
-                                                              float *__restrict__ out, int64_t batch) {
+__global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__restrict__ z4, int nsplit, int64_t split_stride,
+                                                              HeadsParams hp, float *__restrict__ out, int64_t batch) {
     extern __shared__ __align__(16) float smem[];
     const int d4 = hp.d4;
     float *a = smem;                                   // [d4][G]
@@ -45,7 +45,13 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
     // a is stored [k][G] so the L5 loop reads the 8 sites of one k with two 16-byte broadcast loads
     for (int i = tid; i < HEADS_G * d4; i += HEADS_THREADS) {
         const int k = i / HEADS_G, g = i - k * HEADS_G;
-        a[i] = (g < g_n) ? selu(z4[(b0 + g) * d4 + k] + __ldg(hp.b4 + k)) : 0.f;
+        float v = 0.f;
+        if (g < g_n) {
+            v = __ldg(hp.b4 + k);
+            for (int sp = 0; sp < nsplit; ++sp) v += z4[(size_t)sp * split_stride + (b0 + g) * d4 + k];   // split-K partials
+            v = selu(v);
+        }
+        a[i] = v;
     }
 
     const int j = tid & 127;
@@ -163,12 +169,13 @@ int c3b_launch_ingest_fa_f32(const void *x, int dtype, float *out, int64_t n, cu
     return ingest_any(x, dtype, out, n, s);
 }
 
-int c3b_launch_heads(const float *z4, const HeadsParams &hp, float *out, int64_t batch, cudaStream_t s) {
+int c3b_launch_heads(const float *z4, int nsplit, int64_t split_stride, const HeadsParams &hp, float *out, int64_t batch,
+                     cudaStream_t s) {
     if (batch == 0) return 0;
     size_t smem = sizeof(float) * (HEADS_G * hp.d4 + C3B_MAX_HEADS * HEADS_G * 128 + HEADS_G * 96 + 2 * 2 * HEADS_KT * 128);
     int blocks = (int)((batch + HEADS_G - 1) / HEADS_G);
     C3B_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    heads_kernel<<<blocks, HEADS_THREADS, smem, s>>>(z4, hp, out, batch);
+    heads_kernel<<<blocks, HEADS_THREADS, smem, s>>>(z4, nsplit, split_stride, hp, out, batch);
     C3B_CUDA(cudaGetLastError());
     return 0;
 }

@@ -37,8 +37,10 @@ struct PconvDev {
     int nchunks, cpt;
     int w_resident, w_stages, img_bufs, acc_stages;
     int relu;
+    long long *trace;      // optional: CTA 0 stamps [macro][8] (debug option "lstm_trace")
 };
 
+template <int MT>
 __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                 const uint32_t ph = (uint32_t)(li / p.img_bufs) & 1u;
                 ptx::mbar_wait(&img_empty[buf], ph ^ 1u);
                 ptx::mbar_arrive_expect_tx(&img_full[buf], img_bytes);
-                const long long slot0 = (long long)p.G + 128LL * p.MT * macro - (p.Wp + 1);
+                const long long slot0 = (long long)p.G + 128LL * MT * macro - (p.Wp + 1);
                 const uint32_t dst = img_base + (uint32_t)buf * img_bytes;
                 for (int kg = 0; kg < p.C / 8; ++kg)
                     ptx::bulk_g2s(dst + (uint32_t)kg * lbo_img, (const char *)p.in + ((size_t)kg * p.P + slot0) * 16, lbo_img,
@@ -121,11 +123,15 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
             const uint32_t iph = (uint32_t)(li / p.img_bufs) & 1u;
             const int acc = li % p.acc_stages;
             const uint32_t aph = (uint32_t)(li / p.acc_stages) & 1u;
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && li < 8;
+            if (tr) p.trace[li * 8 + 0] = clock64();
             ptx::mbar_wait(&img_full[buf], iph);
+            if (tr) p.trace[li * 8 + 1] = clock64();
             ptx::mbar_wait(&tmem_empty[acc], aph ^ 1u);
             ptx::tc_fence_after();
+            if (tr) p.trace[li * 8 + 2] = clock64();
             const uint32_t img = img_base + (uint32_t)buf * img_bytes;
-            const uint32_t d0 = tmem_base + (uint32_t)(acc * p.MT * p.N);
+            const uint32_t d0 = tmem_base + (uint32_t)(acc * MT * p.N);
             for (int c = 0; c < p.nchunks; ++c) {
                 uint32_t w_addr = smem_base + (uint32_t)c * w_bytes;
                 int s = 0;
@@ -140,15 +146,19 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                     const int tap = c / p.cpt, kc = c - tap * p.cpt;
                     const int dh = tap / 3, dw = tap - dh * 3;
                     const int shift = (dh - 1) * p.Wp + (dw - 1) + (p.Wp + 1);      // >= 0: slot offset inside the chunk
+                    // descriptors differ only in their 14-bit start-address field: build one per operand and add constants
+                    // (rolled k loop + unrolled tile loop keeps the issue loop on the uniform datapath)
+                    const uint64_t a_base = ptx::umma_desc_nosw(img + (uint32_t)(kc * 8) * lbo_img + (uint32_t)shift * 16u, lbo_img, 128u);
+                    const uint64_t b_base = ptx::umma_desc_nosw(w_addr, lbo_w, 128u);
+                    const uint32_t a_step = (2u * lbo_img) >> 4, b_step = (2u * lbo_w) >> 4;
 #pragma unroll 1
                     for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t b_desc = ptx::umma_desc_nosw(w_addr + (uint32_t)ks * 2u * lbo_w, lbo_w, 128u);
-                        const uint32_t a0 = img + (uint32_t)(kc * 8 + ks * 2) * lbo_img + (uint32_t)shift * 16u;
+                        const uint64_t b_desc = b_base + (uint64_t)(ks * b_step);
+                        const uint64_t a_ks = a_base + (uint64_t)(ks * a_step);
                         const uint32_t accum = (c > 0 || ks > 0) ? 1u : 0u;
-                        for (int ti = 0; ti < p.MT; ++ti) {
-                            const uint64_t a_desc = ptx::umma_desc_nosw(a0 + (uint32_t)ti * 2048u, lbo_img, 128u);
-                            ptx::umma_f16(d0 + (uint32_t)(ti * p.N), a_desc, b_desc, idesc, accum);
-                        }
+#pragma unroll
+                        for (int ti = 0; ti < MT; ++ti)
+                            ptx::umma_f16(d0 + (uint32_t)(ti * p.N), a_ks + (uint64_t)(ti * 128), b_desc, idesc, accum);
                     }
                     if (!p.w_resident) ptx::umma_commit(&w_empty[s]);
                     if (c + 1 == p.nchunks) {
@@ -158,6 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                 }
                 __syncwarp();
             }
+            if (tr) p.trace[li * 8 + 3] = clock64();
         }
     } else if (warp >= 4) {
         // ===================================================== epilogue warps 4..7
@@ -167,10 +178,13 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
         for (int macro = blockIdx.x; macro < p.n_macro; macro += gridDim.x, ++li) {
             const int acc = li % p.acc_stages;
             const uint32_t aph = (uint32_t)(li / p.acc_stages) & 1u;
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && tid == 128 && li < 8;
+            if (tr) p.trace[li * 8 + 4] = clock64();
             ptx::mbar_wait(&tmem_full[acc], aph);
             ptx::tc_fence_after();
-            for (int ti = 0; ti < p.MT; ++ti) {
-                const long long g = (128LL * p.MT) * macro + 128LL * ti + r;       // output slot
+            if (tr) p.trace[li * 8 + 5] = clock64();
+            for (int ti = 0; ti < MT; ++ti) {
+                const long long g = (128LL * MT) * macro + 128LL * ti + r;       // output slot
                 const bool in_data = g < p.T;
                 bool real = false;
                 if (in_data) {
@@ -178,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                     const int hh = l / p.Wp, ww = l - hh * p.Wp;
                     real = hh >= 1 && hh <= p.H && ww >= 1 && ww <= p.W;
                 }
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.MT * p.N + ti * p.N);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MT * p.N + ti * p.N);
                 for (int j0 = 0; j0 < p.N; j0 += 16) {
                     float v[16];
                     ptx::tmem_ld16(taddr + (uint32_t)j0, v);
@@ -208,8 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                                     a = fmaxf(a, 0.f);
                                     b = fmaxf(b, 0.f);
                                 }
-                                op2_t h2 = f2op2(op_clamp(a), op_clamp(b));
-                                pw[i] = *reinterpret_cast<uint32_t *>(&h2);
+                                pw[i] = f2op2_sat(a, b);
                             }
                         }
                         *reinterpret_cast<uint4 *>(p.out + o0) = pk[0];
@@ -219,6 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tmem_empty[acc]);
+            if (tr) p.trace[li * 8 + 6] = clock64();
         }
     }
     ptx::tc_fence_before();
@@ -239,43 +253,63 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
     p.C = a.c; p.N = a.n;
     p.H = g.h; p.W = g.w; p.Wp = g.wp; p.S = g.s; p.G = g.g; p.T = g.t; p.P = g.p;
     p.relu = a.relu;
+    p.trace = a.trace;
     p.nchunks = 9 * a.c / 64;
     p.cpt = a.c / 64;
     if (p.nchunks != a.w.nchunks) { c3b_set_error("pconv: weight image has %d chunks, expected %d", a.w.nchunks, p.nchunks); return 1; }
     const size_t budget = 220 * 1024;
     const size_t w_bytes = (size_t)a.n * 128;
-    // accumulators: MT tiles x N columns per stage
-    int mt = a.n <= 64 ? 4 : 2;
-    p.acc_stages = (mt * a.n * 2 <= 512) ? 2 : 1;
-    for (;; --mt) {
-        if (mt < 1) { c3b_set_error("pconv: feature map does not fit shared memory"); return 1; }
-        p.MT = mt;
-        p.n_in = 128 * mt + 2 * (g.wp + 1);
-        const size_t img_bytes = (size_t)(a.c / 8) * p.n_in * 16;
-        p.acc_stages = (mt * a.n * 2 <= 512) ? 2 : 1;
-        const size_t w_all = (size_t)p.nchunks * w_bytes;
-        if (w_all + 2 * img_bytes <= budget) { p.w_resident = 1; p.img_bufs = 2; p.w_stages = 0; break; }
-        if (2 * img_bytes + 2 * w_bytes <= budget) {
-            p.w_resident = 0; p.img_bufs = 2;
-            p.w_stages = (int)((budget - 2 * img_bytes) / w_bytes);
-            break;
-        }
-        if (img_bytes + 2 * w_bytes <= budget) {
-            p.w_resident = 0; p.img_bufs = 1;
-            p.w_stages = (int)((budget - img_bytes) / w_bytes);
-            break;
+    const size_t w_all = (size_t)p.nchunks * w_bytes;
+    // Configuration search over MT in {4,2,1}: resident weights when they fit (then small MT only costs halo re-reads and
+    // balances the tile count over the SMs); streamed weights want MT >= 2 (every piece feeds MT accumulators) and a deep
+    // ring, so the image is single-buffered there.  Cost model = rounds of macro-tiles x MMAs per macro-tile.
+    long long best_cost = -1;
+    for (int mt = (a.n <= 64 ? 4 : 2); mt >= 1; mt >>= 1) {
+        if (mt * a.n > 512) continue;
+        const int n_in = 128 * mt + 2 * (g.wp + 1);
+        const size_t img_bytes = (size_t)(a.c / 8) * n_in * 16;
+        int resident = 0, bufs = 0, stages = 0;
+        if (w_all + 2 * img_bytes <= budget) { resident = 1; bufs = 2; }
+        else if (w_all + img_bytes <= budget) { resident = 1; bufs = 1; }
+        else if (mt >= 2 || a.n <= 64) {
+            if (img_bytes + 2 * w_bytes <= budget) { bufs = 1; stages = (int)((budget - img_bytes) / w_bytes); }
+            if (2 * img_bytes + 6 * w_bytes <= budget) { bufs = 2; stages = (int)((budget - 2 * img_bytes) / w_bytes); }
+            if (!bufs) continue;
+        } else continue;
+        const long long n_macro = (g.t + 128LL * mt - 1) / (128LL * mt);
+        const long long rounds = (n_macro + m->sm_count - 1) / m->sm_count;
+        // + a fixed per-macro-tile cost (image latency is only hidden behind several tiles of MMAs: MT = 1 measured 1.5x slower)
+        long long cost = rounds * mt * 100 + rounds * 60 + (bufs == 1 ? rounds * 12 : 0) + (resident ? 0 : 5);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            p.MT = mt; p.n_in = n_in; p.w_resident = resident; p.img_bufs = bufs; p.w_stages = stages;
+            p.acc_stages = (mt * a.n * 2 <= 512) ? 2 : 1;
         }
     }
+    if (best_cost < 0) { c3b_set_error("pconv: feature map does not fit shared memory"); return 1; }
     if (p.w_stages > kMaxWStages) p.w_stages = kMaxWStages;
     const long long per_macro = 128LL * p.MT;
     p.n_macro = (int)((g.t + per_macro - 1) / per_macro);
     if ((long long)p.n_macro * per_macro + g.g > g.p - g.g + per_macro) { /* plane pitch covers the rounded-up slot range by construction */ }
     const size_t img_bytes = (size_t)(a.c / 8) * p.n_in * 16;
     const size_t smem = (p.w_resident ? (size_t)p.nchunks * w_bytes : (size_t)p.w_stages * w_bytes) + p.img_bufs * img_bytes + 256;
-    C3B_CUDA(cudaFuncSetAttribute(pconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     const int grid = p.n_macro < m->sm_count ? p.n_macro : m->sm_count;
     const_cast<c3b_model *>(m)->launches++;
-    pconv_kernel<<<grid, kThreads, smem, s>>>(p);
+    switch (p.MT) {
+        case 1:
+            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+            pconv_kernel<1><<<grid, kThreads, smem, s>>>(p);
+            break;
+        case 2:
+            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+            pconv_kernel<2><<<grid, kThreads, smem, s>>>(p);
+            break;
+        case 4:
+            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+            pconv_kernel<4><<<grid, kThreads, smem, s>>>(p);
+            break;
+        default: c3b_set_error("pconv: unsupported MT %d", p.MT); return 1;
+    }
     C3B_CUDA(cudaGetLastError());
     return 0;
 }

@@ -94,6 +94,32 @@ def run_igemm():
             print("    out[0,:8]", np.round(out[0, :8], 3), " ref[0,:8]", np.round(ref[0, :8], 3))
 
 
+def run_ptrace():
+    """Cycle stamps of CTA 0 of res_block1.conv1 (pconv): MMA warp and epilogue per macro-tile."""
+    from clair3_b200 import synth
+    from clair3_b200._ffi import check, ffi, lib
+    from clair3_b200.model import Clair3_F
+    sd = synth.fa_state_dict(True, channels=8, seed=0)
+    x = synth.fa_inputs(256, seed=0)
+    m = Clair3_F(add_indel_length=True, predict=True, input_channels=8)
+    m.set_option("lstm_trace", 1)
+    m.to(torch.device("cuda"))
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    xd = torch.from_numpy(x).cuda()
+    for _ in range(3):
+        m(xd)
+    buf = np.zeros(2 * 33 * 4, dtype=np.int64)
+    check(lib().c3b_debug_lstm_trace(m._handle, ffi.cast("int64_t *", buf.ctypes.data)))
+    tr = buf[:64].reshape(8, 8)
+    t0 = tr[0, 0]
+    for li in range(8):
+        r = tr[li]
+        if r[0] == 0:
+            continue
+        print(f"macro {li}: MMA warp: start {r[0]-t0:7d} img_wait {r[1]-r[0]:6d} tmem_wait {r[2]-r[1]:6d} mma_issue+run {r[3]-r[2]:6d} | "
+              f"epilogue: start {r[4]-t0:7d} wait_full {r[5]-r[4]:6d} work {r[6]-r[5]:6d}", flush=True)
+
+
 def run_stress(opts):
     """Concurrent-stream consistency: every pipelined forward must equal the single-stream result."""
     from clair3_b200 import synth
@@ -204,6 +230,8 @@ if __name__ == "__main__":
     cases = cases2 or (GOLDEN_PILEUP + GOLDEN_FA)
     if mode == "igemm":
         run_igemm()
+    elif mode == "ptrace":
+        run_ptrace()
     elif mode == "stress":
         run_stress(opts)
     elif mode == "probe":
