@@ -43,6 +43,7 @@ KERNEL_FLOP_PER_SITE = {
            "l4": 2 * 3584 * 256},
 }
 BATCH = {"pileup": 1024, "fa": 256}
+LSTM_TILE = [0]
 
 
 def peaks():
@@ -202,7 +203,7 @@ def workload_config(workload, streams, pool):
         w = "Pileup net forward, synthetic batch 1024x33x18 int32 per step (BASELINE configs[1])"
     else:
         w = "Full-alignment net forward, synthetic batch 256x89x33x8 int8 per step (BASELINE configs[2])"
-    return {"workload": w, "batch_per_step": BATCH[workload], "streams_in_flight": streams,
+    return {"workload": w, "batch_per_step": BATCH[workload], "streams_in_flight": streams, "lstm_subtile_sites": LSTM_TILE[0],
             "l2_policy": "inputs rotated over %d distinct device-resident batches (> 126 MB L2)" % pool if pool else "n/a",
             "weights": "seeded synthetic checkpoint (clair3_b200.synth), random-init of the reference architecture",
             "parallelism": "site-sharded, one process per GPU"}
@@ -242,7 +243,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="pileup", choices=["pileup", "fa"])
     ap.add_argument("--streams", type=int, default=8)
-    ap.add_argument("--lstm-tile", type=int, default=0)
+    ap.add_argument("--lstm-tile", type=int, default=64,
+                    help="sites per LSTM sub-tile (16|32|64; 0 = library auto = latency-oriented 16 at this batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -266,8 +268,9 @@ def main():
 
     workload = args.workload
     model, sd = make_model(workload, device, load_real_weights=(rank == 0))
-    if args.lstm_tile:
+    if args.lstm_tile and workload == "pileup":
         model.set_option("lstm_tile", args.lstm_tile)
+        LSTM_TILE[0] = args.lstm_tile
     bcast_bytes = 0
     if world > 1:
         from clair3_b200 import sharding
