@@ -44,21 +44,20 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
 
     // a is stored [k][G] so the L5 loop reads the 8 sites of one k with two 16-byte broadcast loads
     for (int i = tid; i < HEADS_G * d4; i += HEADS_THREADS) {
-        const int k = i / HEADS_G, g = i - k * HEADS_G;
+        const int g = i / d4, k = i - g * d4;              // consecutive threads -> consecutive k: coalesced partial-sum reads
         float v = 0.f;
         if (g < g_n) {
             v = __ldg(hp.b4 + k);
-            for (int sp = 0; sp < nsplit; ++sp) v += z4[(size_t)sp * split_stride + (b0 + g) * d4 + k];   // split-K partials
+            for (int sp = 0; sp < nsplit; ++sp) v += z4[(size_t)sp * split_stride + (b0 + g) * d4 + k];   // split-K partials, fixed order
             v = selu(v);
         }
-        a[i] = v;
+        a[k * HEADS_G + g] = v;
     }
 
     const int j = tid & 127;
     const int hsel = tid >> 7;                         // which head of the in-flight pair this thread works on
     const int ntiles = d4 / HEADS_KT;
-    // blockIdx.y selects the head pair (two heads with two, four with one block row each)
-    for (int hp0 = 2 * blockIdx.y; hp0 < 2 * blockIdx.y + 2; hp0 += 2) {
+    for (int hp0 = 0; hp0 < hp.nheads; hp0 += 2) {
         const float *w0 = hp.h[hp0].w5t, *w1 = hp.h[hp0 + 1].w5t;
         // stage loader: 2 heads x 32 rows x 128 floats = 2048 float4, 8 per thread
         auto load_tile = [&](int tile, int stage) {
@@ -108,12 +107,12 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
     }
     __syncthreads();
 
-    const int o_begin = hp.h[2 * blockIdx.y].out_off;
-    const int o_end = hp.h[2 * blockIdx.y + 1].out_off + hp.h[2 * blockIdx.y + 1].n;
-    const int o_cnt = o_end - o_begin;
-    for (int i = tid; i < HEADS_G * o_cnt; i += HEADS_THREADS) {
-        const int g = i / o_cnt, o = o_begin + (i - g * o_cnt);
-        const int h = (o >= hp.h[2 * blockIdx.y + 1].out_off) ? 2 * blockIdx.y + 1 : 2 * blockIdx.y;
+    for (int i = tid; i < HEADS_G * hp.out_dim; i += HEADS_THREADS) {
+        const int g = i / hp.out_dim, o = i - g * hp.out_dim;
+        int h = 0;
+        if (hp.nheads > 1 && o >= hp.h[1].out_off) h = 1;
+        if (hp.nheads > 2 && o >= hp.h[2].out_off) h = 2;
+        if (hp.nheads > 3 && o >= hp.h[3].out_off) h = 3;
         const int n = hp.h[h].n, oo = o - hp.h[h].out_off;
         const float *__restrict__ wy = hp.h[h].wyt + oo;
         const float *lv = l5 + (h * HEADS_G + g) * 128;
@@ -129,8 +128,8 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
     }
     __syncthreads();
 
-    if (tid < g_n * 2) {
-        const int g = tid >> 1, h = 2 * blockIdx.y + (tid & 1);
+    if (tid < g_n * hp.nheads) {
+        const int g = tid / hp.nheads, h = tid - g * hp.nheads;
         const int n = hp.h[h].n, off = hp.h[h].out_off;
         const float *v = yv + g * 96 + off;
         float mx = v[0];
@@ -176,7 +175,7 @@ int c3b_launch_heads(const float *z4, int nsplit, int64_t split_stride, const He
     size_t smem = sizeof(float) * (HEADS_G * hp.d4 + C3B_MAX_HEADS * HEADS_G * 128 + HEADS_G * 96 + 2 * 2 * HEADS_KT * 128);
     int blocks = (int)((batch + HEADS_G - 1) / HEADS_G);
     C3B_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    heads_kernel<<<dim3(blocks, hp.nheads / 2), HEADS_THREADS, smem, s>>>(z4, nsplit, split_stride, hp, out, batch);
+    heads_kernel<<<blocks, HEADS_THREADS, smem, s>>>(z4, nsplit, split_stride, hp, out, batch);
     C3B_CUDA(cudaGetLastError());
     return 0;
 }
