@@ -242,7 +242,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="pileup", choices=["pileup", "fa"])
-    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=12)
     ap.add_argument("--lstm-tile", type=int, default=64,
                     help="sites per LSTM sub-tile (16|32|64; 0 = library auto = latency-oriented 16 at this batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const int S = p.stages;
-    const uint32_t act_bytes = (uint32_t)(p.act_rows + 1) * 128u;      // 8 k-groups x (rows + 1 pad) x 16 B
+    // gathered tiles pad the k-group pitch by one row (conflict-free cp.async writes); bulk-copied planar tiles keep it at
+    // 128 rows so every 8x16-byte core matrix is 128-byte aligned (a misaligned operand costs ~1.7x per MMA, measured)
+    const uint32_t act_pad = p.taps == 0 ? 0u : 1u;
+    const uint32_t act_bytes = (uint32_t)(p.act_rows + act_pad) * 128u;
     const uint32_t w_bytes = (uint32_t)p.w_rows * 128u;
     const uint32_t w_res_bytes = p.w_resident ? (uint32_t)p.wb * p.nchunks * w_bytes : 0u;
     const uint32_t stage_bytes = act_bytes + (p.w_resident ? 0u : w_bytes);
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                                       (const char *)p.w_img + ((size_t)c * p.n_rowblocks + rbr + b) * w_bytes, w_bytes, &w_bar);
             }
             if (p.taps == 0) {
-                const uint32_t lbo_a = (uint32_t)(p.act_rows + 1) * 16u;
+                const uint32_t lbo_a = (uint32_t)p.act_rows * 16u;
                 int it = 0;
                 for (TileWalk tw(p); tw.valid(p); tw.next(p)) {
                     int at, rb0, c_begin, c_end;
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
     } else if (warp == 8) {
         // ===================================================== MMA issuer (whole warp walks the tiles, one elected lane issues)
         const uint32_t idesc = ptx::umma_idesc_f16(128, (uint32_t)ncols);
-        const uint32_t lbo_act = (uint32_t)(p.act_rows + 1) * 16u;
+        const uint32_t lbo_act = (uint32_t)(p.act_rows + act_pad) * 16u;
         const uint32_t lbo_w = (uint32_t)p.w_rows * 16u;
         int it = 0;
         int tcount = 0;
@@ -518,7 +521,7 @@ int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s) {
     p.ksplit = (p.nchunks + p.chunks_per_split - 1) / p.chunks_per_split;   // drop empty splits
 
     const size_t budget = 216 * 1024;
-    const size_t act_bytes = (size_t)(p.act_rows + 1) * 128, w_bytes = (size_t)p.w_rows * 128;
+    const size_t act_bytes = (size_t)(p.act_rows + (a.taps == 0 ? 0 : 1)) * 128, w_bytes = (size_t)p.w_rows * 128;
     // W-stationary when the slab fits beside >= 4 activation stages (and there are enough tiles to amortise the load)
     if (p.ksplit == 1) {
         int wb = (swap && p.n_rowblocks % 2 == 0 && 2 * p.act_rows <= 256) ? 2 : 1;

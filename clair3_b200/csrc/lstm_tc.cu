@@ -265,6 +265,17 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
 #pragma unroll
                 for (int j = 0; j < NB / 8; ++j)
                     pgv[m][j] = *reinterpret_cast<const uint4 *>(pgp + (size_t)m * 128 * NB + j * 8);
+            // the pre-gate tensor (86 MB per 1024 sites) streams from HBM: pull the NEXT step's lines into L2 now so the
+            // loads above find them there one step later
+            if (step + 1 < C3B_T) {
+                const int tn = dir ? t - 1 : t + 1;
+                const __half *pgn = p.pg + ((((size_t)(dir * C3B_T + tn) * ntl + subtile) * 5) * 128 + wt) * NB;
+#pragma unroll
+                for (int m = 0; m < 5; ++m)
+#pragma unroll
+                    for (int j = 0; j < (NB * 2 + 127) / 128; ++j)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pgn + (size_t)m * 128 * NB + j * 64));
+            }
         }
 
         ptx::mbar_wait(&acc_bar[sub], (uint32_t)step & 1u);
