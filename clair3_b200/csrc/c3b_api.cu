@@ -173,6 +173,7 @@ struct Tap {
     int bp;
     PlanarGeom geom;
     int nsplit = 1;  // layout 5: [nsplit][bp][inner] split-K partial sums -> summed [B][inner]
+    int h = 0, w = 0;  // layout 6: four parity planes [4][inner/8][geom.p][8] (geom = NEXT level) of an h x w map -> NHWC
 };
 
 }  // namespace
@@ -453,8 +454,8 @@ static int finalize_impl(c3b_model *m) {
             m->conv_f32[i].stride = kConvStride[i];
             put(fb, wf.data(), wf.size() * 4, (const void **)&m->conv_f32[i].w, true);
             put(fb, bf.data(), bf.size() * 4, (const void **)&m->conv_f32[i].bias, true);
-            // tensor-core image: k = tap*cin_pad + ci, cin_pad = 8|16 for conv1
-            const int cin_pad = (i == 0) ? ((cin + 7) / 8 * 8) : cin;
+            // tensor-core image: k = tap*cin_pad + ci; conv1's input channels are padded to one UMMA k-step (16)
+            const int cin_pad = (i == 0) ? 16 : cin;
             const int kg = 9 * cin_pad / 8;
             std::vector<uint16_t> img = pack_igemm(cout, kg, cout, [&](int co, int k) {
                 const int t = k / cin_pad, ci = k % cin_pad;
@@ -547,12 +548,11 @@ static size_t ws_bytes_needed(const c3b_model *m, int64_t sites, int depth) {
             for (int i = 0; i < 3; ++i) al((size_t)sites * h3 * w3 * 256 * 4);
             al((size_t)bp * 3584 * 4);
         } else {
-            const int cpad = (m->channels + 7) / 8 * 8;
-            al((size_t)sites * depth * 33 * cpad * 2);
-            const int hh[3] = {h1, h2, h3}, ww[3] = {w1, w2, w3}, cc[3] = {64, 128, 256};
+            const int hh[3] = {h1, h2, h3}, ww[3] = {w1, w2, w3}, cc[3] = {64, 128, 256}, sc[3] = {16, 64, 128};
             for (int l = 0; l < 3; ++l) {
                 const PlanarGeom g = c3b_planar_geom(sites, hh[l], ww[l]);
-                for (int i = 0; i < 3; ++i) al((size_t)(cc[l] / 8) * g.p * 16);
+                al((size_t)4 * (sc[l] / 8) * g.p * 16);                              // parity planes feeding the stem conv
+                for (int i = 0; i < (l == 2 ? 3 : 2); ++i) al((size_t)(cc[l] / 8) * g.p * 16);
             }
             al((size_t)bp * 3584 * 2);
         }
@@ -757,60 +757,54 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
         return 0;
     }
 
-    // ---- tensor-core path: NHWC fp16 input, then zero-padded channel-group-planar feature maps (pconv_tc.cu)
-    const int cpad = (m->channels + 7) / 8 * 8;
-    op_t *xin = cv.take<op_t>((size_t)n * depth * 33 * cpad * 2);
+    // ---- tensor-core path: zero-padded channel-group-planar feature maps (pconv_tc.cu).  Every stride-2 stem conv reads its
+    // input as FOUR PARITY PLANES in its own output geometry (written by the ingest kernel / the previous residual block's
+    // epilogue), which turns it into the same shifted-view implicit GEMM as the stride-1 convs: no gathers anywhere.
+    const int cpad = 16;                       // conv1 input channels padded to one UMMA k-step
     PlanarGeom geo[3];
+    op_t *stem_in[3];                          // parity planes feeding conv1 / conv3 / conv5: [4][cin/8][geo[l].p][8]
     op_t *act[3][3];
+    const int stem_c[3] = {cpad, 64, 128};
     const size_t planar_begin = cv.off;
     for (int l = 0; l < 3; ++l) {
         geo[l] = c3b_planar_geom(n, hh[l + 1], ww[l + 1]);
-        for (int i = 0; i < 3; ++i) act[l][i] = cv.take<op_t>((size_t)(chans[l + 1] / 8) * geo[l].p * 16);
+        stem_in[l] = cv.take<op_t>((size_t)4 * (stem_c[l] / 8) * geo[l].p * 16);
+        for (int i = 0; i < (l == 2 ? 3 : 2); ++i) act[l][i] = cv.take<op_t>((size_t)(chans[l + 1] / 8) * geo[l].p * 16);
     }
+    act[0][2] = stem_in[1];
+    act[1][2] = stem_in[2];
     const size_t planar_end = cv.off;
     op_t *sp = cv.take<op_t>((size_t)bp * 3584 * 2);
     float *z4 = cv.take<float>((size_t)16 * bp * 256 * 4);
-    // borders / guards of the planar maps must be zero; convs rewrite borders with zeros and never touch guards, so one
-    // clear per (workspace, geometry) is enough
+    // borders / guards of the planar maps must be zero; convs rewrite borders with zeros (or, for parity planes, never touch
+    // them) and never touch guards, so one clear per (workspace, geometry) is enough
     if (w->fa_zero_sites != n || w->fa_zero_depth != depth) {
         C3B_CUDA(cudaMemsetAsync(w->dev + planar_begin, 0, planar_end - planar_begin, s));
         w->fa_zero_sites = n;
         w->fa_zero_depth = depth;
     }
     static const char *cn[9] = {"conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv8"};
-    { PROF("ingest"); if (c3b_launch_ingest_fa_tc(x, x_dtype, m->channels, cpad, xin, n * depth * 33, s)) return 1; }
+    { PROF("ingest"); if (c3b_launch_ingest_fa_tc(x, x_dtype, m->channels, cpad, stem_in[0], n, depth, geo[0], s)) return 1; }
     m->launches += 1;
     for (int l = 0; l < 3; ++l) {
         op_t *a0 = act[l][0], *a1 = act[l][1], *a2 = act[l][2];
         const int co = chans[l + 1];
-        // strided stem conv: gather implicit GEMM; reads NHWC (l = 0) or the previous level's planar map, writes planar
-        IgemmArgs ca = {};
-        ca.taps = 9;
-        ca.epilogue = IGEMM_EPI_BF16_BIAS_RELU;
-        ca.relu = 1;
-        ca.ldo = co;
-        ca.hout = hh[l + 1];
-        ca.wout = ww[l + 1];
-        ca.m = n * hh[l + 1] * ww[l + 1];
-        ca.hin = hh[l]; ca.win = ww[l]; ca.stride = 2;
-        ca.cin = l == 0 ? cpad : chans[l];
-        ca.a = l == 0 ? xin : act[l - 1][2];
-        ca.in_planar = l == 0 ? 0 : 1;
-        if (l > 0) ca.gin = geo[l - 1];
-        ca.out_planar = 1;
-        ca.gout = geo[l];
-        ca.w = m->conv_tc[3 * l];
-        ca.out = a0;
-        { PROF(cn[3 * l]); if (c3b_launch_igemm(m, ca, s)) return 1; }
-        // residual block: two shifted-view convolutions on the planar map
         PconvArgs pa = {};
         pa.geom = geo[l];
-        pa.c = co; pa.n = co; pa.relu = 1;
+        pa.relu = 1;
+        // stem conv (stride 2): shifted views of the four parity planes
+        pa.c = stem_c[l]; pa.n = co; pa.stride2 = 1;
+        pa.in = stem_in[l]; pa.out = a0; pa.residual = nullptr; pa.w = m->conv_tc[3 * l];
+        { PROF(cn[3 * l]); if (c3b_launch_pconv(m, pa, s)) return 1; }
+        // residual block: two stride-1 shifted-view convolutions; the second one scatters its output into the next stem's
+        // parity planes (levels 0, 1) or writes the plain planar map SPP reads (level 2)
+        pa.c = co; pa.stride2 = 0;
         pa.trace = (m->lstm_trace && l == 0) ? m->lstm_trace : nullptr;   // debug: stamps of res_block1.conv1
-        pa.in = a0; pa.out = a1; pa.residual = nullptr; pa.w = m->conv_tc[3 * l + 1];
+        pa.in = a0; pa.out = a1; pa.w = m->conv_tc[3 * l + 1];
         { PROF(cn[3 * l + 1]); if (c3b_launch_pconv(m, pa, s)) return 1; }
         pa.trace = nullptr;
         pa.in = a1; pa.out = a2; pa.residual = a0; pa.w = m->conv_tc[3 * l + 2];
+        if (l < 2) { pa.out_parity = 1; pa.next = geo[l + 1]; }
         { PROF(cn[3 * l + 2]); if (c3b_launch_pconv(m, pa, s)) return 1; }
     }
     { PROF("spp"); if (c3b_launch_spp_tc(act[2][2], geo[2], sp, n, 256, (int)bp, s)) return 1; }
@@ -834,7 +828,13 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
     if (tap) {
         for (int l = 0; l < 3; ++l) {
             wt.taps[tapname[l][0]] = {act[l][0], 1, 4, chans[l + 1], 0, geo[l]};
-            wt.taps[tapname[l][1]] = {act[l][2], 1, 4, chans[l + 1], 0, geo[l]};
+            if (l < 2) {
+                wt.taps[tapname[l][1]] = {act[l][2], 1, 6, chans[l + 1], 0, geo[l + 1]};
+                wt.taps[tapname[l][1]].h = geo[l].h;
+                wt.taps[tapname[l][1]].w = geo[l].w;
+            } else {
+                wt.taps[tapname[l][1]] = {act[l][2], 1, 4, chans[l + 1], 0, geo[l]};
+            }
         }
         wt.taps["spp"] = {sp, 1, 2, 3584, (int)bp, {}};
         wt.taps["l4_pre"] = {z4, 0, 5, 256, (int)bp, {}, ns_f};
@@ -929,13 +929,16 @@ extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int6
         if (it == git->second.taps.end()) continue;
         const Tap &t = it->second;
         const int64_t n = m->last_batch;
-        const int64_t per_site = t.layout == 4 ? t.inner * t.geom.h * t.geom.w : t.inner * (t.layout == 3 ? C3B_T : 1);
+        const int64_t per_site = t.layout == 4 ? t.inner * t.geom.h * t.geom.w
+                                 : t.layout == 6 ? t.inner * t.h * t.w
+                                                 : t.inner * (t.layout == 3 ? C3B_T : 1);
         const int64_t count = n * per_site;
         if (*count_inout < count || !host_out) { *count_inout = count; c3b_set_error("c3b_get_tap: buffer too small"); return 1; }
         C3B_CUDA(cudaStreamSynchronize(w->stream));
         const int64_t src_count = t.layout == 0 ? count
                                   : t.layout == 5 ? (int64_t)t.nsplit * t.bp * t.inner
                                   : t.layout == 4 ? (t.inner / 8) * t.geom.p * 8
+                                  : t.layout == 6 ? 4 * (t.inner / 8) * t.geom.p * 8
                                                   : t.inner * (int64_t)t.bp * (t.layout == 3 ? C3B_T : 1);
         std::vector<float> tmp((size_t)src_count);
         if (t.fmt == 0) {
@@ -965,6 +968,14 @@ extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int6
                         for (int64_t k = 0; k < t.inner; ++k)
                             host_out[((b * g.h + hh) * g.w + wv) * t.inner + k] =
                                 tmp[((k >> 3) * g.p + g.g + b * g.s + (int64_t)(hh + 1) * g.wp + (wv + 1)) * 8 + (k & 7)];
+        } else if (t.layout == 6) {        // parity planes of the next level -> NHWC
+            const PlanarGeom &g = t.geom;
+            for (int64_t b = 0; b < n; ++b)
+                for (int hh = 0; hh < t.h; ++hh)
+                    for (int wv = 0; wv < t.w; ++wv)
+                        for (int64_t k = 0; k < t.inner; ++k)
+                            host_out[((b * t.h + hh) * t.w + wv) * t.inner + k] =
+                                tmp[c3b_parity_offset(g, (int)t.inner, b, hh + 1, wv + 1) + (size_t)(k >> 3) * g.p * 8 + (k & 7)];
         } else {                           // [inner/8][33*bp][8] -> [n][33][inner]
             const int64_t rows = (int64_t)C3B_T * t.bp;
             for (int64_t b = 0; b < n; ++b)

@@ -214,10 +214,17 @@ struct PconvArgs {
     op_t *out;                 // planar padded, n channels, same geometry
     const op_t *residual;      // optional, planar padded like out
     IgemmW w;                  // per-chunk weight images (k = tap*c + ci)
-    PlanarGeom geom;
+    PlanarGeom geom;           // geometry of the OUTPUT level (= input level for stride 1)
     int c, n, relu;
+    int stride2;               // 1: `in` holds the four parity planes of the previous level, each [c/8][geom.p][8] (see pconv_tc.cu)
+    int out_parity;            // 1: `out` receives the real pixels scattered into the four parity planes of `next` ([n/8][next.p][8] each)
+    PlanarGeom next;
     long long *trace;          // debug: clock stamps of CTA 0 (see pconv_tc.cu)
 };
+// offset (elements) of padded pixel (hp, wp) of site b, channel group 0, inside a parity-plane set of geometry g with c channels
+inline size_t c3b_parity_offset(const PlanarGeom &g, int c, int64_t b, int hp, int wp) {
+    return (size_t)((hp & 1) * 2 + (wp & 1)) * ((size_t)(c / 8) * g.p * 8) + ((size_t)g.g + b * g.s + (size_t)((hp >> 1) + 1) * g.wp + ((wp >> 1) + 1)) * 8;
+}
 int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s);
 
 // Generic implicit GEMM on tcgen05:  D[M x N] = A[M x K] * W[N x K]^T with fused epilogues.
@@ -250,6 +257,7 @@ struct IgemmArgs {
 int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s);
 
 
-int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, op_t *out, int64_t n_pix, cudaStream_t s);
+int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, op_t *out, int64_t batch, int depth, const PlanarGeom &g1,
+                            cudaStream_t s);
 int c3b_launch_spp_tc(const op_t *x, const PlanarGeom &g, op_t *out, int64_t batch, int c, int bp, cudaStream_t s);
 

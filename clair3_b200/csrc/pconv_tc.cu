@@ -37,6 +37,18 @@ struct PconvDev {
     int nchunks, cpt;
     int w_resident, w_stages, img_bufs, acc_stages;
     int relu;
+    // stride-2 stem convs read FOUR parity planes of the previous level (each a planar padded tensor in THIS conv's
+    // geometry): tap (dh,dw) = plane (dh&1, dw&1) viewed (dh>>1)*Wp + (dw>>1) slots later - shifted views again
+    int nplanes;           // 1 (stride 1) or 4 (stride 2)
+    long long plane_elems; // elements between input planes
+    int kpt_shift;         // log2(C/16): k-steps per tap
+    int nksteps;           // 9 * C/16
+    int halo_lo;           // slots loaded before the macro-tile (Wp+1 for stride 1, 0 for stride 2)
+    // output: 0 = planar padded (same geometry); 1 = scatter real pixels into the four parity planes of the NEXT level
+    int out_parity;
+    long long out_plane_elems;
+    int nS, nWp, nG;       // next level: slots per site, padded width, guard
+    long long nP;          // next level: plane pitch
     long long *trace;      // optional: CTA 0 stamps [macro][8] (debug option "lstm_trace")
 };
 
@@ -52,7 +64,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const uint32_t w_bytes = (uint32_t)p.N * 128u;
-    const uint32_t img_bytes = (uint32_t)(p.C / 8) * (uint32_t)p.n_in * 16u;
+    const uint32_t img_bytes = (uint32_t)p.nplanes * (uint32_t)(p.C / 8) * (uint32_t)p.n_in * 16u;
     const uint32_t lbo_img = (uint32_t)p.n_in * 16u;
     const uint32_t lbo_w = (uint32_t)p.N * 16u;
     const uint32_t smem_base = ptx::smem_u32(smem);
@@ -90,11 +102,13 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                 const uint32_t ph = (uint32_t)(li / p.img_bufs) & 1u;
                 ptx::mbar_wait(&img_empty[buf], ph ^ 1u);
                 ptx::mbar_arrive_expect_tx(&img_full[buf], img_bytes);
-                const long long slot0 = (long long)p.G + 128LL * MT * macro - (p.Wp + 1);
+                const long long slot0 = (long long)p.G + 128LL * MT * macro - p.halo_lo;
                 const uint32_t dst = img_base + (uint32_t)buf * img_bytes;
-                for (int kg = 0; kg < p.C / 8; ++kg)
-                    ptx::bulk_g2s(dst + (uint32_t)kg * lbo_img, (const char *)p.in + ((size_t)kg * p.P + slot0) * 16, lbo_img,
-                                  &img_full[buf]);
+                for (int pl = 0; pl < p.nplanes; ++pl)
+                    for (int kg = 0; kg < p.C / 8; ++kg)
+                        ptx::bulk_g2s(dst + (uint32_t)(pl * (p.C / 8) + kg) * lbo_img,
+                                      (const char *)(p.in + (size_t)pl * p.plane_elems) + ((size_t)kg * p.P + slot0) * 16, lbo_img,
+                                      &img_full[buf]);
             };
             int li = 0, wit = 0;
             if ((int)blockIdx.x < p.n_macro) load_img(blockIdx.x, 0);
@@ -143,18 +157,21 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                     ++wit;
                 }
                 if (ptx::elect_one()) {
-                    const int tap = c / p.cpt, kc = c - tap * p.cpt;
-                    const int dh = tap / 3, dw = tap - dh * 3;
-                    const int shift = (dh - 1) * p.Wp + (dw - 1) + (p.Wp + 1);      // >= 0: slot offset inside the chunk
                     // descriptors differ only in their 14-bit start-address field: build one per operand and add constants
                     // (rolled k loop + unrolled tile loop keeps the issue loop on the uniform datapath)
-                    const uint64_t a_base = ptx::umma_desc_nosw(img + (uint32_t)(kc * 8) * lbo_img + (uint32_t)shift * 16u, lbo_img, 128u);
                     const uint64_t b_base = ptx::umma_desc_nosw(w_addr, lbo_w, 128u);
-                    const uint32_t a_step = (2u * lbo_img) >> 4, b_step = (2u * lbo_w) >> 4;
+                    const uint64_t a_img = ptx::umma_desc_nosw(img, lbo_img, 128u);
+                    const uint32_t b_step = (2u * lbo_w) >> 4;
+                    const int ks_n = min(4, p.nksteps - 4 * c);
 #pragma unroll 1
-                    for (int ks = 0; ks < 4; ++ks) {
+                    for (int ks = 0; ks < ks_n; ++ks) {
+                        const int q = 4 * c + ks;                         // global k-step: tap = q / (C/16), kk = q % (C/16)
+                        const int tap = q >> p.kpt_shift, kk = q - (tap << p.kpt_shift);
+                        const int dh = tap / 3, dw = tap - dh * 3;
+                        const int plane = p.nplanes == 4 ? ((dh & 1) * 2 + (dw & 1)) : 0;
+                        const int shift = p.nplanes == 4 ? (dh >> 1) * p.Wp + (dw >> 1) : dh * p.Wp + dw;   // slots into the chunk
+                        const uint64_t a_ks = a_img + (uint64_t)(((uint32_t)(plane * (p.C / 8) + 2 * kk) * lbo_img + (uint32_t)shift * 16u) >> 4);
                         const uint64_t b_desc = b_base + (uint64_t)(ks * b_step);
-                        const uint64_t a_ks = a_base + (uint64_t)(ks * a_step);
                         const uint32_t accum = (c > 0 || ks > 0) ? 1u : 0u;
 #pragma unroll
                         for (int ti = 0; ti < MT; ++ti)
@@ -187,18 +204,23 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                 const long long g = (128LL * MT) * macro + 128LL * ti + r;       // output slot
                 const bool in_data = g < p.T;
                 bool real = false;
+                size_t par_off = 0;                 // parity-scatter destination (plane + slot of the next level)
                 if (in_data) {
-                    const int l = (int)(g % p.S);
+                    const long long b = g / p.S;
+                    const int l = (int)(g - b * p.S);
                     const int hh = l / p.Wp, ww = l - hh * p.Wp;
                     real = hh >= 1 && hh <= p.H && ww >= 1 && ww <= p.W;
+                    if (p.out_parity && real)
+                        par_off = (size_t)((hh & 1) * 2 + (ww & 1)) * p.out_plane_elems +
+                                  ((size_t)p.nG + b * p.nS + (size_t)((hh >> 1) + 1) * p.nWp + ((ww >> 1) + 1)) * 8;
                 }
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MT * p.N + ti * p.N);
                 for (int j0 = 0; j0 < p.N; j0 += 16) {
                     float v[16];
                     ptx::tmem_ld16(taddr + (uint32_t)j0, v);
                     ptx::tmem_ld_wait();
-                    if (in_data) {
-                        const size_t o0 = ((size_t)(j0 >> 3) * p.P + p.G + g) * 8;
+                    if (in_data && (real || !p.out_parity)) {
+                        const size_t o0 = ((size_t)(j0 >> 3) * p.P + p.G + g) * 8;       // this conv's own slot (residual / plain output)
                         const size_t o1 = o0 + (size_t)p.P * 8;
                         uint4 pk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
                         if (real) {
@@ -225,8 +247,14 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                                 pw[i] = f2op2_sat(a, b);
                             }
                         }
-                        *reinterpret_cast<uint4 *>(p.out + o0) = pk[0];
-                        *reinterpret_cast<uint4 *>(p.out + o1) = pk[1];
+                        if (p.out_parity) {
+                            op_t *d0p = p.out + par_off + ((size_t)(j0 >> 3) * p.nP) * 8;
+                            *reinterpret_cast<uint4 *>(d0p) = pk[0];
+                            *reinterpret_cast<uint4 *>(d0p + (size_t)p.nP * 8) = pk[1];
+                        } else {
+                            *reinterpret_cast<uint4 *>(p.out + o0) = pk[0];
+                            *reinterpret_cast<uint4 *>(p.out + o1) = pk[1];
+                        }
                     }
                 }
             }
@@ -247,15 +275,26 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
 
 int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
     const PlanarGeom &g = a.geom;
-    if (a.c % 64 || a.n % 16 || a.n > 256 || a.n < 16) { c3b_set_error("pconv: unsupported channels %d -> %d", a.c, a.n); return 1; }
+    const bool c_ok = a.c == 16 || a.c == 64 || a.c == 128 || a.c == 256;
+    if (!c_ok || a.n % 16 || a.n > 256 || a.n < 16) { c3b_set_error("pconv: unsupported channels %d -> %d", a.c, a.n); return 1; }
     PconvDev p = {};
     p.in = a.in; p.w_img = a.w.w_img; p.bias = a.w.bias; p.residual = a.residual; p.out = a.out;
     p.C = a.c; p.N = a.n;
     p.H = g.h; p.W = g.w; p.Wp = g.wp; p.S = g.s; p.G = g.g; p.T = g.t; p.P = g.p;
     p.relu = a.relu;
     p.trace = a.trace;
-    p.nchunks = 9 * a.c / 64;
+    p.nksteps = 9 * a.c / 16;
+    p.nchunks = (p.nksteps + 3) / 4;
     p.cpt = a.c / 64;
+    p.kpt_shift = a.c == 16 ? 0 : a.c == 64 ? 2 : a.c == 128 ? 3 : 4;
+    p.nplanes = a.stride2 ? 4 : 1;
+    p.plane_elems = (long long)(a.c / 8) * g.p * 8;
+    p.halo_lo = a.stride2 ? 0 : g.wp + 1;
+    p.out_parity = a.out_parity;
+    if (a.out_parity) {
+        p.out_plane_elems = (long long)(a.n / 8) * a.next.p * 8;
+        p.nS = a.next.s; p.nWp = a.next.wp; p.nG = a.next.g; p.nP = a.next.p;
+    }
     if (p.nchunks != a.w.nchunks) { c3b_set_error("pconv: weight image has %d chunks, expected %d", a.w.nchunks, p.nchunks); return 1; }
     const size_t budget = 220 * 1024;
     const size_t w_bytes = (size_t)a.n * 128;
@@ -266,12 +305,12 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
     long long best_cost = -1;
     for (int mt = (a.n <= 64 ? 4 : 2); mt >= 1; mt >>= 1) {
         if (mt * a.n > 512) continue;
-        const int n_in = 128 * mt + 2 * (g.wp + 1);
-        const size_t img_bytes = (size_t)(a.c / 8) * n_in * 16;
+        const int n_in = a.stride2 ? (128 * mt + g.wp + 1 + 7) / 8 * 8 : 128 * mt + 2 * (g.wp + 1);
+        const size_t img_bytes = (size_t)p.nplanes * (a.c / 8) * n_in * 16;
         int resident = 0, bufs = 0, stages = 0;
         if (w_all + 2 * img_bytes <= budget) { resident = 1; bufs = 2; }
         else if (w_all + img_bytes <= budget) { resident = 1; bufs = 1; }
-        else if (mt >= 2 || a.n <= 64) {
+        else if (mt >= 2 || a.n <= 64 || a.stride2) {
             if (img_bytes + 2 * w_bytes <= budget) { bufs = 1; stages = (int)((budget - img_bytes) / w_bytes); }
             if (2 * img_bytes + 6 * w_bytes <= budget) { bufs = 2; stages = (int)((budget - 2 * img_bytes) / w_bytes); }
             if (!bufs) continue;
@@ -291,7 +330,7 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
     const long long per_macro = 128LL * p.MT;
     p.n_macro = (int)((g.t + per_macro - 1) / per_macro);
     if ((long long)p.n_macro * per_macro + g.g > g.p - g.g + per_macro) { /* plane pitch covers the rounded-up slot range by construction */ }
-    const size_t img_bytes = (size_t)(a.c / 8) * p.n_in * 16;
+    const size_t img_bytes = (size_t)p.nplanes * (a.c / 8) * p.n_in * 16;
     const size_t smem = (p.w_resident ? (size_t)p.nchunks * w_bytes : (size_t)p.w_stages * w_bytes) + p.img_bufs * img_bytes + 256;
     const int grid = p.n_macro < m->sm_count ? p.n_macro : m->sm_count;
     const_cast<c3b_model *>(m)->launches++;
