@@ -274,6 +274,7 @@ extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
     } else if (!strcmp(name, "host_async")) {
         m->host_async = value ? 1 : 0;
     } else if (!strcmp(name, "lstm_trace")) {
+        m->trace_conv = value >= 10 ? (int)value - 10 : 1;
         if (value && !m->lstm_trace) {
             C3B_CUDA(cudaSetDevice(m->device));
             C3B_CUDA(cudaMalloc(&m->lstm_trace, sizeof(long long) * 2 * C3B_T * 4));
@@ -795,14 +796,16 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
         // stem conv (stride 2): shifted views of the four parity planes
         pa.c = stem_c[l]; pa.n = co; pa.stride2 = 1;
         pa.in = stem_in[l]; pa.out = a0; pa.residual = nullptr; pa.w = m->conv_tc[3 * l];
+        auto trace_of = [&](int ci) { return (m->lstm_trace && m->trace_conv == ci) ? m->lstm_trace : nullptr; };
+        pa.trace = trace_of(3 * l);
         { PROF(cn[3 * l]); if (c3b_launch_pconv(m, pa, s)) return 1; }
         // residual block: two stride-1 shifted-view convolutions; the second one scatters its output into the next stem's
         // parity planes (levels 0, 1) or writes the plain planar map SPP reads (level 2)
         pa.c = co; pa.stride2 = 0;
-        pa.trace = (m->lstm_trace && l == 0) ? m->lstm_trace : nullptr;   // debug: stamps of res_block1.conv1
+        pa.trace = trace_of(3 * l + 1);
         pa.in = a0; pa.out = a1; pa.w = m->conv_tc[3 * l + 1];
         { PROF(cn[3 * l + 1]); if (c3b_launch_pconv(m, pa, s)) return 1; }
-        pa.trace = nullptr;
+        pa.trace = trace_of(3 * l + 2);
         pa.in = a1; pa.out = a2; pa.residual = a0; pa.w = m->conv_tc[3 * l + 2];
         if (l < 2) { pa.out_parity = 1; pa.next = geo[l + 1]; }
         { PROF(cn[3 * l + 2]); if (c3b_launch_pconv(m, pa, s)) return 1; }

@@ -134,6 +134,7 @@ struct c3b_model {
     int tap_ws = -1;                   // debug: workspace index c3b_get_tap reads
     int host_async = 0;                // 1: host-buffer forwards stay stream-ordered (pinned buffers; caller synchronises)
     long long *lstm_trace = nullptr;   // device [2][33][4] clock stamps (debug option "lstm_trace")
+    int trace_conv = 1;            // which Clair3_F conv (0..8) stamps the trace buffer (option lstm_trace = 10 + index)
     std::map<std::string, std::pair<double, int64_t>> prof_total;   // name -> (ms, launches)
     int sm_count = 148;
     bool finalized = false;

@@ -8,27 +8,36 @@ namespace {
 
 // int8/int32/f32 NHWC [B][D][33][channels] -> fp16, written straight into the four PARITY PLANES the stride-2 stem conv reads
 // (pconv_tc.cu): padded pixel (hp, wp) = (h+1, w+1) goes to plane (hp&1, wp&1), slot (hp>>1, wp>>1) of the level-1 geometry.
-// One thread = one (pixel, channel group of 8): one 16-byte store.  The 1/100 scale is folded into conv1's weights.
+// Threads are ordered like the OUTPUT (site, plane, row, column fastest) so a warp's 16-byte stores are consecutive slots of
+// one plane; the reads are 8-byte pieces two pixels apart.  Channel groups with no real channel (conv1's input is padded to
+// one UMMA k-step = 16 channels) stay zero from the workspace clear and are never written.  The 1/100 scale is folded into
+// conv1's weights.
 template <typename T>
-__global__ void ingest_fa_tc_kernel(const T *__restrict__ x, op_t *__restrict__ out, int64_t n_pix, int channels,
+__global__ void ingest_fa_tc_kernel(const T *__restrict__ x, op_t *__restrict__ out, int64_t batch, int channels,
                                     int cpad, int depth, PlanarGeom g1) {
-    const int groups = cpad / 8;
-    const int64_t total = n_pix * groups;
-    const size_t plane_elems = (size_t)groups * g1.p * 8;
+    const int groups = (channels + 7) / 8;                 // groups holding real channels
+    const int rows = g1.h + 1, cols = g1.w + 1;            // plane cells that can hold a real pixel
+    const int per_site = 4 * rows * cols;
+    const int64_t total = batch * per_site * groups;
+    const size_t plane_elems = (size_t)(cpad / 8) * g1.p * 8;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pix = idx / groups;
-        const int g = (int)(idx - pix * groups);
+        const int64_t cell = idx / groups;
+        const int g = (int)(idx - cell * groups);
+        const int64_t b = cell / per_site;
+        int rem = (int)(cell - b * per_site);
+        const int plane = rem / (rows * cols);
+        rem -= plane * rows * cols;
+        const int i = rem / cols, j = rem - i * cols;
+        const int hp = 2 * i + (plane >> 1), wp = 2 * j + (plane & 1);
+        if (hp < 1 || hp > depth || wp < 1 || wp > 33) continue;
+        const T *src = x + ((b * depth + (hp - 1)) * 33 + (wp - 1)) * channels;
         __align__(16) op_t v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int ch = g * 8 + i;
-            v[i] = f2op(ch < channels ? (float)x[pix * channels + ch] : 0.f);
+        for (int e = 0; e < 8; ++e) {
+            const int ch = g * 8 + e;
+            v[e] = f2op(ch < channels ? (float)src[ch] : 0.f);
         }
-        const int64_t b = pix / (depth * 33);
-        const int rem = (int)(pix - b * depth * 33);
-        const int hp = rem / 33 + 1, wp = rem % 33 + 1;
-        const size_t off = (size_t)((hp & 1) * 2 + (wp & 1)) * plane_elems +
-                           ((size_t)g * g1.p + g1.g + b * g1.s + (size_t)((hp >> 1) + 1) * g1.wp + ((wp >> 1) + 1)) * 8;
+        const size_t off = (size_t)plane * plane_elems + ((size_t)g * g1.p + g1.g + b * g1.s + (size_t)(i + 1) * g1.wp + (j + 1)) * 8;
         *reinterpret_cast<uint4 *>(out + off) = *reinterpret_cast<const uint4 *>(v);
     }
 }
@@ -80,14 +89,14 @@ __global__ void spp_tc_kernel(const op_t *__restrict__ x, PlanarGeom pg, op_t *_
 
 int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, op_t *out, int64_t batch, int depth, const PlanarGeom &g1,
                             cudaStream_t s) {
-    const int64_t n_pix = batch * depth * 33;
-    if (n_pix == 0) return 0;
-    const int64_t total = n_pix * (cpad / 8);
+    if (batch == 0) return 0;
+    if (channels > cpad) { c3b_set_error("full-alignment input has %d channels, at most %d supported", channels, cpad); return 1; }
+    const int64_t total = batch * 4 * (g1.h + 1) * (g1.w + 1) * ((channels + 7) / 8);
     const int blocks = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
     switch (dtype) {
-        case C3B_DT_I8: ingest_fa_tc_kernel<int8_t><<<blocks, 256, 0, s>>>((const int8_t *)x, out, n_pix, channels, cpad, depth, g1); break;
-        case C3B_DT_I32: ingest_fa_tc_kernel<int32_t><<<blocks, 256, 0, s>>>((const int32_t *)x, out, n_pix, channels, cpad, depth, g1); break;
-        case C3B_DT_F32: ingest_fa_tc_kernel<float><<<blocks, 256, 0, s>>>((const float *)x, out, n_pix, channels, cpad, depth, g1); break;
+        case C3B_DT_I8: ingest_fa_tc_kernel<int8_t><<<blocks, 256, 0, s>>>((const int8_t *)x, out, batch, channels, cpad, depth, g1); break;
+        case C3B_DT_I32: ingest_fa_tc_kernel<int32_t><<<blocks, 256, 0, s>>>((const int32_t *)x, out, batch, channels, cpad, depth, g1); break;
+        case C3B_DT_F32: ingest_fa_tc_kernel<float><<<blocks, 256, 0, s>>>((const float *)x, out, batch, channels, cpad, depth, g1); break;
         default: c3b_set_error("unsupported input dtype %d", dtype); return 1;
     }
     C3B_CUDA(cudaGetLastError());

@@ -42,6 +42,12 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
     const int tid = threadIdx.x;
     const int64_t b0 = (int64_t)blockIdx.x * HEADS_G;
     const int g_n = (int)min((int64_t)HEADS_G, batch - b0);
+    // small batches: gridDim.y = nheads/2 and each block serves one PAIR of heads (twice the blocks, half the serial weight
+    // streaming per block); large batches: gridDim.y = 1 and the block walks all pairs
+    const int hp_begin = gridDim.y > 1 ? 2 * (int)blockIdx.y : 0;
+    const int hp_end = gridDim.y > 1 ? hp_begin + 2 : hp.nheads;
+    const int o_begin = hp.h[hp_begin].out_off;
+    const int o_end = hp_end < hp.nheads ? hp.h[hp_end].out_off : hp.out_dim;
 
     // output-layer weights of every head -> shared memory (the 128-long dot products of the Y stage would otherwise wait on
     // L2 once per four terms: measured 85 % of this kernel's time)
@@ -51,6 +57,7 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
         if (hp.nheads > 1 && o >= hp.h[1].out_off) h = 1;
         if (hp.nheads > 2 && o >= hp.h[2].out_off) h = 2;
         if (hp.nheads > 3 && o >= hp.h[3].out_off) h = 3;
+        if (o < o_begin || o >= o_end) continue;
         wys[i] = __ldg(hp.h[h].wyt + jj * hp.h[h].n + (o - hp.h[h].out_off));
     }
     // a is stored [k][G] so the L5 loop reads the 8 sites of one k with two 16-byte broadcast loads
@@ -68,7 +75,7 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
     const int j = tid & 127;
     const int hsel = tid >> 7;                         // which head of the in-flight pair this thread works on
     const int ntiles = d4 / HEADS_KT;
-    for (int hp0 = 0; hp0 < hp.nheads; hp0 += 2) {
+    for (int hp0 = hp_begin; hp0 < hp_end; hp0 += 2) {
         const float *w0 = hp.h[hp0].w5t, *w1 = hp.h[hp0 + 1].w5t;
         // stage loader: 2 heads x 32 rows x 128 floats = 2048 float4, 8 per thread
         auto load_tile = [&](int tile, int stage) {
@@ -120,6 +127,7 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
 
     for (int i = tid; i < HEADS_G * hp.out_dim; i += HEADS_THREADS) {
         const int g = i / hp.out_dim, o = i - g * hp.out_dim;
+        if (o < o_begin || o >= o_end) continue;
         int h = 0;
         if (hp.nheads > 1 && o >= hp.h[1].out_off) h = 1;
         if (hp.nheads > 2 && o >= hp.h[2].out_off) h = 2;
@@ -142,6 +150,7 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
 
     if (tid < g_n * hp.nheads) {
         const int g = tid / hp.nheads, h = tid - g * hp.nheads;
+        if (h < hp_begin || h >= hp_end) return;
         const int n = hp.h[h].n, off = hp.h[h].out_off;
         const float *v = yv + g * 96 + off;
         float mx = v[0];
@@ -188,7 +197,10 @@ int c3b_launch_heads(const float *z4, int nsplit, int64_t split_stride, const He
                                    128 * hp.out_dim);
     int blocks = (int)((batch + HEADS_G - 1) / HEADS_G);
     C3B_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    heads_kernel<<<blocks, HEADS_THREADS, smem, s>>>(z4, nsplit, split_stride, hp, out, batch);
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int pairs = (hp.nheads >= 4 && hp.nheads % 2 == 0 && blocks * 2 <= 2 * sms) ? hp.nheads / 2 : 1;
+    heads_kernel<<<dim3(blocks, pairs), HEADS_THREADS, smem, s>>>(z4, nsplit, split_stride, hp, out, batch);
     C3B_CUDA(cudaGetLastError());
     return 0;
 }

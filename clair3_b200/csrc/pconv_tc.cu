@@ -14,14 +14,18 @@
 // Weights: the host-packed per-chunk images of igemm_tc.cu ([tap*C/64 + kc][8 k-groups][N][8]); resident when they fit
 // (res_block1: 72 KB), otherwise streamed through a ring with each piece applied to MT accumulators.
 //
-// Roles (288 threads): warp 0 lane 0 issues all bulk copies, warp 8 issues tcgen05.mma (one elected lane), warps 4-7 run
-// the epilogue on their TMEM lane quadrant (bias + residual + ReLU + border mask, 16-byte coalesced planar stores).
+// Roles (320 threads): warp 9 lane 0 issues all bulk copies, warp 8 issues tcgen05.mma (one elected lane), warps 0-7 run
+// the epilogue as two groups of four (one TMEM lane quadrant per warp, alternating 16-column chunks per group): bias +
+// residual + ReLU + border mask, 16-byte coalesced planar stores.
+#include <cstdio>
+#include <cstdlib>
+
 #include "c3b_internal.h"
 #include "ptx.cuh"
 
 namespace {
 
-constexpr int kThreads = 288;
+constexpr int kThreads = 320;
 constexpr int kMaxWStages = 8;
 
 struct PconvDev {
@@ -50,6 +54,7 @@ struct PconvDev {
     int nS, nWp, nG;       // next level: slots per site, padded width, guard
     long long nP;          // next level: plane pitch
     long long *trace;      // optional: CTA 0 stamps [macro][8] (debug option "lstm_trace")
+    int debug_align;       // timing experiment only (wrong results): round every tap shift down to 8 slots
 };
 
 template <int MT>
@@ -59,6 +64,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
     __shared__ uint64_t img_full[2], img_empty[2], tmem_full[2], tmem_empty[2], w_res_bar;
     __shared__ uint32_t tmem_base_smem;
     __shared__ float bias_s[256];
+    __shared__ uint32_t a_off_s[144];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -77,7 +83,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
             ptx::mbar_init(&img_full[s], 1);
             ptx::mbar_init(&img_empty[s], 1);
             ptx::mbar_init(&tmem_full[s], 1);
-            ptx::mbar_init(&tmem_empty[s], 128);
+            ptx::mbar_init(&tmem_empty[s], 256);
         }
         ptx::mbar_init(&w_res_bar, 1);
         ptx::fence_barrier_init();
@@ -89,7 +95,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp == 0) {
+    if (warp == 9) {
         // ===================================================== loader (one thread): image chunks + weight pieces
         if (lane == 0) {
             if (p.w_resident) {
@@ -110,18 +116,18 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                                       (const char *)(p.in + (size_t)pl * p.plane_elems) + ((size_t)kg * p.P + slot0) * 16, lbo_img,
                                       &img_full[buf]);
             };
-            int li = 0, wit = 0;
+            int li = 0, w_stage = 0;
+            uint32_t w_phase = 0;
             if ((int)blockIdx.x < p.n_macro) load_img(blockIdx.x, 0);
             for (int macro = blockIdx.x; macro < p.n_macro; macro += gridDim.x, ++li) {
                 const int next = macro + gridDim.x;
                 if (p.img_bufs == 2 && next < p.n_macro) load_img(next, li + 1);      // prefetch while this tile computes
                 if (!p.w_resident) {
-                    for (int c = 0; c < p.nchunks; ++c, ++wit) {
-                        const int s = wit % p.w_stages;
-                        const uint32_t ph = (uint32_t)(wit / p.w_stages) & 1u;
-                        ptx::mbar_wait(&w_empty[s], ph ^ 1u);
-                        ptx::mbar_arrive_expect_tx(&w_full[s], w_bytes);
-                        ptx::bulk_g2s(smem_base + (uint32_t)s * w_bytes, (const char *)p.w_img + (size_t)c * w_bytes, w_bytes, &w_full[s]);
+                    for (int c = 0; c < p.nchunks; ++c) {
+                        ptx::mbar_wait(&w_empty[w_stage], w_phase ^ 1u);
+                        ptx::mbar_arrive_expect_tx(&w_full[w_stage], w_bytes);
+                        ptx::bulk_g2s(smem_base + (uint32_t)w_stage * w_bytes, (const char *)p.w_img + (size_t)c * w_bytes, w_bytes, &w_full[w_stage]);
+                        if (++w_stage == p.w_stages) { w_stage = 0; w_phase ^= 1u; }
                     }
                 }
                 if (p.img_bufs == 1 && next < p.n_macro) load_img(next, li + 1);      // single buffer: after this tile's MMAs
@@ -130,14 +136,31 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
     } else if (warp == 8) {
         // ===================================================== MMA issuer
         const uint32_t idesc = ptx::umma_idesc_f16(128, (uint32_t)p.N);
-        int li = 0, wit = 0;
+        // per-k-step A-view offsets (descriptor start-address units of 16 B): tap (dh,dw), channel block kk ->
+        // plane (stride 2 only), k-group pair 2*kk, slot shift
+        for (int q = lane; q < p.nksteps; q += 32) {
+            const int tap = q >> p.kpt_shift, kk = q - (tap << p.kpt_shift);
+            const int dh = tap / 3, dw = tap - dh * 3;
+            const int plane = p.nplanes == 4 ? ((dh & 1) * 2 + (dw & 1)) : 0;
+            const int shift = p.nplanes == 4 ? (dh >> 1) * p.Wp + (dw >> 1) : dh * p.Wp + dw;   // slots into the chunk
+            a_off_s[q] = ((uint32_t)(plane * (p.C / 8) + 2 * kk) * lbo_img + (uint32_t)shift * 16u) >> 4;
+        }
+        __syncwarp();
+        const uint64_t a_desc0 = ptx::umma_desc_nosw(0, lbo_img, 128u), w_desc0 = ptx::umma_desc_nosw(0, lbo_w, 128u);
+        const uint32_t a_desc_lo = (uint32_t)a_desc0, a_desc_hi = (uint32_t)(a_desc0 >> 32);
+        const uint32_t w_desc_lo = (uint32_t)w_desc0, w_desc_hi = (uint32_t)(w_desc0 >> 32);
+        const uint32_t b_step = (2u * lbo_w) >> 4;
+        int li = 0, w_stage = 0;
+        uint32_t w_phase = 0;
+        // ONE elected thread runs the whole loop (barrier waits included): no per-chunk elect / reconvergence / warp sync
+        if (ptx::elect_one()) {
         if (p.w_resident) ptx::mbar_wait(&w_res_bar, 0);
         for (int macro = blockIdx.x; macro < p.n_macro; macro += gridDim.x, ++li) {
             const int buf = li % p.img_bufs;
             const uint32_t iph = (uint32_t)(li / p.img_bufs) & 1u;
             const int acc = li % p.acc_stages;
             const uint32_t aph = (uint32_t)(li / p.acc_stages) & 1u;
-            const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && li < 8;
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && li < 8;
             if (tr) p.trace[li * 8 + 0] = clock64();
             ptx::mbar_wait(&img_full[buf], iph);
             if (tr) p.trace[li * 8 + 1] = clock64();
@@ -146,50 +169,85 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
             if (tr) p.trace[li * 8 + 2] = clock64();
             const uint32_t img = img_base + (uint32_t)buf * img_bytes;
             const uint32_t d0 = tmem_base + (uint32_t)(acc * MT * p.N);
-            for (int c = 0; c < p.nchunks; ++c) {
-                uint32_t w_addr = smem_base + (uint32_t)c * w_bytes;
-                int s = 0;
-                if (!p.w_resident) {
-                    s = wit % p.w_stages;
-                    ptx::mbar_wait(&w_full[s], (uint32_t)(wit / p.w_stages) & 1u);
-                    ptx::tc_fence_after();
-                    w_addr = smem_base + (uint32_t)s * w_bytes;
-                    ++wit;
+            // The issuing thread is a single in-order instruction stream and tcgen05.mma issue does not run ahead of the tensor
+            // pipe by more than an MMA or so: every integer instruction between two MMAs is tensor-pipe idle time (measured:
+            // 185 cycles per k-step with the tap decode inline, against 49/65/129 cycles per MMA at N = 64/128/256 when the
+            // descriptors are ready).  So: taps unrolled at compile time, descriptors advanced by 32-bit adds on their
+            // start-address field (shared memory < 256 KB: no carry out of the 14 bits), ring stage / phase kept as counters.
+            const uint32_t a_lo = a_desc_lo + (img >> 4);
+            auto acquire_w = [&](int c) -> uint32_t {
+                if (p.w_resident) return smem_base + (uint32_t)c * w_bytes;
+                ptx::mbar_wait(&w_full[w_stage], w_phase);
+                ptx::tc_fence_after();
+                return smem_base + (uint32_t)w_stage * w_bytes;
+            };
+            auto release_w = [&](bool last) {
+                if (!p.w_resident) ptx::umma_commit(&w_empty[w_stage]);
+                if (last) {
+                    ptx::umma_commit(&tmem_full[acc]);
+                    ptx::umma_commit(&img_empty[buf]);
                 }
-                if (ptx::elect_one()) {
-                    // descriptors differ only in their 14-bit start-address field: build one per operand and add constants
-                    // (rolled k loop + unrolled tile loop keeps the issue loop on the uniform datapath)
-                    const uint64_t b_base = ptx::umma_desc_nosw(w_addr, lbo_w, 128u);
-                    const uint64_t a_img = ptx::umma_desc_nosw(img, lbo_img, 128u);
-                    const uint32_t b_step = (2u * lbo_w) >> 4;
-                    const int ks_n = min(4, p.nksteps - 4 * c);
-#pragma unroll 1
-                    for (int ks = 0; ks < ks_n; ++ks) {
-                        const int q = 4 * c + ks;                         // global k-step: tap = q / (C/16), kk = q % (C/16)
-                        const int tap = q >> p.kpt_shift, kk = q - (tap << p.kpt_shift);
-                        const int dh = tap / 3, dw = tap - dh * 3;
-                        const int plane = p.nplanes == 4 ? ((dh & 1) * 2 + (dw & 1)) : 0;
-                        const int shift = p.nplanes == 4 ? (dh >> 1) * p.Wp + (dw >> 1) : dh * p.Wp + dw;   // slots into the chunk
-                        const uint64_t a_ks = a_img + (uint64_t)(((uint32_t)(plane * (p.C / 8) + 2 * kk) * lbo_img + (uint32_t)shift * 16u) >> 4);
-                        const uint64_t b_desc = b_base + (uint64_t)(ks * b_step);
-                        const uint32_t accum = (c > 0 || ks > 0) ? 1u : 0u;
+            };
+            auto advance_w = [&]() {
+                if (!p.w_resident && ++w_stage == p.w_stages) { w_stage = 0; w_phase ^= 1u; }
+            };
+            if (p.kpt_shift >= 2) {
+                // C >= 64: a chunk (4 k-steps) lies inside one tap
+                const uint32_t kstep_a = (2u * lbo_img) >> 4;
+                int c = 0;
 #pragma unroll
-                        for (int ti = 0; ti < MT; ++ti)
-                            ptx::umma_f16(d0 + (uint32_t)(ti * p.N), a_ks + (uint64_t)(ti * 128), b_desc, idesc, accum);
-                    }
-                    if (!p.w_resident) ptx::umma_commit(&w_empty[s]);
-                    if (c + 1 == p.nchunks) {
-                        ptx::umma_commit(&tmem_full[acc]);
-                        ptx::umma_commit(&img_empty[buf]);
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int dh = tap / 3, dw = tap % 3;
+                    const uint32_t tap_off =
+                        p.nplanes == 4 ? ((uint32_t)(((dh & 1) * 2 + (dw & 1)) * (p.C / 8)) * lbo_img + (uint32_t)((dh >> 1) * p.Wp + (dw >> 1)) * 16u) >> 4
+                                       : (uint32_t)(dh * p.Wp + dw);
+                    uint32_t a_c = a_lo + (p.debug_align ? (tap_off & ~7u) : tap_off);
+                    for (int kc = 0; kc < p.cpt; ++kc, ++c, a_c += 4u * kstep_a) {
+                        const uint32_t w_addr = acquire_w(c);
+                        const uint32_t b_lo = w_desc_lo + (w_addr >> 4);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t b_desc = ((uint64_t)w_desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)ks * b_step);
+#pragma unroll
+                            for (int ti = 0; ti < MT; ++ti)
+                                ptx::umma_f16(d0 + (uint32_t)(ti * p.N),
+                                              ((uint64_t)a_desc_hi << 32) | (uint64_t)(a_c + (uint32_t)ks * kstep_a + (uint32_t)(ti * 128)), b_desc, idesc,
+                                              (tap > 0 || ks > 0 || kc > 0) ? 1u : 0u);
+                        }
+                        release_w(tap == 8 && kc + 1 == p.cpt);
+                        advance_w();
                     }
                 }
-                __syncwarp();
+            } else {
+                // C = 16 (conv1): one k-step per tap, A-view offsets from the table
+                for (int c = 0; c < p.nchunks; ++c) {
+                    const uint32_t w_addr = acquire_w(c);
+                    const uint32_t b_lo = w_desc_lo + (w_addr >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const int q = 4 * c + ks;
+                        if (q < p.nksteps) {
+                            const uint32_t ao = a_lo + a_off_s[q];
+                            const uint64_t b_desc = ((uint64_t)w_desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)ks * b_step);
+#pragma unroll
+                            for (int ti = 0; ti < MT; ++ti)
+                                ptx::umma_f16(d0 + (uint32_t)(ti * p.N), ((uint64_t)a_desc_hi << 32) | (uint64_t)(ao + (uint32_t)(ti * 128)), b_desc,
+                                              idesc, q > 0 ? 1u : 0u);
+                        }
+                    }
+                    release_w(c + 1 == p.nchunks);
+                    advance_w();
+                }
             }
             if (tr) p.trace[li * 8 + 3] = clock64();
         }
-    } else if (warp >= 4) {
-        // ===================================================== epilogue warps 4..7
+        }
+        __syncwarp();
+    } else if (warp < 8) {
+        // ===================================================== epilogue: two groups of four warps (one TMEM lane quadrant per
+        // warp), group e takes the 16-column chunks with (chunk & 1) == e; residuals are fetched one chunk ahead
         const int q = warp & 3;
+        const int eg = warp >> 2;
         const int r = q * 32 + lane;
         int li = 0;
         for (int macro = blockIdx.x; macro < p.n_macro; macro += gridDim.x, ++li) {
@@ -214,32 +272,36 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                         par_off = (size_t)((hh & 1) * 2 + (ww & 1)) * p.out_plane_elems +
                                   ((size_t)p.nG + b * p.nS + (size_t)((hh >> 1) + 1) * p.nWp + ((ww >> 1) + 1)) * 8;
                 }
+                const bool wr = in_data && (real || !p.out_parity);
+                const bool use_res = real && p.residual != nullptr;
+                const size_t slot_off = ((size_t)p.G + (size_t)g) * 8;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MT * p.N + ti * p.N);
-                for (int j0 = 0; j0 < p.N; j0 += 16) {
+                uint4 res[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+                if (use_res) {
+                    const op_t *rp0 = p.residual + (size_t)(2 * eg) * p.P * 8 + slot_off;
+                    res[0] = *reinterpret_cast<const uint4 *>(rp0);
+                    res[1] = *reinterpret_cast<const uint4 *>(rp0 + (size_t)p.P * 8);
+                }
+                for (int j0 = 16 * eg; j0 < p.N; j0 += 32) {
                     float v[16];
                     ptx::tmem_ld16(taddr + (uint32_t)j0, v);
+                    uint4 rn[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+                    if (use_res && j0 + 32 < p.N) {
+                        const op_t *rp0 = p.residual + (size_t)((j0 + 32) >> 3) * p.P * 8 + slot_off;
+                        rn[0] = *reinterpret_cast<const uint4 *>(rp0);
+                        rn[1] = *reinterpret_cast<const uint4 *>(rp0 + (size_t)p.P * 8);
+                    }
                     ptx::tmem_ld_wait();
-                    if (in_data && (real || !p.out_parity)) {
-                        const size_t o0 = ((size_t)(j0 >> 3) * p.P + p.G + g) * 8;       // this conv's own slot (residual / plain output)
-                        const size_t o1 = o0 + (size_t)p.P * 8;
+                    if (wr) {
                         uint4 pk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
                         if (real) {
-                            uint4 res[2];
-                            if (p.residual) {
-                                res[0] = *reinterpret_cast<const uint4 *>(p.residual + o0);
-                                res[1] = *reinterpret_cast<const uint4 *>(p.residual + o1);
-                            }
                             uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
                             const op2_t *rp = reinterpret_cast<const op2_t *>(res);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                float a = v[2 * i] + bias_s[j0 + 2 * i];
-                                float b = v[2 * i + 1] + bias_s[j0 + 2 * i + 1];
-                                if (p.residual) {
-                                    const float2 rf = op22f2(rp[i]);
-                                    a += rf.x;
-                                    b += rf.y;
-                                }
+                                const float2 rf = op22f2(rp[i]);          // zeros when there is no residual
+                                float a = v[2 * i] + bias_s[j0 + 2 * i] + rf.x;
+                                float b = v[2 * i + 1] + bias_s[j0 + 2 * i + 1] + rf.y;
                                 if (p.relu) {
                                     a = fmaxf(a, 0.f);
                                     b = fmaxf(b, 0.f);
@@ -247,15 +309,14 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                                 pw[i] = f2op2_sat(a, b);
                             }
                         }
-                        if (p.out_parity) {
-                            op_t *d0p = p.out + par_off + ((size_t)(j0 >> 3) * p.nP) * 8;
-                            *reinterpret_cast<uint4 *>(d0p) = pk[0];
-                            *reinterpret_cast<uint4 *>(d0p + (size_t)p.nP * 8) = pk[1];
-                        } else {
-                            *reinterpret_cast<uint4 *>(p.out + o0) = pk[0];
-                            *reinterpret_cast<uint4 *>(p.out + o1) = pk[1];
-                        }
+                        op_t *d0p = p.out_parity ? p.out + par_off + (size_t)(j0 >> 3) * p.nP * 8
+                                                 : p.out + (size_t)(j0 >> 3) * p.P * 8 + slot_off;
+                        const size_t pitch = (size_t)(p.out_parity ? p.nP : p.P) * 8;
+                        *reinterpret_cast<uint4 *>(d0p) = pk[0];
+                        *reinterpret_cast<uint4 *>(d0p + pitch) = pk[1];
                     }
+                    res[0] = rn[0];
+                    res[1] = rn[1];
                 }
             }
             ptx::tc_fence_before();
@@ -283,6 +344,8 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
     p.H = g.h; p.W = g.w; p.Wp = g.wp; p.S = g.s; p.G = g.g; p.T = g.t; p.P = g.p;
     p.relu = a.relu;
     p.trace = a.trace;
+    static const int dbg_align = getenv("C3B_PCONV_ALIGN") ? atoi(getenv("C3B_PCONV_ALIGN")) : 0;
+    p.debug_align = dbg_align;
     p.nksteps = 9 * a.c / 16;
     p.nchunks = (p.nksteps + 3) / 4;
     p.cpt = a.c / 64;
@@ -296,13 +359,14 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
         p.nS = a.next.s; p.nWp = a.next.wp; p.nG = a.next.g; p.nP = a.next.p;
     }
     if (p.nchunks != a.w.nchunks) { c3b_set_error("pconv: weight image has %d chunks, expected %d", a.w.nchunks, p.nchunks); return 1; }
-    const size_t budget = 220 * 1024;
+    const size_t budget = 225 * 1024 - 256;      // 227 KB per CTA minus the static barriers / bias table
     const size_t w_bytes = (size_t)a.n * 128;
     const size_t w_all = (size_t)p.nchunks * w_bytes;
     // Configuration search over MT in {4,2,1}: resident weights when they fit (then small MT only costs halo re-reads and
     // balances the tile count over the SMs); streamed weights want MT >= 2 (every piece feeds MT accumulators) and a deep
     // ring, so the image is single-buffered there.  Cost model = rounds of macro-tiles x MMAs per macro-tile.
     long long best_cost = -1;
+    static const int force_mt = getenv("C3B_PCONV_MT") ? atoi(getenv("C3B_PCONV_MT")) : 0;   // tuning sweeps only
     for (int mt = (a.n <= 64 ? 4 : 2); mt >= 1; mt >>= 1) {
         if (mt * a.n > 512) continue;
         const int n_in = a.stride2 ? (128 * mt + g.wp + 1 + 7) / 8 * 8 : 128 * mt + 2 * (g.wp + 1);
@@ -317,8 +381,10 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
         } else continue;
         const long long n_macro = (g.t + 128LL * mt - 1) / (128LL * mt);
         const long long rounds = (n_macro + m->sm_count - 1) / m->sm_count;
-        // + a fixed per-macro-tile cost (image latency is only hidden behind several tiles of MMAs: MT = 1 measured 1.5x slower)
+        // + a fixed per-macro-tile cost: measured, MT = 1 is 1.2-1.5x slower than MT = 2/4 on every level even with resident
+        // weights (each macro-tile pays an image-chunk round trip that only several tiles of MMAs hide)
         long long cost = rounds * mt * 100 + rounds * 60 + (bufs == 1 ? rounds * 12 : 0) + (resident ? 0 : 5);
+        if (force_mt > 0) cost = (mt == force_mt) ? 1 : 1000000 + cost;
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
             p.MT = mt; p.n_in = n_in; p.w_resident = resident; p.img_bufs = bufs; p.w_stages = stages;
@@ -326,6 +392,10 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
         }
     }
     if (best_cost < 0) { c3b_set_error("pconv: feature map does not fit shared memory"); return 1; }
+    static const bool dbg = getenv("C3B_DEBUG_PCONV") != nullptr;
+    if (dbg)
+        fprintf(stderr, "[pconv] C=%d N=%d stride2=%d T=%lld: MT=%d resident=%d img_bufs=%d w_stages=%d cost=%lld\n", a.c, a.n, a.stride2,
+                (long long)g.t, p.MT, p.w_resident, p.img_bufs, p.w_stages, best_cost);
     if (p.w_stages > kMaxWStages) p.w_stages = kMaxWStages;
     const long long per_macro = 128LL * p.MT;
     p.n_macro = (int)((g.t + per_macro - 1) / per_macro);
@@ -336,15 +406,15 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
     const_cast<c3b_model *>(m)->launches++;
     switch (p.MT) {
         case 1:
-            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
             pconv_kernel<1><<<grid, kThreads, smem, s>>>(p);
             break;
         case 2:
-            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
             pconv_kernel<2><<<grid, kThreads, smem, s>>>(p);
             break;
         case 4:
-            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
             pconv_kernel<4><<<grid, kThreads, smem, s>>>(p);
             break;
         default: c3b_set_error("pconv: unsupported MT %d", p.MT); return 1;

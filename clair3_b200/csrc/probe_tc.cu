@@ -91,7 +91,77 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __half *a, const __
     if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc<512>(tmem_base); }
 }
 
+// Timing-only probe of operand / accumulator switching: `reps` back-to-back 128 x n x 16 MMAs where MMA i uses
+//   A tile (i % 8) at a_step bytes apart (+ a_mis bytes), B tile ((i / b_div) % 8) at b_step bytes apart, accumulator (i % d_cnt).
+struct MmaProbeMode { int a_step, a_mis, b_step, b_div, d_cnt; };
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int reps, int nmodes, const MmaProbeMode *modes, long long *timing) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { ptx::mbar_init(&bar, 1); ptx::fence_barrier_init(); }
+    if (warp == 0) ptx::tmem_alloc<512>(&tmem_base_smem);
+    for (int i = tid; i < (64 + 80) * 1024 / 16; i += 128) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0x3c003c00u, 0x3c003c00u, 0, 0);
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t idesc = ptx::umma_idesc_f16(128, (uint32_t)n);
+    const uint32_t a0 = ptx::smem_u32(smem), b0 = a0 + 64 * 1024;
+    uint32_t phase = 0;
+    for (int mode = 0; mode < nmodes; ++mode) {
+        const MmaProbeMode md = modes[mode];
+        long long t0 = 0;
+        if (tid == 0) {
+            const uint64_t a_desc = ptx::umma_desc_nosw(a0 + (uint32_t)md.a_mis, 2048 + 512, 128);
+            const uint64_t b_desc = ptx::umma_desc_nosw(b0, (uint32_t)n * 16u, 128);
+            t0 = clock64();
+            // descriptors / accumulator addresses of one period of 8 MMAs are computed up front so the timed loop is only
+            // the MMA issue (b_div and d_cnt are powers of two <= 8)
+            uint64_t av[8], bv[8];
+            uint32_t dv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                av[j] = a_desc + (uint64_t)((j * md.a_step) >> 4);
+                bv[j] = b_desc + (uint64_t)(((j / md.b_div) * md.b_step) >> 4);
+                dv[j] = tmem_base + (uint32_t)((j % md.d_cnt) * n);
+            }
+            t0 = clock64();
+            for (int i = 0; i < reps; i += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ptx::umma_f16(dv[j], av[j], bv[j], idesc, 1);
+            }
+            ptx::umma_commit(&bar);
+            timing[mode * 2 + 0] = clock64() - t0;
+        }
+        ptx::mbar_wait(&bar, phase); phase ^= 1;
+        if (tid == 0) timing[mode * 2 + 1] = clock64() - t0;
+        ptx::tc_fence_after();
+        __syncthreads();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc<512>(tmem_base); }
+}
+
 }  // namespace
+
+// modes: nmodes x 5 ints {a_step, a_mis, b_step, b_div, d_cnt}; timing: nmodes x {issue, done} cycles
+extern "C" int c3b_debug_mma_probe(int n, int reps, int nmodes, const int *modes, int64_t *timing) {
+    if (n % 16 || n < 16 || n > 256 || nmodes < 1 || nmodes > 32) { c3b_set_error("mma probe: bad arguments"); return 1; }
+    void *dm, *dt;
+    C3B_CUDA(cudaMalloc(&dm, (size_t)nmodes * sizeof(MmaProbeMode)));
+    C3B_CUDA(cudaMalloc(&dt, (size_t)nmodes * 16));
+    C3B_CUDA(cudaMemcpy(dm, modes, (size_t)nmodes * sizeof(MmaProbeMode), cudaMemcpyHostToDevice));
+    C3B_CUDA(cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024));
+    mma_probe_kernel<<<1, 128, 144 * 1024>>>(n, reps, nmodes, (const MmaProbeMode *)dm, (long long *)dt);
+    C3B_CUDA(cudaGetLastError());
+    C3B_CUDA(cudaDeviceSynchronize());
+    C3B_CUDA(cudaMemcpy(timing, dt, (size_t)nmodes * 16, cudaMemcpyDeviceToHost));
+    cudaFree(dm); cudaFree(dt);
+    return 0;
+}
 
 // out_d: [128][n] fp32 (TS-form result), timing4: 5 modes x {issue, done} cycles for `reps` MMAs
 extern "C" int c3b_debug_ts_probe(const float *a, const float *b, int n, int reps, float *out_d, int64_t *timing4) {

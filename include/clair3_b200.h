@@ -113,6 +113,8 @@ int c3b_debug_lstm_trace(c3b_model *m, int64_t *out264);
 /* Hardware probe (tools/diag.py probe): one tcgen05.mma with its A operand in TMEM (checks the assumed layout) and the
  * cycles of `reps` back-to-back MMAs with A from shared memory vs TMEM.  a[128][16], b[n][16] -> out_d[128][n]. */
 int c3b_debug_ts_probe(const float *a, const float *b, int n, int reps, float *out_d, int64_t *timing10);
+/* debug: cycles for back-to-back tcgen05.mma under operand / accumulator switching (tools/diag.py mmaprobe) */
+int c3b_debug_mma_probe(int n, int reps, int nmodes, const int *modes, int64_t *timing);
 
 void c3b_destroy(c3b_model *m);
 

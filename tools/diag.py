@@ -94,20 +94,21 @@ def run_igemm():
             print("    out[0,:8]", np.round(out[0, :8], 3), " ref[0,:8]", np.round(ref[0, :8], 3))
 
 
-def run_ptrace():
-    """Cycle stamps of CTA 0 of res_block1.conv1 (pconv): MMA warp and epilogue per macro-tile."""
+def run_ptrace(conv=1):
+    """Cycle stamps of CTA 0 of one Clair3_F conv (pconv): MMA warp and epilogue per macro-tile."""
     from clair3_b200 import synth
     from clair3_b200._ffi import check, ffi, lib
     from clair3_b200.model import Clair3_F
     sd = synth.fa_state_dict(True, channels=8, seed=0)
     x = synth.fa_inputs(256, seed=0)
     m = Clair3_F(add_indel_length=True, predict=True, input_channels=8)
-    m.set_option("lstm_trace", 1)
+    m.set_option("lstm_trace", 10 + conv)
     m.to(torch.device("cuda"))
     m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
     xd = torch.from_numpy(x).cuda()
     for _ in range(3):
         m(xd)
+    print(f"--- conv{conv}")
     buf = np.zeros(2 * 33 * 4, dtype=np.int64)
     check(lib().c3b_debug_lstm_trace(m._handle, ffi.cast("int64_t *", buf.ctypes.data)))
     tr = buf[:64].reshape(8, 8)
@@ -184,6 +185,35 @@ def run_probe():
               f"TS 4-acc {tm[9]/reps:.1f} cycles (issue-only: {tm[0]/reps:.1f}/{tm[2]/reps:.1f}/{tm[4]/reps:.1f}/{tm[6]/reps:.1f}/{tm[8]/reps:.1f})", flush=True)
 
 
+def run_mmaprobe():
+    """Cycles per tcgen05.mma when the A / B tile and the accumulator change from one MMA to the next."""
+    from clair3_b200._ffi import check, ffi, lib
+    all_modes = [
+        ("same A, same B, same D", (0, 0, 0, 1, 1)),
+        ("A rotates", (8192, 0, 0, 1, 1)),
+        ("B rotates", (0, 0, 8192, 1, 1)),
+        ("A+B rotate, 1 acc (MT=1)", (8192, 0, 8192, 1, 1)),
+        ("A+B rotate, 2 acc alternate", (8192, 0, 8192, 1, 2)),
+        ("A rotates misaligned 16B", (8192, 16, 0, 1, 1)),
+        ("MT=1 misaligned 48B", (8192, 48, 8192, 1, 1)),
+        ("MT=2 (B per 2, 2 acc)", (8192, 0, 8192, 2, 2)),
+        ("MT=2 misaligned", (8192, 16, 8192, 2, 2)),
+        ("MT=4 (B per 4, 4 acc)", (8192, 0, 8192, 4, 4)),
+        ("MT=4 misaligned", (8192, 16, 8192, 4, 4)),
+        ("MT=8 (B per 8, 8 acc)", (8192, 0, 8192, 8, 8)),
+        ("same A, B rotates, 4 acc", (0, 0, 8192, 1, 4)),
+        ("same A+B, 4 acc", (0, 0, 0, 1, 4)),
+    ]
+    reps = 256
+    for n in (64, 128, 256):
+        modes = [(nm, md) for nm, md in all_modes if md[4] * n <= 512]
+        arr = np.array([md for _, md in modes], dtype=np.int32)
+        tm = np.zeros(2 * len(modes), dtype=np.int64)
+        check(lib().c3b_debug_mma_probe(n, reps, len(modes), ffi.cast("int *", arr.ctypes.data), ffi.cast("int64_t *", tm.ctypes.data)))
+        for i, (nm, _) in enumerate(modes):
+            print(f"N={n:3d} {nm:32s}: {tm[2*i+1]/reps:6.1f} cycles/MMA (issue {tm[2*i]/reps:5.1f})", flush=True)
+
+
 def run_trace(opts):
     """Per-step cycle breakdown of the persistent LSTM kernels (CTA 0, thread 0)."""
     from clair3_b200 import synth
@@ -231,11 +261,14 @@ if __name__ == "__main__":
     if mode == "igemm":
         run_igemm()
     elif mode == "ptrace":
-        run_ptrace()
+        for c in ([int(d) for d in str(opts["convs"])] if "convs" in opts else [1]):
+            run_ptrace(c)
     elif mode == "stress":
         run_stress(opts)
     elif mode == "probe":
         run_probe()
+    elif mode == "mmaprobe":
+        run_mmaprobe()
     elif mode == "trace":
         run_trace(opts)
     else:
