@@ -316,6 +316,7 @@ static int finalize_impl(c3b_model *m) {
     m->heads.out_dim = m->out_dim;
     put(blob, P(m, "L4.bias").data(), (size_t)m->d4 * 4, (const void **)&m->heads.b4, false);
     int off = 0;
+    std::vector<float> wy_all((size_t)128 * m->out_dim);
     for (int h = 0; h < m->nheads; ++h) {
         const std::vector<float> &w5 = P(m, std::string(kHeadNames[h][0]) + ".weight");   // [128][d4]
         const std::vector<float> &wy = P(m, std::string(kHeadNames[h][1]) + ".weight");   // [n][128]
@@ -324,7 +325,10 @@ static int finalize_impl(c3b_model *m) {
         for (int j = 0; j < 128; ++j)
             for (int k = 0; k < m->d4; ++k) w5t[(size_t)k * 128 + j] = w5[(size_t)j * m->d4 + k];
         for (int o = 0; o < n; ++o)
-            for (int j = 0; j < 128; ++j) wyt[(size_t)j * n + o] = wy[(size_t)o * 128 + j];
+            for (int j = 0; j < 128; ++j) {
+                wyt[(size_t)j * n + o] = wy[(size_t)o * 128 + j];
+                wy_all[(size_t)j * m->out_dim + off + o] = wy[(size_t)o * 128 + j];
+            }
         put(blob, w5t.data(), w5t.size() * 4, (const void **)&m->heads.h[h].w5t, false);
         put(blob, P(m, std::string(kHeadNames[h][0]) + ".bias").data(), 128 * 4, (const void **)&m->heads.h[h].b5, false);
         put(blob, wyt.data(), wyt.size() * 4, (const void **)&m->heads.h[h].wyt, false);
@@ -333,6 +337,7 @@ static int finalize_impl(c3b_model *m) {
         m->heads.h[h].out_off = off;
         off += n;
     }
+    put(blob, wy_all.data(), wy_all.size() * 4, (const void **)&m->heads.wy_all, false);
 
     // ---- L4: fp32 transposed (debug) + tensor-core image (swapped orientation: 128-row blocks)
     {

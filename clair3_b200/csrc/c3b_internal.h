@@ -65,6 +65,7 @@ struct HeadWeights {
 struct HeadsParams {
     HeadWeights h[C3B_MAX_HEADS];
     const float *b4;    // [D4]
+    const float *wy_all; // [128][out_dim]: every head's output weights side by side (column = global output index)
     int nheads;
     int d4;
     int out_dim;

@@ -44,16 +44,26 @@ __global__ void ingest_fa_tc_kernel(const T *__restrict__ x, op_t *__restrict__ 
 
 // One thread = one (pyramid cell, channel group of 8): 16-byte loads from the planar padded map, 8 running maxima,
 // one 16-byte store into the k-group-planar L4 operand.  grid = B, block = 14 * C/8 threads (448 for C = 256).
+// The loads of one window row are issued together (a rolled loop with a running max serialises one L2 round trip per
+// pixel), and the 1x1 cell is the max of the four 2x2 cells (their windows tile the map), taken from shared memory.
 __global__ void spp_tc_kernel(const op_t *__restrict__ x, PlanarGeom pg, op_t *__restrict__ out, int c, int bp) {
+    __shared__ float p2max[4][32][8];
     const int h = pg.h, w = pg.w;
     const int64_t b = blockIdx.x;
-    const int ncg = c >> 3;
-    for (int i = threadIdx.x; i < 14 * ncg; i += blockDim.x) {
+    const int ncg = c >> 3;                                  // <= 32
+    auto store = [&](int cell, int cg, const float *m) {
+        // feature index f = cell*c + cg*8 + k (the reference's flatten order) -> k-group (f >> 3), planar [3584/8][bp][8]
+        uint4 o;
+        op2_t *oh2 = reinterpret_cast<op2_t *>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh2[k] = f2op2(m[2 * k], m[2 * k + 1]);
+        *reinterpret_cast<uint4 *>(out + ((size_t)(cell * ncg + cg) * bp + b) * 8) = o;
+    };
+    for (int i = threadIdx.x; i < 13 * ncg; i += blockDim.x) {
         const int cell = i / ncg, cg = i - cell * ncg;
         int p, idx;
         if (cell < 9) { p = 3; idx = cell; }
-        else if (cell < 13) { p = 2; idx = cell - 9; }
-        else { p = 1; idx = 0; }
+        else { p = 2; idx = cell - 9; }
         const int wh = (h + p - 1) / p, ww = (w + p - 1) / p;
         const int oh = (h + wh - 1) / wh, ow = (w + ww - 1) / ww;
         const int ph = max((oh - 1) * wh + wh - h, 0), pw = max((ow - 1) * ww + ww - w, 0);
@@ -66,22 +76,36 @@ __global__ void spp_tc_kernel(const op_t *__restrict__ x, PlanarGeom pg, op_t *_
         for (int k = 0; k < 8; ++k) m[k] = 0.f;              // inputs are post-ReLU: zero padding == floor at 0
         const op_t *plane = x + ((size_t)cg * pg.p + pg.g + b * pg.s) * 8;
         for (int hh = h0; hh < h1; ++hh)
-            for (int wv = w0; wv < w1; ++wv) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(plane + ((size_t)(hh + 1) * pg.wp + (wv + 1)) * 8);
-                const op2_t *hp = reinterpret_cast<const op2_t *>(&v);
+            for (int wb = w0; wb < w1; wb += 4) {
+                uint4 v[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float2 f = op22f2(hp[k]);
-                    m[2 * k] = fmaxf(m[2 * k], f.x);
-                    m[2 * k + 1] = fmaxf(m[2 * k + 1], f.y);
+                for (int j = 0; j < 4; ++j)
+                    v[j] = wb + j < w1 ? *reinterpret_cast<const uint4 *>(plane + ((size_t)(hh + 1) * pg.wp + (wb + j + 1)) * 8)
+                                       : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const op2_t *hp = reinterpret_cast<const op2_t *>(&v[j]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 f = op22f2(hp[k]);
+                        m[2 * k] = fmaxf(m[2 * k], f.x);
+                        m[2 * k + 1] = fmaxf(m[2 * k + 1], f.y);
+                    }
                 }
             }
-        // feature index f = cell*c + cg*8 + k (the reference's flatten order) -> k-group (f >> 3), planar [3584/8][bp][8]
-        uint4 o;
-        op2_t *oh2 = reinterpret_cast<op2_t *>(&o);
+        store(cell, cg, m);
+        if (cell >= 9) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) oh2[k] = f2op2(m[2 * k], m[2 * k + 1]);
-        *reinterpret_cast<uint4 *>(out + ((size_t)(cell * ncg + cg) * bp + b) * 8) = o;
+            for (int k = 0; k < 8; ++k) p2max[cell - 9][cg][k] = m[k];
+        }
+    }
+    __syncthreads();
+    for (int cg = threadIdx.x; cg < ncg; cg += blockDim.x) {
+        float m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            m[k] = fmaxf(fmaxf(p2max[0][cg][k], p2max[1][cg][k]), fmaxf(p2max[2][cg][k], p2max[3][cg][k]));
+        store(13, cg, m);
     }
 }
 

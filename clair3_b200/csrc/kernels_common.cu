@@ -21,6 +21,7 @@ __global__ void ingest_f32_kernel(const T *__restrict__ x, float *__restrict__ o
 constexpr int HEADS_G = 8;        // sites per block
 constexpr int HEADS_THREADS = 256;
 constexpr int HEADS_KT = 32;      // k rows of an L5 weight tile staged in shared memory
+constexpr int HEADS_STAGES = 3;   // L5 weight tiles in the shared-memory ring
 
 __device__ __forceinline__ void heads_cp16(float *dst_smem, const float *src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
@@ -37,8 +38,8 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
     float *a = smem;                                   // [d4][G]
     float *l5 = a + HEADS_G * d4;                      // [nheads][G][128]
     float *yv = l5 + C3B_MAX_HEADS * HEADS_G * 128;    // [G][96]
-    float *wt = yv + HEADS_G * 96;                     // [2 stages][2 heads][HEADS_KT][128]
-    float *wys = wt + 2 * 2 * HEADS_KT * 128;          // [128][out_dim]: all heads' output weights, column = global output index
+    float *wt = yv + HEADS_G * 96;                     // [HEADS_STAGES][2 heads][HEADS_KT][128]
+    float *wys = wt + HEADS_STAGES * 2 * HEADS_KT * 128;          // [128][out_dim]: all heads' output weights, column = global output index
     const int tid = threadIdx.x;
     const int64_t b0 = (int64_t)blockIdx.x * HEADS_G;
     const int g_n = (int)min((int64_t)HEADS_G, batch - b0);
@@ -49,24 +50,25 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
     const int o_begin = hp.h[hp_begin].out_off;
     const int o_end = hp_end < hp.nheads ? hp.h[hp_end].out_off : hp.out_dim;
 
-    // output-layer weights of every head -> shared memory (the 128-long dot products of the Y stage would otherwise wait on
-    // L2 once per four terms: measured 85 % of this kernel's time)
-    for (int i = tid; i < 128 * hp.out_dim; i += HEADS_THREADS) {
-        const int jj = i / hp.out_dim, o = i - jj * hp.out_dim;
-        int h = 0;
-        if (hp.nheads > 1 && o >= hp.h[1].out_off) h = 1;
-        if (hp.nheads > 2 && o >= hp.h[2].out_off) h = 2;
-        if (hp.nheads > 3 && o >= hp.h[3].out_off) h = 3;
-        if (o < o_begin || o >= o_end) continue;
-        wys[i] = __ldg(hp.h[h].wyt + jj * hp.h[h].n + (o - hp.h[h].out_off));
-    }
+    // output-layer weights of every head -> shared memory, asynchronously (oldest cp.async group: complete by the first
+    // wait of the L5 loop); the 128-long dot products of the Y stage would otherwise wait on L2 once per four terms
+    for (int i = tid * 4; i < 128 * hp.out_dim; i += HEADS_THREADS * 4) heads_cp16(wys + i, hp.wy_all + i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
     // a is stored [k][G] so the L5 loop reads the 8 sites of one k with two 16-byte broadcast loads
+    // (all split-K partial loads of a thread are independent: issue them together, then add in a fixed order - a rolled
+    //  loop with a running sum serialises ~64 L2 round trips per thread, which was 60 % of this kernel's time)
+#pragma unroll 2
     for (int i = tid; i < HEADS_G * d4; i += HEADS_THREADS) {
         const int g = i / d4, k = i - g * d4;              // consecutive threads -> consecutive k: coalesced partial-sum reads
         float v = 0.f;
         if (g < g_n) {
+            const float *zp = z4 + (b0 + g) * d4 + k;
+            float part[16];
+#pragma unroll
+            for (int sp = 0; sp < 16; ++sp) part[sp] = sp < nsplit ? __ldg(zp + (size_t)sp * split_stride) : 0.f;
             v = __ldg(hp.b4 + k);
-            for (int sp = 0; sp < nsplit; ++sp) v += z4[(size_t)sp * split_stride + (b0 + g) * d4 + k];   // split-K partials, fixed order
+#pragma unroll
+            for (int sp = 0; sp < 16; ++sp) v += part[sp];                                          // split-K partials, fixed order
             v = selu(v);
         }
         a[k * HEADS_G + g] = v;
@@ -93,16 +95,20 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
         const float bias = __ldg(hp.h[hp0 + hsel].b5 + j);
 #pragma unroll
         for (int g = 0; g < HEADS_G; ++g) acc[g] = bias;
+        // three-stage ring: two tiles in flight while one is consumed (an L2 round trip is ~2x a tile's FMA time)
         load_tile(0, 0);
+        if (ntiles > 1) load_tile(1, 1);
         for (int t = 0; t < ntiles; ++t) {
-            if (t + 1 < ntiles) {
-                load_tile(t + 1, (t + 1) & 1);
+            if (t + 2 < ntiles) {
+                load_tile(t + 2, (t + 2) % HEADS_STAGES);
+                asm volatile("cp.async.wait_group 2;" ::: "memory");
+            } else if (t + 1 < ntiles) {
                 asm volatile("cp.async.wait_group 1;" ::: "memory");
             } else {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             __syncthreads();
-            const float *ws = wt + (t & 1) * (2 * HEADS_KT * 128) + hsel * (HEADS_KT * 128) + j;
+            const float *ws = wt + (t % HEADS_STAGES) * (2 * HEADS_KT * 128) + hsel * (HEADS_KT * 128) + j;
             const float *as = a + (size_t)t * HEADS_KT * HEADS_G;
 #pragma unroll 8
             for (int k = 0; k < HEADS_KT; ++k) {
@@ -193,7 +199,8 @@ int c3b_launch_ingest_fa_f32(const void *x, int dtype, float *out, int64_t n, cu
 int c3b_launch_heads(const float *z4, int nsplit, int64_t split_stride, const HeadsParams &hp, float *out, int64_t batch,
                      cudaStream_t s) {
     if (batch == 0) return 0;
-    size_t smem = sizeof(float) * (HEADS_G * hp.d4 + C3B_MAX_HEADS * HEADS_G * 128 + HEADS_G * 96 + 2 * 2 * HEADS_KT * 128 +
+    if (nsplit < 1 || nsplit > 16) { c3b_set_error("heads: %d split-K partials (1..16 supported)", nsplit); return 1; }
+    size_t smem = sizeof(float) * (HEADS_G * hp.d4 + C3B_MAX_HEADS * HEADS_G * 128 + HEADS_G * 96 + HEADS_STAGES * 2 * HEADS_KT * 128 +
                                    128 * hp.out_dim);
     int blocks = (int)((batch + HEADS_G - 1) / HEADS_G);
     C3B_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

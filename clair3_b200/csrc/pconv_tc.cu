@@ -27,6 +27,7 @@ namespace {
 
 constexpr int kThreads = 320;
 constexpr int kMaxWStages = 8;
+constexpr int kMetaSlots = 1024;
 
 struct PconvDev {
     const op_t *in;
@@ -57,14 +58,107 @@ struct PconvDev {
     int debug_align;       // timing experiment only (wrong results): round every tap shift down to 8 slots
 };
 
+// Border mask and parity-scatter target of slot l of a site (the epilogue looks this up instead of dividing per tile).
+__device__ __forceinline__ uint32_t slot_meta(const PconvDev &p, int l) {
+    const int hh = l / p.Wp, ww = l - hh * p.Wp;
+    if (!(hh >= 1 && hh <= p.H && ww >= 1 && ww <= p.W)) return 0u;
+    uint32_t m = 0x80000000u;
+    if (p.out_parity) m |= (uint32_t)((hh & 1) * 2 + (ww & 1)) << 20 | (uint32_t)(((hh >> 1) + 1) * p.nWp + ((ww >> 1) + 1));
+    return m;
+}
+
+// Epilogue of one macro-tile for one thread (TMEM lane = output slot): bias + residual + ReLU + border mask + fp16 pack +
+// 16-byte stores, over the 16-column chunks of this thread's warp group.  TMEM reads are software-pipelined (the load of the
+// next chunk - of this or the next tile - is in flight while the current one is finished); residuals are fetched one chunk
+// ahead.  RES / PAR are compile-time so the no-residual and planar-output cases carry no dead work.
+template <int MT, bool RES, bool PAR>
+__device__ __forceinline__ void epilogue_tiles(const PconvDev &p, uint32_t tbase, long long g0, int eg, const float *bias_s,
+                                               const uint32_t *meta_s) {
+    const int cpg = p.N >> 5;                                            // chunks per group per tile (2, 4 or 8)
+    const uint32_t in_pitch = (uint32_t)p.P * 16u;                       // bytes between k-group planes (< 4 GB, host-checked)
+    const uint32_t out_pitch = PAR ? (uint32_t)p.nP * 16u : in_pitch;
+    float v0[16], v1[16];
+    ptx::tmem_ld16(tbase, v0);
+#pragma unroll
+    for (int ti = 0; ti < MT; ++ti) {
+        const long long g = g0 + 128LL * ti;                             // output slot
+        const bool in_data = g < p.T;
+        bool real = false;
+        size_t par_off = 0;                                              // parity-scatter destination (plane + slot of the next level)
+        if (in_data) {
+            const uint32_t b = (uint32_t)g / (uint32_t)p.S;              // T < 2^31 (checked on the host)
+            const int l = (int)((uint32_t)g - b * (uint32_t)p.S);
+            const uint32_t meta = p.S <= kMetaSlots ? meta_s[l] : slot_meta(p, l);
+            real = (meta >> 31) != 0;
+            if (PAR && real)
+                par_off = (size_t)((meta >> 20) & 3u) * p.out_plane_elems + ((size_t)p.nG + (size_t)b * p.nS + (meta & 0xFFFFFu)) * 8;
+        }
+        const bool wr = in_data && (real || !PAR);
+        const size_t slot_off = ((size_t)p.G + (size_t)g) * 8;
+        const uint32_t taddr = tbase + (uint32_t)(ti * p.N);
+        char *const obase = reinterpret_cast<char *>(PAR ? p.out + par_off : p.out + slot_off);
+        const char *const rbase = reinterpret_cast<const char *>(p.residual + slot_off);
+        uint4 res[2], rn[2];
+        if (RES && real) {
+            res[0] = *reinterpret_cast<const uint4 *>(rbase + (uint32_t)(2 * eg) * in_pitch);
+            res[1] = *reinterpret_cast<const uint4 *>(rbase + (uint32_t)(2 * eg + 1) * in_pitch);
+        }
+        auto finish = [&](const float *v, int j0) {       // one chunk: 16 channels of this slot
+            if (!wr) return;
+            uint4 pk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            if (real) {
+                uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
+                const float4 *b4 = reinterpret_cast<const float4 *>(bias_s + j0);
+                const op2_t *rp = reinterpret_cast<const op2_t *>(res);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 bb = b4[i];
+                    float x0 = v[4 * i] + bb.x, x1 = v[4 * i + 1] + bb.y, x2 = v[4 * i + 2] + bb.z, x3 = v[4 * i + 3] + bb.w;
+                    if (RES) {
+                        const float2 ra = op22f2(rp[2 * i]), rb = op22f2(rp[2 * i + 1]);
+                        x0 += ra.x; x1 += ra.y; x2 += rb.x; x3 += rb.y;
+                    }
+                    if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+                    pw[2 * i] = f2op2_sat(x0, x1);
+                    pw[2 * i + 1] = f2op2_sat(x2, x3);
+                }
+            }
+            char *d0p = obase + (uint32_t)(j0 >> 3) * out_pitch;
+            *reinterpret_cast<uint4 *>(d0p) = pk[0];
+            *reinterpret_cast<uint4 *>(d0p + out_pitch) = pk[1];
+        };
+        auto next_res = [&](int j0n) {                     // residual of the chunk after the current one
+            if (RES && real && j0n < p.N) {
+                rn[0] = *reinterpret_cast<const uint4 *>(rbase + (uint32_t)(j0n >> 3) * in_pitch);
+                rn[1] = *reinterpret_cast<const uint4 *>(rbase + (uint32_t)((j0n >> 3) + 1) * in_pitch);
+            }
+        };
+        for (int jc = 0; jc < cpg; jc += 2) {
+            const int j0 = 16 * eg + 32 * jc;
+            ptx::tmem_ld_wait();                                         // v0 = chunk jc
+            ptx::tmem_ld16(taddr + (uint32_t)(32 * (jc + 1)), v1);
+            next_res(j0 + 32);
+            finish(v0, j0);
+            if (RES) { res[0] = rn[0]; res[1] = rn[1]; }
+            ptx::tmem_ld_wait();                                         // v1 = chunk jc + 1
+            if (jc + 2 < cpg) ptx::tmem_ld16(taddr + (uint32_t)(32 * (jc + 2)), v0);
+            else if (ti + 1 < MT) ptx::tmem_ld16(taddr + (uint32_t)p.N, v0);      // first chunk of the next tile
+            next_res(j0 + 64);
+            finish(v1, j0 + 32);
+            if (RES) { res[0] = rn[0]; res[1] = rn[1]; }
+        }
+    }
+}
+
 template <int MT>
 __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
     __shared__ uint64_t img_full[2], img_empty[2], tmem_full[2], tmem_empty[2], w_res_bar;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float bias_s[256];
+    __shared__ __align__(16) float bias_s[256];
     __shared__ uint32_t a_off_s[144];
+    __shared__ uint32_t meta_s[kMetaSlots];   // per slot-in-site: bit 31 = real pixel, bits 20..21 = parity plane, low 20 = slot in the next level's site
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -90,6 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
     }
     if (warp == 8) ptx::tmem_alloc<512>(&tmem_base_smem);
     for (int i = tid; i < p.N; i += kThreads) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+    for (int l = tid; l < p.S && l < kMetaSlots; l += kThreads) meta_s[l] = slot_meta(p, l);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -258,66 +353,14 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
             ptx::mbar_wait(&tmem_full[acc], aph);
             ptx::tc_fence_after();
             if (tr) p.trace[li * 8 + 5] = clock64();
-            for (int ti = 0; ti < MT; ++ti) {
-                const long long g = (128LL * MT) * macro + 128LL * ti + r;       // output slot
-                const bool in_data = g < p.T;
-                bool real = false;
-                size_t par_off = 0;                 // parity-scatter destination (plane + slot of the next level)
-                if (in_data) {
-                    const long long b = g / p.S;
-                    const int l = (int)(g - b * p.S);
-                    const int hh = l / p.Wp, ww = l - hh * p.Wp;
-                    real = hh >= 1 && hh <= p.H && ww >= 1 && ww <= p.W;
-                    if (p.out_parity && real)
-                        par_off = (size_t)((hh & 1) * 2 + (ww & 1)) * p.out_plane_elems +
-                                  ((size_t)p.nG + b * p.nS + (size_t)((hh >> 1) + 1) * p.nWp + ((ww >> 1) + 1)) * 8;
-                }
-                const bool wr = in_data && (real || !p.out_parity);
-                const bool use_res = real && p.residual != nullptr;
-                const size_t slot_off = ((size_t)p.G + (size_t)g) * 8;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MT * p.N + ti * p.N);
-                uint4 res[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-                if (use_res) {
-                    const op_t *rp0 = p.residual + (size_t)(2 * eg) * p.P * 8 + slot_off;
-                    res[0] = *reinterpret_cast<const uint4 *>(rp0);
-                    res[1] = *reinterpret_cast<const uint4 *>(rp0 + (size_t)p.P * 8);
-                }
-                for (int j0 = 16 * eg; j0 < p.N; j0 += 32) {
-                    float v[16];
-                    ptx::tmem_ld16(taddr + (uint32_t)j0, v);
-                    uint4 rn[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-                    if (use_res && j0 + 32 < p.N) {
-                        const op_t *rp0 = p.residual + (size_t)((j0 + 32) >> 3) * p.P * 8 + slot_off;
-                        rn[0] = *reinterpret_cast<const uint4 *>(rp0);
-                        rn[1] = *reinterpret_cast<const uint4 *>(rp0 + (size_t)p.P * 8);
-                    }
-                    ptx::tmem_ld_wait();
-                    if (wr) {
-                        uint4 pk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-                        if (real) {
-                            uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
-                            const op2_t *rp = reinterpret_cast<const op2_t *>(res);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float2 rf = op22f2(rp[i]);          // zeros when there is no residual
-                                float a = v[2 * i] + bias_s[j0 + 2 * i] + rf.x;
-                                float b = v[2 * i + 1] + bias_s[j0 + 2 * i + 1] + rf.y;
-                                if (p.relu) {
-                                    a = fmaxf(a, 0.f);
-                                    b = fmaxf(b, 0.f);
-                                }
-                                pw[i] = f2op2_sat(a, b);
-                            }
-                        }
-                        op_t *d0p = p.out_parity ? p.out + par_off + (size_t)(j0 >> 3) * p.nP * 8
-                                                 : p.out + (size_t)(j0 >> 3) * p.P * 8 + slot_off;
-                        const size_t pitch = (size_t)(p.out_parity ? p.nP : p.P) * 8;
-                        *reinterpret_cast<uint4 *>(d0p) = pk[0];
-                        *reinterpret_cast<uint4 *>(d0p + pitch) = pk[1];
-                    }
-                    res[0] = rn[0];
-                    res[1] = rn[1];
-                }
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MT * p.N) + (uint32_t)(16 * eg);
+            const long long g0 = (128LL * MT) * macro + r;
+            if (p.residual) {
+                if (p.out_parity) epilogue_tiles<MT, true, true>(p, tbase, g0, eg, bias_s, meta_s);
+                else epilogue_tiles<MT, true, false>(p, tbase, g0, eg, bias_s, meta_s);
+            } else {
+                if (p.out_parity) epilogue_tiles<MT, false, true>(p, tbase, g0, eg, bias_s, meta_s);
+                else epilogue_tiles<MT, false, false>(p, tbase, g0, eg, bias_s, meta_s);
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tmem_empty[acc]);
@@ -338,6 +381,7 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
     const PlanarGeom &g = a.geom;
     const bool c_ok = a.c == 16 || a.c == 64 || a.c == 128 || a.c == 256;
     if (!c_ok || a.n % 16 || a.n > 256 || a.n < 16) { c3b_set_error("pconv: unsupported channels %d -> %d", a.c, a.n); return 1; }
+    if (g.p * 2 * a.n >= (1LL << 32) || (a.out_parity && a.next.p * 2 * a.n >= (1LL << 32)) || g.t >= (1LL << 31) || (a.out_parity && a.next.s >= (1 << 20))) { c3b_set_error("pconv: batch too large for one launch"); return 1; }
     PconvDev p = {};
     p.in = a.in; p.w_img = a.w.w_img; p.bias = a.w.bias; p.residual = a.residual; p.out = a.out;
     p.C = a.c; p.N = a.n;
@@ -359,7 +403,7 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
         p.nS = a.next.s; p.nWp = a.next.wp; p.nG = a.next.g; p.nP = a.next.p;
     }
     if (p.nchunks != a.w.nchunks) { c3b_set_error("pconv: weight image has %d chunks, expected %d", a.w.nchunks, p.nchunks); return 1; }
-    const size_t budget = 225 * 1024 - 256;      // 227 KB per CTA minus the static barriers / bias table
+    const size_t budget = 221 * 1024 - 256;      // 227 KB per CTA minus the static barriers, bias and slot tables
     const size_t w_bytes = (size_t)a.n * 128;
     const size_t w_all = (size_t)p.nchunks * w_bytes;
     // Configuration search over MT in {4,2,1}: resident weights when they fit (then small MT only costs halo re-reads and
@@ -406,15 +450,15 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
     const_cast<c3b_model *>(m)->launches++;
     switch (p.MT) {
         case 1:
-            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
             pconv_kernel<1><<<grid, kThreads, smem, s>>>(p);
             break;
         case 2:
-            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
             pconv_kernel<2><<<grid, kThreads, smem, s>>>(p);
             break;
         case 4:
-            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
             pconv_kernel<4><<<grid, kThreads, smem, s>>>(p);
             break;
         default: c3b_set_error("pconv: unsupported MT %d", p.MT); return 1;
