@@ -732,6 +732,7 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
     const char *tapname[3][2] = {{"conv1", "res_block1"}, {"conv3", "res_block2"}, {"conv5", "res_block3"}};
 
     if (f32) {
+        w->fa_zero_sites = -1;      // this path overwrites the region the tensor-core path keeps zero-bordered
         float *xin = cv.take<float>((size_t)n * depth * 33 * m->channels * 4);
         float *act[3][3];
         for (int l = 0; l < 3; ++l)
@@ -782,8 +783,8 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
     const size_t planar_end = cv.off;
     op_t *sp = cv.take<op_t>((size_t)bp * 3584 * 2);
     float *z4 = cv.take<float>((size_t)16 * bp * 256 * 4);
-    // borders / guards of the planar maps must be zero; convs rewrite borders with zeros (or, for parity planes, never touch
-    // them) and never touch guards, so one clear per (workspace, geometry) is enough
+    // borders / guards of the planar maps must be zero; the convs only ever store real pixels, so one clear per
+    // (workspace, geometry) is enough
     if (w->fa_zero_sites != n || w->fa_zero_depth != depth) {
         C3B_CUDA(cudaMemsetAsync(w->dev + planar_begin, 0, planar_end - planar_begin, s));
         w->fa_zero_sites = n;
@@ -890,6 +891,7 @@ extern "C" int c3b_forward(c3b_model *m, const void *x, int x_dtype, int x_on_de
     if (w->dev_bytes < need) {
         C3B_CUDA(cudaStreamSynchronize(s));
         if (ensure_dev((void **)&w->dev, &w->dev_bytes, need)) return 1;
+        w->fa_zero_sites = -1;      // fresh memory: the planar maps' borders / guards must be cleared again
     }
     const void *xd = x;
     float *yd = y;

@@ -68,6 +68,7 @@ struct IgemmDev {
     int64_t split_stride;  // split-K partial epilogue: elements between ks slices
     int pg_bp;             // pre-gate epilogue: padded batch (multiple of 128)
     int pg_nbl;            //                    LSTM tile (batch columns per LSTM CTA)
+    int stage_out;         // pre-gate epilogue: 1 = stage [32 rows][NBL] blocks in shared memory and bulk-store them
 };
 
 // Tile walk shared by the three roles.  Streaming mode: tile = ((at * n_rowblocks) + rb) * ksplit + ks over a flat grid.
@@ -153,36 +154,36 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
     if (warp == 9) {
         // ===================================================== bulk-copy loader (one thread): resident weight slab and, for
         // k-group-planar activations, every stage (8 contiguous 2 KB runs per chunk; TMA engine, async proxy, no fences)
-        if (lane == 0) {
-            if (p.w_resident) {
-                const int rbr = (blockIdx.x % (p.n_rowblocks / p.wb)) * p.wb;
-                ptx::mbar_arrive_expect_tx(&w_bar, w_res_bytes);
-                for (int c = 0; c < p.nchunks; ++c)
-                    for (int b = 0; b < p.wb; ++b)
-                        ptx::bulk_g2s(smem_base + (uint32_t)(c * p.wb + b) * w_bytes,
-                                      (const char *)p.w_img + ((size_t)c * p.n_rowblocks + rbr + b) * w_bytes, w_bytes, &w_bar);
-            }
-            if (p.taps == 0) {
-                const uint32_t lbo_a = (uint32_t)p.act_rows * 16u;
-                int it = 0;
-                for (TileWalk tw(p); tw.valid(p); tw.next(p)) {
-                    int at, rb0, c_begin, c_end;
-                    tw.decode(p, at, rb0, c_begin, c_end);
-                    for (int c = c_begin; c < c_end; ++c, ++it) {
-                        const int s = it % S;
-                        const uint32_t ph = (uint32_t)(it / S) & 1u;
-                        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-                        const uint32_t stage = stages_base + (uint32_t)s * stage_bytes;
-                        const int kgs = min(8, p.kgroups - c * 8);
-                        ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)kgs * 2048u + (p.w_resident ? 0u : w_bytes));
-                        if (!p.w_resident)
-                            ptx::bulk_g2s(stage + act_bytes, (const char *)p.w_img + ((size_t)c * p.n_rowblocks + rb0) * w_bytes,
-                                          w_bytes, &full_bar[s]);
-                        for (int kg = 0; kg < kgs; ++kg)
-                            ptx::bulk_g2s(stage + (uint32_t)kg * lbo_a,
-                                          (const char *)p.act + ((size_t)(c * 8 + kg) * p.ld_rows + (size_t)at * 128) * 16, 2048u,
-                                          &full_bar[s]);
-                    }
+        // The whole warp walks the tiles; per chunk lane 0 arms the barrier and lanes 0..7 each issue ONE 2 KB run (lane 8 the
+        // streamed weight piece), so the per-copy address arithmetic runs in parallel instead of as one thread's serial
+        // instruction stream (measured: the single-thread loader, not the tensor pipe, bounded the LSTM2 projection).
+        if (p.w_resident && lane == 0) {
+            const int rbr = (blockIdx.x % (p.n_rowblocks / p.wb)) * p.wb;
+            ptx::mbar_arrive_expect_tx(&w_bar, w_res_bytes);
+            for (int c = 0; c < p.nchunks; ++c)
+                for (int b = 0; b < p.wb; ++b)
+                    ptx::bulk_g2s(smem_base + (uint32_t)(c * p.wb + b) * w_bytes,
+                                  (const char *)p.w_img + ((size_t)c * p.n_rowblocks + rbr + b) * w_bytes, w_bytes, &w_bar);
+        }
+        if (p.taps == 0) {
+            const uint32_t lbo_a = (uint32_t)p.act_rows * 16u;
+            const size_t kg_pitch = (size_t)p.ld_rows * 16;
+            int s = 0;
+            uint32_t ph = 0;
+            for (TileWalk tw(p); tw.valid(p); tw.next(p)) {
+                int at, rb0, c_begin, c_end;
+                tw.decode(p, at, rb0, c_begin, c_end);
+                const char *src_lane = (const char *)p.act + (size_t)at * 2048 + (size_t)(c_begin * 8 + lane) * kg_pitch;
+                for (int c = c_begin; c < c_end; ++c, src_lane += 8 * kg_pitch) {
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+                    const uint32_t stage = stages_base + (uint32_t)s * stage_bytes;
+                    const int kgs = min(8, p.kgroups - c * 8);
+                    if (lane == 0) ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)kgs * 2048u + (p.w_resident ? 0u : w_bytes));
+                    __syncwarp();
+                    if (lane < kgs) ptx::bulk_g2s(stage + (uint32_t)lane * lbo_a, src_lane, 2048u, &full_bar[s]);
+                    else if (lane == 8 && !p.w_resident)
+                        ptx::bulk_g2s(stage + act_bytes, (const char *)p.w_img + ((size_t)c * p.n_rowblocks + rb0) * w_bytes, w_bytes, &full_bar[s]);
+                    if (++s == S) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -292,44 +293,74 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
         const uint32_t idesc = ptx::umma_idesc_f16(128, (uint32_t)ncols);
         const uint32_t lbo_act = (uint32_t)(p.act_rows + act_pad) * 16u;
         const uint32_t lbo_w = (uint32_t)p.w_rows * 16u;
-        int it = 0;
-        int tcount = 0;
-        if (p.w_resident) ptx::mbar_wait(&w_bar, 0);
-        for (TileWalk tw(p); tw.valid(p); tw.next(p), ++tcount) {
-            int at, rb0, c_begin, c_end;
-            tw.decode(p, at, rb0, c_begin, c_end);
-            const int acc = tcount & 1;
-            const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
-            ptx::mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);
-            ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
-            for (int c = c_begin; c < c_end; ++c, ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                ptx::mbar_wait(&full_bar[s], ph);
+        // ONE elected thread runs the whole loop (barrier waits included).  tcgen05.mma issue does not run ahead of the
+        // tensor pipe, so every instruction between two MMAs is pipe idle time: descriptors are advanced with 32-bit adds on
+        // their start-address field (shared memory < 256 KB: no carry out of the 14 bits), ring position kept as counters.
+        if (ptx::elect_one()) {
+            const uint64_t act_d0 = ptx::umma_desc_nosw(0, lbo_act, 128u), w_d0 = ptx::umma_desc_nosw(0, lbo_w, 128u);
+            const uint32_t act_lo0 = (uint32_t)act_d0, act_hi = (uint32_t)(act_d0 >> 32);
+            const uint32_t w_lo0 = (uint32_t)w_d0, w_hi = (uint32_t)(w_d0 >> 32);
+            const uint32_t act_kstep = (2u * lbo_act) >> 4, w_kstep = (2u * lbo_w) >> 4;
+            const uint32_t w_bstep = w_bytes >> 4;          // next resident row block of the same chunk
+            int s = 0;
+            uint32_t ph = 0;
+            int tcount = 0;
+            if (p.w_resident) ptx::mbar_wait(&w_bar, 0);
+            for (TileWalk tw(p); tw.valid(p); tw.next(p), ++tcount) {
+                int at, rb0, c_begin, c_end;
+                tw.decode(p, at, rb0, c_begin, c_end);
+                const int acc = tcount & 1;
+                const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+                ptx::mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);
                 ptx::tc_fence_after();
-                const uint32_t stage = stages_base + (uint32_t)s * stage_bytes;
-                const int kgs = min(8, p.kgroups - c * 8);
-                const int ksteps = (kgs + 1) >> 1;
-                if (ptx::elect_one()) {
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint64_t act_desc = ptx::umma_desc_nosw(stage + (uint32_t)k * 2u * lbo_act, lbo_act, 128u);
-                        const uint32_t accum = (c > c_begin || k > 0) ? 1u : 0u;
-                        for (int b = 0; b < p.wb; ++b) {
-                            const uint32_t w_addr = p.w_resident ? smem_base + (uint32_t)(c * p.wb + b) * w_bytes : stage + act_bytes;
-                            const uint64_t w_desc = ptx::umma_desc_nosw(w_addr + (uint32_t)k * 2u * lbo_w, lbo_w, 128u);
-                            if (SWAP)
-                                ptx::umma_f16(d_tmem + (uint32_t)(b * ncols), w_desc, act_desc, idesc, accum);
-                            else
-                                ptx::umma_f16(d_tmem, act_desc, w_desc, idesc, accum);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+                for (int c = c_begin; c < c_end; ++c) {
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t stage = stages_base + (uint32_t)s * stage_bytes;
+                    const int kgs = min(8, p.kgroups - c * 8);
+                    const int ksteps = (kgs + 1) >> 1;
+                    const uint32_t act_lo = act_lo0 + (stage >> 4);
+                    const uint32_t w_lo = w_lo0 + ((p.w_resident ? smem_base + (uint32_t)(c * p.wb) * w_bytes : stage + act_bytes) >> 4);
+                    if (ksteps == 4 && p.wb == 2) {             // the hot shape (LSTM2 input projection): fully unrolled
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = ((uint64_t)act_hi << 32) | (uint64_t)(act_lo + (uint32_t)k * act_kstep);
+                            const uint32_t accum = (c > c_begin || k > 0) ? 1u : 0u;
+#pragma unroll
+                            for (int b = 0; b < 2; ++b) {
+                                const uint64_t wd = ((uint64_t)w_hi << 32) | (uint64_t)(w_lo + (uint32_t)b * w_bstep + (uint32_t)k * w_kstep);
+                                if (SWAP) ptx::umma_f16(d_tmem + (uint32_t)(b * ncols), wd, ad, idesc, accum);
+                                else ptx::umma_f16(d_tmem, ad, wd, idesc, accum);
+                            }
+                        }
+                    } else if (ksteps == 4 && p.wb == 1) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = ((uint64_t)act_hi << 32) | (uint64_t)(act_lo + (uint32_t)k * act_kstep);
+                            const uint64_t wd = ((uint64_t)w_hi << 32) | (uint64_t)(w_lo + (uint32_t)k * w_kstep);
+                            const uint32_t accum = (c > c_begin || k > 0) ? 1u : 0u;
+                            if (SWAP) ptx::umma_f16(d_tmem, wd, ad, idesc, accum);
+                            else ptx::umma_f16(d_tmem, ad, wd, idesc, accum);
+                        }
+                    } else {
+                        for (int k = 0; k < ksteps; ++k) {
+                            const uint64_t ad = ((uint64_t)act_hi << 32) | (uint64_t)(act_lo + (uint32_t)k * act_kstep);
+                            const uint32_t accum = (c > c_begin || k > 0) ? 1u : 0u;
+                            for (int b = 0; b < p.wb; ++b) {
+                                const uint64_t wd = ((uint64_t)w_hi << 32) | (uint64_t)(w_lo + (uint32_t)b * w_bstep + (uint32_t)k * w_kstep);
+                                if (SWAP) ptx::umma_f16(d_tmem + (uint32_t)(b * ncols), wd, ad, idesc, accum);
+                                else ptx::umma_f16(d_tmem, ad, wd, idesc, accum);
+                            }
                         }
                     }
                     ptx::umma_commit(&empty_bar[s]);
                     if (c + 1 == c_end) ptx::umma_commit(&tmem_full_bar[acc]);
+                    if (++s == S) { s = 0; ph ^= 1u; }
                 }
-                __syncwarp();
             }
         }
+        __syncwarp();
     } else {
         // ===================================================== epilogue warps 4..7 (+ warps 0..3 as a second group when the
         // operands arrive by bulk copy): with two row blocks per tile each group takes one, otherwise half the columns
@@ -417,22 +448,46 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                                                ((size_t)blk * 128 + r) * p.pg_nbl;
                         const size_t st_stride = (size_t)5 * 128 * p.pg_nbl;
                         int st_i = j_lo / p.pg_nbl, in_st = j_lo % p.pg_nbl;
-                        for (int j0 = j_lo; j0 < j_hi; j0 += 16) {
-                            float v[16];
-                            ptx::tmem_ld16(tb + (uint32_t)j0, v);
-                            ptx::tmem_ld_wait();
-                            const size_t off = row_off + (size_t)st_i * st_stride + in_st;
-                            in_st += 16;
-                            if (in_st == p.pg_nbl) { in_st = 0; ++st_i; }
-                            uint4 pk[2];
-                            uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
+                        // A thread owns a ROW of the output (its sites are 128 B apart from the next lane's): direct 16-byte
+                        // stores touch 32 lines per instruction, and LSU wavefronts are what the concurrent MMA operand fetches
+                        // starve (measured: an epilogue chunk costs 2.7x more under a running MMA stream).  So each warp
+                        // transposes its [32 rows][NBL] block through shared memory (XOR-swizzled 16-byte chunks: both phases
+                        // conflict-free) and writes it back with fully coalesced 16-byte stores: 96 wavefronts per 4 KB block
+                        // instead of 256.  (Handing the block to the TMA engine was no faster, and a swizzled GLOBAL layout
+                        // cost the LSTM2 kernel more than it saved here.)
+                        {
+                            const uint32_t row_bytes = (uint32_t)p.pg_nbl * 2u;
+                            const uint32_t nc = (uint32_t)p.pg_nbl >> 3;                        // 16-byte chunks per row: 2, 4 or 8
+                            const uint32_t rsh = nc == 8 ? 0u : nc == 4 ? 1u : 2u;              // rows sharing a 128-byte bank row
+                            const uint32_t ncs = nc == 8 ? 3u : nc == 4 ? 2u : 1u;              // log2(nc)
+                            uint8_t *stg = smem + w_res_bytes + (uint32_t)S * stage_bytes + (uint32_t)warp * 32u * row_bytes;
+                            uint8_t *my_row = stg + (uint32_t)lane * row_bytes;
+                            const uint32_t sw = ((uint32_t)lane >> rsh) & (nc - 1u);
+                            const size_t blk_off = row_off - (size_t)lane * p.pg_nbl;          // row q*32 of this block
+                            for (int j0 = j_lo; j0 < j_hi; j0 += 16) {
+                                float v[16];
+                                ptx::tmem_ld16(tb + (uint32_t)j0, v);
+                                if (in_st == 0) __syncwarp();           // the previous block has been read back
+                                ptx::tmem_ld_wait();
+                                uint4 pk[2];
+                                uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                pw[i] = f2op2_sat(v[2 * i] + bias, v[2 * i + 1] + bias);
+                                for (int i = 0; i < 8; ++i) pw[i] = f2op2_sat(v[2 * i] + bias, v[2 * i + 1] + bias);
+                                const uint32_t c0 = (uint32_t)in_st >> 3;
+                                *reinterpret_cast<uint4 *>(my_row + ((c0 ^ sw) << 4)) = pk[0];
+                                *reinterpret_cast<uint4 *>(my_row + (((c0 + 1u) ^ sw) << 4)) = pk[1];
+                                in_st += 16;
+                                if (in_st == p.pg_nbl) {
+                                    __syncwarp();
+                                    uint4 *gdst = reinterpret_cast<uint4 *>((__half *)p.out + blk_off + (size_t)st_i * st_stride);
+                                    for (uint32_t u = (uint32_t)lane; u < 32u * nc; u += 32u) {   // 16-byte unit u of the contiguous block
+                                        const uint32_t row = u >> ncs, c = u & (nc - 1u);
+                                        gdst[u] = *reinterpret_cast<const uint4 *>(stg + row * row_bytes + ((c ^ ((row >> rsh) & (nc - 1u))) << 4));
+                                    }
+                                    in_st = 0;
+                                    ++st_i;
+                                }
                             }
-                            __half *dst = (__half *)p.out + off;
-                            *reinterpret_cast<uint4 *>(dst) = pk[0];
-                            *reinterpret_cast<uint4 *>(dst + 8) = pk[1];
                         }
                     } else {
                         // split-K partial sums: partial[ks][pos][R], plain stores (consecutive lanes = consecutive R: 128-byte
@@ -473,7 +528,7 @@ int ilog2(int v) {
 template <bool SWAP, int EPI>
 int launch(const IgemmDev &p, int grid, size_t smem, cudaStream_t s) {
     auto kern = igemm_kernel<SWAP, EPI>;
-    C3B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    C3B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     kern<<<grid, kThreads, smem, s>>>(p);
     C3B_CUDA(cudaGetLastError());
     return 0;
@@ -520,14 +575,19 @@ int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s) {
     p.chunks_per_split = (p.nchunks + p.ksplit - 1) / p.ksplit;
     p.ksplit = (p.nchunks + p.chunks_per_split - 1) / p.chunks_per_split;   // drop empty splits
 
-    const size_t budget = 216 * 1024;
+    // pre-gate epilogue: each of the 8 epilogue warps transposes a [32 rows][NBL] fp16 block through shared memory
+    const bool stage_out = a.epilogue == IGEMM_EPI_F16_BIAS;
+    if (stage_out && a.taps != 0) { c3b_set_error("igemm: the pre-gate epilogue needs k-group-planar activations"); return 1; }
+    p.stage_out = stage_out ? 1 : 0;
+    const size_t stage_out_bytes = stage_out ? (size_t)8 * 32 * (size_t)a.win * 2 : 0;
+    const size_t budget = (stage_out ? 224 : 216) * 1024 - stage_out_bytes;
     const size_t act_bytes = (size_t)(p.act_rows + (a.taps == 0 ? 0 : 1)) * 128, w_bytes = (size_t)p.w_rows * 128;
     // W-stationary when the slab fits beside >= 4 activation stages (and there are enough tiles to amortise the load)
     if (p.ksplit == 1) {
         int wb = (swap && p.n_rowblocks % 2 == 0 && 2 * p.act_rows <= 256) ? 2 : 1;
         for (; wb >= 1; --wb) {
             const size_t slab = (size_t)wb * p.nchunks * w_bytes;
-            if (slab + 5 * act_bytes <= budget && p.n_act_tiles >= 2 * (m->sm_count / (p.n_rowblocks / wb))) {
+            if (slab + (stage_out ? 4 : 5) * act_bytes <= budget && p.n_act_tiles >= 2 * (m->sm_count / (p.n_rowblocks / wb))) {
                 p.w_resident = 1;
                 p.wb = wb;
                 break;
@@ -540,7 +600,7 @@ int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s) {
         const size_t slab = (size_t)p.wb * p.nchunks * w_bytes;
         int stages = (int)((budget - slab) / act_bytes);
         p.stages = stages > kMaxStages ? kMaxStages : stages;
-        smem = slab + act_bytes * p.stages + 256;
+        smem = slab + act_bytes * p.stages + stage_out_bytes + 256;
         const int n_rg = p.n_rowblocks / p.wb;
         int per = m->sm_count / n_rg;
         if (per > p.n_act_tiles) per = p.n_act_tiles;
@@ -549,11 +609,11 @@ int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s) {
         const size_t stage_bytes = act_bytes + w_bytes;
         int stages = (int)(budget / stage_bytes);
         p.stages = stages > kMaxStages ? kMaxStages : stages;
-        smem = stage_bytes * p.stages + 256;
+        smem = stage_bytes * p.stages + stage_out_bytes + 256;
         const int num_tiles = p.n_act_tiles * p.n_rowblocks * p.ksplit;
         grid = num_tiles < m->sm_count ? num_tiles : m->sm_count;
     }
-    if (p.stages < kLag + 1) { c3b_set_error("igemm: tile too large for the shared-memory pipeline"); return 1; }
+    if (p.stages < (a.taps == 0 ? 2 : kLag + 1)) { c3b_set_error("igemm: tile too large for the shared-memory pipeline"); return 1; }
     const_cast<c3b_model *>(m)->launches++;
     switch (a.epilogue) {
         case IGEMM_EPI_BF16_BIAS_RELU: return launch<false, IGEMM_EPI_BF16_BIAS_RELU>(p, grid, smem, s);

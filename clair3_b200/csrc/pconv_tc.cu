@@ -9,8 +9,9 @@
 //     no im2col expansion, no proxy fences) in exactly the SWIZZLE_NONE K-major UMMA layout [k-group][slot][8];
 //   * the A operand of tap (dh,dw) is the SAME image viewed (dh-1)*Wp + (dw-1) slots later: only the descriptor's start
 //     address changes, so every input byte is fetched once per macro-tile and used by all nine taps;
-//   * border slots are computed like any other row and overwritten with zeros in the epilogue, so the output is again a
-//     valid planar padded tensor for the next convolution (and the residual add reads the same slot of its own input).
+//   * border slots are computed like any other row but never stored: they keep the zeros of the one-time workspace clear,
+//     so the output is again a valid planar padded tensor for the next convolution (and the residual add reads the same
+//     slot of its own input).
 // Weights: the host-packed per-chunk images of igemm_tc.cu ([tap*C/64 + kc][8 k-groups][N][8]); resident when they fit
 // (res_block1: 72 KB), otherwise streamed through a ring with each piece applied to MT accumulators.
 //
@@ -93,7 +94,7 @@ __device__ __forceinline__ void epilogue_tiles(const PconvDev &p, uint32_t tbase
             if (PAR && real)
                 par_off = (size_t)((meta >> 20) & 3u) * p.out_plane_elems + ((size_t)p.nG + (size_t)b * p.nS + (meta & 0xFFFFFu)) * 8;
         }
-        const bool wr = in_data && (real || !PAR);
+        const bool wr = real;       // border slots are never written: they stay zero from the workspace clear (one clear per geometry)
         const size_t slot_off = ((size_t)p.G + (size_t)g) * 8;
         const uint32_t taddr = tbase + (uint32_t)(ti * p.N);
         char *const obase = reinterpret_cast<char *>(PAR ? p.out + par_off : p.out + slot_off);
@@ -105,8 +106,8 @@ __device__ __forceinline__ void epilogue_tiles(const PconvDev &p, uint32_t tbase
         }
         auto finish = [&](const float *v, int j0) {       // one chunk: 16 channels of this slot
             if (!wr) return;
-            uint4 pk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            if (real) {
+            uint4 pk[2];
+            {
                 uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
                 const float4 *b4 = reinterpret_cast<const float4 *>(bias_s + j0);
                 const op2_t *rp = reinterpret_cast<const op2_t *>(res);

@@ -145,7 +145,103 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int reps, int 
     if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc<512>(tmem_base); }
 }
 
+// TMEM read probe: warps 0-3 time `reps` x (tcgen05.ld 32x32b.x16 + wait::ld), singly and in batches of four loads per
+// wait, first with the tensor pipe idle and then while warp 4 streams 128 x 128 x 16 MMAs into other TMEM columns.
+__global__ void __launch_bounds__(160, 1) tmem_probe_kernel(int reps, long long *timing, float *sink) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ volatile int stop_flag;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { ptx::mbar_init(&bar, 1); ptx::fence_barrier_init(); stop_flag = 0; }
+    if (warp == 0) ptx::tmem_alloc<512>(&tmem_base_smem);
+    for (int i = tid; i < 32 * 1024 / 16; i += 160) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0x3c003c00u, 0x3c003c00u, 0, 0);
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t lane_t = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    float acc = 0.f;
+    for (int phase = 0; phase < 2; ++phase) {          // 0: tensor pipe idle, 1: MMA stream running
+        if (warp == 4) {
+            if (phase == 1 && ptx::elect_one()) {
+                const uint32_t idesc = ptx::umma_idesc_f16(128, 128);
+                const uint64_t a_desc = ptx::umma_desc_nosw(ptx::smem_u32(smem), 2048, 128);
+                const uint64_t b_desc = ptx::umma_desc_nosw(ptx::smem_u32(smem) + 8192, 2048, 128);
+                while (!stop_flag) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) ptx::umma_f16(tmem_base + 256 + (uint32_t)((i & 1) * 128), a_desc, b_desc, idesc, 1);
+                }
+                ptx::umma_commit(&bar);
+                ptx::mbar_wait(&bar, 0);
+            }
+            __syncwarp();
+        } else {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            long long t0 = clock64();
+            for (int i = 0; i < reps; ++i) {                              // one load per wait
+                float v[16];
+                ptx::tmem_ld16(lane_t + (uint32_t)((i & 7) * 16), v);
+                ptx::tmem_ld_wait();
+                acc += v[0] + v[15];
+            }
+            long long t1 = clock64();
+            for (int i = 0; i < reps; i += 4) {                           // four loads per wait
+                float v0[16], v1[16], v2[16], v3[16];
+                ptx::tmem_ld16(lane_t + 0, v0);
+                ptx::tmem_ld16(lane_t + 16, v1);
+                ptx::tmem_ld16(lane_t + 32, v2);
+                ptx::tmem_ld16(lane_t + 48, v3);
+                ptx::tmem_ld_wait();
+                acc += v0[0] + v1[1] + v2[2] + v3[3];
+            }
+            long long t2 = clock64();
+            // a chunk as the conv epilogue does it: load, wait, 16 adds, 8 packs, two 16-byte stores (coalesced)
+            for (int i = 0; i < reps; ++i) {
+                float v[16];
+                ptx::tmem_ld16(lane_t + (uint32_t)((i & 7) * 16), v);
+                ptx::tmem_ld_wait();
+                uint4 pk[2];
+                uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) pw[k] = f2op2_sat(v[2 * k] + 1.f, v[2 * k + 1] + 1.f);
+                uint4 *dst = reinterpret_cast<uint4 *>(sink) + ((size_t)(i & 63) * 2 * 128 + tid);
+                dst[0] = pk[0];
+                dst[128] = pk[1];
+            }
+            long long t3 = clock64();
+            if (tid == 0) {
+                timing[phase * 3 + 0] = t1 - t0;
+                timing[phase * 3 + 1] = t2 - t1;
+                timing[phase * 3 + 2] = t3 - t2;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (phase == 1 && tid == 0) stop_flag = 1;
+        }
+        if (phase == 0) __syncthreads();
+    }
+    if (acc == 123.456f) sink[0] = acc;
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc<512>(tmem_base); }
+}
+
 }  // namespace
+
+// timing[6]: {1 ld/wait, 4 ld/wait, full chunk} x {tensor idle, MMA stream running}, cycles for `reps` chunks
+extern "C" int c3b_debug_tmem_probe(int reps, int64_t *timing) {
+    void *dt, *ds;
+    C3B_CUDA(cudaMalloc(&dt, 6 * 8));
+    C3B_CUDA(cudaMalloc(&ds, 64 * 2 * 128 * 16 + 64));
+    C3B_CUDA(cudaFuncSetAttribute(tmem_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    tmem_probe_kernel<<<1, 160, 64 * 1024>>>(reps, (long long *)dt, (float *)ds);
+    C3B_CUDA(cudaGetLastError());
+    C3B_CUDA(cudaDeviceSynchronize());
+    C3B_CUDA(cudaMemcpy(timing, dt, 48, cudaMemcpyDeviceToHost));
+    cudaFree(dt); cudaFree(ds);
+    return 0;
+}
 
 // modes: nmodes x 5 ints {a_step, a_mis, b_step, b_div, d_cnt}; timing: nmodes x {issue, done} cycles
 extern "C" int c3b_debug_mma_probe(int n, int reps, int nmodes, const int *modes, int64_t *timing) {

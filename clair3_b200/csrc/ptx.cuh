@@ -52,6 +52,20 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uin
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// Bulk shared -> global store (TMA engine; the data leaves through the async proxy, not the LSU).  bytes % 16 == 0.  The
+// issuing thread tracks completion with bulk groups: commit, then wait_group.read before the shared buffer is rewritten.
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+// Same with an L2 evict_last policy: the consumer kernel reads the data next, so it should stay in L2.
+__device__ __forceinline__ void bulk_s2g_keep(void *dst, uint32_t src_smem, uint32_t bytes) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src_smem), "r"(bytes), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // Make generic-proxy shared-memory writes (st.shared / cp.async) visible to the async proxy (UMMA operand reads).
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

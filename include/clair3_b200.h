@@ -115,6 +115,8 @@ int c3b_debug_lstm_trace(c3b_model *m, int64_t *out264);
 int c3b_debug_ts_probe(const float *a, const float *b, int n, int reps, float *out_d, int64_t *timing10);
 /* debug: cycles for back-to-back tcgen05.mma under operand / accumulator switching (tools/diag.py mmaprobe) */
 int c3b_debug_mma_probe(int n, int reps, int nmodes, const int *modes, int64_t *timing);
+/* debug: cycles of TMEM reads / an epilogue chunk with the tensor pipe idle and busy (tools/diag.py tmemprobe) */
+int c3b_debug_tmem_probe(int reps, int64_t *timing6);
 
 void c3b_destroy(c3b_model *m);
 

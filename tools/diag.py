@@ -214,6 +214,16 @@ def run_mmaprobe():
             print(f"N={n:3d} {nm:32s}: {tm[2*i+1]/reps:6.1f} cycles/MMA (issue {tm[2*i]/reps:5.1f})", flush=True)
 
 
+def run_tmemprobe():
+    from clair3_b200._ffi import check, ffi, lib
+    reps = 256
+    tm = np.zeros(6, dtype=np.int64)
+    check(lib().c3b_debug_tmem_probe(reps, ffi.cast("int64_t *", tm.ctypes.data)))
+    for ph, nm in enumerate(("tensor pipe idle", "MMA stream running")):
+        print(f"{nm:20s}: ld16+wait {tm[ph*3]/reps:6.1f} | 4 x ld16 per wait {tm[ph*3+1]/reps:6.1f} per ld | "
+              f"full epilogue chunk {tm[ph*3+2]/reps:6.1f} cycles", flush=True)
+
+
 def run_trace(opts):
     """Per-step cycle breakdown of the persistent LSTM kernels (CTA 0, thread 0)."""
     from clair3_b200 import synth
@@ -269,6 +279,8 @@ if __name__ == "__main__":
         run_probe()
     elif mode == "mmaprobe":
         run_mmaprobe()
+    elif mode == "tmemprobe":
+        run_tmemprobe()
     elif mode == "trace":
         run_trace(opts)
     else:
