@@ -274,7 +274,7 @@ extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
     } else if (!strcmp(name, "host_async")) {
         m->host_async = value ? 1 : 0;
     } else if (!strcmp(name, "lstm_trace")) {
-        m->trace_conv = value >= 10 ? (int)value - 10 : 1;
+        m->trace_conv = value >= 10 ? (int)value - 10 : 1;       // 10..18: Clair3_F conv index; 30: the LSTM2 input projection
         if (value && !m->lstm_trace) {
             C3B_CUDA(cudaSetDevice(m->device));
             C3B_CUDA(cudaMalloc(&m->lstm_trace, sizeof(long long) * 2 * C3B_T * 4));
@@ -693,6 +693,7 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
     pa.w = m->proj2;
     pa.out = b.pg;
     pa.epilogue = IGEMM_EPI_F16_BIAS;
+    pa.trace = (m->lstm_trace && m->trace_conv == 20) ? m->lstm_trace : nullptr;   // debug option lstm_trace = 30
     { PROF("proj2"); if (c3b_launch_igemm(m, pa, s)) return 1; }
     { PROF("lstm2"); if (c3b_launch_lstm2_tc(m, b, n, tile2, s)) return 1; }
     IgemmArgs la = {};
@@ -706,7 +707,10 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
     la.out = b.z4;
     la.ldo = 128;
     la.epilogue = IGEMM_EPI_F32_ATOMIC;
-    la.ksplit = 11;
+    static const int l4_ksplit_env = getenv("C3B_L4_KSPLIT") ? atoi(getenv("C3B_L4_KSPLIT")) : 0;   // tuning sweeps only
+    // 5 splits (33 of 165 chunks each): fewer, longer CTAs cost a few us of single-launch latency but 40 % less SM time than
+    // 11 splits - with several batches in flight that is +4 % sites/s (measured)
+    la.ksplit = l4_ksplit_env > 0 ? l4_ksplit_env : 5;
     la.split_stride = (int64_t)bp * 128;
     const int ns_p = c3b_effective_ksplit(m->l4_tc.nchunks, la.ksplit);
     { PROF("l4"); if (c3b_launch_igemm(m, la, s)) return 1; }

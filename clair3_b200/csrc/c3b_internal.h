@@ -255,6 +255,7 @@ struct IgemmArgs {
     // conv mode with planar padded tensors on either side (strided stem convs between pconv layers)
     int in_planar, out_planar;
     PlanarGeom gin, gout;
+    long long *trace;         // debug: clock stamps of CTA 0 ([tile][8]: MMA thread 0..3, epilogue thread 4..6)
 };
 int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s);
 

@@ -68,6 +68,7 @@ struct IgemmDev {
     int64_t split_stride;  // split-K partial epilogue: elements between ks slices
     int pg_bp;             // pre-gate epilogue: padded batch (multiple of 128)
     int pg_nbl;            //                    LSTM tile (batch columns per LSTM CTA)
+    long long *trace;      // optional clock stamps of CTA 0, [tile][8]
     int stage_out;         // pre-gate epilogue: 1 = stage [32 rows][NBL] blocks in shared memory and bulk-store them
 };
 
@@ -311,12 +312,16 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                 tw.decode(p, at, rb0, c_begin, c_end);
                 const int acc = tcount & 1;
                 const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+                const bool tr = p.trace != nullptr && blockIdx.x == 0 && tcount < 8;
+                if (tr) p.trace[tcount * 8 + 0] = clock64();
                 ptx::mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);
                 ptx::tc_fence_after();
+                if (tr) p.trace[tcount * 8 + 1] = clock64();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
                 for (int c = c_begin; c < c_end; ++c) {
                     ptx::mbar_wait(&full_bar[s], ph);
                     ptx::tc_fence_after();
+                    if (tr && c == c_begin) p.trace[tcount * 8 + 2] = clock64();
                     const uint32_t stage = stages_base + (uint32_t)s * stage_bytes;
                     const int kgs = min(8, p.kgroups - c * 8);
                     const int ksteps = (kgs + 1) >> 1;
@@ -358,6 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
                     if (c + 1 == c_end) ptx::umma_commit(&tmem_full_bar[acc]);
                     if (++s == S) { s = 0; ph ^= 1u; }
                 }
+                if (tr) p.trace[tcount * 8 + 3] = clock64();
             }
         }
         __syncwarp();
@@ -373,8 +379,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
             tw.decode(p, at, rb0, c_begin, c_end);
             const int acc = tcount & 1;
             const uint32_t acc_ph = (uint32_t)(tcount >> 1) & 1u;
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && tid == 128 && tcount < 8;
+            if (tr) p.trace[tcount * 8 + 4] = clock64();
             ptx::mbar_wait(&tmem_full_bar[acc], acc_ph);
             ptx::tc_fence_after();
+            if (tr) p.trace[tcount * 8 + 5] = clock64();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
             if (!SWAP) {
                 // thread = pixel row, columns = output channels
@@ -509,6 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tmem_empty_bar[acc]);
+            if (tr) p.trace[tcount * 8 + 6] = clock64();
         }
     }
     ptx::tc_fence_before();
@@ -548,6 +558,7 @@ int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s) {
     p.lda = a.lda;
     p.ldo = a.ldo;
     p.taps = a.taps;
+    p.trace = a.trace;
     p.ld_rows = a.ld_rows;
     if (a.taps == 0 && (a.w.kgroups & 1)) { c3b_set_error("igemm(planar): K/8 must be even"); return 1; }
     p.hin = a.hin; p.win = a.win; p.cin = a.cin; p.hout = a.hout; p.wout = a.wout; p.stride = a.stride;

@@ -18,7 +18,6 @@ __global__ void ingest_f32_kernel(const T *__restrict__ x, float *__restrict__ o
     for (; i < n; i += stride) out[i] = (float)x[i];
 }
 
-constexpr int HEADS_G = 8;        // sites per block
 constexpr int HEADS_THREADS = 256;
 constexpr int HEADS_KT = 32;      // k rows of an L5 weight tile staged in shared memory
 constexpr int HEADS_STAGES = 3;   // L5 weight tiles in the shared-memory ring
@@ -31,6 +30,7 @@ __device__ __forceinline__ void heads_cp16(float *dst_smem, const float *src) {
 // z4: [B][D4] L4 pre-activation WITHOUT bias.  One block = HEADS_G sites x all heads.  L5: thread (t/128, t%128) owns one
 // unit of one head (two heads in flight, four heads in two passes); the [D4][128] weight matrix of each head streams through
 // shared memory in double-buffered 32-row tiles (16-byte cp.async, fully coalesced) so the FMA loop never waits on L2.
+template <int HEADS_G>      // sites per block: 8 (small batches: more blocks) or 16 (large batches: half the weight streaming per site)
 __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__restrict__ z4, int nsplit, int64_t split_stride,
                                                               HeadsParams hp, float *__restrict__ out, int64_t batch) {
     extern __shared__ __align__(16) float smem[];
@@ -113,16 +113,14 @@ __global__ void __launch_bounds__(HEADS_THREADS) heads_kernel(const float *__res
 #pragma unroll 8
             for (int k = 0; k < HEADS_KT; ++k) {
                 const float wv = ws[k * 128];
-                const float4 a0 = *reinterpret_cast<const float4 *>(as + k * HEADS_G);
-                const float4 a1 = *reinterpret_cast<const float4 *>(as + k * HEADS_G + 4);
-                acc[0] = fmaf(a0.x, wv, acc[0]);
-                acc[1] = fmaf(a0.y, wv, acc[1]);
-                acc[2] = fmaf(a0.z, wv, acc[2]);
-                acc[3] = fmaf(a0.w, wv, acc[3]);
-                acc[4] = fmaf(a1.x, wv, acc[4]);
-                acc[5] = fmaf(a1.y, wv, acc[5]);
-                acc[6] = fmaf(a1.z, wv, acc[6]);
-                acc[7] = fmaf(a1.w, wv, acc[7]);
+#pragma unroll
+                for (int g4 = 0; g4 < HEADS_G / 4; ++g4) {
+                    const float4 av = *reinterpret_cast<const float4 *>(as + k * HEADS_G + 4 * g4);
+                    acc[4 * g4 + 0] = fmaf(av.x, wv, acc[4 * g4 + 0]);
+                    acc[4 * g4 + 1] = fmaf(av.y, wv, acc[4 * g4 + 1]);
+                    acc[4 * g4 + 2] = fmaf(av.z, wv, acc[4 * g4 + 2]);
+                    acc[4 * g4 + 3] = fmaf(av.w, wv, acc[4 * g4 + 3]);
+                }
             }
             __syncthreads();
         }
@@ -200,14 +198,20 @@ int c3b_launch_heads(const float *z4, int nsplit, int64_t split_stride, const He
                      cudaStream_t s) {
     if (batch == 0) return 0;
     if (nsplit < 1 || nsplit > 16) { c3b_set_error("heads: %d split-K partials (1..16 supported)", nsplit); return 1; }
-    size_t smem = sizeof(float) * (HEADS_G * hp.d4 + C3B_MAX_HEADS * HEADS_G * 128 + HEADS_G * 96 + HEADS_STAGES * 2 * HEADS_KT * 128 +
-                                   128 * hp.out_dim);
-    int blocks = (int)((batch + HEADS_G - 1) / HEADS_G);
-    C3B_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int sms = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    const int pairs = (hp.nheads >= 4 && hp.nheads % 2 == 0 && blocks * 2 <= 2 * sms) ? hp.nheads / 2 : 1;
-    heads_kernel<<<dim3(blocks, pairs), HEADS_THREADS, smem, s>>>(z4, nsplit, split_stride, hp, out, batch);
+    const int G = batch >= 512 ? 16 : 8;      // SM-time per site (weight streaming) matters more than block count once a launch has 32+ blocks
+    size_t smem = sizeof(float) * ((size_t)G * hp.d4 + (size_t)C3B_MAX_HEADS * G * 128 + (size_t)G * 96 + HEADS_STAGES * 2 * HEADS_KT * 128 +
+                                   128 * hp.out_dim);
+    int blocks = (int)((batch + G - 1) / G);
+    const int pairs = (hp.nheads >= 4 && hp.nheads % 2 == 0 && blocks <= sms) ? hp.nheads / 2 : 1;
+    if (G == 16) {
+        C3B_CUDA(cudaFuncSetAttribute(heads_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        heads_kernel<16><<<dim3(blocks, pairs), HEADS_THREADS, smem, s>>>(z4, nsplit, split_stride, hp, out, batch);
+    } else {
+        C3B_CUDA(cudaFuncSetAttribute(heads_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        heads_kernel<8><<<dim3(blocks, pairs), HEADS_THREADS, smem, s>>>(z4, nsplit, split_stride, hp, out, batch);
+    }
     C3B_CUDA(cudaGetLastError());
     return 0;
 }

@@ -435,7 +435,7 @@ int c3b_launch_lstm1_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t ba
     p.bias = (m->channels < 32) ? nullptr : m->lstm_tc[0][0].bias;   // bias folded into the GEMM when a spare input column exists
     p.xs = b.xs;
     p.hout = b.h1;
-    p.trace = m->lstm_trace ? m->lstm_trace : nullptr;
+    p.trace = (m->lstm_trace && m->trace_conv == 1) ? m->lstm_trace : nullptr;
     p.bp = (int)((batch + 127) / 128 * 128);
     const_cast<c3b_model *>(m)->launches++;
     switch (tile) {
@@ -452,7 +452,7 @@ int c3b_launch_lstm2_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t ba
     p.w_img = m->lstm_tc[1][0].w_img;
     p.pg = b.pg;
     p.hout = b.h2;
-    p.trace = m->lstm_trace ? m->lstm_trace + C3B_T * 4 : nullptr;
+    p.trace = (m->lstm_trace && m->trace_conv == 1) ? m->lstm_trace + C3B_T * 4 : nullptr;
     p.bp = (int)((batch + 127) / 128 * 128);
     const_cast<c3b_model *>(m)->launches++;
     switch (tile) {

@@ -214,6 +214,33 @@ def run_mmaprobe():
             print(f"N={n:3d} {nm:32s}: {tm[2*i+1]/reps:6.1f} cycles/MMA (issue {tm[2*i]/reps:5.1f})", flush=True)
 
 
+def run_itrace():
+    """Cycle stamps of CTA 0 of the LSTM2 input projection (igemm): MMA thread and one epilogue thread per tile."""
+    from clair3_b200 import synth
+    from clair3_b200._ffi import check, ffi, lib
+    from clair3_b200.model import Clair3_P
+    sd = synth.pileup_state_dict(False, seed=0)
+    x = synth.pileup_inputs(1024, seed=0)
+    m = Clair3_P(add_indel_length=False, predict=True, input_channels=18)
+    m.set_option("lstm_tile", 64)
+    m.set_option("lstm_trace", 30)
+    m.to(torch.device("cuda"))
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    xd = torch.from_numpy(x).cuda()
+    for _ in range(3):
+        m(xd)
+    buf = np.zeros(2 * 33 * 4, dtype=np.int64)
+    check(lib().c3b_debug_lstm_trace(m._handle, ffi.cast("int64_t *", buf.ctypes.data)))
+    tr = buf[:64].reshape(8, 8)
+    t0 = tr[0, 0]
+    for li in range(8):
+        r = tr[li]
+        if r[0] == 0:
+            continue
+        print(f"tile {li}: MMA: start {r[0]-t0:7d} tmem_wait {r[1]-r[0]:6d} first_stage_wait {r[2]-r[1]:6d} issue+run {r[3]-r[2]:6d} | "
+              f"epilogue: start {r[4]-t0:7d} wait_full {r[5]-r[4]:6d} work {r[6]-r[5]:6d}", flush=True)
+
+
 def run_tmemprobe():
     from clair3_b200._ffi import check, ffi, lib
     reps = 256
@@ -279,6 +306,8 @@ if __name__ == "__main__":
         run_probe()
     elif mode == "mmaprobe":
         run_mmaprobe()
+    elif mode == "itrace":
+        run_itrace()
     elif mode == "tmemprobe":
         run_tmemprobe()
     elif mode == "trace":
