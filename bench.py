@@ -243,6 +243,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="pileup", choices=["pileup", "fa"])
     ap.add_argument("--streams", type=int, default=12)
+    ap.add_argument("--lstm-wg", type=int, default=0, help="epilogue warpgroups per LSTM sub-tile (0 = library default)")
     ap.add_argument("--lstm-tile", type=int, default=64,
                     help="sites per LSTM sub-tile (16|32|64; 0 = library auto = latency-oriented 16 at this batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -268,6 +269,8 @@ def main():
 
     workload = args.workload
     model, sd = make_model(workload, device, load_real_weights=(rank == 0))
+    if args.lstm_wg and workload == "pileup":
+        model.set_option("lstm_wg", args.lstm_wg)
     if args.lstm_tile and workload == "pileup":
         model.set_option("lstm_tile", args.lstm_tile)
         LSTM_TILE[0] = args.lstm_tile
@@ -389,12 +392,35 @@ def main():
                 k["tflops"] = fl * b / (k["ms_per_launch"] * 1e-3) / 1e12
                 k["frac_of_bf16_burst"] = k["tflops"] / pk["bf16_burst"]
         dom = max((n for n in kernels if n in KERNEL_FLOP_PER_SITE[workload]), key=lambda n: kernels[n]["ms_per_launch"])
+        # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json, written by
+        # tools/ncu_summary.py from `ncu --set full`: dram__bytes_read.sum + dram__bytes_write.sum), if it was taken at this
+        # workload's batch size
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))
+            ent = tj.get(workload, {}).get(dom)
+            if ent and ent.get("batch") == b:
+                traffic = ent["dram_bytes_per_launch"]
+        except (OSError, ValueError):
+            pass
         roofline = {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["tflops"], "peak": pk["bf16_burst"],
-                    "unit": "TFLOP/s", "frac": kernels[dom]["tflops"] / pk["bf16_burst"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": kernels[dom]["tflops"] / pk["bf16_burst"], "traffic": traffic,
                     "peak_source": pk["which"] + ", burst figure (kernel timed alone between CUDA events)",
                     "flop_per_launch": KERNEL_FLOP_PER_SITE[workload][dom] * b,
                     "whole_step": {"achieved": FLOP_PER_SITE[workload] * value / world / 1e12,
                                    "frac_of_sustained": FLOP_PER_SITE[workload] * value / world / 1e12 / pk["bf16_sustained"]}}
+        if dom in ("lstm1", "lstm2"):
+            # The recurrent kernels are not tensor-bound: their epilogue needs 5 MUFU.TANH per (site, step, direction, unit)
+            # and the SFU pipe issues 16 lanes/clk/SM.  One launch occupies 2 * ceil(B / (2*tile)) CTAs (one per SM), so the
+            # honest ceiling for THIS launch is those SMs' SFU rate; the other SMs are filled by the other streams.
+            units = 128 if dom == "lstm1" else 160
+            tile = int(args.lstm_tile)
+            ctas = 2 * ((b + 2 * tile - 1) // (2 * tile))
+            mufu = 5.0 * 33 * 2 * units * b
+            clk_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            per_clk_sm = mufu / (kernels[dom]["ms_per_launch"] * 1e-3 * clk_hz) / ctas
+            roofline["limiter"] = {"resource": "SFU (MUFU.TANH) issue, 16 lanes/clk/SM", "mufu_ops_per_launch": mufu, "ctas": ctas,
+                                   "achieved_per_clk_per_sm": per_clk_sm, "peak_per_clk_per_sm": 16.0, "frac": per_clk_sm / 16.0}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
@@ -409,7 +435,7 @@ def main():
         line = {
             "metric": "candidate-sites/sec", "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": workload_config(workload, n_streams, pool),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": b * model.out_dim * 4,

@@ -267,6 +267,9 @@ extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
             for (auto &r : w->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
             w->prof.clear();
         }
+    } else if (!strcmp(name, "lstm_wg")) {
+        if (value != 1 && value != 2) { c3b_set_error("lstm_wg must be 1 or 2"); return 1; }
+        m->lstm_wg = (int)value;
     } else if (!strcmp(name, "lstm_mufu16")) {
         m->lstm_mufu16 = value ? 1 : 0;
     } else if (!strcmp(name, "tap_ws")) {

@@ -131,6 +131,7 @@ struct c3b_model {
     int chunk_sites = 0;
     int lstm_tile = 0;
     int profile = 0;
+    int lstm_wg = 2;                   // epilogue warpgroups per LSTM sub-tile (option "lstm_wg": 1 or 2)
     int lstm_mufu16 = 0;               // 1: packed tanh.approx.f16x2 gate activations, 0 (default, faster: the epilogue is issue-bound): fp32 tanh.approx
     int tap_ws = -1;                   // debug: workspace index c3b_get_tap reads
     int host_async = 0;                // 1: host-buffer forwards stay stream-ordered (pinned buffers; caller synchronises)

@@ -29,7 +29,8 @@
 namespace {
 
 constexpr int kWgThreads = 128;                // one epilogue warpgroup = one thread per TMEM lane
-constexpr int kBlockThreads = 288;             // 2 epilogue warpgroups + the MMA warp
+// block = 2 sub-tiles x WG epilogue warpgroups + the MMA warp (WG = 2: the two warpgroups of a sub-tile split its sites,
+// so twice as many warps hide the epilogue's TMEM / MUFU / shared-memory latencies: the epilogue is latency-bound)
 constexpr int kBlkBytes = 20 * 128 * 16;       // one 128-row x K=160 weight block: [K/8][128][8] fp16
 
 struct LstmDev {
@@ -90,8 +91,13 @@ __device__ __forceinline__ void unpack_half8(const uint4 &v, float *f) {
     }
 }
 
-template <int NB, bool LAYER2, bool MUFU16>
-__global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev p) {
+template <int NB, bool LAYER2, bool MUFU16, int WG>
+__global__ void __launch_bounds__(2 * 128 * WG + 32, 1) lstm_tc_kernel(const LstmDev p) {
+    constexpr int kGroupThreads = kWgThreads * WG;  // threads working on one sub-tile
+    constexpr int kBlockThreads = 2 * kGroupThreads + 32;
+    constexpr int kMmaWarp = 8 * WG;
+    constexpr int NBH = NB / WG;                    // sites per epilogue thread
+    static_assert(NBH % 8 == 0, "each warpgroup takes whole 8-site chunks");
     constexpr int H = LAYER2 ? 160 : 128;
     constexpr int KX = LAYER2 ? 0 : 32;
     constexpr int K = KX + H;                       // 160 for both layers
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 8) ptx::tmem_alloc<TCOLS>(&tmem_base_smem);
+    if (warp == kMmaWarp) ptx::tmem_alloc<TCOLS>(&tmem_base_smem);
     for (uint32_t i = tid * 16; i < 2 * B_BYTES; i += kBlockThreads * 16)
         *reinterpret_cast<uint4 *>(b_smem0 + i) = make_uint4(0, 0, 0, 0);
     ptx::tc_fence_before();
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
     }
 
     const uint32_t idesc = ptx::umma_idesc_f16(128, NB);
-    if (warp == 8) {
+    if (warp == kMmaWarp) {
         // ===================================================== MMA warp: alternate between the two sub-tiles
         ptx::mbar_wait(&w_bar, 0);
         for (int step = 0; step < C3B_T; ++step) {
@@ -181,9 +187,12 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
     }
 
     // ========================================================= epilogue warpgroup `sub` (0 or 1)
-    const int sub = warp >> 2;
+    const int sub = (warp >> 2) & 1;                // warps [0,4) sub 0, [4,8) sub 1, then (WG = 2) the second halves
+    const int half = warp >> 3;                     // which NBH-site half of the sub-tile this warpgroup owns
     const int q = warp & 3;                         // TMEM lane quadrant
     const int wt = tid & 127;                       // thread index in the warpgroup = TMEM lane = hidden unit
+    const int gt = wt + 128 * half;                 // thread index among the sub-tile's kGroupThreads
+    const int j0h = half * (NBH / 8);               // first 8-site chunk of this warpgroup
     const int subtile = blockIdx.x * 2 + sub;       // index of this NB-site sub-tile in the padded batch
     const int b0 = subtile * NB;
     uint8_t *b_smem = b_smem0 + sub * B_BYTES;
@@ -192,7 +201,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
     const int ntl = p.bp / NB;
     const uint32_t bar_id = 1 + sub;
 
-    if (LAYER2 && sub == 0) {
+    if (LAYER2 && sub == 0 && half == 0) {
         // tail-block weights (units 128..159) -> TMEM columns [ACC_COLS, ACC_COLS+80): thread = row, 16 halves per k-step
         const op_t *wt_img = p.w_img + ((size_t)dir * NBLK + 4) * (kBlkBytes / 2);
 #pragma unroll 1
@@ -217,12 +226,12 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
         bias_o = bp[384 + wt];
     }
 
-    float c[NB];
+    float c[NBH];
 #pragma unroll
-    for (int i = 0; i < NB; ++i) c[i] = 0.f;
-    float c_tail[LAYER2 ? NB / 4 : 1];
+    for (int i = 0; i < NBH; ++i) c[i] = 0.f;
+    float c_tail[LAYER2 ? NBH / 4 : 1];
 #pragma unroll
-    for (int i = 0; i < (LAYER2 ? NB / 4 : 1); ++i) c_tail[i] = 0.f;
+    for (int i = 0; i < (LAYER2 ? NBH / 4 : 1); ++i) c_tail[i] = 0.f;
 
     int t_prev = 0;
     for (int step = 0; step < C3B_T; ++step) {
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
 
         if (!LAYER2) {
             // stage x_t: xs[t][b0+n][0..31] -> operand k-groups 0..3
-            for (int idx = wt; idx < NB * 4; idx += kWgThreads) {
+            for (int idx = gt; idx < NB * 4; idx += kGroupThreads) {
                 const int n = idx >> 2, kg = idx & 3;
                 const uint4 v = *reinterpret_cast<const uint4 *>(p.xs + ((size_t)t * p.bp + b0 + n) * 32 + kg * 8);
                 *reinterpret_cast<uint4 *>(b_smem + kg * LBO_B + n * 16) = v;
@@ -240,15 +249,15 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
         ptx::tc_fence_before();
         // S1: every thread of the warpgroup has written its h_t / x_t and finished its TMEM reads.  The barrier (not just
         // per-thread mbarrier arrivals) matters: the copy-out below reads 16-byte chunks of h written by OTHER threads.
-        ptx::named_bar_sync(bar_id, kWgThreads);
-        if (wt == 0) ptx::mbar_arrive(&ready_bar[sub]);
+        ptx::named_bar_sync(bar_id, kGroupThreads);
+        if (gt == 0) ptx::mbar_arrive(&ready_bar[sub]);
         const bool tr = p.trace != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
         if (tr) p.trace[step * 4 + 0] = clock64();
         if (tr) p.trace[step * 4 + 1] = clock64();
 
         // while the MMAs run: ship h_{t_prev} (still in the operand buffer) to global memory
         if (step > 0) {
-            for (int idx = wt; idx < NB * (H / 8); idx += kWgThreads) {
+            for (int idx = gt; idx < NB * (H / 8); idx += kGroupThreads) {
                 const int kgh = idx / NB, n = idx % NB;           // consecutive threads -> consecutive sites: 16 B x NB runs
                 const uint4 v = *reinterpret_cast<const uint4 *>(b_smem + (KX / 8 + kgh) * LBO_B + n * 16);
                 op_t *dst = LAYER2 ? p.hout + ((size_t)(t_prev * 40 + dir * 20 + kgh) * p.bp + b0 + n) * 8
@@ -257,14 +266,14 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
             }
         }
         // LSTM2: prefetch this step's pre-gates (fp16, NB contiguous values per (block,row))
-        uint4 pgv[LAYER2 ? 5 : 1][LAYER2 ? NB / 8 : 1];
+        uint4 pgv[LAYER2 ? 5 : 1][LAYER2 ? NBH / 8 : 1];
         if (LAYER2) {
             const __half *pgp = p.pg + ((((size_t)(dir * C3B_T + t) * ntl + subtile) * 5) * 128 + wt) * NB;
 #pragma unroll
             for (int m = 0; m < 5; ++m)
 #pragma unroll
-                for (int j = 0; j < NB / 8; ++j)
-                    pgv[m][j] = *reinterpret_cast<const uint4 *>(pgp + (size_t)m * 128 * NB + j * 8);
+                for (int j = 0; j < NBH / 8; ++j)
+                    pgv[m][j] = *reinterpret_cast<const uint4 *>(pgp + (size_t)m * 128 * NB + (j0h + j) * 8);
             // the pre-gate tensor (86 MB per 1024 sites) streams from HBM: pull the NEXT step's lines into L2 now so the
             // loads above find them there one step later
             if (step + 1 < C3B_T) {
@@ -281,34 +290,34 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
         ptx::mbar_wait(&acc_bar[sub], (uint32_t)step & 1u);
         ptx::tc_fence_after();
         if (tr) p.trace[step * 4 + 2] = clock64();
-        ptx::named_bar_sync(bar_id, kWgThreads);                            // S2: the warpgroup is done reading h_{t_prev}
+        ptx::named_bar_sync(bar_id, kGroupThreads);                         // S2: the sub-tile's threads are done reading h_{t_prev}
 
         if (LAYER2) {
             // tail block (units 128..159): warp q holds gate q; activate and publish to the exchange buffer
 #pragma unroll
-            for (int j = 0; j < NB / 8; ++j) {
+            for (int j = 0; j < NBH / 8; ++j) {
                 float v[8], pgf[8];
-                ptx::tmem_ld8(lane_taddr + 4 * NB + j * 8, v);
+                ptx::tmem_ld8(lane_taddr + 4 * NB + (j0h + j) * 8, v);
                 ptx::tmem_ld_wait();
                 unpack_half8(pgv[4][j], pgf);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float x = v[i] + pgf[i];
                     const float a = (q == 2) ? ptx::tanh_approx(x) : ptx::sigmoid_prehalved(x);
-                    xch[(j * 8 + i) * 128 + wt] = a;
+                    xch[((j0h + j) * 8 + i) * 128 + wt] = a;
                 }
             }
-            ptx::named_bar_sync(bar_id, kWgThreads);
+            ptx::named_bar_sync(bar_id, kGroupThreads);
         }
 
         // main blocks: thread = hidden unit `wt`, 8 sites at a time
 #pragma unroll
-        for (int j = 0; j < NB / 8; ++j) {
+        for (int j = 0; j < NBH / 8; ++j) {
             float gi[8], gf[8], gg[8], go[8], h[8];
-            ptx::tmem_ld8(lane_taddr + 0 * NB + j * 8, gi);
-            ptx::tmem_ld8(lane_taddr + 1 * NB + j * 8, gf);
-            ptx::tmem_ld8(lane_taddr + 2 * NB + j * 8, gg);
-            ptx::tmem_ld8(lane_taddr + 3 * NB + j * 8, go);
+            ptx::tmem_ld8(lane_taddr + 0 * NB + (j0h + j) * 8, gi);
+            ptx::tmem_ld8(lane_taddr + 1 * NB + (j0h + j) * 8, gf);
+            ptx::tmem_ld8(lane_taddr + 2 * NB + (j0h + j) * 8, gg);
+            ptx::tmem_ld8(lane_taddr + 3 * NB + (j0h + j) * 8, go);
             ptx::tmem_ld_wait();
             if (LAYER2) {
                 float pf[8];
@@ -339,14 +348,15 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
             const uint32_t kcol = KX + wt;
             uint8_t *dst = b_smem + (kcol >> 3) * LBO_B + (kcol & 7) * 2;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<op_t *>(dst + (j * 8 + i) * 16) = f2op(h[i]);
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<op_t *>(dst + ((j0h + j) * 8 + i) * 16) = f2op(h[i]);
         }
 
         if (LAYER2) {
-            // tail cells: unit 128 + lane, sites n = q + 4*k
+            // tail cells: unit 128 + lane, sites n = q + 4*k of this warpgroup's half (their activations were published by
+            // this same warpgroup, and the barrier above covers both)
 #pragma unroll
-            for (int k = 0; k < NB / 4; ++k) {
-                const int n = q + 4 * k;
+            for (int k = 0; k < NBH / 4; ++k) {
+                const int n = half * NBH + q + 4 * k;
                 const float iv = xch[n * 128 + lane];
                 const float fv = xch[n * 128 + 32 + lane];
                 const float gv = xch[n * 128 + 64 + lane];
@@ -362,8 +372,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) lstm_tc_kernel(const LstmDev
     }
 
     // last h
-    ptx::named_bar_sync(bar_id, kWgThreads);
-    for (int idx = wt; idx < NB * (H / 8); idx += kWgThreads) {
+    ptx::named_bar_sync(bar_id, kGroupThreads);
+    for (int idx = gt; idx < NB * (H / 8); idx += kGroupThreads) {
         const int kgh = idx / NB, n = idx % NB;
         const uint4 v = *reinterpret_cast<const uint4 *>(b_smem + (KX / 8 + kgh) * LBO_B + n * 16);
         op_t *dst = LAYER2 ? p.hout + ((size_t)(t_prev * 40 + dir * 20 + kgh) * p.bp + b0 + n) * 8
@@ -396,20 +406,22 @@ __global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, op_t *__restric
     }
 }
 
-template <int NB, bool LAYER2, bool MUFU16>
+template <int NB, bool LAYER2, bool MUFU16, int WG>
 int launch_lstm_impl(const LstmDev &p, cudaStream_t s) {
     const size_t smem = (size_t)4 * kBlkBytes + 2 * 20 * (NB + 1) * 16 + (LAYER2 ? (size_t)2 * NB * 128 * 4 : 0);
-    auto kern = lstm_tc_kernel<NB, LAYER2, MUFU16>;
+    auto kern = lstm_tc_kernel<NB, LAYER2, MUFU16, WG>;
     C3B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(p.bp / (2 * NB), 2);
-    kern<<<grid, kBlockThreads, smem, s>>>(p);
+    kern<<<grid, 2 * 128 * WG + 32, smem, s>>>(p);
     C3B_CUDA(cudaGetLastError());
     return 0;
 }
 
+// wg = epilogue warpgroups per sub-tile (2 by default; 1 = the original layout, also used by the f16x2 MUFU variant)
 template <int NB, bool LAYER2>
-int launch_lstm(const LstmDev &p, bool mufu16, cudaStream_t s) {
-    return mufu16 ? launch_lstm_impl<NB, LAYER2, true>(p, s) : launch_lstm_impl<NB, LAYER2, false>(p, s);
+int launch_lstm(const LstmDev &p, bool mufu16, int wg, cudaStream_t s) {
+    if (mufu16) return launch_lstm_impl<NB, LAYER2, true, 1>(p, s);
+    return wg == 1 ? launch_lstm_impl<NB, LAYER2, false, 1>(p, s) : launch_lstm_impl<NB, LAYER2, false, 2>(p, s);
 }
 
 }  // namespace
@@ -439,9 +451,9 @@ int c3b_launch_lstm1_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t ba
     p.bp = (int)((batch + 127) / 128 * 128);
     const_cast<c3b_model *>(m)->launches++;
     switch (tile) {
-        case 16: return launch_lstm<16, false>(p, m->lstm_mufu16 != 0, s);
-        case 32: return launch_lstm<32, false>(p, m->lstm_mufu16 != 0, s);
-        case 64: return launch_lstm<64, false>(p, m->lstm_mufu16 != 0, s);
+        case 16: return launch_lstm<16, false>(p, m->lstm_mufu16 != 0, m->lstm_wg, s);
+        case 32: return launch_lstm<32, false>(p, m->lstm_mufu16 != 0, m->lstm_wg, s);
+        case 64: return launch_lstm<64, false>(p, m->lstm_mufu16 != 0, m->lstm_wg, s);
     }
     c3b_set_error("lstm1: unsupported tile %d", tile);
     return 1;
@@ -456,8 +468,8 @@ int c3b_launch_lstm2_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t ba
     p.bp = (int)((batch + 127) / 128 * 128);
     const_cast<c3b_model *>(m)->launches++;
     switch (tile) {
-        case 16: return launch_lstm<16, true>(p, m->lstm_mufu16 != 0, s);
-        case 32: return launch_lstm<32, true>(p, m->lstm_mufu16 != 0, s);
+        case 16: return launch_lstm<16, true>(p, m->lstm_mufu16 != 0, m->lstm_wg, s);
+        case 32: return launch_lstm<32, true>(p, m->lstm_mufu16 != 0, m->lstm_wg, s);
     }
     c3b_set_error("lstm2: unsupported tile %d", tile);
     return 1;

@@ -60,7 +60,7 @@ int c3b_set_param(c3b_model *m, const char *key, const void *host_data, int dtyp
  * packs bf16 UMMA operand images and uploads them once. */
 int c3b_finalize(c3b_model *m);
 
-/* name: "precision" (C3B_PREC_*), "chunk_sites" (sites per internal pass), "lstm_tile" (batch columns per LSTM CTA: 16|32|64, 0 = auto), "lstm_trace" (debug clock stamps),
+/* name: "precision" (C3B_PREC_*), "chunk_sites" (sites per internal pass), "lstm_tile" (batch columns per LSTM CTA: 16|32|64, 0 = auto), "lstm_wg" (epilogue warpgroups per LSTM sub-tile: 1|2), "lstm_trace" (debug clock stamps),
  * "lstm_mufu16" (1: gate activations with packed tanh.approx.f16x2, two sites per MUFU op; 0 default: fp32 tanh.approx, measured faster),
  * "host_async" (1: forwards with HOST buffers do not synchronise; the buffers must be pinned and the caller synchronises the
  * stream before reading y - lets a caller pipeline H2D / forward / D2H of consecutive batches over several streams),

@@ -150,6 +150,18 @@ def test_lstm_tiles_agree():
     assert np.abs(outs[0] - outs[1]).max() < 1e-5 and np.abs(outs[0] - outs[2]).max() < 1e-5
 
 
+@pytest.mark.parametrize("tile", [16, 32, 64])
+def test_lstm_warpgroup_layouts_agree(tile):
+    """One or two epilogue warpgroups per LSTM sub-tile (option lstm_wg) run the same per-cell arithmetic: identical output."""
+    z, meta, sd, x = golden_case("p90")
+    outs = []
+    for wg in (1, 2):
+        m = _model(meta, sd, TC, lstm_tile=tile, lstm_wg=wg)
+        outs.append(m(torch.from_numpy(x).cuda()).cpu().numpy())
+    assert np.abs(outs[0] - outs[1]).max() < 1e-6
+    _check_probs(outs[1], z["y"], 2e-2, 2e-3, 0.99)
+
+
 def test_fp32_mufu_variant_matches_reference():
     """The packed tanh.approx.f16x2 gate path (default) and the fp32 tanh.approx path both meet the stated tolerance."""
     z, meta, sd, x = golden_case("p24")

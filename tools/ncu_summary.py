@@ -41,5 +41,43 @@ def main(path):
         print("| `%s` | " % name + " | ".join(cells) + " |")
 
 
+def traffic(path, workload, batch, out_json):
+    """Append DRAM bytes per launch (read + write) of each captured kernel to profiles/traffic.json (bench.py's roofline.traffic)."""
+    import json
+    import os
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    ent = {}
+    nconv = 0
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]]
+        byts = sum(float(r[idx[k]]) * scale[units[idx[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        key = None
+        if "lstm_tc_kernel" in name:
+            key = "lstm2" if ", 1, " in name.replace("(bool)", "") or ",1," in name else "lstm1"
+        elif "igemm_kernel" in name:
+            key = "proj2" if ("1, 1>" in name.replace("(bool)", "").replace("(IgemmEpilogue)", "")) else "l4"
+        elif "pconv_kernel" in name:
+            key = "conv%d" % nconv
+            nconv += 1
+        elif "heads_kernel" in name:
+            key = "heads"
+        elif "spp_tc_kernel" in name:
+            key = "spp"
+        if key and key not in ent:
+            ent[key] = {"batch": batch, "dram_bytes_per_launch": byts, "kernel": name.replace("<unnamed>::", "")[:80],
+                        "duration_us_under_ncu": float(r[idx["gpu__time_duration.sum"]])}
+    cur = {}
+    if os.path.exists(out_json):
+        cur = json.load(open(out_json))
+    cur[workload] = ent
+    json.dump(cur, open(out_json, "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if len(sys.argv) >= 5 and sys.argv[1] == "--traffic":
+        traffic(sys.argv[2], sys.argv[3], int(sys.argv[4]), sys.argv[5] if len(sys.argv) > 5 else "profiles/traffic.json")
+    else:
+        main(sys.argv[1])

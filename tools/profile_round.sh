@@ -15,7 +15,7 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 130 -c 
     python bench.py --workload fa --steps 8 --warmup 8 --no-cpu-baseline > gpurun_out/${R}_ncu_launch_f.log 2>&1
 # full captures of the dominant kernels
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:"lstm_tc_kernel|igemm_kernel|heads_kernel" -s 60 -c 5 \
-    -o gpurun_out/${R}_prof_pileup python bench.py --steps 4 --warmup 8 --no-cpu-baseline > gpurun_out/${R}_ncu_full_p.log 2>&1
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:"pconv_kernel|igemm_kernel" -s 110 -c 10 \
-    -o gpurun_out/${R}_prof_fa python bench.py --workload fa --steps 4 --warmup 8 --no-cpu-baseline > gpurun_out/${R}_ncu_full_f.log 2>&1
+    -o gpurun_out/${R}_prof_pileup python bench.py --steps 4 --warmup 8 --streams 1 --no-cpu-baseline > gpurun_out/${R}_ncu_full_p.log 2>&1
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:"pconv_kernel|igemm_kernel|heads_kernel|spp_tc_kernel" -s 120 -c 12 \
+    -o gpurun_out/${R}_prof_fa python bench.py --workload fa --steps 4 --warmup 8 --streams 1 --no-cpu-baseline > gpurun_out/${R}_ncu_full_f.log 2>&1
 ls -la gpurun_out | grep ${R}_ | head -30
