@@ -414,7 +414,9 @@ def main():
             # and the SFU pipe issues 16 lanes/clk/SM.  One launch occupies 2 * ceil(B / (2*tile)) CTAs (one per SM), so the
             # honest ceiling for THIS launch is those SMs' SFU rate; the other SMs are filled by the other streams.
             units = 128 if dom == "lstm1" else 160
-            tile = int(args.lstm_tile)
+            tile = int(args.lstm_tile) or 64
+            if dom == "lstm2":
+                tile = min(tile, 32)        # LSTM2's ten accumulator blocks fit TMEM only up to 32 sites per sub-tile
             ctas = 2 * ((b + 2 * tile - 1) // (2 * tile))
             mufu = 5.0 * 33 * 2 * units * b
             clk_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
