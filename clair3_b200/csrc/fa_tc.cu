@@ -32,10 +32,17 @@ __global__ void ingest_fa_tc_kernel(const T *__restrict__ x, op_t *__restrict__ 
         if (hp < 1 || hp > depth || wp < 1 || wp > 33) continue;
         const T *src = x + ((b * depth + (hp - 1)) * 33 + (wp - 1)) * channels;
         __align__(16) op_t v[8];
+        if (sizeof(T) == 1 && channels == 8 && (reinterpret_cast<uintptr_t>(x) & 7) == 0) {   // the common case: one aligned 8-byte load per pixel
+            const uint2 q = *reinterpret_cast<const uint2 *>(src);
+            const int8_t *b8 = reinterpret_cast<const int8_t *>(&q);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int ch = g * 8 + e;
-            v[e] = f2op(ch < channels ? (float)src[ch] : 0.f);
+            for (int e = 0; e < 8; ++e) v[e] = f2op((float)b8[e]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int ch = g * 8 + e;
+                v[e] = f2op(ch < channels ? (float)src[ch] : 0.f);
+            }
         }
         const size_t off = (size_t)plane * plane_elems + ((size_t)g * g1.p + g1.g + b * g1.s + (size_t)(i + 1) * g1.wp + (j + 1)) * 8;
         *reinterpret_cast<uint4 *>(out + off) = *reinterpret_cast<const uint4 *>(v);

@@ -23,6 +23,8 @@
 // The sigmoid gates' rows are pre-halved on the host so sigma(x) = 0.5*tanh(x/2)+0.5 is one MUFU + one FMA.
 //
 // h_t leaves the CTA as 16-byte chunks copied from the operand buffer while the next step's MMAs run.
+#include <type_traits>
+
 #include "c3b_internal.h"
 #include "ptx.cuh"
 
@@ -395,12 +397,29 @@ __global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, op_t *__restric
         const int b = (int)(tb % bp);
         const int t = (int)(tb / bp);
         __align__(16) op_t v[8];
+        const T *src = x + ((int64_t)b * C3B_T + t) * channels + kg * 8;
+        if (sizeof(T) == 4 && b < batch && kg * 8 + 8 <= channels && (channels & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0) {
+            // a full group of 32-bit inputs: rows are channels*4 bytes apart, so 8-byte alignment always holds
+            const int2 *s2 = reinterpret_cast<const int2 *>(src);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int ch = kg * 8 + i;
-            float f = (ch == channels) ? 1.f : 0.f;          // constant-1 column: LSTM1's bias is folded into the gate GEMM
-            if (b < batch && ch < channels) f = (float)x[((int64_t)b * C3B_T + t) * channels + ch];
-            v[i] = f2op(f);
+            for (int i = 0; i < 4; ++i) {
+                const int2 q = s2[i];
+                if (std::is_floating_point<T>::value) {
+                    v[2 * i] = f2op(__int_as_float(q.x));
+                    v[2 * i + 1] = f2op(__int_as_float(q.y));
+                } else {
+                    v[2 * i] = f2op((float)q.x);
+                    v[2 * i + 1] = f2op((float)q.y);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int ch = kg * 8 + i;
+                float f = (ch == channels) ? 1.f : 0.f;          // constant-1 column: LSTM1's bias is folded into the gate GEMM
+                if (b < batch && ch < channels) f = (float)src[i];
+                v[i] = f2op(f);
+            }
         }
         *reinterpret_cast<uint4 *>(xs + idx * 8) = *reinterpret_cast<const uint4 *>(v);
     }
