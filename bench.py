@@ -168,6 +168,34 @@ def time_cpu(workload, sd, budget_s, threads, min_iters=2):
     return BATCH[workload] * iters / dt, iters, dt, threads
 
 
+def cpu_deployment_shape(workload, ncores, seconds=6.0, steps=0):
+    """The reference's own CPU deployment: many single-threaded worker processes (`--threads N` -> N*3/4 callers with
+    torch.set_num_threads(1), scripts/clair3_c_impl.sh + CallVariantsFromCffi.py:56-63).  Runs min(3/4 cores, 64) processes of
+    the oracle port concurrently - for `seconds` each, or (steps > 0) exactly `steps` calls sized to take about `seconds` - and
+    sums their rates."""
+    nproc = max(1, min(ncores * 3 // 4, 64))
+    sites = 64 if workload == "pileup" else 8
+    env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    root = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "oracle.torch_port", workload, str(seconds), str(sites)] + ([str(steps)] if steps > 0 else [])
+    procs = [subprocess.Popen(cmd, cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+             for _ in range(nproc)]
+    total, ok, per_call, secs = 0.0, 0, 0, 0.0
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=seconds * 10 + 180)
+            r = json.loads(out.strip().splitlines()[-1])
+            total += r["sites"] / r["seconds"]
+            per_call = r["sites_per_call"]
+            secs = max(secs, r["seconds"])
+            ok += 1
+        except Exception:
+            p.kill()
+    return {"value": total, "unit": "sites/s", "processes": ok, "threads_each": 1, "seconds": secs,
+            "sample": "%d single-thread processes, %s of ~%d-site calls each, rates summed"
+                      % (ok, ("%d calls" % steps) if steps > 0 else ("%.0f s" % seconds), per_call)}
+
+
 def run_reference_arm(args, rank, world):
     """The reference's CPU path on this box's host cores (rank 0 only under torchrun)."""
     if rank != 0:
@@ -193,14 +221,19 @@ def run_reference_arm(args, rank, world):
         port(xs[i % 2])
     dt = time.perf_counter() - t0
     val = n_sites * args.steps / dt
+    single = {"value": val, "cores": threads, "sample": "%d steps of %d sites in one process" % (args.steps, n_sites)}
+    dep = cpu_deployment_shape(workload, len(os.sched_getaffinity(0)), seconds=20.0, steps=args.steps)
+    cores, sample, ms_step = threads, "%d steps of %d sites, torch CPU ops of the reference forward (oracle/torch_port.py)" % (args.steps, n_sites), dt / args.steps * 1e3
+    if dep["value"] > val:            # all the host threads the reference can use: its many-single-thread-workers deployment
+        val, cores, sample = dep["value"], dep["processes"], dep["sample"] + ", torch CPU ops of the reference forward (oracle/torch_port.py)"
+        ms_step = dep["seconds"] / args.steps * 1e3
     line = {
         "impl": "reference", "metric": "candidate-sites/sec", "value": val, "unit": "sites/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(workload, 0, 0),
-        "cpu_baseline": {"value": val, "unit": "sites/s", "cores": threads, "kind": "port",
-                         "sample": "%d steps of %d sites, torch CPU ops of the reference forward (oracle/torch_port.py)"
-                                   % (args.steps, n_sites)},
+        "cpu_baseline": {"value": val, "unit": "sites/s", "cores": cores, "kind": "port", "sample": sample,
+                         "single_process": single, "deployment_shape": dep},
         "e2e": {"value": val, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -446,6 +479,12 @@ def main():
         cpu = {"value": v, "unit": "sites/s", "cores": threads, "kind": "port",
                "sample": "%d steps of %d sites in %.1f s; torch CPU ops of the reference forward (oracle/torch_port.py), "
                          "fastest of {8,16,32,64,all=%d} threads" % (iters, b, dt, len(os.sched_getaffinity(0)))}
+        cpu["single_process"] = {"value": v, "cores": threads}
+        dep = cpu_deployment_shape(workload, len(os.sched_getaffinity(0)))
+        cpu["deployment_shape"] = dep
+        if dep["value"] > v:          # report the stronger CPU configuration as the baseline
+            cpu["value"], cpu["cores"] = dep["value"], dep["processes"]
+            cpu["sample"] = dep["sample"] + " (the reference's --threads deployment; beats one multi-threaded process)"
 
     if rank == 0:
         line = {

@@ -111,3 +111,40 @@ class FullAlignmentPort:
             x = self._spp(x)
             x = F.selu(F.linear(x, sd["L4.weight"], sd["L4.bias"]))
             return _heads(x, sd, self.add_indel_length)
+
+
+if __name__ == "__main__":
+    # Worker of bench.py's cpu_baseline "deployment shape" leg: one single-threaded process of the reference's CPU forward
+    # (what `--threads 1` gives each worker, clair3/CallVariantsFromCffi.py:56-63), run N at a time and summed by the caller.
+    #   python -m oracle.torch_port <pileup|fa> <seconds> <sites per call>
+    import json
+    import sys
+    import time
+
+    from clair3_b200 import synth
+
+    workload, seconds, sites = sys.argv[1], float(sys.argv[2]), int(sys.argv[3])
+    steps = int(sys.argv[4]) if len(sys.argv) > 4 else 0      # > 0: exactly that many calls, sized to take ~`seconds` in total
+    torch.set_num_threads(1)
+    full = 1024 if workload == "pileup" else 256
+    if workload == "pileup":
+        port = PileupPort(synth.pileup_state_dict(False, seed=0), False)
+        make = synth.pileup_inputs
+    else:
+        port = FullAlignmentPort(synth.fa_state_dict(True, channels=8, seed=0), True)
+        make = synth.fa_inputs
+    x = make(sites, seed=900)
+    port(x)
+    if steps > 0:
+        t0 = time.perf_counter()
+        port(x)
+        rate = sites / (time.perf_counter() - t0)
+        sites = max(8, min(full, int(rate * seconds / steps) // 8 * 8))
+        x = make(sites, seed=900)
+        port(x)
+    t0 = time.perf_counter()
+    n = 0
+    while (n < steps) if steps > 0 else (time.perf_counter() - t0 < seconds):
+        port(x)
+        n += 1
+    print(json.dumps({"sites": n * sites, "seconds": time.perf_counter() - t0, "sites_per_call": sites, "calls": n}), flush=True)
