@@ -1,0 +1,33 @@
+"""bench.py contract checks that need no GPU: the reference arm runs on host cores only and must print ONE JSON line with
+the keys the driver reads; under a multi-rank launch only rank 0 works and prints."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(extra_env, *args):
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", **extra_env)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", *args], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_reference_arm_prints_one_contract_line():
+    lines = _run({}, "--steps", "1", "--warmup", "1", "--workload", "fa")
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "candidate-sites/sec" and d["unit"] == "sites/s"
+    assert d["higher_is_better"] is True and d["steps"] == 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] >= 1 and "sample" in cb
+    assert cb["single_process"]["value"] > 0 and cb["deployment_shape"]["processes"] >= 1
+    assert "Full-alignment" in d["config"]["workload"]
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--steps", "1", "--warmup", "1", "--gpus", "2") == []
