@@ -56,7 +56,6 @@ struct PconvDev {
     int nS, nWp, nG;       // next level: slots per site, padded width, guard
     long long nP;          // next level: plane pitch
     long long *trace;      // optional: CTA 0 stamps [macro][8] (debug option "lstm_trace")
-    int debug_align;       // timing experiment only (wrong results): round every tap shift down to 8 slots
 };
 
 // Border mask and parity-scatter target of slot l of a site (the epilogue looks this up instead of dividing per tile).
@@ -297,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                     const uint32_t tap_off =
                         p.nplanes == 4 ? ((uint32_t)(((dh & 1) * 2 + (dw & 1)) * (p.C / 8)) * lbo_img + (uint32_t)((dh >> 1) * p.Wp + (dw >> 1)) * 16u) >> 4
                                        : (uint32_t)(dh * p.Wp + dw);
-                    uint32_t a_c = a_lo + (p.debug_align ? (tap_off & ~7u) : tap_off);
+                    uint32_t a_c = a_lo + tap_off;
                     for (int kc = 0; kc < p.cpt; ++kc, ++c, a_c += 4u * kstep_a) {
                         const uint32_t w_addr = acquire_w(c);
                         const uint32_t b_lo = w_desc_lo + (w_addr >> 4);
@@ -389,8 +388,6 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
     p.H = g.h; p.W = g.w; p.Wp = g.wp; p.S = g.s; p.G = g.g; p.T = g.t; p.P = g.p;
     p.relu = a.relu;
     p.trace = a.trace;
-    static const int dbg_align = getenv("C3B_PCONV_ALIGN") ? atoi(getenv("C3B_PCONV_ALIGN")) : 0;
-    p.debug_align = dbg_align;
     p.nksteps = 9 * a.c / 16;
     p.nchunks = (p.nksteps + 3) / 4;
     p.cpt = a.c / 64;
