@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const IgemmDev p) {
     const int lane = tid & 31;
     const int S = p.stages;
     // gathered tiles pad the k-group pitch by one row (conflict-free cp.async writes); bulk-copied planar tiles keep it at
-    // 128 rows so every 8x16-byte core matrix is 128-byte aligned (a misaligned operand costs ~1.7x per MMA, measured)
+    // 128 rows (one contiguous 2 KB run per k-group: a single bulk copy each)
     const uint32_t act_pad = p.taps == 0 ? 0u : 1u;
     const uint32_t act_bytes = (uint32_t)(p.act_rows + act_pad) * 128u;
     const uint32_t w_bytes = (uint32_t)p.w_rows * 128u;
