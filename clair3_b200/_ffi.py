@@ -14,13 +14,14 @@ import cffi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "clair3_b200.h")
+DEBUG_HEADER = os.path.join(os.path.dirname(_HERE), "include", "clair3_b200_debug.h")     # taps / probes, not the drop-in surface
 LIB_PATH = os.path.join(_HERE, "libclair3b200.so")
 
 ffi = cffi.FFI()
 
 
-def _cdef_source():
-    src = open(HEADER).read()
+def _cdef_source(path):
+    src = open(path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     consts = {m.group(1): m.group(2) for m in re.finditer(r"^#define\s+(C3B_\w+)\s+(\d+)\s*$", src, flags=re.M)}
     body = "\n".join(l for l in src.splitlines() if not l.lstrip().startswith("#")
@@ -28,9 +29,11 @@ def _cdef_source():
     return body, {k: int(v) for k, v in consts.items()}
 
 
-_body, CONSTANTS = _cdef_source()
+_body, CONSTANTS = _cdef_source(HEADER)
+_dbg_body, _ = _cdef_source(DEBUG_HEADER)
 ffi.cdef(_body)
-DECLARED_FUNCTIONS = sorted(set(re.findall(r"\b(c3b_\w+)\s*\(", _body)))
+ffi.cdef(_dbg_body)
+DECLARED_FUNCTIONS = sorted(set(re.findall(r"\b(c3b_\w+)\s*\(", _body + _dbg_body)))
 
 _lib = None
 

@@ -137,7 +137,7 @@ void build_expected(c3b_model *m) {
 
 const std::vector<float> &P(const c3b_model *m, const std::string &k) { return m->params.at(k).data; }
 
-// UMMA SWIZZLE_NONE K-major operand image of a [rows][k] matrix: [chunk][rowblock][8 kgroups][rb rows][8] bf16.
+// UMMA SWIZZLE_NONE K-major operand image of a [rows][k] matrix: [chunk][rowblock][8 kgroups][rb rows][8] fp16.
 // get(row, k) supplies the (already folded / permuted) element; out-of-range k is zero.
 template <typename F>
 std::vector<uint16_t> pack_igemm(int rows, int kgroups, int rb, F get) {
@@ -163,25 +163,7 @@ int lstm2_torch_row(int r640) {
     return (r / 32) * C3B_H2 + 128 + (r % 32);
 }
 
-struct Tap {
-    const void *ptr;
-    int fmt;        // 0 f32, 1 fp16
-    int layout;     // 0 [B][inner] row-major; 2 k-group-planar [inner/8][bp][8] (row = site);
-                    // 3 k-group-planar time-major [inner/8][33*bp][8] (row = t*bp + site) -> [B][33][inner]
-                    // 4 zero-padded planar feature map [inner/8][geom.p][8] -> NHWC [B][h][w][inner]
-    int64_t inner;
-    int bp;
-    PlanarGeom geom;
-    int nsplit = 1;  // layout 5: [nsplit][bp][inner] split-K partial sums -> summed [B][inner]
-    int h = 0, w = 0;  // layout 6: four parity planes [4][inner/8][geom.p][8] (geom = NEXT level) of an h x w map -> NHWC
-};
-
 }  // namespace
-
-struct WorkspaceTaps {
-    std::map<std::string, Tap> taps;
-};
-static std::map<const Workspace *, WorkspaceTaps> g_taps;   // debug only
 
 // ------------------------------------------------------------------------------------------------ create / params
 extern "C" int c3b_create(c3b_model **out, int kind, int channels, int add_indel_length, int device_ordinal) {
@@ -255,7 +237,7 @@ extern "C" int c3b_set_param(c3b_model *m, const char *key, const void *host_dat
 extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
     if (!m || !name) { c3b_set_error("c3b_set_option: null argument"); return 1; }
     if (!strcmp(name, "precision")) {
-        if (value != C3B_PREC_BF16_TC && value != C3B_PREC_FP32) { c3b_set_error("bad precision %d", value); return 1; }
+        if (value != C3B_PREC_F16_TC && value != C3B_PREC_FP32) { c3b_set_error("bad precision %d", value); return 1; }
         m->precision = value;
     } else if (!strcmp(name, "chunk_sites")) {
         if (value < 0) { c3b_set_error("bad chunk_sites %d", value); return 1; }
@@ -274,8 +256,9 @@ extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
         m->lstm_mufu16 = value ? 1 : 0;
     } else if (!strcmp(name, "tap_ws")) {
         m->tap_ws = value;           // which stream workspace (creation order) c3b_get_tap reads; -1 = first that has the tap
-    } else if (!strcmp(name, "host_async")) {
-        m->host_async = value ? 1 : 0;
+    } else if (!strcmp(name, "taps")) {
+        m->taps = value ? 1 : 0;
+        if (!value) for (Workspace *w : m->ws) w->taps.clear();
     } else if (!strcmp(name, "lstm_trace")) {
         m->trace_conv = value >= 10 ? (int)value - 10 : 1;       // 10..18: Clair3_F conv index; 30: the LSTM2 input projection
         if (value && !m->lstm_trace) {
@@ -504,10 +487,11 @@ extern "C" int c3b_finalize(c3b_model *m) {
     }
 }
 
-extern "C" int c3b_weight_blob(c3b_model *m, void **device_ptr, size_t *bytes) {
+extern "C" int c3b_weight_blob(c3b_model *m, int which, void **device_ptr, size_t *bytes) {
     if (!m || !m->finalized) { c3b_set_error("c3b_weight_blob: model not finalized"); return 1; }
-    if (device_ptr) *device_ptr = m->blob;
-    if (bytes) *bytes = m->blob_bytes;
+    if (which != 0 && which != 1) { c3b_set_error("c3b_weight_blob: image %d (0 = tensor-core operands + heads, 1 = fp32 debug weights)", which); return 1; }
+    if (device_ptr) *device_ptr = which ? m->f32blob : m->blob;
+    if (bytes) *bytes = which ? m->f32blob_bytes : m->blob_bytes;
     return 0;
 }
 
@@ -523,8 +507,12 @@ extern "C" int c3b_bcast_weights(c3b_model *m, void *nccl_comm, int root, void *
         if (!fn) { c3b_set_error("c3b_bcast_weights: ncclBroadcast not found"); return 1; }
     }
     C3B_CUDA(cudaSetDevice(m->device));
-    const int rc = fn(m->blob, m->blob, m->blob_bytes, /*ncclUint8*/ 1, root, nccl_comm, (cudaStream_t)cuda_stream);
+    // both packed images travel: the tensor-core operands / head weights and the fp32 debug weights, so every option keeps
+    // working on the receiving ranks
+    int rc = fn(m->blob, m->blob, m->blob_bytes, /*ncclUint8*/ 1, root, nccl_comm, (cudaStream_t)cuda_stream);
+    if (rc == 0) rc = fn(m->f32blob, m->f32blob, m->f32blob_bytes, /*ncclUint8*/ 1, root, nccl_comm, (cudaStream_t)cuda_stream);
     if (rc != 0) { c3b_set_error("ncclBroadcast failed with %d", rc); return 1; }
+    m->weights_by_broadcast = true;
     return 0;
 }
 
@@ -645,26 +633,40 @@ extern "C" int c3b_get_profile(c3b_model *m, const char *kernel, double *total_m
 }
 
 // ------------------------------------------------------------------------------------------------ forward passes
-static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x_dtype, int64_t n, float *y, bool tap,
+// Where a pileup chunk's sites come from: a dense [n,33,C] tensor, or 33-row windows of a per-column count matrix
+// ([n_cols][C], libclair3's plp_data.matrix) starting at rows starts[b] (rows outside the matrix read as zero)
+struct PileupSrc {
+    const void *x;          // dense: first site of the chunk; windows: the column matrix
+    int dtype;
+    const int64_t *starts;  // windows: device pointer to this chunk's first start row; nullptr = dense
+    int64_t n_cols;
+};
+
+static int forward_pileup_chunk(c3b_model *m, Workspace *w, const PileupSrc &src, int64_t n, float *y, bool tap,
                                 cudaStream_t s) {
+    const void *x = src.x;
+    const int x_dtype = src.dtype;
     Carver cv{w->dev};
     const int64_t bp = round128(n);
-    WorkspaceTaps &wt = g_taps[w];
+    std::map<std::string, Tap> &taps = w->taps;
+    tap = tap && m->taps;
     if (m->precision == C3B_PREC_FP32) {
         float *xf = cv.take<float>((size_t)n * C3B_T * m->channels * 4);
         float *l1 = cv.take<float>((size_t)n * C3B_T * 256 * 4);
         float *l2 = cv.take<float>((size_t)n * C3B_T * 320 * 4);
         float *z4 = cv.take<float>((size_t)bp * 128 * 4);
-        if (c3b_launch_ingest_pileup_f32(x, x_dtype, xf, n * C3B_T * m->channels, s)) return 1;
+        if (src.starts) {
+            if (c3b_launch_gather_windows_f32(x, x_dtype, m->channels, src.starts, src.n_cols, xf, n, s)) return 1;
+        } else if (c3b_launch_ingest_pileup_f32(x, x_dtype, xf, n * C3B_T * m->channels, s)) return 1;
         if (c3b_launch_lstm_f32(xf, m->lstm_f32[0][0], m->lstm_f32[0][1], l1, n, m->channels, C3B_H1, s)) return 1;
         if (c3b_launch_lstm_f32(l1, m->lstm_f32[1][0], m->lstm_f32[1][1], l2, n, 256, C3B_H2, s)) return 1;
         if (c3b_launch_dense_f32(l2, m->l4_f32_t, z4, n, m->l4_in, 128, s)) return 1;
         if (c3b_launch_heads(z4, 1, 0, m->heads, y, n, s)) return 1;
         m->launches += 5;
         if (tap) {
-            wt.taps["lstm1"] = {l1, 0, 0, (int64_t)C3B_T * 256, 0, {}};
-            wt.taps["lstm2"] = {l2, 0, 0, (int64_t)C3B_T * 320, 0, {}};
-            wt.taps["l4_pre"] = {z4, 0, 0, 128, 0, {}};
+            taps["lstm1"] = {l1, 0, 0, (int64_t)C3B_T * 256, 0, {}};
+            taps["lstm2"] = {l2, 0, 0, (int64_t)C3B_T * 320, 0, {}};
+            taps["l4_pre"] = {z4, 0, 0, 128, 0, {}};
         }
         return 0;
     }
@@ -681,7 +683,7 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
         tile2 = tile1;
     }
     if (tile2 > 32) tile2 = 32;
-    { PROF("ingest"); if (c3b_launch_ingest_pileup_tc(x, x_dtype, m->channels, b.xs, n, s)) return 1; }
+    { PROF("ingest"); if (c3b_launch_ingest_pileup_tc(x, x_dtype, m->channels, src.starts, src.n_cols, b.xs, n, s)) return 1; }
     m->launches += 1;
     { PROF("lstm1"); if (c3b_launch_lstm1_tc(m, b, n, tile1, s)) return 1; }
     IgemmArgs pa = {};
@@ -720,9 +722,9 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const void *x, int x
     { PROF("heads"); if (c3b_launch_heads(b.z4, ns_p, la.split_stride, m->heads, y, n, s)) return 1; }
     m->launches += 1;
     if (tap) {
-        wt.taps["lstm1"] = {b.h1, 1, 3, 256, (int)bp, {}};
-        wt.taps["lstm2"] = {b.h2, 1, 2, (int64_t)C3B_T * 320, (int)bp, {}};
-        wt.taps["l4_pre"] = {b.z4, 0, 5, 128, (int)bp, {}, ns_p};
+        taps["lstm1"] = {b.h1, 1, 3, 256, (int)bp, {}};
+        taps["lstm2"] = {b.h2, 1, 2, (int64_t)C3B_T * 320, (int)bp, {}};
+        taps["l4_pre"] = {b.z4, 0, 5, 128, (int)bp, {}, ns_p};
     }
     return 0;
 }
@@ -731,7 +733,8 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
                             cudaStream_t s) {
     Carver cv{w->dev};
     const int64_t bp = round128(n);
-    WorkspaceTaps &wt = g_taps[w];
+    std::map<std::string, Tap> &taps = w->taps;
+    tap = tap && m->taps;
     int hh[4] = {depth, 0, 0, 0}, ww[4] = {33, 0, 0, 0};
     for (int i = 1; i < 4; ++i) { hh[i] = conv_out(hh[i - 1]); ww[i] = conv_out(ww[i - 1]); }
     const int chans[4] = {m->channels, 64, 128, 256};
@@ -739,7 +742,7 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
     const char *tapname[3][2] = {{"conv1", "res_block1"}, {"conv3", "res_block2"}, {"conv5", "res_block3"}};
 
     if (f32) {
-        w->fa_zero_sites = -1;      // this path overwrites the region the tensor-core path keeps zero-bordered
+        w->fa_zeroed = false;       // this path overwrites the region the tensor-core path keeps zero-bordered
         float *xin = cv.take<float>((size_t)n * depth * 33 * m->channels * 4);
         float *act[3][3];
         for (int l = 0; l < 3; ++l)
@@ -762,11 +765,11 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
         if (tap) {
             for (int l = 0; l < 3; ++l) {
                 const int64_t inner = (int64_t)hh[l + 1] * ww[l + 1] * chans[l + 1];
-                wt.taps[tapname[l][0]] = {act[l][0], 0, 0, inner, 0, {}};
-                wt.taps[tapname[l][1]] = {act[l][2], 0, 0, inner, 0, {}};
+                taps[tapname[l][0]] = {act[l][0], 0, 0, inner, 0, {}};
+                taps[tapname[l][1]] = {act[l][2], 0, 0, inner, 0, {}};
             }
-            wt.taps["spp"] = {sp, 0, 0, 3584, 0, {}};
-            wt.taps["l4_pre"] = {z4, 0, 0, 256, 0, {}};
+            taps["spp"] = {sp, 0, 0, 3584, 0, {}};
+            taps["l4_pre"] = {z4, 0, 0, 256, 0, {}};
         }
         return 0;
     }
@@ -781,7 +784,7 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
     const int stem_c[3] = {cpad, 64, 128};
     const size_t planar_begin = cv.off;
     for (int l = 0; l < 3; ++l) {
-        geo[l] = c3b_planar_geom(n, hh[l + 1], ww[l + 1]);
+        geo[l] = c3b_planar_geom(n, hh[l + 1], ww[l + 1], w->fa_cap_sites);
         stem_in[l] = cv.take<op_t>((size_t)4 * (stem_c[l] / 8) * geo[l].p * 16);
         for (int i = 0; i < (l == 2 ? 3 : 2); ++i) act[l][i] = cv.take<op_t>((size_t)(chans[l + 1] / 8) * geo[l].p * 16);
     }
@@ -790,12 +793,12 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
     const size_t planar_end = cv.off;
     op_t *sp = cv.take<op_t>((size_t)bp * 3584 * 2);
     float *z4 = cv.take<float>((size_t)16 * bp * 256 * 4);
-    // borders / guards of the planar maps must be zero; the convs only ever store real pixels, so one clear per
-    // (workspace, geometry) is enough
-    if (w->fa_zero_sites != n || w->fa_zero_depth != depth) {
+    // borders / guards of the planar maps must be zero; the convs only ever store real pixels and the layout is that of the
+    // workspace's largest chunk (fa_cap_sites), so one clear per (workspace, capacity, depth) is enough: a ragged tail chunk
+    // reuses the zeros already there (stale pixels of sites >= n only feed outputs of sites >= n, which are never stored)
+    if (!w->fa_zeroed) {
         C3B_CUDA(cudaMemsetAsync(w->dev + planar_begin, 0, planar_end - planar_begin, s));
-        w->fa_zero_sites = n;
-        w->fa_zero_depth = depth;
+        w->fa_zeroed = true;
     }
     static const char *cn[9] = {"conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv8"};
     { PROF("ingest"); if (c3b_launch_ingest_fa_tc(x, x_dtype, m->channels, cpad, stem_in[0], n, depth, geo[0], s)) return 1; }
@@ -843,37 +846,46 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
     m->launches += 3;
     if (tap) {
         for (int l = 0; l < 3; ++l) {
-            wt.taps[tapname[l][0]] = {act[l][0], 1, 4, chans[l + 1], 0, geo[l]};
+            taps[tapname[l][0]] = {act[l][0], 1, 4, chans[l + 1], 0, geo[l]};
             if (l < 2) {
-                wt.taps[tapname[l][1]] = {act[l][2], 1, 6, chans[l + 1], 0, geo[l + 1]};
-                wt.taps[tapname[l][1]].h = geo[l].h;
-                wt.taps[tapname[l][1]].w = geo[l].w;
+                taps[tapname[l][1]] = {act[l][2], 1, 6, chans[l + 1], 0, geo[l + 1]};
+                taps[tapname[l][1]].h = geo[l].h;
+                taps[tapname[l][1]].w = geo[l].w;
             } else {
-                wt.taps[tapname[l][1]] = {act[l][2], 1, 4, chans[l + 1], 0, geo[l]};
+                taps[tapname[l][1]] = {act[l][2], 1, 4, chans[l + 1], 0, geo[l]};
             }
         }
-        wt.taps["spp"] = {sp, 1, 2, 3584, (int)bp, {}};
-        wt.taps["l4_pre"] = {z4, 0, 5, 256, (int)bp, {}, ns_f};
+        taps["spp"] = {sp, 1, 2, 3584, (int)bp, {}};
+        taps["l4_pre"] = {z4, 0, 5, 256, (int)bp, {}, ns_f};
     }
     return 0;
 }
 
-extern "C" int c3b_forward(c3b_model *m, const void *x, int x_dtype, int x_on_device, int64_t batch, int depth, float *y,
-                           int y_on_device, void *cuda_stream) {
-    if (!m) { c3b_set_error("c3b_forward: null model"); return 1; }
-    if (!m->finalized) { c3b_set_error("c3b_forward: load_state_dict/c3b_finalize has not completed"); return 1; }
-    if (batch < 0) { c3b_set_error("c3b_forward: negative batch"); return 1; }
-    if (batch == 0) return 0;
-    if (!x || !y) { c3b_set_error("c3b_forward: null buffer"); return 1; }
-    size_t esz;
-    switch (x_dtype) {
-        case C3B_DT_I8: esz = 1; break;
-        case C3B_DT_I32: esz = 4; break;
-        case C3B_DT_F32: esz = 4; break;
-        default: c3b_set_error("c3b_forward: unsupported input dtype %d", x_dtype); return 1;
+static size_t dtype_size(int dt) {
+    switch (dt) {
+        case C3B_DT_I8: return 1;
+        case C3B_DT_I32: return 4;
+        case C3B_DT_F32: return 4;
+        case C3B_DT_I64: return 8;
     }
+    return 0;
+}
+
+// Shared body of c3b_forward / c3b_forward_async / c3b_forward_windows.  starts != nullptr: x is the per-column count matrix
+// [n_cols][channels] and site b is its rows [starts[b], starts[b]+33).  sync_host: block until y is complete when a host
+// buffer is involved (the _torch_predict contract); otherwise everything stays stream-ordered (pinned host buffers).
+static int forward_impl(c3b_model *m, const void *x, int x_dtype, int x_on_device, int64_t batch, int depth, const int64_t *starts,
+                        int64_t n_cols, float *y, int y_on_device, cudaStream_t s, bool sync_host, const char *who) {
+    if (!m) { c3b_set_error("%s: null model", who); return 1; }
+    if (!m->finalized) { c3b_set_error("%s: load_state_dict/c3b_finalize has not completed", who); return 1; }
+    if (batch < 0) { c3b_set_error("%s: negative batch", who); return 1; }
+    if (batch == 0) return 0;
+    if (!x || !y) { c3b_set_error("%s: null buffer", who); return 1; }
+    const size_t esz = dtype_size(x_dtype);
+    if (!esz || (x_dtype == C3B_DT_I64 && !starts)) { c3b_set_error("%s: unsupported input dtype %d", who, x_dtype); return 1; }
     if (m->kind == C3B_FULL_ALIGNMENT) {
-        if (depth < 8 || depth > 512) { c3b_set_error("c3b_forward: bad full-alignment depth %d", depth); return 1; }
+        if (starts) { c3b_set_error("%s: window input is a pileup feature", who); return 1; }
+        if (depth < 8 || depth > 512) { c3b_set_error("%s: bad full-alignment depth %d", who, depth); return 1; }
         int h = depth, w = 33;
         for (int i = 0; i < 3; ++i) { h = conv_out(h); w = conv_out(w); }
         for (int p = 1; p <= 3; ++p) {
@@ -887,48 +899,142 @@ extern "C" int c3b_forward(c3b_model *m, const void *x, int x_dtype, int x_on_de
         depth = 0;
     }
     C3B_CUDA(cudaSetDevice(m->device));
-    cudaStream_t s = (cudaStream_t)cuda_stream;
     Workspace *w = get_workspace(m, s);
     if (!w) return 1;
     const size_t site_elems = m->kind == C3B_PILEUP ? (size_t)C3B_T * m->channels : (size_t)depth * 33 * m->channels;
     int64_t chunk = m->chunk_sites > 0 ? m->chunk_sites : (m->kind == C3B_PILEUP ? 1024 : 256);
     if (chunk > batch) chunk = batch;
+    // the workspace keeps the layout of the largest chunk it has served (full-alignment planar maps: see forward_fa_chunk)
+    int64_t cap = chunk;
+    if (m->kind == C3B_FULL_ALIGNMENT) {
+        if (w->fa_cap_depth == depth && w->fa_cap_sites > cap) cap = w->fa_cap_sites;
+        if (w->fa_cap_depth != depth || w->fa_cap_sites != cap) w->fa_zeroed = false;
+        w->fa_cap_depth = depth;
+        w->fa_cap_sites = cap;
+    }
 
-    const size_t need = ws_bytes_needed(m, chunk, depth);
+    const size_t need = ws_bytes_needed(m, cap, depth);
     if (w->dev_bytes < need) {
         C3B_CUDA(cudaStreamSynchronize(s));
         if (ensure_dev((void **)&w->dev, &w->dev_bytes, need)) return 1;
-        w->fa_zero_sites = -1;      // fresh memory: the planar maps' borders / guards must be cleared again
+        w->fa_zeroed = false;       // fresh memory: the planar maps' borders / guards must be cleared again
     }
     const void *xd = x;
+    const int64_t *sd = starts;
     float *yd = y;
     if (!x_on_device) {
-        if (w->dev_x_bytes < batch * site_elems * esz) C3B_CUDA(cudaStreamSynchronize(s));
-        if (ensure_dev(&w->dev_x, &w->dev_x_bytes, batch * site_elems * esz)) return 1;
-        C3B_CUDA(cudaMemcpyAsync(w->dev_x, x, batch * site_elems * esz, cudaMemcpyHostToDevice, s));
+        const size_t xbytes = starts ? (size_t)n_cols * m->channels * esz : (size_t)batch * site_elems * esz;
+        if (w->dev_x_bytes < xbytes) C3B_CUDA(cudaStreamSynchronize(s));
+        if (ensure_dev(&w->dev_x, &w->dev_x_bytes, xbytes)) return 1;
+        C3B_CUDA(cudaMemcpyAsync(w->dev_x, x, xbytes, cudaMemcpyHostToDevice, s));
         xd = w->dev_x;
+        if (starts) {
+            if (w->dev_aux_bytes < (size_t)batch * 8) C3B_CUDA(cudaStreamSynchronize(s));
+            if (ensure_dev(&w->dev_aux, &w->dev_aux_bytes, (size_t)batch * 8)) return 1;
+            C3B_CUDA(cudaMemcpyAsync(w->dev_aux, starts, (size_t)batch * 8, cudaMemcpyHostToDevice, s));
+            sd = (const int64_t *)w->dev_aux;
+        }
     }
     if (!y_on_device) {
         if (w->dev_y_bytes < (size_t)batch * m->out_dim * 4) C3B_CUDA(cudaStreamSynchronize(s));
         if (ensure_dev((void **)&w->dev_y, &w->dev_y_bytes, (size_t)batch * m->out_dim * 4)) return 1;
         yd = w->dev_y;
     }
-    g_taps[w].taps.clear();
+    if (m->taps) w->taps.clear();
     for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
         const int64_t n = std::min(chunk, batch - b0);
-        const void *xc = (const char *)xd + (size_t)b0 * site_elems * esz;
         float *yc = yd + (size_t)b0 * m->out_dim;
-        int rc = m->kind == C3B_PILEUP ? forward_pileup_chunk(m, w, xc, x_dtype, n, yc, b0 == 0, s)
-                                       : forward_fa_chunk(m, w, xc, x_dtype, n, depth, yc, b0 == 0, s);
+        int rc;
+        if (m->kind == C3B_PILEUP) {
+            PileupSrc src;
+            src.dtype = x_dtype;
+            src.n_cols = n_cols;
+            src.starts = starts ? sd + b0 : nullptr;
+            src.x = starts ? xd : (const void *)((const char *)xd + (size_t)b0 * site_elems * esz);
+            rc = forward_pileup_chunk(m, w, src, n, yc, b0 == 0, s);
+        } else {
+            rc = forward_fa_chunk(m, w, (const char *)xd + (size_t)b0 * site_elems * esz, x_dtype, n, depth, yc, b0 == 0, s);
+        }
         if (rc) return rc;
     }
     m->last_batch = std::min(chunk, batch);
     m->last_depth = depth;
     if (!y_on_device) C3B_CUDA(cudaMemcpyAsync(y, yd, (size_t)batch * m->out_dim * 4, cudaMemcpyDeviceToHost, s));
-    if ((!x_on_device || !y_on_device) && !m->host_async) {
+    if ((!x_on_device || !y_on_device) && sync_host) {
         C3B_CUDA(cudaStreamSynchronize(s));
         C3B_CUDA(cudaGetLastError());
     }
+    return 0;
+}
+
+extern "C" int c3b_forward(c3b_model *m, const void *x, int x_dtype, int x_on_device, int64_t batch, int depth, float *y,
+                           int y_on_device, void *cuda_stream) {
+    return forward_impl(m, x, x_dtype, x_on_device, batch, depth, nullptr, 0, y, y_on_device, (cudaStream_t)cuda_stream, true,
+                        "c3b_forward");
+}
+
+extern "C" int c3b_forward_async(c3b_model *m, const void *x_pinned, int x_dtype, int64_t batch, int depth, float *y_pinned,
+                                 void *cuda_stream) {
+    return forward_impl(m, x_pinned, x_dtype, 0, batch, depth, nullptr, 0, y_pinned, 0, (cudaStream_t)cuda_stream, false,
+                        "c3b_forward_async");
+}
+
+extern "C" int c3b_forward_windows(c3b_model *m, const void *cols, int cols_dtype, int64_t n_cols, const int64_t *starts,
+                                   int on_device, int64_t batch, float *y, int y_on_device, int host_sync, void *cuda_stream) {
+    if (m && m->kind != C3B_PILEUP) { c3b_set_error("c3b_forward_windows: pileup models only"); return 1; }
+    if (batch > 0 && (!starts || n_cols <= 0)) { c3b_set_error("c3b_forward_windows: null starts / empty matrix"); return 1; }
+    return forward_impl(m, cols, cols_dtype, on_device, batch, 0, starts, n_cols, y, y_on_device, (cudaStream_t)cuda_stream,
+                        host_sync != 0, "c3b_forward_windows");
+}
+
+// ------------------------------------------------------------------------------------------------ decode, stage 1 (N1)
+extern "C" int c3b_decode_stage1(c3b_model *m, const float *y, const uint8_t *ref_gt21, int64_t batch, int on_device,
+                                 uint8_t *is_ref, float *ref_prob, int32_t *argmax, float *maxprob, double *qual,
+                                 int32_t *nonref_idx, int32_t *n_nonref, void *cuda_stream) {
+    if (!m) { c3b_set_error("c3b_decode_stage1: null model"); return 1; }
+    if (batch < 0) { c3b_set_error("c3b_decode_stage1: negative batch"); return 1; }
+    if (!n_nonref) { c3b_set_error("c3b_decode_stage1: null n_nonref"); return 1; }
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    C3B_CUDA(cudaSetDevice(m->device));
+    if (batch == 0) {
+        if (on_device) C3B_CUDA(cudaMemsetAsync(n_nonref, 0, 4, s));
+        else *n_nonref = 0;
+        return 0;
+    }
+    if (!y || !ref_gt21 || !is_ref || !ref_prob || !argmax || !maxprob || !qual || !nonref_idx) {
+        c3b_set_error("c3b_decode_stage1: null buffer");
+        return 1;
+    }
+    const int nh = m->nheads;
+    if (on_device) {
+        m->launches++;
+        return c3b_launch_decode_stage1(y, ref_gt21, batch, m->out_dim, is_ref, ref_prob, argmax, maxprob, qual, nonref_idx, n_nonref, s);
+    }
+    // host buffers: stage through the stream's workspace, one packed region [qual | y | ref_prob | maxprob | argmax | idx | n | gt | flag]
+    Workspace *w = get_workspace(m, s);
+    if (!w) return 1;
+    const size_t B = (size_t)batch;
+    size_t o_qual = 0, o_y = o_qual + B * 8, o_rp = o_y + B * m->out_dim * 4, o_mp = o_rp + B * 4, o_am = o_mp + B * nh * 4,
+           o_idx = o_am + B * nh * 4, o_n = o_idx + B * 4, o_gt = o_n + 16, o_flag = o_gt + (B + 15) / 16 * 16,
+           total = o_flag + (B + 15) / 16 * 16;
+    if (w->dev_aux_bytes < total) C3B_CUDA(cudaStreamSynchronize(s));
+    if (ensure_dev(&w->dev_aux, &w->dev_aux_bytes, total)) return 1;
+    char *d = (char *)w->dev_aux;
+    C3B_CUDA(cudaMemcpyAsync(d + o_y, y, B * m->out_dim * 4, cudaMemcpyHostToDevice, s));
+    C3B_CUDA(cudaMemcpyAsync(d + o_gt, ref_gt21, B, cudaMemcpyHostToDevice, s));
+    m->launches++;
+    if (c3b_launch_decode_stage1((const float *)(d + o_y), (const uint8_t *)(d + o_gt), batch, m->out_dim, (uint8_t *)(d + o_flag),
+                                 (float *)(d + o_rp), (int32_t *)(d + o_am), (float *)(d + o_mp), (double *)(d + o_qual),
+                                 (int32_t *)(d + o_idx), (int32_t *)(d + o_n), s))
+        return 1;
+    C3B_CUDA(cudaMemcpyAsync(is_ref, d + o_flag, B, cudaMemcpyDeviceToHost, s));
+    C3B_CUDA(cudaMemcpyAsync(ref_prob, d + o_rp, B * 4, cudaMemcpyDeviceToHost, s));
+    C3B_CUDA(cudaMemcpyAsync(argmax, d + o_am, B * nh * 4, cudaMemcpyDeviceToHost, s));
+    C3B_CUDA(cudaMemcpyAsync(maxprob, d + o_mp, B * nh * 4, cudaMemcpyDeviceToHost, s));
+    C3B_CUDA(cudaMemcpyAsync(qual, d + o_qual, B * 8, cudaMemcpyDeviceToHost, s));
+    C3B_CUDA(cudaMemcpyAsync(nonref_idx, d + o_idx, B * 4, cudaMemcpyDeviceToHost, s));
+    C3B_CUDA(cudaMemcpyAsync(n_nonref, d + o_n, 4, cudaMemcpyDeviceToHost, s));
+    C3B_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
 
@@ -940,10 +1046,8 @@ extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int6
     for (Workspace *w : m->ws) {
         ++wi;
         if (m->tap_ws >= 0 && wi != m->tap_ws) continue;
-        auto git = g_taps.find(w);
-        if (git == g_taps.end()) continue;
-        auto it = git->second.taps.find(name);
-        if (it == git->second.taps.end()) continue;
+        auto it = w->taps.find(name);
+        if (it == w->taps.end()) continue;
         const Tap &t = it->second;
         const int64_t n = m->last_batch;
         const int64_t per_site = t.layout == 4 ? t.inner * t.geom.h * t.geom.w
@@ -1003,7 +1107,7 @@ extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int6
         *count_inout = count;
         return 0;
     }
-    c3b_set_error("c3b_get_tap: no tap named \"%s\" (run a forward first)", name);
+    c3b_set_error("c3b_get_tap: no tap named \"%s\" (set option \"taps\" to 1 and run a forward first)", name);
     return 1;
 }
 
@@ -1092,11 +1196,11 @@ extern "C" void c3b_destroy(c3b_model *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (Workspace *w : m->ws) {
-        g_taps.erase(w);
         for (auto &r : w->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
         if (w->dev) cudaFree(w->dev);
         if (w->dev_x) cudaFree(w->dev_x);
         if (w->dev_y) cudaFree(w->dev_y);
+        if (w->dev_aux) cudaFree(w->dev_aux);
         delete w;
     }
     if (m->blob) cudaFree(m->blob);

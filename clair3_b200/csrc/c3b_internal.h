@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/clair3_b200.h"
+#include "../../include/clair3_b200_debug.h"
 
 #define C3B_T 33            // positions per site (shared/param_p.py:34-35)
 #define C3B_H1 128          // LSTM1 hidden (clair3/model.py:46)
@@ -25,6 +26,12 @@ typedef __half2 op2_t;
 #ifdef __CUDACC__
 __device__ __forceinline__ float op_clamp(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
 __device__ __forceinline__ op_t f2op(float x) { return __float2half_rn(x); }
+// saturating variant for values that are not bounded by construction (raw input counts): +-65504 instead of inf
+__device__ __forceinline__ op_t f2op_sat(float x) {
+    unsigned short r;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+    return __ushort_as_half(r);
+}
 __device__ __forceinline__ op2_t f2op2(float a, float b) { return __floats2half2_rn(a, b); }
 __device__ __forceinline__ float2 op22f2(op2_t v) { return __half22float2(v); }
 // two floats -> packed fp16 pair in ONE instruction, saturating at +-65504 instead of overflowing to inf
@@ -85,11 +92,11 @@ struct ConvF32 {
 
 // ---- tensor-core path packed operands (device pointers into the weight blob) ----
 struct LstmTC {
-    const op_t *w_img;   // UMMA A-operand image: [nblk][K/8][128 rows][8] bf16, rows permuted (see lstm_tc.cu)
+    const op_t *w_img;   // UMMA A-operand image: [nblk][K/8][128 rows][8] fp16, rows permuted (see lstm_tc.cu)
     const float *bias;            // [nblk*128] permuted, b_ih + b_hh (LSTM1 only; LSTM2's bias rides in the projection)
 };
 struct IgemmW {
-    const op_t *w_img;   // UMMA B-operand image per k-chunk: [nchunks][8 kgroups][N rows][8] bf16
+    const op_t *w_img;   // UMMA B-operand image per k-chunk: [nchunks][8 kgroups][N rows][8] fp16
     const float *bias;            // [N]
     int n;                        // output columns (Cout / gate rows / dense units)
     int kgroups;                  // K/8 (16-byte k-groups), real
@@ -100,25 +107,55 @@ struct ConvGeom {
     int hin, win, cin, hout, wout, cout, stride;
 };
 
+// Zero-padded channel-group-planar feature map [C/8][p][8]: slot(b,h,w) = g + b*s + (h+1)*wp + (w+1)  (see pconv_tc.cu)
+struct PlanarGeom {
+    int h, w, wp, s, g;        // real dims, padded width (w+2), slots per site ((h+2)*wp), guard slots
+    int64_t t, p;              // data slots (B*s), plane pitch in slots (g + roundup(t,512) + g)
+};
+// `cap` >= batch: the site count the plane pitch is laid out for (a workspace keeps the layout of its largest chunk, so smaller
+// chunks find their borders / guards already zero)
+inline PlanarGeom c3b_planar_geom(int64_t batch, int h, int w, int64_t cap = 0) {
+    PlanarGeom g;
+    g.h = h; g.w = w; g.wp = w + 2; g.s = (h + 2) * (w + 2);
+    g.g = (g.wp + 1 + 7) / 8 * 8;
+    g.t = batch * g.s;
+    const int64_t tc = (cap > batch ? cap : batch) * g.s;
+    g.p = g.g + (tc + 511) / 512 * 512 + g.g;
+    return g;
+}
+
+// Debug tap: where an intermediate activation of the last forward lives and how to unpack it (c3b_get_tap, option "taps")
+struct Tap {
+    const void *ptr;
+    int fmt;        // 0 f32, 1 fp16
+    int layout;     // 0 [B][inner] row-major; 2 k-group-planar [inner/8][bp][8] (row = site);
+                    // 3 k-group-planar time-major [inner/8][33*bp][8] (row = t*bp + site) -> [B][33][inner]
+                    // 4 zero-padded planar feature map [inner/8][geom.p][8] -> NHWC [B][h][w][inner]
+    int64_t inner;
+    int bp;
+    PlanarGeom geom;
+    int nsplit = 1;  // layout 5: [nsplit][bp][inner] split-K partial sums -> summed [B][inner]
+    int h = 0, w = 0;  // layout 6: four parity planes [4][inner/8][geom.p][8] (geom = NEXT level) of an h x w map -> NHWC
+};
+
 struct Workspace {
     cudaStream_t stream = nullptr;
-    bool in_use = false;
-    int64_t cap_sites = 0;
-    int depth = 0;
     // generic device scratch, carved by the forward pass
     char *dev = nullptr;
     size_t dev_bytes = 0;
     // staging for host-side callers
-    void *pin_x = nullptr;
-    size_t pin_x_bytes = 0;
-    float *pin_y = nullptr;
-    size_t pin_y_bytes = 0;
     void *dev_x = nullptr;
     size_t dev_x_bytes = 0;
     float *dev_y = nullptr;
     size_t dev_y_bytes = 0;
-    int64_t fa_zero_sites = -1;      // geometry for which the planar FA feature maps' borders / guards were last cleared
-    int fa_zero_depth = -1;
+    void *dev_aux = nullptr;         // window offsets / decode inputs of host-side callers
+    size_t dev_aux_bytes = 0;
+    // full-alignment planar maps are laid out for `fa_cap_sites` sites (the largest chunk seen on this workspace); smaller
+    // chunks reuse that layout (their borders / guards are already zero), so a ragged tail never re-clears the region
+    int64_t fa_cap_sites = 0;
+    int fa_cap_depth = -1;
+    bool fa_zeroed = false;
+    std::map<std::string, Tap> taps;   // per workspace, filled only while option "taps" is on
     // per-kernel CUDA-event pairs recorded while option "profile" is on (resolved lazily by c3b_get_profile)
     struct ProfRec { const char *name; cudaEvent_t e0, e1; };
     std::vector<ProfRec> prof;
@@ -127,14 +164,15 @@ struct Workspace {
 struct c3b_model {
     int kind = 0, channels = 0, add_indel = 0, device = 0;
     int nheads = 2, out_dim = 24, d4 = 128, l4_in = 0;
-    int precision = C3B_PREC_BF16_TC;
+    int precision = C3B_PREC_F16_TC;
     int chunk_sites = 0;
     int lstm_tile = 0;
     int profile = 0;
     int lstm_wg = 2;                   // epilogue warpgroups per LSTM sub-tile (option "lstm_wg": 1 or 2)
     int lstm_mufu16 = 0;               // 1: packed tanh.approx.f16x2 gate activations, 0 (default, faster: the epilogue is issue-bound): fp32 tanh.approx
     int tap_ws = -1;                   // debug: workspace index c3b_get_tap reads
-    int host_async = 0;                // 1: host-buffer forwards stay stream-ordered (pinned buffers; caller synchronises)
+    int taps = 0;                      // debug option "taps": record where the intermediate activations of a forward live
+    bool weights_by_broadcast = false; // the packed images arrived by c3b_bcast_weights (no host-side parameters behind them)
     long long *lstm_trace = nullptr;   // device [2][33][4] clock stamps (debug option "lstm_trace")
     int trace_conv = 1;            // which Clair3_F conv (0..8) stamps the trace buffer (option lstm_trace = 10 + index)
     std::map<std::string, std::pair<double, int64_t>> prof_total;   // name -> (ms, launches)
@@ -179,6 +217,10 @@ inline int c3b_effective_ksplit(int nchunks, int ksplit) {
     return (nchunks + cps - 1) / cps;
 }
 
+// ---- decode.cu ----
+int c3b_launch_decode_stage1(const float *y, const uint8_t *ref_gt21, int64_t batch, int out_dim, uint8_t *is_ref, float *ref_prob,
+                             int32_t *argmax, float *maxprob, double *qual, int32_t *nonref_idx, int32_t *n_nonref, cudaStream_t s);
+
 // ---- kernels_fp32.cu ----
 int c3b_launch_lstm_f32(const float *x, const LstmF32 &fwd, const LstmF32 &bwd, float *out, int64_t batch, int in_dim,
                         int hidden, cudaStream_t s);
@@ -189,29 +231,21 @@ int c3b_launch_spp_f32(const float *x, float *out, int64_t batch, int h, int w, 
 
 // ---- tensor-core path (lstm_tc.cu / igemm_tc.cu) ----
 struct TcPileupBuffers {
-    op_t *xs;     // [33][B][32] bf16, time-major, channels zero-padded 18 -> 32
+    op_t *xs;     // [33][B][32] fp16, time-major, channels zero-padded 18 -> 32
     op_t *h1;     // k-group-planar [32][33*Bp][8]: row = t*Bp + b, k = dir*128 + j  (projection GEMM operand)
     __half *pg;            // [33*B][1280] fp16 pre-gates of LSTM2 (bias included), permuted gate columns
     op_t *h2;     // k-group-planar [1320][Bp][8]: row = b, k = t*320 + dir*160 + j (flatten order of clair3/model.py:135)
     float *z4;             // [B][128] fp32, L4 pre-activation without bias (split-K accumulated)
 };
-int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, op_t *xs, int64_t batch, cudaStream_t s);
+// starts == nullptr: x is the dense [batch][33][channels] tensor; otherwise x is the per-column matrix [n_cols][channels] and
+// site b is its rows [starts[b], starts[b] + 33) (rows outside the matrix read as zero)
+int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, const int64_t *starts, int64_t n_cols, op_t *xs, int64_t batch,
+                                cudaStream_t s);
+int c3b_launch_gather_windows_f32(const void *cols, int dtype, int channels, const int64_t *starts, int64_t n_cols, float *out,
+                                  int64_t batch, cudaStream_t s);
 int c3b_launch_lstm1_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t batch, int tile, cudaStream_t s);
 int c3b_launch_lstm2_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t batch, int tile, cudaStream_t s);
 
-// Zero-padded channel-group-planar feature map [C/8][p][8]: slot(b,h,w) = g + b*s + (h+1)*wp + (w+1)  (see pconv_tc.cu)
-struct PlanarGeom {
-    int h, w, wp, s, g;        // real dims, padded width (w+2), slots per site ((h+2)*wp), guard slots
-    int64_t t, p;              // data slots (B*s), plane pitch in slots (g + roundup(t,512) + g)
-};
-inline PlanarGeom c3b_planar_geom(int64_t batch, int h, int w) {
-    PlanarGeom g;
-    g.h = h; g.w = w; g.wp = w + 2; g.s = (h + 2) * (w + 2);
-    g.g = (g.wp + 1 + 7) / 8 * 8;
-    g.t = batch * g.s;
-    g.p = g.g + (g.t + 511) / 512 * 512 + g.g;
-    return g;
-}
 struct PconvArgs {
     const op_t *in;            // planar padded, c channels
     op_t *out;                 // planar padded, n channels, same geometry
@@ -232,7 +266,7 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s);
 
 // Generic implicit GEMM on tcgen05:  D[M x N] = A[M x K] * W[N x K]^T with fused epilogues.
 enum IgemmEpilogue {
-    IGEMM_EPI_BF16_BIAS_RELU = 0,   // bf16 NHWC store, + bias, optional residual add, ReLU      (convs)
+    IGEMM_EPI_BF16_BIAS_RELU = 0,   // fp16 NHWC store (name kept), + bias, optional residual add, ReLU      (convs)
     IGEMM_EPI_F16_BIAS = 1,         // fp16 row-major store, + bias                              (LSTM2 pre-gates)
     IGEMM_EPI_F32_ATOMIC = 2,       // fp32 split-K partial sums partial[ks][M][N] (plain stores; name kept)   (L4)
 };
@@ -246,9 +280,9 @@ struct IgemmArgs {
     int hout, wout, stride;   // conv output geometry
     int64_t lda;              // plain mode: row stride in elements
     IgemmW w;
-    void *out;                // bf16 / f16 / f32
+    void *out;                // f16 / f32
     int64_t ldo;              // output row stride in elements
-    const op_t *residual;   // optional (same layout as out, bf16)
+    const op_t *residual;   // optional (same layout as out, fp16)
     int relu;
     int epilogue;
     int ksplit;               // >1: split the K chunks over `ksplit` CTAs per tile (partial-sum epilogue only)

@@ -1,6 +1,6 @@
 // Small memory-bound kernels around the tensor-core convolution stack of Clair3_F:
-//  * ingest: int8 NHWC read image [B,D,33,C] -> bf16 [B,D,33,Cpad] (Cpad = 8 or 16); the 1/100 normalisation of
-//    clair3/model.py:378 is folded into conv1's weights, and int8 values are exact in bf16.
+//  * ingest: int8 NHWC read image [B,D,33,C] -> fp16 parity planes (Cpad = 8 or 16); the 1/100 normalisation of
+//    clair3/model.py:378 is folded into conv1's weights, and int8 values are exact in fp16.
 //  * spp: 3-level spatial pyramid max pool (clair3/model.py:250-279) on the planar padded res_block3 output.
 #include "c3b_internal.h"
 
@@ -41,7 +41,7 @@ __global__ void ingest_fa_tc_kernel(const T *__restrict__ x, op_t *__restrict__ 
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int ch = g * 8 + e;
-                v[e] = f2op(ch < channels ? (float)src[ch] : 0.f);
+                v[e] = f2op_sat(ch < channels ? (float)src[ch] : 0.f);
             }
         }
         const size_t off = (size_t)plane * plane_elems + ((size_t)g * g1.p + g1.g + b * g1.s + (size_t)(i + 1) * g1.wp + (j + 1)) * 8;

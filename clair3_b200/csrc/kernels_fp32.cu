@@ -1,5 +1,5 @@
 // fp32 CUDA-core debug path (C3B_PREC_FP32): the same layer graph as the tensor-core path, written for
-// obviousness, used to separate layout bugs from bf16 precision loss.  Not the product path.
+// obviousness, used to separate layout bugs from fp16 precision loss.  Not the product path.
 #include "c3b_internal.h"
 
 namespace {

@@ -387,8 +387,15 @@ __global__ void __launch_bounds__(2 * 128 * WG + 32, 1) lstm_tc_kernel(const Lst
 }
 
 template <typename T>
-__global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, op_t *__restrict__ xs, int64_t batch, int bp,
-                                        int channels) {
+__device__ __forceinline__ float ingest_to_float(T v) { return (float)v; }
+
+// Dense [batch][33][channels] tensor, or (starts != nullptr) 33-row windows of the per-column count matrix [n_cols][channels]
+// (libclair3's plp_data.matrix; preprocess/CreateTensorPileupFromCffi.py:362-394 slices the same windows on the host, zero
+// rows where a window overhangs the matrix) -> xs[t][bp][32] fp16, channel `channels` = constant 1 (LSTM1's bias column).
+// Counts are unbounded integers: the conversion saturates at +-65504 instead of overflowing to inf.
+template <typename T>
+__global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, const int64_t *__restrict__ starts, int64_t n_cols,
+                                        op_t *__restrict__ xs, int64_t batch, int bp, int channels) {
     // one thread per 8-channel group of xs[t][b][32]
     const int64_t total = (int64_t)C3B_T * bp * 4;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -397,29 +404,23 @@ __global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, op_t *__restric
         const int b = (int)(tb % bp);
         const int t = (int)(tb / bp);
         __align__(16) op_t v[8];
-        const T *src = x + ((int64_t)b * C3B_T + t) * channels + kg * 8;
-        if (sizeof(T) == 4 && b < batch && kg * 8 + 8 <= channels && (channels & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0) {
-            // a full group of 32-bit inputs: rows are channels*4 bytes apart, so 8-byte alignment always holds
-            const int2 *s2 = reinterpret_cast<const int2 *>(src);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int2 q = s2[i];
-                if (std::is_floating_point<T>::value) {
-                    v[2 * i] = f2op(__int_as_float(q.x));
-                    v[2 * i + 1] = f2op(__int_as_float(q.y));
-                } else {
-                    v[2 * i] = f2op((float)q.x);
-                    v[2 * i + 1] = f2op((float)q.y);
-                }
+        bool have = b < batch;
+        const T *src = x;
+        if (have) {
+            if (starts) {
+                const int64_t row = starts[b] + t;
+                have = row >= 0 && row < n_cols;
+                src = x + row * channels + kg * 8;
+            } else {
+                src = x + ((int64_t)b * C3B_T + t) * channels + kg * 8;
             }
-        } else {
+        }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int ch = kg * 8 + i;
-                float f = (ch == channels) ? 1.f : 0.f;          // constant-1 column: LSTM1's bias is folded into the gate GEMM
-                if (b < batch && ch < channels) f = (float)src[i];
-                v[i] = f2op(f);
-            }
+        for (int i = 0; i < 8; ++i) {
+            const int ch = kg * 8 + i;
+            float f = (ch == channels) ? 1.f : 0.f;          // constant-1 column: LSTM1's bias is folded into the gate GEMM
+            if (have && ch < channels) f = ingest_to_float(src[i]);
+            v[i] = f2op_sat(f);
         }
         *reinterpret_cast<uint4 *>(xs + idx * 8) = *reinterpret_cast<const uint4 *>(v);
     }
@@ -445,14 +446,16 @@ int launch_lstm(const LstmDev &p, bool mufu16, int wg, cudaStream_t s) {
 
 }  // namespace
 
-int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, op_t *xs, int64_t batch, cudaStream_t s) {
+int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, const int64_t *starts, int64_t n_cols, op_t *xs, int64_t batch,
+                                cudaStream_t s) {
     const int bp = (int)((batch + 127) / 128 * 128);
     const int64_t total = (int64_t)C3B_T * bp * 4;
     const int blocks = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
     switch (dtype) {
-        case C3B_DT_I8: ingest_pileup_tc_kernel<int8_t><<<blocks, 256, 0, s>>>((const int8_t *)x, xs, batch, bp, channels); break;
-        case C3B_DT_I32: ingest_pileup_tc_kernel<int32_t><<<blocks, 256, 0, s>>>((const int32_t *)x, xs, batch, bp, channels); break;
-        case C3B_DT_F32: ingest_pileup_tc_kernel<float><<<blocks, 256, 0, s>>>((const float *)x, xs, batch, bp, channels); break;
+        case C3B_DT_I8: ingest_pileup_tc_kernel<int8_t><<<blocks, 256, 0, s>>>((const int8_t *)x, starts, n_cols, xs, batch, bp, channels); break;
+        case C3B_DT_I32: ingest_pileup_tc_kernel<int32_t><<<blocks, 256, 0, s>>>((const int32_t *)x, starts, n_cols, xs, batch, bp, channels); break;
+        case C3B_DT_I64: ingest_pileup_tc_kernel<int64_t><<<blocks, 256, 0, s>>>((const int64_t *)x, starts, n_cols, xs, batch, bp, channels); break;
+        case C3B_DT_F32: ingest_pileup_tc_kernel<float><<<blocks, 256, 0, s>>>((const float *)x, starts, n_cols, xs, batch, bp, channels); break;
         default: c3b_set_error("unsupported input dtype %d", dtype); return 1;
     }
     C3B_CUDA(cudaGetLastError());

@@ -42,13 +42,80 @@ class _DevBlob:
                                          "strides": None}
 
 
-def broadcast_weights(model, src: int = 0, group=None):
-    """Broadcast rank `src`'s packed weight image into every rank's model (in place, device to device)."""
-    ptr, nbytes = model.weight_blob()
-    t = torch.as_tensor(_DevBlob(ptr, nbytes), device=model._device)
-    dist.broadcast(t, src=src, group=group)
-    torch.cuda.synchronize(model._device)
-    return nbytes
+def _libnccl():
+    """The libnccl torch itself uses (the wheel-bundled one), else the system library."""
+    import ctypes
+    import importlib.util
+    import os
+    spec = importlib.util.find_spec("nvidia")
+    for root in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(root, "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return ctypes.CDLL(cand, mode=ctypes.RTLD_GLOBAL)
+    return ctypes.CDLL("libnccl.so.2", mode=ctypes.RTLD_GLOBAL)
+
+
+class NcclComm:
+    """A raw ``ncclComm_t`` over the ranks of the default torch.distributed group, for the C-ABI's ``c3b_bcast_weights``
+    (torch does not expose its own communicator).  The 128-byte unique id travels through the existing process group."""
+
+    def __init__(self, device, group=None):
+        import ctypes
+        self._lib = _libnccl()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        uid = (ctypes.c_byte * 128)()
+        if rank == 0:
+            rc = self._lib.ncclGetUniqueId(ctypes.byref(uid))
+            if rc != 0:
+                raise RuntimeError("ncclGetUniqueId failed: %d" % rc)
+        t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device=device if dist.get_backend(group) == "nccl" else "cpu")
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        uid = (ctypes.c_byte * 128).from_buffer_copy(raw)
+        self.comm = ctypes.c_void_p()
+        torch.cuda.set_device(device)
+        # ncclResult_t ncclCommInitRank(ncclComm_t* comm, int nranks, ncclUniqueId commId /* by value */, int rank)
+        self._lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_byte * 128, ctypes.c_int]
+        rc = self._lib.ncclCommInitRank(ctypes.byref(self.comm), world, uid, rank)
+        if rc != 0:
+            raise RuntimeError("ncclCommInitRank failed: %d" % rc)
+
+    def destroy(self):
+        if self.comm:
+            self._lib.ncclCommDestroy.argtypes = [__import__("ctypes").c_void_p]
+            self._lib.ncclCommDestroy(self.comm)
+            self.comm = None
+
+
+def broadcast_weights(model, src: int = 0, group=None, native=True):
+    """Broadcast rank `src`'s packed weight images into every rank's model (in place, device to device, one collective per
+    image).  ``native``: through the C-ABI's ``c3b_bcast_weights`` on a raw ``ncclComm_t`` (what a C caller does); otherwise
+    (or if the raw communicator cannot be created) ``torch.distributed.broadcast`` on tensors aliasing the images.
+    Returns (bytes broadcast, "c3b_bcast_weights" | "torch.distributed")."""
+    from ._ffi import check, ffi, lib
+    total = sum(model.weight_blob(w)[1] for w in (0, 1))
+    how = "torch.distributed"
+    comm = None
+    if native and dist.get_backend(group) == "nccl":
+        try:
+            comm = NcclComm(model._device, group)
+        except Exception:          # no raw libnccl handle: the torch path below is equivalent
+            comm = None
+    if comm is not None:
+        stream = torch.cuda.current_stream(model._device).cuda_stream
+        check(lib().c3b_bcast_weights(model._handle, ffi.cast("void *", comm.comm.value), src, ffi.cast("void *", stream)))
+        torch.cuda.synchronize(model._device)
+        comm.destroy()
+        how = "c3b_bcast_weights"
+    else:
+        for which in (0, 1):
+            ptr, nbytes = model.weight_blob(which)
+            t = torch.as_tensor(_DevBlob(ptr, nbytes), device=model._device)
+            dist.broadcast(t, src=src, group=group)
+        torch.cuda.synchronize(model._device)
+    if dist.get_rank(group) != src:
+        model._by_broadcast = True
+    return total, how
 
 
 def broadcast_state_dict_cpu(state_dict, src: int = 0, group=None):

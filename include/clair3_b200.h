@@ -39,10 +39,11 @@ typedef struct c3b_model c3b_model;
 #define C3B_DT_I8   0             /* full-alignment wire dtype (shared/param_f.py:92) and GPU-mode pileup .npy (CreateTensorPileupFromCffi.py:447) */
 #define C3B_DT_I32  1             /* pileup wire dtype (CreateTensorPileupFromCffi.py:397) */
 #define C3B_DT_F32  2
-#define C3B_DT_I64  3             /* only for c3b_set_param (BatchNorm num_batches_tracked) */
+
+#define C3B_DT_I64  3             /* BatchNorm num_batches_tracked in c3b_set_param; libclair3's size_t count matrix in c3b_forward_windows */
 
 /* arithmetic used by the kernels (c3b_set_option "precision") */
-#define C3B_PREC_BF16_TC 0        /* production: bf16 operands on tcgen05 tensor cores, fp32 accumulate/state/softmax */
+#define C3B_PREC_F16_TC  0        /* production: fp16 operands on tcgen05 tensor cores, fp32 accumulate / cell state / SELU / softmax */
 #define C3B_PREC_FP32    1        /* debug: the same layer graph on fp32 CUDA cores (separates layout bugs from precision) */
 
 /* Replaces Clair3_P.__init__ / Clair3_F.__init__ (clair3/model.py:61-128, 285-368) + m.to(device) (CallVariantsFromCffi.py:246).
@@ -57,14 +58,14 @@ int c3b_set_param(c3b_model *m, const char *key, const void *host_data, int dtyp
 
 /* Ends load_state_dict: checks every expected key is present (strict), folds BatchNorm into the convolutions
  * (eps 1e-3, clair3/model.py:192), sums the LSTM bias pairs, folds 1/NORMALIZE_NUM (shared/param_f.py:36) into conv1,
- * packs bf16 UMMA operand images and uploads them once. */
+ * packs fp16 UMMA operand images and uploads them once. */
 int c3b_finalize(c3b_model *m);
 
-/* name: "precision" (C3B_PREC_*), "chunk_sites" (sites per internal pass), "lstm_tile" (batch columns per LSTM CTA: 16|32|64, 0 = auto), "lstm_wg" (epilogue warpgroups per LSTM sub-tile: 1|2), "lstm_trace" (debug clock stamps),
- * "lstm_mufu16" (1: gate activations with packed tanh.approx.f16x2, two sites per MUFU op; 0 default: fp32 tanh.approx, measured faster),
- * "host_async" (1: forwards with HOST buffers do not synchronise; the buffers must be pinned and the caller synchronises the
- * stream before reading y - lets a caller pipeline H2D / forward / D2H of consecutive batches over several streams),
- * "profile" (1: bracket every kernel launch with CUDA events on its stream and accumulate per-kernel time; setting it resets the totals). */
+/* name: "precision" (C3B_PREC_*), "chunk_sites" (sites per internal pass), "lstm_tile" (batch columns per LSTM CTA sub-tile:
+ * 16|32|64, 0 = auto), "lstm_wg" (epilogue warpgroups per LSTM sub-tile: 1|2),
+ * "profile" (1: bracket every kernel launch with CUDA events on its stream and accumulate per-kernel time; setting it resets the
+ * totals), "taps" (1: remember where the intermediate activations of a forward live, for c3b_get_tap in clair3_b200_debug.h).
+ * Debug-only options are listed in clair3_b200_debug.h. */
 int c3b_set_option(c3b_model *m, const char *name, int value);
 
 /* Replaces Y = m(X) (clair3/model.py:130-161 / 377-416) including the H2D/D2H of _torch_predict
@@ -76,47 +77,59 @@ int c3b_set_option(c3b_model *m, const char *name, int value);
 int c3b_forward(c3b_model *m, const void *x, int x_dtype, int x_on_device, int64_t batch, int depth,
                 float *y, int y_on_device, void *cuda_stream);
 
+/* The same forward on PINNED host buffers without the host synchronisation: H2D, kernels and D2H are enqueued on cuda_stream
+ * and the call returns at once; the caller synchronises the stream (or an event) before reading y and keeps both buffers
+ * alive until then.  This is what lets a caller overlap the copies and kernels of consecutive batches over several streams
+ * (each stream owns an activation workspace) - the double-buffered replacement of the serial H2D / forward / D2H loop at
+ * clair3/CallVariantsFromCffi.py:300-331. */
+int c3b_forward_async(c3b_model *m, const void *x_pinned, int x_dtype, int64_t batch, int depth, float *y_pinned,
+                      void *cuda_stream);
+
+/* Pileup only.  Replaces the host-side window slicing of preprocess/CreateTensorPileupFromCffi.py:362-394: instead of
+ * materialising one [33,18] tensor per candidate (windows of neighbouring candidates overlap in 32 of 33 rows), hand over
+ * libclair3's per-column count matrix once - plp_data.matrix, size_t[n_cols][18] (src/clair3_pileup.h:5-17), i.e.
+ * cols_dtype C3B_DT_I64; C3B_DT_I32 / I8 / F32 also accepted - plus the first row of every candidate's window:
+ * site b = rows [starts[b], starts[b]+33) of cols; rows outside [0, n_cols) read as zero (the reference's zero padding at a
+ * sequence head / tail, :372-394).  The windows are gathered on the GPU straight into the LSTM operand layout.
+ * on_device: cols and starts are device pointers (else host; they are copied on cuda_stream).  host_sync: 1 = return after y
+ * is complete when a host buffer is involved, 0 = stay stream-ordered (pinned buffers, caller synchronises). */
+int c3b_forward_windows(c3b_model *m, const void *cols, int cols_dtype, int64_t n_cols, const int64_t *starts,
+                        int on_device, int64_t batch, float *y, int y_on_device, int host_sync, void *cuda_stream);
+
 /* 24 or 90 (clair3/model.py:153-159). */
 int c3b_out_dim(const c3b_model *m);
 
-/* Packed device weight image (what one rank broadcasts to the others at start-up). */
-int c3b_weight_blob(c3b_model *m, void **device_ptr, size_t *bytes);
+/* First, data-parallel stage of the reference's per-site decoder on the GPU (batch_output -> output_with -> output_from ->
+ * possible_outcome_probabilites_from; clair3/CallVariants.py:1069-1116, 676-700, 510-576) so that only the sites that are not
+ * an early-out homozygous-reference call go on to the per-site Python decoder:
+ *   y         [batch, out_dim] probabilities from c3b_forward            ref_gt21 [batch]: gt21 index of ref_base+ref_base
+ *                                                                         (AA=0 CC=4 GG=7 TT=9, clair3/task/gt21.py:29-50)
+ *   is_ref    [batch] 1 = early-out: homo_reference >= 0.5 and gt21[ref] >= 0.5 (and both variant_length[0] >= 0.5 with the
+ *             indel heads)                                                CallVariants.py:532-534, 573-576
+ *   ref_prob  [batch] homo_Ref_probability (float32 products in the reference's order)   CallVariants.py:527, 569-572
+ *   argmax / maxprob [batch][2|4] per head, first maximum        qual [batch] quality_score_from(ref_prob) before round(.,2)  :375-381
+ *   nonref_idx[0 .. *n_nonref) ascending indices of the sites with is_ref == 0
+ * on_device: every pointer is a device pointer and the call is asynchronous on cuda_stream; else host pointers, returns
+ * when the outputs are complete. */
+int c3b_decode_stage1(c3b_model *m, const float *y, const uint8_t *ref_gt21, int64_t batch, int on_device,
+                      uint8_t *is_ref, float *ref_prob, int32_t *argmax, float *maxprob, double *qual,
+                      int32_t *nonref_idx, int32_t *n_nonref, void *cuda_stream);
 
-/* One-time ncclBroadcast of the packed weight image from rank `root` over NVLink (libnccl is dlopen'ed; the comm is
+/* Packed device weight images (what one rank broadcasts to the others at start-up).
+ * which: 0 = fp16 tensor-core operand images + fp32 head weights, 1 = fp32 debug-path weights. */
+int c3b_weight_blob(c3b_model *m, int which, void **device_ptr, size_t *bytes);
+
+/* One-time ncclBroadcast of both packed weight images from rank `root` over NVLink (libnccl is dlopen'ed; the comm is
  * the caller's ncclComm_t).  Multi-GPU inference in the reference is N independent processes over file lists
  * (clair3/CallVariantsFromCffiGPU.py:141-199); there is no per-batch collective to replace. */
 int c3b_bcast_weights(c3b_model *m, void *nccl_comm, int root, void *cuda_stream);
 
-/* Debug tap: copy an intermediate activation of the most recent forward (default stream slot, first chunk) to the host
- * as float32.  names: pileup "lstm1"[B,33,256] "lstm2"[B,33,320] "l4_pre"[B,128]; full-alignment "conv1" "res_block1"
- * "conv3" "res_block2" "conv5" "res_block3" (NHWC) "spp"[B,3584] "l4_pre"[B,256].  *count_inout: capacity in / elements out. */
-int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int64_t *count_inout);
-
 /* Per-kernel device time accumulated while option "profile" is on.  kernel names: pileup "ingest" "lstm1" "proj2" "lstm2"
- * "l4" "heads"; full-alignment "ingest" "conv0".."conv8" "spp" "l4" "heads".  Synchronises the streams it recorded on. */
+ * "tail" (L4 + heads); full-alignment "ingest" "conv0".."conv8" "spp" "tail".  Synchronises the streams it recorded on. */
 int c3b_get_profile(c3b_model *m, const char *kernel, double *total_ms, int64_t *launches);
 
 /* Number of this library's kernels launched on behalf of m so far (bench.py's gpu_launches). */
 int64_t c3b_launch_count(const c3b_model *m);
-
-/* Kernel unit-test hook (tests/test_igemm.py), not part of the drop-in surface: run the tcgen05 implicit-GEMM kernel on
- * caller matrices.  out[M][N] = a[M][K] * w[N][K]^T; swapped=0: standard orientation, +bias, optional ReLU, bf16-rounded;
- * swapped=1: weights on the TMEM lanes, split-K (ksplit) fp32 atomic accumulation, no bias.  K % 8 == 0; N % 16 == 0
- * (N % 128 == 0 when swapped). */
-int c3b_debug_gemm(c3b_model *m, int swapped, int64_t M, int N, int K, const float *a, const float *w, const float *bias,
-                   int relu, int ksplit, float *out);
-
-/* Kernel timing hook: with option "lstm_trace" on, CTA (0,0) of each LSTM kernel stamps clock64 at four points of every
- * step (operands ready, MMAs issued, accumulator ready, epilogue done); copies [2 layers][33 steps][4] stamps out. */
-int c3b_debug_lstm_trace(c3b_model *m, int64_t *out264);
-
-/* Hardware probe (tools/diag.py probe): one tcgen05.mma with its A operand in TMEM (checks the assumed layout) and the
- * cycles of `reps` back-to-back MMAs with A from shared memory vs TMEM.  a[128][16], b[n][16] -> out_d[128][n]. */
-int c3b_debug_ts_probe(const float *a, const float *b, int n, int reps, float *out_d, int64_t *timing10);
-/* debug: cycles for back-to-back tcgen05.mma under operand / accumulator switching (tools/diag.py mmaprobe) */
-int c3b_debug_mma_probe(int n, int reps, int nmodes, const int *modes, int64_t *timing);
-/* debug: cycles of TMEM reads / an epilogue chunk with the tensor pipe idle and busy (tools/diag.py tmemprobe) */
-int c3b_debug_tmem_probe(int reps, int64_t *timing6);
 
 void c3b_destroy(c3b_model *m);
 

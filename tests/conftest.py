@@ -16,6 +16,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run by `pytest -m gpu` on the GPU box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests need a B200 (compute capability 10.x): skip them cleanly anywhere else, so a plain `pytest` on a CPU
+    host passes instead of dying in the CUDA driver."""
+    try:
+        import torch
+        ok = torch.cuda.is_available() and torch.cuda.get_device_capability(0)[0] == 10
+    except Exception:
+        ok = False
+    if ok:
+        return
+    skip = pytest.mark.skip(reason="needs a B200 (sm_100) GPU")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     meta = ast.literal_eval(str(z["meta"]))

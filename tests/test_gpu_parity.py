@@ -28,6 +28,7 @@ def _model(meta, sd, precision, **opts):
     ch = 18 if meta["kind"] == "pileup" else meta["channels"]
     m = cls(add_indel_length=meta["add_indel_length"], predict=True, input_channels=ch)
     m.set_option("precision", precision)
+    m.set_option("taps", 1)
     for k, v in opts.items():
         m.set_option(k, v)
     m.to(torch.device("cuda"))
@@ -236,7 +237,7 @@ def test_strict_state_dict_errors():
 
 def test_large_batch_properties():
     """BASELINE.json full sizes through size-independent properties: rows are probability vectors, every site is
-    independent of its batch neighbours (permutation equivariance), and the fp32 and bf16 paths agree."""
+    independent of its batch neighbours (permutation equivariance), and the fp32 and fp16 tensor-core paths agree."""
     from clair3_b200 import synth
     sd = synth.pileup_state_dict(False, seed=11)
     x = synth.pileup_inputs(1024, seed=11)

@@ -62,3 +62,33 @@ def test_depth_rescale_truncates_toward_zero():
     out = orc.depth_rescale_with(x, [288])          # scale 2.0 -> -3 (trunc), 3, 150
     assert out.tolist() == [[[-3, 3, 150]]]
     assert orc.depth_rescale_with(x, [200]).tolist() == x.tolist()   # <= 1.5*144: untouched
+
+
+@pytest.mark.parametrize("out_dim", [24, 90])
+def test_decode_oracle_matches_reference(out_dim):
+    """oracle/decode_oracle.py vs the reference's own possible_outcome_probabilites_from / quality_score_from
+    (fixture minted by tests/golden/make_decode_golden.py): flags and float32 products bit-exact, QUAL to double rounding."""
+    import os
+
+    from conftest import GOLDEN_DIR
+    from oracle import decode_oracle as dec
+    z = np.load(os.path.join(GOLDEN_DIR, "decode_stage1.npz"))
+    y, ref_gt21 = z["y%d" % out_dim], z["ref_gt21_%d" % out_dim]
+    assert np.array_equal(dec.ref_gt21_from_bases(str(z["bases%d" % out_dim])), ref_gt21)
+    d = dec.decode_stage1(y, ref_gt21)
+    assert np.array_equal(d["is_ref"], z["early%d" % out_dim])
+    assert np.array_equal(d["ref_prob"], z["prob%d" % out_dim])                  # bit-exact float32
+    assert np.allclose(d["qual"], z["qual%d" % out_dim], rtol=1e-13, atol=1e-13)
+    assert np.array_equal(np.round(d["qual"], 2), z["qual_rounded%d" % out_dim])
+    assert np.array_equal(d["nonref_idx"], np.nonzero(z["early%d" % out_dim] == 0)[0])
+    assert 0 < d["n_nonref"][0] < len(y)
+
+
+def test_pileup_windows_restatement():
+    from oracle import decode_oracle as dec
+    cols = np.arange(100 * 18, dtype=np.int64).reshape(100, 18) + 1
+    w = dec.pileup_windows(cols, [0, 10, 67, -5, 90, 200])
+    assert np.array_equal(w[1], cols[10:43]) and np.array_equal(w[2], cols[67:100])
+    assert (w[3][:5] == 0).all() and np.array_equal(w[3][5:], cols[0:28])        # head overhang -> zero rows
+    assert np.array_equal(w[4][:10], cols[90:100]) and (w[4][10:] == 0).all()    # tail overhang
+    assert (w[5] == 0).all()
