@@ -144,6 +144,19 @@ class _C3BModule:
 
     __call__ = forward
 
+    def forward_into(self, x, y):
+        """``forward`` on device tensors with a caller-provided output (no allocation per call; asynchronous on the current
+        stream).  x, y on the model's device, y float32 [B, out_dim] contiguous."""
+        batch, depth = self._check_input(x, "forward_into")
+        if x.device != self._device or y.device != self._device or x.dtype not in _DT or not x.is_contiguous():
+            raise C3BError("forward_into: contiguous int8/int32/float32 x and y on %s" % self._device)
+        if tuple(y.shape) != (batch, self.out_dim) or y.dtype != torch.float32 or not y.is_contiguous():
+            raise C3BError("forward_into: y must be contiguous float32 [batch, %d]" % self.out_dim)
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        check(lib().c3b_forward(self._handle, ffi.cast("void *", x.data_ptr()), _DT[x.dtype], 1, batch, depth,
+                                ffi.cast("float *", y.data_ptr()), 1, ffi.cast("void *", stream)))
+        return y
+
     def forward_async(self, x_host, y_host):
         """Stream-ordered forward on PINNED host tensors (H2D -> kernels -> D2H on the current CUDA stream, no host
         synchronisation; ``c3b_forward_async``): the double-buffered caller of SURVEY.md §8f N1.  The caller synchronises the
