@@ -534,7 +534,7 @@ def run_forward_workload(ctx, wname, model):
             cnt += len(y)
         return cnt
     run_stream(2 * n_streams)
-    n_ps = max(K, int(K * re["repeats"] // 2))
+    n_ps = max(K, int(K * re["repeats"] // 2)) if MIN_REGION_S > 0 else K
     ctx.barrier()
     t0 = time.perf_counter()
     run_stream(n_ps)
@@ -545,7 +545,7 @@ def run_forward_workload(ctx, wname, model):
     for i in range(3):
         model(xs_pin[i % len(xs_pin)])
     torch.cuda.synchronize(dev)
-    n_sync = max(K, int(0.5e3 / max(re["ms"] / (K * re["repeats"]) * 4, 1e-3)))        # ~0.5+ s
+    n_sync = max(K, int(0.5e3 / max(re["ms"] / (K * re["repeats"]) * 4, 1e-3))) if MIN_REGION_S > 0 else K       # ~0.5+ s
     ctx.barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
@@ -654,9 +654,14 @@ def main():
     ap.add_argument("--lstm-wg", type=int, default=0, help="epilogue warpgroups per LSTM sub-tile (0 = library default)")
     ap.add_argument("--lstm-tile", type=int, default=64,
                     help="sites per LSTM sub-tile (16|32|64; 0 = library auto = latency-oriented 16 at this batch)")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value for the pileup model (tuning runs), repeatable")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-region-s", type=float, default=2.0,
+                    help="minimum length of every timed region (profiling runs under ncu pass 0: one pass of the K steps)")
     args = ap.parse_args()
     args.workloads = [x for x in (args.workload or args.workloads).split(",") if x]
+    global MIN_REGION_S
+    MIN_REGION_S = max(0.0, args.min_region_s)
     if args.steps <= 0:
         args.steps = 20
     requested_warmup = args.warmup
@@ -695,6 +700,9 @@ def main():
                 m.set_option("lstm_wg", args.lstm_wg)
             if args.lstm_tile:
                 m.set_option("lstm_tile", args.lstm_tile)
+            for kv in args.opt:
+                k, v = kv.split("=")
+                m.set_option(k, int(v))
         if world > 1:
             from clair3_b200 import sharding
             nbytes, how = sharding.broadcast_weights(m, src=0)        # the one NCCL collective per model, before any timed region

@@ -295,12 +295,12 @@ static int finalize_impl(c3b_model *m) {
         fixes.push_back({b.add(src, bytes), dst, f32b});
     };
 
-    // ---- dense heads (fp32, shared by both precisions): transposed for coalesced reads
+    // ---- dense heads of the fp32 debug path: transposed for coalesced reads
     m->heads = HeadsParams();
     m->heads.nheads = m->nheads;
     m->heads.d4 = m->d4;
     m->heads.out_dim = m->out_dim;
-    put(blob, P(m, "L4.bias").data(), (size_t)m->d4 * 4, (const void **)&m->heads.b4, false);
+    put(fb, P(m, "L4.bias").data(), (size_t)m->d4 * 4, (const void **)&m->heads.b4, true);
     int off = 0;
     std::vector<float> wy_all((size_t)128 * m->out_dim);
     for (int h = 0; h < m->nheads; ++h) {
@@ -315,32 +315,49 @@ static int finalize_impl(c3b_model *m) {
                 wyt[(size_t)j * n + o] = wy[(size_t)o * 128 + j];
                 wy_all[(size_t)j * m->out_dim + off + o] = wy[(size_t)o * 128 + j];
             }
-        put(blob, w5t.data(), w5t.size() * 4, (const void **)&m->heads.h[h].w5t, false);
-        put(blob, P(m, std::string(kHeadNames[h][0]) + ".bias").data(), 128 * 4, (const void **)&m->heads.h[h].b5, false);
-        put(blob, wyt.data(), wyt.size() * 4, (const void **)&m->heads.h[h].wyt, false);
-        put(blob, P(m, std::string(kHeadNames[h][1]) + ".bias").data(), (size_t)n * 4, (const void **)&m->heads.h[h].by, false);
+        put(fb, w5t.data(), w5t.size() * 4, (const void **)&m->heads.h[h].w5t, true);
+        put(fb, P(m, std::string(kHeadNames[h][0]) + ".bias").data(), 128 * 4, (const void **)&m->heads.h[h].b5, true);
+        put(fb, wyt.data(), wyt.size() * 4, (const void **)&m->heads.h[h].wyt, true);
+        put(fb, P(m, std::string(kHeadNames[h][1]) + ".bias").data(), (size_t)n * 4, (const void **)&m->heads.h[h].by, true);
         m->heads.h[h].n = n;
         m->heads.h[h].out_off = off;
         off += n;
     }
-    put(blob, wy_all.data(), wy_all.size() * 4, (const void **)&m->heads.wy_all, false);
+    put(fb, wy_all.data(), wy_all.size() * 4, (const void **)&m->heads.wy_all, true);
 
-    // ---- L4: fp32 transposed (debug) + tensor-core image (swapped orientation: 128-row blocks)
+    // ---- L4 + heads: fp32 transposed (debug) + tensor-core operand images of the fused tail
     {
         const std::vector<float> &w4 = P(m, "L4.weight");   // [d4][l4_in]
         std::vector<float> w4t((size_t)m->l4_in * m->d4);
         for (int o = 0; o < m->d4; ++o)
             for (int k = 0; k < m->l4_in; ++k) w4t[(size_t)k * m->d4 + o] = w4[(size_t)o * m->l4_in + k];
         put(fb, w4t.data(), w4t.size() * 4, (const void **)&m->l4_f32_t, true);
+        // tensor-core tail (tail_tc.cu): L4 as the B operand of a sites-on-lanes GEMM, one contiguous piece per 64-wide k-chunk
         const int kg = m->l4_in / 8;
-        const int l4_in = m->l4_in;
-        std::vector<uint16_t> img = pack_igemm(m->d4, kg, 128, [&](int r, int k) { return w4[(size_t)r * l4_in + k]; });
-        m->l4_tc = IgemmW();
-        m->l4_tc.n = m->d4;
-        m->l4_tc.kgroups = kg;
-        m->l4_tc.nchunks = (kg + 7) / 8;
-        m->l4_tc.bias = nullptr;
-        put(blob, img.data(), img.size() * 2, (const void **)&m->l4_tc.w_img, false);
+        const int l4_in = m->l4_in, d4 = m->d4;
+        m->tail = TailW();
+        std::vector<uint16_t> img = pack_igemm(d4, kg, d4, [&](int r, int k) { return w4[(size_t)r * l4_in + k]; });
+        put(blob, img.data(), img.size() * 2, (const void **)&m->tail.w4, false);
+        put(blob, P(m, "L4.bias").data(), (size_t)d4 * 4, (const void **)&m->tail.b4, false);
+        int toff = 0;
+        for (int h = 0; h < m->nheads; ++h) {
+            const std::vector<float> &w5 = P(m, std::string(kHeadNames[h][0]) + ".weight");   // [128][d4]
+            const std::vector<float> &wy = P(m, std::string(kHeadNames[h][1]) + ".weight");   // [n][128]
+            const std::vector<float> &byv = P(m, std::string(kHeadNames[h][1]) + ".bias");
+            const int n = kHeadDims[h], npad = (n + 15) / 16 * 16;
+            std::vector<uint16_t> i5 = pack_igemm(128, d4 / 8, 128, [&](int r, int k) { return w5[(size_t)r * d4 + k]; });
+            std::vector<uint16_t> iy = pack_igemm(npad, 16, npad, [&](int r, int k) { return r < n ? wy[(size_t)r * 128 + k] : 0.f; });
+            std::vector<float> byp(npad, 0.f);
+            for (int o = 0; o < n; ++o) byp[o] = byv[o];
+            put(blob, i5.data(), i5.size() * 2, (const void **)&m->tail.w5[h], false);
+            put(blob, P(m, std::string(kHeadNames[h][0]) + ".bias").data(), 128 * 4, (const void **)&m->tail.b5[h], false);
+            put(blob, iy.data(), iy.size() * 2, (const void **)&m->tail.wy[h], false);
+            put(blob, byp.data(), byp.size() * 4, (const void **)&m->tail.by[h], false);
+            m->tail.n[h] = n;
+            m->tail.npad[h] = npad;
+            m->tail.off[h] = toff;
+            toff += n;
+        }
     }
 
     if (m->kind == C3B_PILEUP) {
@@ -413,7 +430,8 @@ static int finalize_impl(c3b_model *m) {
             }
             put(blob, img.data(), img.size() * 2, (const void **)&m->lstm_tc[1][0].w_img, false);
             m->lstm_tc[1][0].bias = nullptr;
-            std::vector<uint16_t> pimg = pack_igemm(1280, 32, 128, [&](int R, int k) {
+            // one 256-row slab per column group of the projection kernel (proj_tc.cu): [chunk 4][group 5][8 kg][256 rows][8]
+            std::vector<uint16_t> pimg = pack_igemm(1280, 32, 256, [&](int R, int k) {
                 const int d = R / 640;
                 const int row = lstm2_torch_row(R % 640);
                 return (*wih_d[d])[(size_t)row * 256 + k] * ((row / C3B_H2 == 2) ? 1.0f : 0.5f);
@@ -686,45 +704,14 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const PileupSrc &src
     { PROF("ingest"); if (c3b_launch_ingest_pileup_tc(x, x_dtype, m->channels, src.starts, src.n_cols, b.xs, n, s)) return 1; }
     m->launches += 1;
     { PROF("lstm1"); if (c3b_launch_lstm1_tc(m, b, n, tile1, s)) return 1; }
-    IgemmArgs pa = {};
-    pa.a = b.h1;
-    pa.m = (int64_t)C3B_T * bp;
-    pa.taps = 0;                // k-group-planar operand
-    pa.ld_rows = (int64_t)C3B_T * bp;
-    pa.hin = (int)bp;          // pre-gate geometry (padded batch, LSTM2 tile) rides in hin / win
-    pa.win = tile2;
-    pa.cin = 256;
-    pa.lda = 256;
-    pa.w = m->proj2;
-    pa.out = b.pg;
-    pa.epilogue = IGEMM_EPI_F16_BIAS;
-    pa.trace = (m->lstm_trace && m->trace_conv == 20) ? m->lstm_trace : nullptr;   // debug option lstm_trace = 30
-    { PROF("proj2"); if (c3b_launch_igemm(m, pa, s)) return 1; }
+    { PROF("proj2");
+      if (c3b_launch_proj2(m, b.h1, m->proj2, b.pg, (int)bp, tile2, (m->lstm_trace && m->trace_conv == 20) ? m->lstm_trace : nullptr, s)) return 1; }
     { PROF("lstm2"); if (c3b_launch_lstm2_tc(m, b, n, tile2, s)) return 1; }
-    IgemmArgs la = {};
-    la.a = b.h2;
-    la.m = n;
-    la.taps = 0;
-    la.ld_rows = bp;
-    la.cin = m->l4_in;
-    la.lda = m->l4_in;
-    la.w = m->l4_tc;
-    la.out = b.z4;
-    la.ldo = 128;
-    la.epilogue = IGEMM_EPI_F32_ATOMIC;
-    static const int l4_ksplit_env = getenv("C3B_L4_KSPLIT") ? atoi(getenv("C3B_L4_KSPLIT")) : 0;   // tuning sweeps only
-    // 5 splits (33 of 165 chunks each): fewer, longer CTAs cost a few us of single-launch latency but 40 % less SM time than
-    // 11 splits - with several batches in flight that is +4 % sites/s (measured)
-    la.ksplit = l4_ksplit_env > 0 ? l4_ksplit_env : 5;
-    la.split_stride = (int64_t)bp * 128;
-    const int ns_p = c3b_effective_ksplit(m->l4_tc.nchunks, la.ksplit);
-    { PROF("l4"); if (c3b_launch_igemm(m, la, s)) return 1; }
-    { PROF("heads"); if (c3b_launch_heads(b.z4, ns_p, la.split_stride, m->heads, y, n, s)) return 1; }
-    m->launches += 1;
+    { PROF("tail"); if (c3b_launch_tail(m, b.h2, n, (int)bp, y, tap ? b.z4 : nullptr, s)) return 1; }
     if (tap) {
         taps["lstm1"] = {b.h1, 1, 3, 256, (int)bp, {}};
         taps["lstm2"] = {b.h2, 1, 2, (int64_t)C3B_T * 320, (int)bp, {}};
-        taps["l4_pre"] = {b.z4, 0, 5, 128, (int)bp, {}, ns_p};
+        taps["l4_pre"] = {b.z4, 0, 0, 128, 0, {}};
     }
     return 0;
 }
@@ -827,23 +814,8 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
         { PROF(cn[3 * l + 2]); if (c3b_launch_pconv(m, pa, s)) return 1; }
     }
     { PROF("spp"); if (c3b_launch_spp_tc(act[2][2], geo[2], sp, n, 256, (int)bp, s)) return 1; }
-    IgemmArgs la = {};
-    la.a = sp;
-    la.m = n;
-    la.taps = 0;
-    la.ld_rows = bp;
-    la.cin = 3584;
-    la.lda = 3584;
-    la.w = m->l4_tc;
-    la.out = z4;
-    la.ldo = 256;
-    la.epilogue = IGEMM_EPI_F32_ATOMIC;
-    la.ksplit = 8;
-    la.split_stride = (int64_t)bp * 256;
-    const int ns_f = c3b_effective_ksplit(m->l4_tc.nchunks, la.ksplit);
-    { PROF("l4"); if (c3b_launch_igemm(m, la, s)) return 1; }
-    { PROF("heads"); if (c3b_launch_heads(z4, ns_f, la.split_stride, m->heads, y, n, s)) return 1; }
-    m->launches += 3;
+    { PROF("tail"); if (c3b_launch_tail(m, sp, n, (int)bp, y, tap ? z4 : nullptr, s)) return 1; }
+    m->launches += 1;          // spp (ingest, the convolutions and the tail count themselves)
     if (tap) {
         for (int l = 0; l < 3; ++l) {
             taps[tapname[l][0]] = {act[l][0], 1, 4, chans[l + 1], 0, geo[l]};
@@ -856,7 +828,7 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
             }
         }
         taps["spp"] = {sp, 1, 2, 3584, (int)bp, {}};
-        taps["l4_pre"] = {z4, 0, 5, 256, (int)bp, {}, ns_f};
+        taps["l4_pre"] = {z4, 0, 0, 256, 0, {}};
     }
     return 0;
 }

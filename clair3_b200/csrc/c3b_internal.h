@@ -103,6 +103,17 @@ struct IgemmW {
     int nchunks;                  // ceil(kgroups/8)
 };
 
+// fused dense tail (tail_tc.cu): L4 as a [d4 rows] B-operand image per k-chunk, per head L5 / Y operand images + fp32 biases
+struct TailW {
+    const op_t *w4;                      // [l4_in/64 chunks][8 kg][d4 rows][8]
+    const float *b4;                     // [d4]
+    const op_t *w5[C3B_MAX_HEADS];       // [d4/8 kg][128 rows][8]
+    const float *b5[C3B_MAX_HEADS];      // [128]
+    const op_t *wy[C3B_MAX_HEADS];       // [16 kg][npad rows][8], rows >= n zero
+    const float *by[C3B_MAX_HEADS];      // [npad]
+    int n[C3B_MAX_HEADS], npad[C3B_MAX_HEADS], off[C3B_MAX_HEADS];
+};
+
 struct ConvGeom {
     int hin, win, cin, hout, wout, cout, stride;
 };
@@ -196,7 +207,7 @@ struct c3b_model {
     // tc path
     LstmTC lstm_tc[2][2];
     IgemmW proj2;                      // LSTM2 input projection, both directions: N = 1280
-    IgemmW l4_tc;
+    TailW tail;                        // L4 + heads on the tensor cores
     IgemmW conv_tc[9];
 
     std::vector<Workspace *> ws;
@@ -243,6 +254,8 @@ int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, const in
                                 cudaStream_t s);
 int c3b_launch_gather_windows_f32(const void *cols, int dtype, int channels, const int64_t *starts, int64_t n_cols, float *out,
                                   int64_t batch, cudaStream_t s);
+int c3b_launch_proj2(const c3b_model *m, const op_t *h1, const IgemmW &w, __half *pg, int bp, int nbl, long long *trace, cudaStream_t s);
+int c3b_launch_tail(const c3b_model *m, const op_t *act, int64_t batch, int bp, float *out, float *z4_tap, cudaStream_t s);
 int c3b_launch_lstm1_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t batch, int tile, cudaStream_t s);
 int c3b_launch_lstm2_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t batch, int tile, cudaStream_t s);
 

@@ -153,34 +153,44 @@ __global__ void __launch_bounds__(2 * 128 * WG + 32, 1) lstm_tc_kernel(const Lst
 
     const uint32_t idesc = ptx::umma_idesc_f16(128, NB);
     if (warp == kMmaWarp) {
-        // ===================================================== MMA warp: alternate between the two sub-tiles
+        // ===================================================== MMA warp: alternate between the two sub-tiles.
+        // ONE elected thread runs the whole 33-step loop, barrier waits included (tcgen05.mma issue does not run ahead of the
+        // tensor pipe: a per-step elect / reconvergence / __syncwarp and 64-bit descriptor rebuilds between MMAs were pipe idle
+        // time - measured 68 cycles per MMA against the 48-cycle floor of a 128 x NB x 16 MMA).  Descriptors: constant high
+        // words, low words advanced by 32-bit adds on the start-address field (shared memory < 256 KB: no carry).
         ptx::mbar_wait(&w_bar, 0);
-        for (int step = 0; step < C3B_T; ++step) {
-#pragma unroll 1
-            for (int s = 0; s < 2; ++s) {
-                ptx::mbar_wait(&ready_bar[s], (uint32_t)step & 1u);
-                ptx::tc_fence_after();
-                if (ptx::elect_one()) {
+        if (ptx::elect_one()) {
+            const uint64_t a_d0 = ptx::umma_desc_nosw(w_addr, 2048, 128), b_d0 = ptx::umma_desc_nosw(b_addr0, LBO_B, 128);
+            const uint32_t a_lo0 = (uint32_t)a_d0, a_hi = (uint32_t)(a_d0 >> 32);
+            const uint32_t b_lo0 = (uint32_t)b_d0, b_hi = (uint32_t)(b_d0 >> 32);
+            constexpr uint32_t a_kstep = (2u * 2048u) >> 4, a_mstep = (uint32_t)kBlkBytes >> 4;
+            constexpr uint32_t b_kstep = (2u * LBO_B) >> 4, b_sstep = B_BYTES >> 4;
+            for (int step = 0; step < C3B_T; ++step) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    ptx::mbar_wait(&ready_bar[s], (uint32_t)step & 1u);
+                    ptx::tc_fence_after();
                     const uint32_t d0 = tmem_base + (uint32_t)(s * NBLK * NB);
-                    const uint32_t bs = b_addr0 + (uint32_t)s * B_BYTES;
-                    // rolled k loop: descriptors are re-derived from the loop counter on the uniform datapath (a fully
-                    // unrolled loop makes ptxas hoist every descriptor into vector registers and pay R2UR moves)
+                    uint32_t b_lo = b_lo0 + (uint32_t)s * b_sstep, a_lo = a_lo0, wt_col = tmem_base + ACC_COLS;
+                    // k loop rolled (a fully unrolled one makes ptxas park every descriptor in vector registers and pay R2UR /
+                    // spill moves between MMAs); its body is four or five MMAs and three uniform adds
 #pragma unroll 1
                     for (int ks = 0; ks < K / 16; ++ks) {
-                        const uint64_t b_desc = ptx::umma_desc_nosw(bs + ks * 2 * LBO_B, LBO_B, 128);
+                        const uint64_t b_desc = ((uint64_t)b_hi << 32) | (uint64_t)b_lo;
                         const uint32_t acc = ks > 0 ? 1u : 0u;
 #pragma unroll
-                        for (int m = 0; m < NBLK_S; ++m) {
-                            const uint64_t a_desc = ptx::umma_desc_nosw(w_addr + m * kBlkBytes + ks * 2 * 2048, 2048, 128);
-                            ptx::umma_f16(d0 + m * NB, a_desc, b_desc, idesc, acc);
-                        }
-                        if (LAYER2) ptx::umma_f16_ts(d0 + 4 * NB, tmem_base + ACC_COLS + ks * 8, b_desc, idesc, acc);
+                        for (int m = 0; m < NBLK_S; ++m)
+                            ptx::umma_f16(d0 + m * NB, ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)m * a_mstep), b_desc, idesc, acc);
+                        if (LAYER2) ptx::umma_f16_ts(d0 + 4 * NB, wt_col, b_desc, idesc, acc);
+                        a_lo += a_kstep;
+                        b_lo += b_kstep;
+                        wt_col += 8;
                     }
                     ptx::umma_commit(&acc_bar[s]);
                 }
-                __syncwarp();
             }
         }
+        __syncwarp();
         ptx::tc_fence_before();
         __syncthreads();                      // matches the epilogue threads' final barrier
         ptx::tc_fence_after();
@@ -440,7 +450,7 @@ int launch_lstm_impl(const LstmDev &p, cudaStream_t s) {
 // wg = epilogue warpgroups per sub-tile (2 by default; 1 = the original layout, also used by the f16x2 MUFU variant)
 template <int NB, bool LAYER2>
 int launch_lstm(const LstmDev &p, bool mufu16, int wg, cudaStream_t s) {
-    if (mufu16) return launch_lstm_impl<NB, LAYER2, true, 1>(p, s);
+    if (mufu16) return wg == 1 ? launch_lstm_impl<NB, LAYER2, true, 1>(p, s) : launch_lstm_impl<NB, LAYER2, true, 2>(p, s);
     return wg == 1 ? launch_lstm_impl<NB, LAYER2, false, 1>(p, s) : launch_lstm_impl<NB, LAYER2, false, 2>(p, s);
 }
 

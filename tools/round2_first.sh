@@ -3,7 +3,11 @@ set -u
 mkdir -p gpurun_out
 R=${1:-r2a}
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > gpurun_out/${R}_info.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -q --timeout=900 > gpurun_out/${R}_pytest.log 2>&1; tail -5 gpurun_out/${R}_pytest.log
+# gate: the golden-vector parity of the tensor-core path must pass before anything long runs (a hung kernel costs GPU minutes)
+timeout 420 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout=120 -k "tensor_core_kernels_match_reference or conv_taps" > gpurun_out/${R}_gate.log 2>&1
+if [ $? -ne 0 ]; then echo "GATE FAILED"; tail -40 gpurun_out/${R}_gate.log; exit 1; fi
+tail -2 gpurun_out/${R}_gate.log
+timeout 1500 python -m pytest tests -m gpu -q --timeout=600 > gpurun_out/${R}_pytest.log 2>&1; tail -5 gpurun_out/${R}_pytest.log
 timeout 120 python __graft_entry__.py smoke > gpurun_out/${R}_smoke.log 2>&1; tail -2 gpurun_out/${R}_smoke.log
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err; tail -c 600 gpurun_out/${R}_bench.err
 python - "$R" <<'PY'
