@@ -170,7 +170,10 @@ extern "C" int c3b_create(c3b_model **out, int kind, int channels, int add_indel
     if (!out) { c3b_set_error("c3b_create: null out"); return 1; }
     *out = nullptr;
     if (kind != C3B_PILEUP && kind != C3B_FULL_ALIGNMENT) { c3b_set_error("c3b_create: bad kind %d", kind); return 1; }
-    if (kind == C3B_PILEUP && (channels < 1 || channels > 32)) { c3b_set_error("pileup channels must be in [1,32], got %d", channels); return 1; }
+    if (kind == C3B_PILEUP && (channels < 1 || channels > C3B_MAX_PILEUP_CHANNELS)) {
+        c3b_set_error("pileup channels must be in [1,%d], got %d", C3B_MAX_PILEUP_CHANNELS, channels);
+        return 1;
+    }
     if (kind == C3B_FULL_ALIGNMENT && (channels < 1 || channels > 16)) { c3b_set_error("full-alignment channels must be in [1,16], got %d", channels); return 1; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -381,10 +384,12 @@ static int finalize_impl(c3b_model *m) {
                 put(fb, whh_t.data(), whh_t.size() * 4, (const void **)&m->lstm_f32[l][d].whh_t, true);
                 put(fb, bias.data(), bias.size() * 4, (const void **)&m->lstm_f32[l][d].bias, true);
             }
-        // tensor-core LSTM1 image: [dir][4 blocks][20 kgroups][128][8]; K = [x(32: 18 real) ; h(128)]
+        // tensor-core LSTM1 image: [dir][4 blocks][22 kgroups][128][8]; K = [x columns (48) ; h (128)] with the x columns
+        // [hi(x) (I) | 1 | lo(x) (I) | 0..]: W_ih multiplies both halves of the hi/lo split of the raw counts, the constant-1 column
+        // carries b_ih + b_hh (lstm_tc.cu)
         {
-            std::vector<uint16_t> img((size_t)2 * 4 * 20 * 128 * 8, 0);
-            std::vector<float> bias((size_t)2 * 512);
+            const int KX = C3B_X1_COLS, KG = (KX + 128) / 8;
+            std::vector<uint16_t> img((size_t)2 * 4 * KG * 128 * 8, 0);
             for (int d = 0; d < 2; ++d) {
                 const std::string sfx = d ? "_l0_reverse" : "_l0";
                 const std::vector<float> &wih = P(m, "LSTM1.weight_ih" + sfx), &whh = P(m, "LSTM1.weight_hh" + sfx);
@@ -395,19 +400,18 @@ static int finalize_impl(c3b_model *m) {
                         const int row = blk * 128 + r;
                         // sigmoid gates (i,f,o) are pre-halved: sigma(x) = 0.5*tanh(x/2)+0.5 costs one MUFU + one FMA
                         const float gs = (blk == 2) ? 1.0f : 0.5f;
-                        bias[(size_t)d * 512 + row] = (bih[row] + bhh[row]) * gs;
-                        for (int k = 0; k < 160; ++k) {
+                        for (int k = 0; k < KX + 128; ++k) {
                             float v = 0.f;
-                            if (k < 32) {
-                                if (k < I) v = wih[(size_t)row * I + k];
-                                else if (k == I && I < 32) v = bih[row] + bhh[row];   // bias rides on a constant-1 input column
-                            } else v = whh[(size_t)row * 128 + (k - 32)];
-                            img[((((size_t)d * 4 + blk) * 20 + k / 8) * 128 + r) * 8 + k % 8] = c3b_f2op(v * gs);
+                            if (k < I) v = wih[(size_t)row * I + k];
+                            else if (k == I) v = bih[row] + bhh[row];
+                            else if (k <= 2 * I) v = wih[(size_t)row * I + (k - I - 1)];
+                            else if (k >= KX) v = whh[(size_t)row * 128 + (k - KX)];
+                            img[((((size_t)d * 4 + blk) * KG + k / 8) * 128 + r) * 8 + k % 8] = c3b_f2op(v * gs);
                         }
                     }
             }
             put(blob, img.data(), img.size() * 2, (const void **)&m->lstm_tc[0][0].w_img, false);
-            put(blob, bias.data(), bias.size() * 4, (const void **)&m->lstm_tc[0][0].bias, false);
+            m->lstm_tc[0][0].bias = nullptr;
         }
         // tensor-core LSTM2: recurrent image [dir][5 blocks][20][128][8] (permuted rows) + input projection GEMM (1280 rows)
         {
@@ -548,7 +552,7 @@ static size_t ws_bytes_needed(const c3b_model *m, int64_t sites, int depth) {
             al((size_t)sites * C3B_T * 256 * 4);
             al((size_t)sites * C3B_T * 320 * 4);
         } else {
-            al((size_t)C3B_T * bp * 32 * 2);
+            al((size_t)C3B_T * bp * C3B_X1_COLS * 2);
             al((size_t)C3B_T * bp * 256 * 2);
             al((size_t)C3B_T * bp * 1280 * 2);
             al((size_t)bp * C3B_T * 320 * 2);
@@ -689,7 +693,7 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const PileupSrc &src
         return 0;
     }
     TcPileupBuffers b;
-    b.xs = cv.take<op_t>((size_t)C3B_T * bp * 32 * 2);
+    b.xs = cv.take<op_t>((size_t)C3B_T * bp * C3B_X1_COLS * 2);
     b.h1 = cv.take<op_t>((size_t)C3B_T * bp * 256 * 2);
     b.pg = cv.take<__half>((size_t)C3B_T * bp * 1280 * 2);
     b.h2 = cv.take<op_t>((size_t)bp * C3B_T * 320 * 2);

@@ -15,6 +15,8 @@
 #define C3B_H1 128          // LSTM1 hidden (clair3/model.py:46)
 #define C3B_H2 160          // LSTM2 hidden (clair3/model.py:47)
 #define C3B_MAX_HEADS 4
+#define C3B_X1_COLS 48      // LSTM1 x operand columns: [hi(x) (channels) | 1 | lo(x) (channels) | 0...]  (lstm_tc.cu)
+#define C3B_MAX_PILEUP_CHANNELS ((C3B_X1_COLS - 1) / 2)
 
 void c3b_set_error(const char *fmt, ...);
 
@@ -93,7 +95,7 @@ struct ConvF32 {
 // ---- tensor-core path packed operands (device pointers into the weight blob) ----
 struct LstmTC {
     const op_t *w_img;   // UMMA A-operand image: [nblk][K/8][128 rows][8] fp16, rows permuted (see lstm_tc.cu)
-    const float *bias;            // [nblk*128] permuted, b_ih + b_hh (LSTM1 only; LSTM2's bias rides in the projection)
+    const float *bias;            // unused (LSTM1's bias is a weight column against the constant-1 input; LSTM2's rides in the projection)
 };
 struct IgemmW {
     const op_t *w_img;   // UMMA B-operand image per k-chunk: [nchunks][8 kgroups][N rows][8] fp16
@@ -242,7 +244,7 @@ int c3b_launch_spp_f32(const float *x, float *out, int64_t batch, int h, int w, 
 
 // ---- tensor-core path (lstm_tc.cu / igemm_tc.cu) ----
 struct TcPileupBuffers {
-    op_t *xs;     // [33][B][32] fp16, time-major, channels zero-padded 18 -> 32
+    op_t *xs;     // [33][B][48] fp16, time-major: hi(x) | 1 | lo(x) columns
     op_t *h1;     // k-group-planar [32][33*Bp][8]: row = t*Bp + b, k = dir*128 + j  (projection GEMM operand)
     __half *pg;            // [33*B][1280] fp16 pre-gates of LSTM2 (bias included), permuted gate columns
     op_t *h2;     // k-group-planar [1320][Bp][8]: row = b, k = t*320 + dir*160 + j (flatten order of clair3/model.py:135)

@@ -15,8 +15,12 @@
 //     Measured on B200: a 128xNx16 tcgen05.mma costs ~44 cycles for any N <= 64 (65 at N=128, 128 at N=256), so the
 //     per-step tensor time is fixed (40-50 MMAs) and wide sub-tiles amortise it.
 //
-// LSTM1 (H=128, x has 18 channels zero-padded to 32): K = 32 + 128, the x projection is fused into the same MMAs, bias
-// added in the epilogue.  LSTM2 (H=160, input 256): the input projection W_ih*h1 (+bias) is a separate big GEMM
+// LSTM1 (H=128): K = 48 + 128.  The 48 x columns are [hi(x) (18) | 1 | lo(x) (18) | 0...]: the raw counts are unbounded integers
+// (the reference's GPU branch does not rescale depth, clair3/CallVariantsFromCffi.py:299-353), fp16 is exact only to 2048, so
+// every count is split as x = hi + lo with hi = fp16(x) and lo = fp16(x - hi) - exact for |x| <= 131 008, saturating beyond -
+// and W_ih multiplies both parts (fp32 accumulate: the same result as an exact-input product).  Column 18 is a constant 1 that
+// carries b_ih + b_hh, so the x projection and the bias are fused into the same MMAs.  
+// LSTM2 (H=160, input 256): the input projection W_ih*h1 (+bias) is a separate big GEMM
 // (igemm_tc.cu) that leaves fp16 pre-gates in the thread-friendly layout pgT[dir][t][subtile][blk][row][NB]; this kernel
 // keeps only W_hh on chip (K = 160).  Units 0..127 are lane-aligned in row blocks 0..3; units 128..159 live in a fifth
 // block laid out [i(32) f(32) g(32) o(32)] whose activated gates cross warps through a small shared-memory exchange.
@@ -33,12 +37,10 @@ namespace {
 constexpr int kWgThreads = 128;                // one epilogue warpgroup = one thread per TMEM lane
 // block = 2 sub-tiles x WG epilogue warpgroups + the MMA warp (WG = 2: the two warpgroups of a sub-tile split its sites,
 // so twice as many warps hide the epilogue's TMEM / MUFU / shared-memory latencies: the epilogue is latency-bound)
-constexpr int kBlkBytes = 20 * 128 * 16;       // one 128-row x K=160 weight block: [K/8][128][8] fp16
 
 struct LstmDev {
-    const op_t *w_img;             // [dir][NBLK][20][128][8]
-    const float *bias;             // [dir][NBLK*128] (LSTM1)
-    const op_t *xs;                // LSTM1 input  [33][Bp][32]
+    const op_t *w_img;             // [dir][NBLK][K/8][128][8]
+    const op_t *xs;                // LSTM1 input  [33][Bp][48]: hi | 1 | lo columns
     const __half *pg;              // LSTM2 pre-gates pgT[dir][33][Bp/NB][5][128][NB]
     op_t *hout;                    // k-group-planar: LSTM1 h1p[32][33*Bp][8] (row t*Bp+b); LSTM2 h2p[1320][Bp][8] (k = t*320+dir*160+j)
     int bp;                        // padded batch
@@ -101,9 +103,10 @@ __global__ void __launch_bounds__(2 * 128 * WG + 32, 1) lstm_tc_kernel(const Lst
     constexpr int NBH = NB / WG;                    // sites per epilogue thread
     static_assert(NBH % 8 == 0, "each warpgroup takes whole 8-site chunks");
     constexpr int H = LAYER2 ? 160 : 128;
-    constexpr int KX = LAYER2 ? 0 : 32;
-    constexpr int K = KX + H;                       // 160 for both layers
-    static_assert(K == 160, "weight block image assumes K = 160");
+    constexpr int KX = LAYER2 ? 0 : C3B_X1_COLS;
+    constexpr int K = KX + H;                       // 176 (LSTM1) | 160 (LSTM2)
+    constexpr int kBlkBytes = (K / 8) * 128 * 16;   // one 128-row weight block: [K/8][128][8] fp16
+    static_assert(K % 16 == 0, "whole UMMA k-steps");
     constexpr int NBLK = LAYER2 ? 5 : 4;            // accumulator row blocks
     constexpr int NBLK_S = 4;                       // row blocks whose weights live in shared memory
     constexpr uint32_t LBO_B = (NB + 1) * 16;       // padded: conflict-free h stores
@@ -226,18 +229,6 @@ __global__ void __launch_bounds__(2 * 128 * WG + 32, 1) lstm_tc_kernel(const Lst
         ptx::tmem_st_wait();
     }
 
-    // LSTM1 with fewer than 32 input channels: the bias is column `channels` of the weight image (the ingest kernel
-    // writes a constant 1 there), so the epilogue adds nothing.
-    const bool BIAS_IN_GEMM = !LAYER2 && p.bias == nullptr;
-    float bias_i = 0.f, bias_f = 0.f, bias_g = 0.f, bias_o = 0.f;
-    if (!LAYER2 && !BIAS_IN_GEMM) {
-        const float *bp = p.bias + dir * (NBLK * 128);
-        bias_i = bp[wt];
-        bias_f = bp[128 + wt];
-        bias_g = bp[256 + wt];
-        bias_o = bp[384 + wt];
-    }
-
     float c[NBH];
 #pragma unroll
     for (int i = 0; i < NBH; ++i) c[i] = 0.f;
@@ -249,11 +240,11 @@ __global__ void __launch_bounds__(2 * 128 * WG + 32, 1) lstm_tc_kernel(const Lst
     for (int step = 0; step < C3B_T; ++step) {
         const int t = dir ? (C3B_T - 1 - step) : step;
 
-        if (!LAYER2) {
-            // stage x_t: xs[t][b0+n][0..31] -> operand k-groups 0..3
-            for (int idx = gt; idx < NB * 4; idx += kGroupThreads) {
-                const int n = idx >> 2, kg = idx & 3;
-                const uint4 v = *reinterpret_cast<const uint4 *>(p.xs + ((size_t)t * p.bp + b0 + n) * 32 + kg * 8);
+        if constexpr (!LAYER2) {
+            // stage x_t: xs[t][b0+n][0..47] -> operand k-groups 0..5
+            for (int idx = gt; idx < NB * (KX / 8); idx += kGroupThreads) {
+                const int n = idx / (KX / 8), kg = idx % (KX / 8);
+                const uint4 v = *reinterpret_cast<const uint4 *>(p.xs + ((size_t)t * p.bp + b0 + n) * KX + kg * 8);
                 *reinterpret_cast<uint4 *>(b_smem + kg * LBO_B + n * 16) = v;
             }
         }
@@ -345,14 +336,6 @@ __global__ void __launch_bounds__(2 * 128 * WG + 32, 1) lstm_tc_kernel(const Lst
                 unpack_half8(pgv[3][j], pf);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) go[i] += pf[i];
-            } else if (!BIAS_IN_GEMM) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    gi[i] += bias_i;
-                    gf[i] += bias_f;
-                    gg[i] += bias_g;
-                    go[i] += bias_o;
-                }
             }
             if (MUFU16) lstm_cell8_h2(gi, gf, gg, go, &c[j * 8], h);
             else lstm_cell8(gi, gf, gg, go, &c[j * 8], h);
@@ -401,44 +384,49 @@ __device__ __forceinline__ float ingest_to_float(T v) { return (float)v; }
 
 // Dense [batch][33][channels] tensor, or (starts != nullptr) 33-row windows of the per-column count matrix [n_cols][channels]
 // (libclair3's plp_data.matrix; preprocess/CreateTensorPileupFromCffi.py:362-394 slices the same windows on the host, zero
-// rows where a window overhangs the matrix) -> xs[t][bp][32] fp16, channel `channels` = constant 1 (LSTM1's bias column).
-// Counts are unbounded integers: the conversion saturates at +-65504 instead of overflowing to inf.
+// rows where a window overhangs the matrix) -> xs[t][bp][48] fp16 with columns [hi(x) | 1 | lo(x) | 0..]: hi = fp16(x)
+// (saturating at +-65504), lo = fp16(x - hi), so hi + lo == x exactly for |x| <= 131 008; column `channels` = constant 1
+// (LSTM1's bias column).
 template <typename T>
 __global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, const int64_t *__restrict__ starts, int64_t n_cols,
                                         op_t *__restrict__ xs, int64_t batch, int bp, int channels) {
-    // one thread per 8-channel group of xs[t][b][32]
-    const int64_t total = (int64_t)C3B_T * bp * 4;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int kg = (int)(idx & 3);
-        const int64_t tb = idx >> 2;
+    // one thread per (t, site): six 16-byte stores
+    const int64_t total = (int64_t)C3B_T * bp;
+    for (int64_t tb = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; tb < total; tb += (int64_t)gridDim.x * blockDim.x) {
         const int b = (int)(tb % bp);
         const int t = (int)(tb / bp);
-        __align__(16) op_t v[8];
         bool have = b < batch;
         const T *src = x;
         if (have) {
             if (starts) {
                 const int64_t row = starts[b] + t;
                 have = row >= 0 && row < n_cols;
-                src = x + row * channels + kg * 8;
+                src = x + row * channels;
             } else {
-                src = x + ((int64_t)b * C3B_T + t) * channels + kg * 8;
+                src = x + ((int64_t)b * C3B_T + t) * channels;
             }
         }
+        __align__(16) op_t v[C3B_X1_COLS];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int ch = kg * 8 + i;
-            float f = (ch == channels) ? 1.f : 0.f;          // constant-1 column: LSTM1's bias is folded into the gate GEMM
-            if (have && ch < channels) f = ingest_to_float(src[i]);
-            v[i] = f2op_sat(f);
+        for (int k = 0; k < C3B_X1_COLS; ++k) {          // static indices: v stays in registers
+            float f = (k == channels) ? 1.f : 0.f;
+            if (have && k != channels && k <= 2 * channels) {
+                const float xv = ingest_to_float(src[k < channels ? k : k - channels - 1]);
+                const op_t hi = f2op_sat(xv);
+                f = k < channels ? op2f(hi) : xv - op2f(hi);
+            }
+            v[k] = f2op_sat(f);
         }
-        *reinterpret_cast<uint4 *>(xs + idx * 8) = *reinterpret_cast<const uint4 *>(v);
+        uint4 *dst = reinterpret_cast<uint4 *>(xs + tb * C3B_X1_COLS);
+#pragma unroll
+        for (int k = 0; k < C3B_X1_COLS / 8; ++k) dst[k] = reinterpret_cast<const uint4 *>(v)[k];
     }
 }
 
 template <int NB, bool LAYER2, bool MUFU16, int WG>
 int launch_lstm_impl(const LstmDev &p, cudaStream_t s) {
-    const size_t smem = (size_t)4 * kBlkBytes + 2 * 20 * (NB + 1) * 16 + (LAYER2 ? (size_t)2 * NB * 128 * 4 : 0);
+    constexpr int K = (LAYER2 ? 0 : C3B_X1_COLS) + (LAYER2 ? 160 : 128);
+    const size_t smem = (size_t)4 * (K / 8) * 2048 + 2 * (K / 8) * (NB + 1) * 16 + (LAYER2 ? (size_t)2 * NB * 128 * 4 : 0);
     auto kern = lstm_tc_kernel<NB, LAYER2, MUFU16, WG>;
     C3B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(p.bp / (2 * NB), 2);
@@ -459,13 +447,13 @@ int launch_lstm(const LstmDev &p, bool mufu16, int wg, cudaStream_t s) {
 int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, const int64_t *starts, int64_t n_cols, op_t *xs, int64_t batch,
                                 cudaStream_t s) {
     const int bp = (int)((batch + 127) / 128 * 128);
-    const int64_t total = (int64_t)C3B_T * bp * 4;
-    const int blocks = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+    const int64_t total = (int64_t)C3B_T * bp;
+    const int blocks = (int)((total + 127) / 128 < 2048 ? (total + 127) / 128 : 2048);
     switch (dtype) {
-        case C3B_DT_I8: ingest_pileup_tc_kernel<int8_t><<<blocks, 256, 0, s>>>((const int8_t *)x, starts, n_cols, xs, batch, bp, channels); break;
-        case C3B_DT_I32: ingest_pileup_tc_kernel<int32_t><<<blocks, 256, 0, s>>>((const int32_t *)x, starts, n_cols, xs, batch, bp, channels); break;
-        case C3B_DT_I64: ingest_pileup_tc_kernel<int64_t><<<blocks, 256, 0, s>>>((const int64_t *)x, starts, n_cols, xs, batch, bp, channels); break;
-        case C3B_DT_F32: ingest_pileup_tc_kernel<float><<<blocks, 256, 0, s>>>((const float *)x, starts, n_cols, xs, batch, bp, channels); break;
+        case C3B_DT_I8: ingest_pileup_tc_kernel<int8_t><<<blocks, 128, 0, s>>>((const int8_t *)x, starts, n_cols, xs, batch, bp, channels); break;
+        case C3B_DT_I32: ingest_pileup_tc_kernel<int32_t><<<blocks, 128, 0, s>>>((const int32_t *)x, starts, n_cols, xs, batch, bp, channels); break;
+        case C3B_DT_I64: ingest_pileup_tc_kernel<int64_t><<<blocks, 128, 0, s>>>((const int64_t *)x, starts, n_cols, xs, batch, bp, channels); break;
+        case C3B_DT_F32: ingest_pileup_tc_kernel<float><<<blocks, 128, 0, s>>>((const float *)x, starts, n_cols, xs, batch, bp, channels); break;
         default: c3b_set_error("unsupported input dtype %d", dtype); return 1;
     }
     C3B_CUDA(cudaGetLastError());
@@ -476,7 +464,6 @@ int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, const in
 int c3b_launch_lstm1_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t batch, int tile, cudaStream_t s) {
     LstmDev p = {};
     p.w_img = m->lstm_tc[0][0].w_img;     // both directions are contiguous
-    p.bias = (m->channels < 32) ? nullptr : m->lstm_tc[0][0].bias;   // bias folded into the GEMM when a spare input column exists
     p.xs = b.xs;
     p.hout = b.h1;
     p.trace = (m->lstm_trace && m->trace_conv == 1) ? m->lstm_trace : nullptr;
