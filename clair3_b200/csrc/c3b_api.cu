@@ -255,6 +255,9 @@ extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
     } else if (!strcmp(name, "lstm_wg")) {
         if (value != 1 && value != 2) { c3b_set_error("lstm_wg must be 1 or 2"); return 1; }
         m->lstm_wg = (int)value;
+    } else if (!strcmp(name, "lstm2_impl")) {
+        if (value != 0 && value != 1) { c3b_set_error("lstm2_impl must be 0 (gate rows on the lanes) or 1 (CTA-pair kernel)"); return 1; }
+        m->lstm2_impl = value;
     } else if (!strcmp(name, "lstm_mufu16")) {
         m->lstm_mufu16 = value ? 1 : 0;
     } else if (!strcmp(name, "tap_ws")) {
@@ -446,6 +449,37 @@ static int finalize_impl(c3b_model *m) {
             m->proj2.nchunks = 4;
             put(blob, pimg.data(), pimg.size() * 2, (const void **)&m->proj2.w_img, false);
             put(blob, pbias.data(), pbias.size() * 4, (const void **)&m->proj2.bias, false);
+            // ---- the CTA-pair LSTM2 kernel (lstm2x_tc.cu): per direction the 640 gate columns are ordered
+            // [phase 5][gate 4 (i,f,g,o)][unit-in-phase 32], i.e. column R2 -> torch row gate*160 + 32*phase + u
+            auto x_row = [](int R2) { return ((R2 % 128) / 32) * C3B_H2 + 32 * (R2 / 128) + (R2 % 32); };
+            auto x_gs = [](int R2) { return ((R2 % 128) / 32) == 2 ? 1.0f : 0.5f; };
+            std::vector<float> pbias2(1280);
+            for (int d = 0; d < 2; ++d) {
+                const std::string sfx = d ? "_l0_reverse" : "_l0";
+                const std::vector<float> &bih = P(m, "LSTM2.bias_ih" + sfx), &bhh = P(m, "LSTM2.bias_hh" + sfx);
+                for (int R2 = 0; R2 < 640; ++R2) pbias2[(size_t)d * 640 + R2] = (bih[x_row(R2)] + bhh[x_row(R2)]) * x_gs(R2);
+            }
+            std::vector<uint16_t> pimg2 = pack_igemm(1280, 32, 256, [&](int R, int k) {
+                return (*wih_d[R / 640])[(size_t)x_row(R % 640) * 256 + k] * x_gs(R % 640);
+            });
+            m->proj2x = m->proj2;
+            put(blob, pimg2.data(), pimg2.size() * 2, (const void **)&m->proj2x.w_img, false);
+            put(blob, pbias2.data(), pbias2.size() * 4, (const void **)&m->proj2x.bias, false);
+            // W_hh as B-operand halves: [dir][rank][phase][20 kg][64 rows][8]; rank 0 = gates (i, f), rank 1 = (g, o)
+            std::vector<uint16_t> wx((size_t)2 * 2 * 5 * 20 * 64 * 8, 0);
+            for (int d = 0; d < 2; ++d) {
+                const std::vector<float> &whh = P(m, std::string("LSTM2.weight_hh") + (d ? "_l0_reverse" : "_l0"));
+                for (int rk = 0; rk < 2; ++rk)
+                    for (int ph = 0; ph < 5; ++ph)
+                        for (int r = 0; r < 64; ++r) {
+                            const int gate = 2 * rk + r / 32, unit = 32 * ph + r % 32;
+                            const float gs = gate == 2 ? 1.0f : 0.5f;
+                            for (int k = 0; k < 160; ++k)
+                                wx[(((((size_t)d * 2 + rk) * 5 + ph) * 20 + k / 8) * 64 + r) * 8 + k % 8] =
+                                    c3b_f2op(whh[(size_t)(gate * C3B_H2 + unit) * 160 + k] * gs);
+                        }
+            }
+            put(blob, wx.data(), wx.size() * 2, (const void **)&m->lstm2x_w, false);
         }
     } else {
         for (int i = 0; i < 9; ++i) {
@@ -540,10 +574,11 @@ extern "C" int c3b_bcast_weights(c3b_model *m, void *nccl_comm, int root, void *
 
 // ------------------------------------------------------------------------------------------------ workspaces
 static int64_t round128(int64_t b) { return (b + 127) / 128 * 128; }
+static int64_t round256(int64_t b) { return (b + 255) / 256 * 256; }   // pileup: a CTA pair of the LSTM2 kernel covers 256 sites
 static int conv_out(int v) { return (v - 1) / 2 + 1; }   // 3x3, stride 2, pad 1
 
 static size_t ws_bytes_needed(const c3b_model *m, int64_t sites, int depth) {
-    const int64_t bp = round128(sites);
+    const int64_t bp = m->kind == C3B_PILEUP ? round256(sites) : round128(sites);
     size_t total = 0;
     auto al = [&](size_t b) { total += (b + 255) / 256 * 256; };
     if (m->kind == C3B_PILEUP) {
@@ -669,7 +704,7 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const PileupSrc &src
     const void *x = src.x;
     const int x_dtype = src.dtype;
     Carver cv{w->dev};
-    const int64_t bp = round128(n);
+    const int64_t bp = round256(n);
     std::map<std::string, Tap> &taps = w->taps;
     tap = tap && m->taps;
     if (m->precision == C3B_PREC_FP32) {
@@ -698,6 +733,7 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const PileupSrc &src
     b.pg = cv.take<__half>((size_t)C3B_T * bp * 1280 * 2);
     b.h2 = cv.take<op_t>((size_t)bp * C3B_T * 320 * 2);
     b.z4 = cv.take<float>((size_t)16 * bp * 128 * 4);
+    b.bp = (int)bp;
     // sub-tile width (sites per MMA column block); a CTA ping-pongs two sub-tiles -> 2 directions x bp / (2*tile) CTAs
     int tile1 = m->lstm_tile, tile2 = m->lstm_tile;
     if (tile1 == 0) {
@@ -705,12 +741,18 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const PileupSrc &src
         tile2 = tile1;
     }
     if (tile2 > 32) tile2 = 32;
-    { PROF("ingest"); if (c3b_launch_ingest_pileup_tc(x, x_dtype, m->channels, src.starts, src.n_cols, b.xs, n, s)) return 1; }
+    { PROF("ingest"); if (c3b_launch_ingest_pileup_tc(x, x_dtype, m->channels, src.starts, src.n_cols, b.xs, n, (int)bp, s)) return 1; }
     m->launches += 1;
     { PROF("lstm1"); if (c3b_launch_lstm1_tc(m, b, n, tile1, s)) return 1; }
-    { PROF("proj2");
-      if (c3b_launch_proj2(m, b.h1, m->proj2, b.pg, (int)bp, tile2, (m->lstm_trace && m->trace_conv == 20) ? m->lstm_trace : nullptr, s)) return 1; }
-    { PROF("lstm2"); if (c3b_launch_lstm2_tc(m, b, n, tile2, s)) return 1; }
+    long long *ptrace = (m->lstm_trace && m->trace_conv == 20) ? m->lstm_trace : nullptr;
+    if (m->lstm2_impl == 1) {
+        { PROF("proj2"); if (c3b_launch_proj2(m, b.h1, m->proj2x, b.pg, (int)bp, 0, ptrace, s)) return 1; }
+        { PROF("lstm2");
+          if (c3b_launch_lstm2x(m, m->lstm2x_w, b.pg, b.h2, (int)bp, (m->lstm_trace && m->trace_conv == 1) ? m->lstm_trace + C3B_T * 4 : nullptr, s)) return 1; }
+    } else {
+        { PROF("proj2"); if (c3b_launch_proj2(m, b.h1, m->proj2, b.pg, (int)bp, tile2, ptrace, s)) return 1; }
+        { PROF("lstm2"); if (c3b_launch_lstm2_tc(m, b, n, tile2, s)) return 1; }
+    }
     { PROF("tail"); if (c3b_launch_tail(m, b.h2, n, (int)bp, y, tap ? b.z4 : nullptr, s)) return 1; }
     if (tap) {
         taps["lstm1"] = {b.h1, 1, 3, 256, (int)bp, {}};

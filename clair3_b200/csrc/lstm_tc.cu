@@ -445,8 +445,7 @@ int launch_lstm(const LstmDev &p, bool mufu16, int wg, cudaStream_t s) {
 }  // namespace
 
 int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, const int64_t *starts, int64_t n_cols, op_t *xs, int64_t batch,
-                                cudaStream_t s) {
-    const int bp = (int)((batch + 127) / 128 * 128);
+                                int bp, cudaStream_t s) {
     const int64_t total = (int64_t)C3B_T * bp;
     const int blocks = (int)((total + 127) / 128 < 2048 ? (total + 127) / 128 : 2048);
     switch (dtype) {
@@ -467,7 +466,7 @@ int c3b_launch_lstm1_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t ba
     p.xs = b.xs;
     p.hout = b.h1;
     p.trace = (m->lstm_trace && m->trace_conv == 1) ? m->lstm_trace : nullptr;
-    p.bp = (int)((batch + 127) / 128 * 128);
+    p.bp = b.bp;
     const_cast<c3b_model *>(m)->launches++;
     switch (tile) {
         case 16: return launch_lstm<16, false>(p, m->lstm_mufu16 != 0, m->lstm_wg, s);
@@ -484,7 +483,7 @@ int c3b_launch_lstm2_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t ba
     p.pg = b.pg;
     p.hout = b.h2;
     p.trace = (m->lstm_trace && m->trace_conv == 1) ? m->lstm_trace + C3B_T * 4 : nullptr;
-    p.bp = (int)((batch + 127) / 128 * 128);
+    p.bp = b.bp;
     const_cast<c3b_model *>(m)->launches++;
     switch (tile) {
         case 16: return launch_lstm<16, true>(p, m->lstm_mufu16 != 0, m->lstm_wg, s);

@@ -37,6 +37,9 @@ struct ProjDev {
     long long *trace;
 };
 
+// NBL > 0: pgT layout for the round-1 recurrent kernel with NBL-site sub-tiles (2-byte stores, 64 contiguous bytes per warp
+// instruction); NBL == 0: pg2 layout for the CTA-pair kernel (lstm2x_tc.cu): [dir][t][128-site tile][80 column groups][128][8],
+// two 16-byte stores per 16 columns, 512 contiguous bytes per warp instruction.
 template <int NBL>
 __global__ void __launch_bounds__(kThreads, 1) proj2_kernel(const ProjDev p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -125,9 +128,10 @@ __global__ void __launch_bounds__(kThreads, 1) proj2_kernel(const ProjDev p) {
     } else {
         // ===================================================== epilogue: thread = position (site), 128 gate rows of one (dir, blk)
         const int q = warp & 3, g = warp >> 2;
-        const int R0 = group * 256 + g * 128;                 // first permuted gate row of this half: exactly one (dir, blk)
+        const int R0 = group * 256 + g * 128;                 // first permuted gate row of this half: one direction, 128 rows
         const int dir = R0 / 640, blk = (R0 % 640) >> 7;
-        const int ntl = p.bp / NBL;
+        constexpr int NB1 = NBL > 0 ? NBL : 1;
+        const int ntl = p.bp / NB1;
         const float4 *b4 = reinterpret_cast<const float4 *>(bias_s + g * 128);
         int tcount = 0;
         for (int at = at0; at < p.n_tiles; at += at_step, ++tcount) {
@@ -136,7 +140,8 @@ __global__ void __launch_bounds__(kThreads, 1) proj2_kernel(const ProjDev p) {
             const long long pos0 = (long long)at * 128;
             const int t = (int)(pos0 / p.bp);
             const int b = (int)(pos0 % p.bp) + q * 32 + lane;     // site index in the padded batch
-            __half *dst = p.out + ((((size_t)(dir * C3B_T + t) * ntl + b / NBL) * 5 + blk) * 128) * NBL + b % NBL;
+            __half *dst = NBL > 0 ? p.out + ((((size_t)(dir * C3B_T + t) * ntl + b / NB1) * 5 + blk) * 128) * NB1 + b % NB1
+                                  : p.out + ((((size_t)(dir * C3B_T + t) * (p.bp >> 7) + (b >> 7)) * 80 + (size_t)blk * 16) * 128 + (b & 127)) * 8;
             const bool tr = p.trace != nullptr && blockIdx.x == 0 && tid == 0 && tcount < 8;
             if (tr) p.trace[tcount * 8 + 4] = clock64();
             ptx::mbar_wait(&tmem_full[acc], acc_ph);
@@ -145,30 +150,38 @@ __global__ void __launch_bounds__(kThreads, 1) proj2_kernel(const ProjDev p) {
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + g * 128);
             float v0[16], v1[16];
             ptx::tmem_ld16(taddr, v0);
+            auto emit = [&](const float *v, int ch) {          // 16 gate columns ch*16 .. +16 of this half
+                if (NBL > 0) {
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const float4 bb = b4[ch * 4 + i4];
+                        __half *d = dst + (size_t)(ch * 16 + i4 * 4) * NB1;
+                        d[0 * NB1] = f2op(v[i4 * 4 + 0] + bb.x);
+                        d[1 * NB1] = f2op(v[i4 * 4 + 1] + bb.y);
+                        d[2 * NB1] = f2op(v[i4 * 4 + 2] + bb.z);
+                        d[3 * NB1] = f2op(v[i4 * 4 + 3] + bb.w);
+                    }
+                } else {
+                    uint4 pk[2];
+                    uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const float4 bb = b4[ch * 4 + i4];
+                        pw[2 * i4] = f2op2_sat(v[i4 * 4 + 0] + bb.x, v[i4 * 4 + 1] + bb.y);
+                        pw[2 * i4 + 1] = f2op2_sat(v[i4 * 4 + 2] + bb.z, v[i4 * 4 + 3] + bb.w);
+                    }
+                    *reinterpret_cast<uint4 *>(dst + (size_t)(2 * ch) * 128 * 8) = pk[0];
+                    *reinterpret_cast<uint4 *>(dst + (size_t)(2 * ch + 1) * 128 * 8) = pk[1];
+                }
+            };
 #pragma unroll
             for (int ch = 0; ch < 8; ch += 2) {
                 ptx::tmem_ld_wait();
                 ptx::tmem_ld16(taddr + (uint32_t)(16 * (ch + 1)), v1);
-#pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
-                    const float4 bb = b4[ch * 4 + i4];
-                    __half *d = dst + (size_t)(ch * 16 + i4 * 4) * NBL;
-                    d[0 * NBL] = f2op(v0[i4 * 4 + 0] + bb.x);
-                    d[1 * NBL] = f2op(v0[i4 * 4 + 1] + bb.y);
-                    d[2 * NBL] = f2op(v0[i4 * 4 + 2] + bb.z);
-                    d[3 * NBL] = f2op(v0[i4 * 4 + 3] + bb.w);
-                }
+                emit(v0, ch);
                 ptx::tmem_ld_wait();
                 if (ch + 2 < 8) ptx::tmem_ld16(taddr + (uint32_t)(16 * (ch + 2)), v0);
-#pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
-                    const float4 bb = b4[(ch + 1) * 4 + i4];
-                    __half *d = dst + (size_t)((ch + 1) * 16 + i4 * 4) * NBL;
-                    d[0 * NBL] = f2op(v1[i4 * 4 + 0] + bb.x);
-                    d[1 * NBL] = f2op(v1[i4 * 4 + 1] + bb.y);
-                    d[2 * NBL] = f2op(v1[i4 * 4 + 2] + bb.z);
-                    d[3 * NBL] = f2op(v1[i4 * 4 + 3] + bb.w);
-                }
+                emit(v1, ch + 1);
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tmem_empty[acc]);
@@ -186,8 +199,9 @@ __global__ void __launch_bounds__(kThreads, 1) proj2_kernel(const ProjDev p) {
 }  // namespace
 
 // h1: k-group-planar [32][33*bp][8]; w_img: pack_igemm(1280, 32, 256) image; pg: pgT for LSTM2 sub-tiles of `nbl` sites
+// nbl = 16 | 32: pgT for the round-1 recurrent kernel; nbl = 0: pg2 for the CTA-pair kernel
 int c3b_launch_proj2(const c3b_model *m, const op_t *h1, const IgemmW &w, __half *pg, int bp, int nbl, long long *trace, cudaStream_t s) {
-    if (bp % 128 || (nbl != 16 && nbl != 32)) { c3b_set_error("proj2: bad geometry bp=%d nbl=%d", bp, nbl); return 1; }
+    if (bp % 128 || (nbl != 0 && nbl != 16 && nbl != 32)) { c3b_set_error("proj2: bad geometry bp=%d nbl=%d", bp, nbl); return 1; }
     ProjDev p = {};
     p.act = h1; p.w_img = w.w_img; p.bias = w.bias; p.out = pg;
     p.ld_rows = (long long)C3B_T * bp;
@@ -203,9 +217,12 @@ int c3b_launch_proj2(const c3b_model *m, const op_t *h1, const IgemmW &w, __half
     if (nbl == 32) {
         C3B_CUDA(cudaFuncSetAttribute(proj2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         proj2_kernel<32><<<grid, kThreads, smem, s>>>(p);
-    } else {
+    } else if (nbl == 16) {
         C3B_CUDA(cudaFuncSetAttribute(proj2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         proj2_kernel<16><<<grid, kThreads, smem, s>>>(p);
+    } else {
+        C3B_CUDA(cudaFuncSetAttribute(proj2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        proj2_kernel<0><<<grid, kThreads, smem, s>>>(p);
     }
     C3B_CUDA(cudaGetLastError());
     return 0;

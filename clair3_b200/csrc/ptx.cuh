@@ -136,6 +136,61 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2) and clusters
+// Two CTAs of a cluster on the two SMs of one TPC execute one tcgen05.mma together: M = 256 (rows 0-127 accumulate in the
+// leader CTA's TMEM from the leader's A tile, rows 128-255 in the peer's from the peer's A tile), and each CTA's shared memory
+// supplies half of the B tile's N rows (leader: columns [0, N/2), peer: [N/2, N)).  Only the leader (cluster rank 0) issues;
+// descriptors and TMEM addresses are CTA-relative and identical in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {       // every thread of both CTAs
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <uint32_t NCOLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem) {   // one full warp in EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t NCOLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrive on the SAME barrier (same shared-memory offset) in both CTAs once all previously issued MMAs of this thread completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// Arrive (release at cluster scope) on the barrier at the same offset as `local_bar` in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *local_bar, uint32_t rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// Wait with acquire at cluster scope (the arrivals come from both CTAs)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
 // One lane of a fully-converged warp (the canonical way to issue tcgen05.mma: the compiler keeps the issue loop on the
 // uniform datapath instead of wrapping every UTCHMMA in an ELECT/branch loop as it does under `if (lane == 0)`).
 __device__ __forceinline__ bool elect_one() {

@@ -103,6 +103,45 @@ def test_full_alignment_full_size_matches_oracle(name, channels, depth, sites):
     _assert_tol(_stats("%s_%d" % (name, sites), y, ref))
 
 
+@pytest.mark.parametrize("name", ["p24", "p90", "p24_int8"])
+def test_pair_lstm2_kernel_matches_reference_goldens(name):
+    """The CTA-pair LSTM2 kernel (option lstm2_impl = 1: sites on the TMEM lanes, cta_group::2 MMAs, packed-fp16 gate activations)
+    against the goldens minted from the reference module, taps included."""
+    z, meta, sd, x = golden_case(name)
+    m = _pileup(sd, meta["add_indel_length"], lstm2_impl=1, taps=1)
+    y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    got = m.tap("lstm2").reshape(x.shape[0], -1)
+    want = z["tap_lstm2"]
+    n = want.shape[0]
+    rel = float(np.linalg.norm(got[:n].reshape(want.shape).astype(np.float64) - want) / np.linalg.norm(want))
+    assert rel < 2e-2, rel
+    _assert_tol(_stats("pair_lstm2_golden_%s" % name, y, z["y"]))
+
+
+def test_pair_lstm2_kernel_full_size_and_streams():
+    from clair3_b200 import synth
+    from oracle import clair3_oracle as orc
+    sd = synth.pileup_state_dict(False, seed=31)
+    x = synth.pileup_inputs(1024, seed=31)
+    m = _pileup(sd, False, lstm2_impl=1, lstm_tile=64)
+    y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    _assert_tol(_stats("pileup_1024_pair_lstm2", y, orc.pileup_forward(sd, x, False)))
+    # ragged batches (odd number of 128-site tiles: the second CTA of the last pair works on padding) and stream consistency
+    for n in (1, 129, 300, 1000):
+        assert np.abs(m(torch.from_numpy(x[:n]).cuda()).cpu().numpy() - y[:n]).max() < 1e-5
+    xd = [torch.from_numpy(synth.pileup_inputs(1024, seed=300 + i)).cuda() for i in range(8)]
+    ref = [m(v).cpu().numpy() for v in xd]
+    streams = [torch.cuda.Stream() for _ in range(8)]
+    for rep in range(3):
+        outs = [None] * 8
+        for i in range(8):
+            with torch.cuda.stream(streams[i]):
+                outs[i] = m(xd[i])
+        torch.cuda.synchronize()
+        for i in range(8):
+            assert np.abs(outs[i].cpu().numpy() - ref[i]).max() < 1e-4
+
+
 # ---------------------------------------------------------------------------------------------- deep sites, depth rescale
 @pytest.mark.parametrize("scale,label", [(25, "counts_to_3000"), (75, "counts_to_9000"), (600, "counts_to_70000")])
 def test_deep_sites_raw_counts(scale, label):

@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > gpurun_out/
 timeout 420 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout=120 -k "tensor_core_kernels_match_reference or conv_taps" > gpurun_out/${R}_gate.log 2>&1
 if [ $? -ne 0 ]; then echo "GATE FAILED"; tail -40 gpurun_out/${R}_gate.log; exit 1; fi
 tail -2 gpurun_out/${R}_gate.log
-timeout 1500 python -m pytest tests -m gpu -q --timeout=600 > gpurun_out/${R}_pytest.log 2>&1; tail -5 gpurun_out/${R}_pytest.log
+timeout 1500 python -m pytest tests -m gpu -q --timeout=240 > gpurun_out/${R}_pytest.log 2>&1; tail -5 gpurun_out/${R}_pytest.log
 timeout 120 python __graft_entry__.py smoke > gpurun_out/${R}_smoke.log 2>&1; tail -2 gpurun_out/${R}_smoke.log
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err; tail -c 600 gpurun_out/${R}_bench.err
 python - "$R" <<'PY'
