@@ -61,27 +61,43 @@ __device__ __forceinline__ void lstm_cell8(const float *gi, const float *gf, con
 }
 
 // Packed variant: the four gate activations and tanh(c) of two neighbouring sites share one MUFU op each
-// (tanh.approx.f16x2), halving the MUFU work that bounds the epilogue; c, the products and h stay fp32.
-__device__ __forceinline__ __half2 tanh_h2(float a, float b) {
-    const __half2 x = __floats2half2_rn(a, b);
+// (tanh.approx.f16x2: 2.5 MUFU ops per cell instead of 5 - the SFU is what bounds the fp32 epilogue); i*g and o*tanh(c) are packed
+// fp16 multiplies, the cell state and its update stay fp32.  Returns h as four packed (site, site+1) fp16 pairs.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     uint32_t r;
-    asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t *>(&x)));
-    return *reinterpret_cast<__half2 *>(&r);
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t tanh_f16x2(uint32_t x) {
+    uint32_t r;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+__device__ __forceinline__ uint32_t sigm_f16x2(uint32_t xh) {      // sigma of a pre-halved argument pair: 0.5 * tanh(xh) + 0.5
+    uint32_t r;
+    const uint32_t half2 = 0x38003800u;
+    asm("fma.rn.f16x2 %0, %1, %2, %2;" : "=r"(r) : "r"(tanh_f16x2(xh)), "r"(half2));
+    return r;
+}
+__device__ __forceinline__ uint32_t mul_f16x2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
 }
 __device__ __forceinline__ void lstm_cell8_h2(const float *gi, const float *gf, const float *gg, const float *go, float *c,
-                                              float *h) {
-    const __half2 half = __floats2half2_rn(0.5f, 0.5f);
+                                              uint32_t *hp) {
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
-        const float2 iv = __half22float2(__hfma2(tanh_h2(gi[i], gi[i + 1]), half, half));
-        const float2 fv = __half22float2(__hfma2(tanh_h2(gf[i], gf[i + 1]), half, half));
-        const float2 gv = __half22float2(tanh_h2(gg[i], gg[i + 1]));
-        const float2 ov = __half22float2(__hfma2(tanh_h2(go[i], go[i + 1]), half, half));
-        c[i] = fmaf(fv.x, c[i], iv.x * gv.x);
-        c[i + 1] = fmaf(fv.y, c[i + 1], iv.y * gv.y);
-        const float2 tc = __half22float2(tanh_h2(c[i], c[i + 1]));
-        h[i] = ov.x * tc.x;
-        h[i + 1] = ov.y * tc.y;
+        const uint32_t iv = sigm_f16x2(pack_f16x2(gi[i], gi[i + 1]));
+        const uint32_t gv = tanh_f16x2(pack_f16x2(gg[i], gg[i + 1]));
+        const uint32_t ig = mul_f16x2(iv, gv);
+        const uint32_t fv = sigm_f16x2(pack_f16x2(gf[i], gf[i + 1]));
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&fv));
+        const float2 g2 = __half22float2(*reinterpret_cast<const __half2 *>(&ig));
+        c[i] = fmaf(f2.x, c[i], g2.x);
+        c[i + 1] = fmaf(f2.y, c[i + 1], g2.y);
+        const uint32_t ov = sigm_f16x2(pack_f16x2(go[i], go[i + 1]));
+        hp[i >> 1] = mul_f16x2(ov, tanh_f16x2(pack_f16x2(c[i], c[i + 1])));
     }
 }
 
@@ -337,13 +353,22 @@ __global__ void __launch_bounds__(2 * 128 * WG + 32, 1) lstm_tc_kernel(const Lst
 #pragma unroll
                 for (int i = 0; i < 8; ++i) go[i] += pf[i];
             }
-            if (MUFU16) lstm_cell8_h2(gi, gf, gg, go, &c[j * 8], h);
-            else lstm_cell8(gi, gf, gg, go, &c[j * 8], h);
             // h[n][unit] -> operand buffer (fp16), element (n, k = KX + wt)
             const uint32_t kcol = KX + wt;
             uint8_t *dst = b_smem + (kcol >> 3) * LBO_B + (kcol & 7) * 2;
+            if (MUFU16) {
+                uint32_t hp[4];
+                lstm_cell8_h2(gi, gf, gg, go, &c[j * 8], hp);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<op_t *>(dst + ((j0h + j) * 8 + i) * 16) = f2op(h[i]);
+                for (int i = 0; i < 4; ++i) {
+                    *reinterpret_cast<uint16_t *>(dst + ((j0h + j) * 8 + 2 * i) * 16) = (uint16_t)(hp[i] & 0xffffu);
+                    *reinterpret_cast<uint16_t *>(dst + ((j0h + j) * 8 + 2 * i + 1) * 16) = (uint16_t)(hp[i] >> 16);
+                }
+            } else {
+                lstm_cell8(gi, gf, gg, go, &c[j * 8], h);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) *reinterpret_cast<op_t *>(dst + ((j0h + j) * 8 + i) * 16) = f2op(h[i]);
+            }
         }
 
         if (LAYER2) {
