@@ -57,6 +57,14 @@ def traffic(path, workload, batch, out_json):
         key = None
         if "lstm_tc_kernel" in name:
             key = "lstm2" if ", 1, " in name.replace("(bool)", "") or ",1," in name else "lstm1"
+        elif "lstm2x_kernel" in name:
+            key = "lstm2"
+        elif "proj2_kernel" in name:
+            key = "proj2"
+        elif "tail_kernel" in name:
+            key = "tail"
+        elif "ingest_pileup_tc_kernel" in name or "ingest_fa_tc_kernel" in name:
+            key = "ingest"
         elif "igemm_kernel" in name:
             key = "proj2" if ("1, 1>" in name.replace("(bool)", "").replace("(IgemmEpilogue)", "")) else "l4"
         elif "pconv_kernel" in name:
