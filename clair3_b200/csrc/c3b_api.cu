@@ -1095,10 +1095,10 @@ extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int6
                 for (int sp = 0; sp < t.nsplit; ++sp) acc += tmp[(size_t)sp * t.bp * t.inner + i];
                 host_out[i] = acc;
             }
-        } else if (t.layout == 2) {        // [inner/8][bp][8] -> [n][inner]
+        } else if (t.layout == 2) {        // tile-major [bp/128][inner/8][128][8] -> [n][inner]
             for (int64_t b = 0; b < n; ++b)
                 for (int64_t k = 0; k < t.inner; ++k)
-                    host_out[b * t.inner + k] = tmp[((k >> 3) * t.bp + b) * 8 + (k & 7)];
+                    host_out[b * t.inner + k] = tmp[c3b_tile_major_offset((size_t)b, (int)(k >> 3), (int)(t.inner >> 3)) + (k & 7)];
         } else if (t.layout == 4) {        // planar padded -> NHWC
             const PlanarGeom &g = t.geom;
             for (int64_t b = 0; b < n; ++b)
@@ -1115,12 +1115,12 @@ extern "C" int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int6
                         for (int64_t k = 0; k < t.inner; ++k)
                             host_out[((b * t.h + hh) * t.w + wv) * t.inner + k] =
                                 tmp[c3b_parity_offset(g, (int)t.inner, b, hh + 1, wv + 1) + (size_t)(k >> 3) * g.p * 8 + (k & 7)];
-        } else {                           // [inner/8][33*bp][8] -> [n][33][inner]
-            const int64_t rows = (int64_t)C3B_T * t.bp;
+        } else {                           // tile-major, rows t*bp + b: [33*bp/128][inner/8][128][8] -> [n][33][inner]
             for (int64_t b = 0; b < n; ++b)
                 for (int tt = 0; tt < C3B_T; ++tt)
                     for (int64_t k = 0; k < t.inner; ++k)
-                        host_out[(b * C3B_T + tt) * t.inner + k] = tmp[((k >> 3) * rows + (int64_t)tt * t.bp + b) * 8 + (k & 7)];
+                        host_out[(b * C3B_T + tt) * t.inner + k] =
+                            tmp[c3b_tile_major_offset((size_t)tt * t.bp + b, (int)(k >> 3), (int)(t.inner >> 3)) + (k & 7)];
         }
         *count_inout = count;
         return 0;

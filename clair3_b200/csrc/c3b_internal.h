@@ -44,6 +44,16 @@ __device__ __forceinline__ uint32_t f2op2_sat(float lo, float hi) {
 }
 __device__ __forceinline__ float op2f(op_t v) { return __half2float(v); }
 #endif
+// "Tile-major k-group-planar" activation matrices (h1, h2, spp): [row tile of 128][K/8 k-groups][128 rows][8] fp16.  A GEMM
+// tile's 64-wide k-chunk (8 k-groups) is then ONE contiguous 16 KB run = one cp.async.bulk (measured: a 2 KB bulk copy costs
+// ~150 cycles of the SM's TMA issue whatever its size, so eight 2 KB runs per chunk bound the streaming kernels at ~14 B/clk).
+// Returns the element offset of (row, k-group kg, lane 0).
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline size_t c3b_tile_major_offset(size_t row, int kg, int kgroups) {
+    return (((row >> 7) * (size_t)kgroups + (size_t)kg) * 128 + (row & 127)) * 8;
+}
 uint16_t c3b_f2op(float f);     // host: fp32 -> fp16 bits, round-to-nearest-even, saturating
 float c3b_op2f(uint16_t h);     // host: fp16 bits -> fp32
 
@@ -248,9 +258,9 @@ int c3b_launch_spp_f32(const float *x, float *out, int64_t batch, int h, int w, 
 // ---- tensor-core path (lstm_tc.cu / igemm_tc.cu) ----
 struct TcPileupBuffers {
     op_t *xs;     // [33][B][48] fp16, time-major: hi(x) | 1 | lo(x) columns
-    op_t *h1;     // k-group-planar [32][33*Bp][8]: row = t*Bp + b, k = dir*128 + j  (projection GEMM operand)
+    op_t *h1;     // tile-major k-group-planar, 32 k-groups: row = t*Bp + b, k = dir*128 + j  (projection GEMM operand)
     __half *pg;            // [33*B][1280] fp16 pre-gates of LSTM2 (bias included), permuted gate columns
-    op_t *h2;     // k-group-planar [1320][Bp][8]: row = b, k = t*320 + dir*160 + j (flatten order of clair3/model.py:135)
+    op_t *h2;     // tile-major k-group-planar, 1320 k-groups: row = b, k = t*320 + dir*160 + j (flatten order of clair3/model.py:135)
     float *z4;             // [B][128] fp32, L4 pre-activation without bias (debug tap only)
     int bp;                // padded batch: multiple of 256 (a CTA pair of the LSTM2 kernel covers 256 sites)
 };

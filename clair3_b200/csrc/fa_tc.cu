@@ -59,12 +59,12 @@ __global__ void spp_tc_kernel(const op_t *__restrict__ x, PlanarGeom pg, op_t *_
     const int64_t b = blockIdx.x;
     const int ncg = c >> 3;                                  // <= 32
     auto store = [&](int cell, int cg, const float *m) {
-        // feature index f = cell*c + cg*8 + k (the reference's flatten order) -> k-group (f >> 3), planar [3584/8][bp][8]
+        // feature index f = cell*c + cg*8 + k (the reference's flatten order) -> k-group (f >> 3), tile-major [bp/128][3584/8][128][8]
         uint4 o;
         op2_t *oh2 = reinterpret_cast<op2_t *>(&o);
 #pragma unroll
         for (int k = 0; k < 4; ++k) oh2[k] = f2op2(m[2 * k], m[2 * k + 1]);
-        *reinterpret_cast<uint4 *>(out + ((size_t)(cell * ncg + cg) * bp + b) * 8) = o;
+        *reinterpret_cast<uint4 *>(out + c3b_tile_major_offset((size_t)b, cell * ncg + cg, 14 * ncg)) = o;
     };
     for (int i = threadIdx.x; i < 13 * ncg; i += blockDim.x) {
         const int cell = i / ncg, cg = i - cell * ncg;

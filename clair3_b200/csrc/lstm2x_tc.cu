@@ -19,7 +19,7 @@
 // 32 p .. 32 p + 31 (sigmoid rows pre-halved: sigma(x) = 0.5 tanh(x/2) + 0.5).  Accumulator stage: columns [0,32) i, [32,64) f,
 // [64,96) g, [96,128) o.  Pre-gates (W_ih h1 + b, written by proj_tc.cu in its second layout):
 // pg2[dir][t][128-site tile][80 column groups][128 sites][8] fp16, column group = 16 phase + 4 gate + (unit % 32) / 8.
-// Output h2: k-group-planar [1320][bp][8], k = t*320 + dir*160 + unit (the flatten order of clair3/model.py:135).
+// Output h2: tile-major k-group-planar [bp/128][1320][128][8], k = t*320 + dir*160 + unit (the flatten order of clair3/model.py:135).
 //
 // Roles (576 threads per CTA): warps 0-15 epilogue (warpgroup w = 8-unit group of each phase, warp & 3 = TMEM lane quadrant),
 // warp 16: one elected thread of the LEADER CTA issues every MMA, warp 17: weights loader + TMEM allocation.
@@ -41,7 +41,7 @@ constexpr uint32_t kABytes = 20 * 128 * 16;              // one h operand buffer
 struct Lstm2xDev {
     const op_t *w_img;      // [dir][rank][phase][20][64][8]
     const __half *pg;       // pg2
-    op_t *hout;             // h2p [1320][bp][8]
+    op_t *hout;             // h2, tile-major [bp/128][1320][128][8]
     int bp;                 // padded batch (multiple of 256)
     long long *trace;
 };
@@ -174,7 +174,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm2x_
             const int t = dir ? (C3B_T - 1 - step) : step;
             uint8_t *a_next = a_smem + (uint32_t)((step + 1) & 1) * kABytes + (uint32_t)site * 16u;
             const __half *pg_t = p.pg + ((((size_t)(dir * C3B_T + t) * ntile + tile128) * 80) * 128 + site) * 8;
-            op_t *h_t = p.hout + ((size_t)(t * 40 + dir * 20) * p.bp + gsite) * 8;
+            op_t *h_t = p.hout + c3b_tile_major_offset(gsite, t * 40 + dir * 20, 1320);
             if (tr) p.trace[step * 4 + 0] = clock64();
 #pragma unroll
             for (int ph = 0; ph < kPhases; ++ph) {
@@ -236,7 +236,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm2x_
                 }
                 // h_t[site][units 32 ph + 8 wg .. + 8): next step's A operand (k-group 4 ph + wg) and the layer output
                 *reinterpret_cast<uint4 *>(a_next + (uint32_t)(4 * ph + wg) * 2048u) = hv;
-                *reinterpret_cast<uint4 *>(h_t + (size_t)(4 * ph + wg) * p.bp * 8) = hv;
+                *reinterpret_cast<uint4 *>(h_t + (size_t)(4 * ph + wg) * 128 * 8) = hv;
                 if (++st == kStages) { st = 0; full_par ^= 1u; }
             }
             // every h_t value of this warp's sites and unit groups is in the operand buffer: tell the MMA issuer

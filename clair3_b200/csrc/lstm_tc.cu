@@ -42,7 +42,7 @@ struct LstmDev {
     const op_t *w_img;             // [dir][NBLK][K/8][128][8]
     const op_t *xs;                // LSTM1 input  [33][Bp][48]: hi | 1 | lo columns
     const __half *pg;              // LSTM2 pre-gates pgT[dir][33][Bp/NB][5][128][NB]
-    op_t *hout;                    // k-group-planar: LSTM1 h1p[32][33*Bp][8] (row t*Bp+b); LSTM2 h2p[1320][Bp][8] (k = t*320+dir*160+j)
+    op_t *hout;                    // tile-major k-group-planar: LSTM1 h1 (rows t*Bp+b, 32 k-groups); LSTM2 h2 (rows b, 1320 k-groups)
     int bp;                        // padded batch
     long long *trace;              // optional [33][4] clock64 stamps of CTA (0,0) thread 0 (debug option "lstm_trace")
 };
@@ -99,6 +99,15 @@ __device__ __forceinline__ void lstm_cell8_h2(const float *gi, const float *gf, 
         const uint32_t ov = sigm_f16x2(pack_f16x2(go[i], go[i + 1]));
         hp[i >> 1] = mul_f16x2(ov, tanh_f16x2(pack_f16x2(c[i], c[i + 1])));
     }
+}
+
+// Element offset of the 8-unit group `kgh` of site `b` at time t in the layer's output, TILE-MAJOR k-group-planar
+// [row tile of 128][k-groups][128 rows][8] (c3b_tile_major_offset): LSTM1 -> h1 (row = t*bp + b, 32 k-groups: dir*16 + kgh),
+// LSTM2 -> h2 (row = b, 1320 k-groups: t*40 + dir*20 + kgh = the flatten order of clair3/model.py:135).
+template <bool LAYER2>
+__device__ __forceinline__ size_t h_out_offset(int t, int dir, int kgh, int b, int bp) {
+    return LAYER2 ? c3b_tile_major_offset((size_t)b, t * 40 + dir * 20 + kgh, 1320)
+                  : c3b_tile_major_offset((size_t)t * bp + b, dir * 16 + kgh, 32);
 }
 
 __device__ __forceinline__ void unpack_half8(const uint4 &v, float *f) {
@@ -210,14 +219,10 @@ __global__ void __launch_bounds__(2 * 128 * WG + 32, 1) lstm_tc_kernel(const Lst
             }
         }
         __syncwarp();
-        ptx::tc_fence_before();
-        __syncthreads();                      // matches the epilogue threads' final barrier
-        ptx::tc_fence_after();
-        ptx::tmem_dealloc<TCOLS>(tmem_base);
-        return;
     }
 
     // ========================================================= epilogue warpgroup `sub` (0 or 1)
+    if (warp != kMmaWarp) {
     const int sub = (warp >> 2) & 1;                // warps [0,4) sub 0, [4,8) sub 1, then (WG = 2) the second halves
     const int half = warp >> 3;                     // which NBH-site half of the sub-tile this warpgroup owns
     const int q = warp & 3;                         // TMEM lane quadrant
@@ -279,8 +284,7 @@ __global__ void __launch_bounds__(2 * 128 * WG + 32, 1) lstm_tc_kernel(const Lst
             for (int idx = gt; idx < NB * (H / 8); idx += kGroupThreads) {
                 const int kgh = idx / NB, n = idx % NB;           // consecutive threads -> consecutive sites: 16 B x NB runs
                 const uint4 v = *reinterpret_cast<const uint4 *>(b_smem + (KX / 8 + kgh) * LBO_B + n * 16);
-                op_t *dst = LAYER2 ? p.hout + ((size_t)(t_prev * 40 + dir * 20 + kgh) * p.bp + b0 + n) * 8
-                                   : p.hout + ((size_t)(dir * 16 + kgh) * (C3B_T * (size_t)p.bp) + (size_t)t_prev * p.bp + b0 + n) * 8;
+                op_t *dst = p.hout + h_out_offset<LAYER2>(t_prev, dir, kgh, b0 + n, p.bp);
                 *reinterpret_cast<uint4 *>(dst) = v;
             }
         }
@@ -396,12 +400,18 @@ __global__ void __launch_bounds__(2 * 128 * WG + 32, 1) lstm_tc_kernel(const Lst
     for (int idx = gt; idx < NB * (H / 8); idx += kGroupThreads) {
         const int kgh = idx / NB, n = idx % NB;
         const uint4 v = *reinterpret_cast<const uint4 *>(b_smem + (KX / 8 + kgh) * LBO_B + n * 16);
-        op_t *dst = LAYER2 ? p.hout + ((size_t)(t_prev * 40 + dir * 20 + kgh) * p.bp + b0 + n) * 8
-                           : p.hout + ((size_t)(dir * 16 + kgh) * (C3B_T * (size_t)p.bp) + (size_t)t_prev * p.bp + b0 + n) * 8;
+        op_t *dst = p.hout + h_out_offset<LAYER2>(t_prev, dir, kgh, b0 + n, p.bp);
         *reinterpret_cast<uint4 *>(dst) = v;
     }
+    }   // epilogue warps
+
+    // teardown: ONE barrier for every role (the MMA warp and the epilogue warps meet at the same __syncthreads)
     ptx::tc_fence_before();
     __syncthreads();
+    if (warp == kMmaWarp) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<TCOLS>(tmem_base);
+    }
 }
 
 template <typename T>

@@ -27,7 +27,7 @@ constexpr uint32_t kStageBytes = 8 * 2048;
 constexpr uint32_t kSlabBytes = 4 * 8 * 4096;   // 256 weight rows x K = 256: 4 chunks x 8 k-groups x 4 KB
 
 struct ProjDev {
-    const op_t *act;        // h1, k-group-planar [32][ld_rows][8]
+    const op_t *act;        // h1, tile-major k-group-planar [ld_rows/128][32][128][8]
     const op_t *w_img;      // [chunk 4][group 5][8 kg][256 rows][8]
     const float *bias;      // [1280]
     __half *out;            // pgT
@@ -73,17 +73,18 @@ __global__ void __launch_bounds__(kThreads, 1) proj2_kernel(const ProjDev p) {
             for (int c = 0; c < 4; ++c)
                 ptx::bulk_g2s(slab + (uint32_t)c * 32768u, (const char *)p.w_img + ((size_t)c * 5 + group) * 32768u, 32768u, &w_bar);
         }
-        const size_t kg_pitch = (size_t)p.ld_rows * 16;
-        int s = 0;
-        uint32_t ph = 0;
-        for (int at = at0; at < p.n_tiles; at += at_step) {
-            const char *src_lane = (const char *)p.act + (size_t)at * 2048 + (size_t)lane * kg_pitch;
-            for (int c = 0; c < 4; ++c, src_lane += 8 * kg_pitch) {
-                ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-                if (lane == 0) ptx::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-                __syncwarp();
-                if (lane < 8) ptx::bulk_g2s(ring + (uint32_t)s * kStageBytes + (uint32_t)lane * 2048u, src_lane, 2048u, &full_bar[s]);
-                if (++s == kStages) { s = 0; ph ^= 1u; }
+        // h1 is tile-major: the 64-wide k-chunk c of position tile `at` is one contiguous 16 KB run
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int at = at0; at < p.n_tiles; at += at_step) {
+                const char *src = (const char *)p.act + (size_t)at * (32 * 2048);
+                for (int c = 0; c < 4; ++c, src += kStageBytes) {
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                    ptx::bulk_g2s(ring + (uint32_t)s * kStageBytes, src, kStageBytes, &full_bar[s]);
+                    if (++s == kStages) { s = 0; ph ^= 1u; }
+                }
             }
         }
     } else if (warp == 8) {

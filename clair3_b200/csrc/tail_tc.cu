@@ -24,7 +24,7 @@ constexpr float kSeluScale = 1.0507009873554805f;
 __device__ __forceinline__ float selu(float x) { return kSeluScale * (x > 0.f ? x : kSeluAlpha * expm1f(x)); }
 
 struct TailDev {
-    const op_t *act;          // k-group-planar [K/8][bp][8]
+    const op_t *act;          // tile-major k-group-planar [bp/128][K/8][128][8]
     const op_t *w4;           // [nchunks][8 kg][d4 rows][8]
     const float *b4;          // [d4]
     const op_t *w5[C3B_MAX_HEADS];    // per head [d4/8 kg][128 rows][8]
@@ -84,18 +84,19 @@ __global__ void __launch_bounds__(kThreads, 1) tail_kernel(const TailDev p) {
 
     if (warp == 5) {
         // ===================================================== loader
-        const size_t kg_pitch = (size_t)p.bp * 16;
-        const char *src_lane = (const char *)p.act + (size_t)at * 2048 + (size_t)lane * kg_pitch;
-        int s = 0;
-        uint32_t ph = 0;
-        for (int c = 0; c < p.nchunks; ++c, src_lane += 8 * kg_pitch) {
-            ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-            const uint32_t stage = base + (uint32_t)s * kStageBytes;
-            if (lane == 0) ptx::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-            __syncwarp();
-            if (lane < 8) ptx::bulk_g2s(stage + (uint32_t)lane * 2048u, src_lane, 2048u, &full_bar[s]);
-            else if (lane == 8) ptx::bulk_g2s(stage + kActBytes, (const char *)p.w4 + (size_t)c * kW4Bytes, kW4Bytes, &full_bar[s]);
-            if (++s == S) { s = 0; ph ^= 1u; }
+        // activations are tile-major: k-chunk c of this CTA's 128-site tile is one contiguous 16 KB run
+        if (lane == 0) {
+            const char *src = (const char *)p.act + (size_t)at * ((size_t)p.nchunks * kActBytes);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int c = 0; c < p.nchunks; ++c, src += kActBytes) {
+                ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+                const uint32_t stage = base + (uint32_t)s * kStageBytes;
+                ptx::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                ptx::bulk_g2s(stage, src, kActBytes, &full_bar[s]);
+                ptx::bulk_g2s(stage + kActBytes, (const char *)p.w4 + (size_t)c * kW4Bytes, kW4Bytes, &full_bar[s]);
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
         }
         if (lane == 0) {
             // phase 2 weights land in the ring's memory: wait until every L4 MMA has read its operands
