@@ -255,6 +255,9 @@ extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
     } else if (!strcmp(name, "lstm_wg")) {
         if (value != 1 && value != 2) { c3b_set_error("lstm_wg must be 1 or 2"); return 1; }
         m->lstm_wg = (int)value;
+    } else if (!strcmp(name, "lstm1_impl")) {
+        if (value != 0 && value != 1) { c3b_set_error("lstm1_impl must be 0 (gate rows on the lanes) or 1 (CTA-pair kernel)"); return 1; }
+        m->lstm1_impl = value;
     } else if (!strcmp(name, "lstm2_impl")) {
         if (value != 0 && value != 1) { c3b_set_error("lstm2_impl must be 0 (gate rows on the lanes) or 1 (CTA-pair kernel)"); return 1; }
         m->lstm2_impl = value;
@@ -415,6 +418,30 @@ static int finalize_impl(c3b_model *m) {
             }
             put(blob, img.data(), img.size() * 2, (const void **)&m->lstm_tc[0][0].w_img, false);
             m->lstm_tc[0][0].bias = nullptr;
+            // the same matrix as B-operand halves for the CTA-pair kernel: [dir][rank][phase 4][22 kg][64 rows][8],
+            // rank 0 = gates (i, f), rank 1 = (g, o) of units 32 ph .. 32 ph + 31
+            std::vector<uint16_t> wx((size_t)2 * 2 * 4 * KG * 64 * 8, 0);
+            for (int d = 0; d < 2; ++d) {
+                const std::string sfx = d ? "_l0_reverse" : "_l0";
+                const std::vector<float> &wih = P(m, "LSTM1.weight_ih" + sfx), &whh = P(m, "LSTM1.weight_hh" + sfx);
+                const std::vector<float> &bih = P(m, "LSTM1.bias_ih" + sfx), &bhh = P(m, "LSTM1.bias_hh" + sfx);
+                const int I = m->channels;
+                for (int rk = 0; rk < 2; ++rk)
+                    for (int ph = 0; ph < 4; ++ph)
+                        for (int r = 0; r < 64; ++r) {
+                            const int gate = 2 * rk + r / 32, row = gate * C3B_H1 + 32 * ph + r % 32;
+                            const float gs = gate == 2 ? 1.0f : 0.5f;
+                            for (int k = 0; k < KX + 128; ++k) {
+                                float v = 0.f;
+                                if (k < I) v = wih[(size_t)row * I + k];
+                                else if (k == I) v = bih[row] + bhh[row];
+                                else if (k <= 2 * I) v = wih[(size_t)row * I + (k - I - 1)];
+                                else if (k >= KX) v = whh[(size_t)row * 128 + (k - KX)];
+                                wx[(((((size_t)d * 2 + rk) * 4 + ph) * KG + k / 8) * 64 + r) * 8 + k % 8] = c3b_f2op(v * gs);
+                            }
+                        }
+            }
+            put(blob, wx.data(), wx.size() * 2, (const void **)&m->lstm1x_w, false);
         }
         // tensor-core LSTM2: recurrent image [dir][5 blocks][20][128][8] (permuted rows) + input projection GEMM (1280 rows)
         {
@@ -741,9 +768,15 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const PileupSrc &src
         tile2 = tile1;
     }
     if (tile2 > 32) tile2 = 32;
-    { PROF("ingest"); if (c3b_launch_ingest_pileup_tc(x, x_dtype, m->channels, src.starts, src.n_cols, b.xs, n, (int)bp, s)) return 1; }
+    { PROF("ingest"); if (c3b_launch_ingest_pileup_tc(x, x_dtype, m->channels, src.starts, src.n_cols, b.xs, n, (int)bp, m->lstm1_impl, s)) return 1; }
     m->launches += 1;
-    { PROF("lstm1"); if (c3b_launch_lstm1_tc(m, b, n, tile1, s)) return 1; }
+    if (m->lstm1_impl == 1) {
+        PROF("lstm1");
+        if (c3b_launch_lstm1x(m, m->lstm1x_w, b.xs, b.h1, (int)bp, (m->lstm_trace && m->trace_conv == 1) ? m->lstm_trace : nullptr, s)) return 1;
+    } else {
+        PROF("lstm1");
+        if (c3b_launch_lstm1_tc(m, b, n, tile1, s)) return 1;
+    }
     long long *ptrace = (m->lstm_trace && m->trace_conv == 20) ? m->lstm_trace : nullptr;
     if (m->lstm2_impl == 1) {
         { PROF("proj2"); if (c3b_launch_proj2(m, b.h1, m->proj2x, b.pg, (int)bp, 0, ptrace, s)) return 1; }

@@ -192,6 +192,7 @@ struct c3b_model {
     int lstm_tile = 0;
     int profile = 0;
     int lstm_wg = 2;                   // epilogue warpgroups per LSTM sub-tile (option "lstm_wg": 1 or 2)
+    int lstm1_impl = 0;                // the same choice for LSTM1
     int lstm2_impl = 0;                // 0: gate rows on the TMEM lanes (lstm_tc.cu), 1: CTA-pair kernel with the sites on the lanes (lstm2x_tc.cu)
     int lstm_mufu16 = 0;               // 1: packed tanh.approx.f16x2 gate activations, 0 (default, faster: the epilogue is issue-bound): fp32 tanh.approx
     int tap_ws = -1;                   // debug: workspace index c3b_get_tap reads
@@ -221,6 +222,7 @@ struct c3b_model {
     LstmTC lstm_tc[2][2];
     IgemmW proj2;                      // LSTM2 input projection, both directions: N = 1280 (row order of lstm_tc.cu)
     IgemmW proj2x;                     // the same projection in the column order of the CTA-pair kernel (lstm2x_tc.cu)
+    const op_t *lstm1x_w = nullptr;    // LSTM1 [W_ih (hi | bias | lo columns) ; W_hh] as B-operand halves [dir][rank][phase 4][22][64][8]
     const op_t *lstm2x_w = nullptr;    // W_hh as B-operand halves [dir][rank][phase][20][64][8]
     TailW tail;                        // L4 + heads on the tensor cores
     IgemmW conv_tc[9];
@@ -267,11 +269,12 @@ struct TcPileupBuffers {
 // starts == nullptr: x is the dense [batch][33][channels] tensor; otherwise x is the per-column matrix [n_cols][channels] and
 // site b is its rows [starts[b], starts[b] + 33) (rows outside the matrix read as zero)
 int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, const int64_t *starts, int64_t n_cols, op_t *xs, int64_t batch,
-                                int bp, cudaStream_t s);
+                                int bp, int tiled, cudaStream_t s);
 int c3b_launch_gather_windows_f32(const void *cols, int dtype, int channels, const int64_t *starts, int64_t n_cols, float *out,
                                   int64_t batch, cudaStream_t s);
 int c3b_launch_proj2(const c3b_model *m, const op_t *h1, const IgemmW &w, __half *pg, int bp, int nbl, long long *trace, cudaStream_t s);
 int c3b_launch_lstm2x(const c3b_model *m, const op_t *w_img, const __half *pg2, op_t *h2, int bp, long long *trace, cudaStream_t s);
+int c3b_launch_lstm1x(const c3b_model *m, const op_t *w_img, const op_t *xs2, op_t *h1, int bp, long long *trace, cudaStream_t s);
 int c3b_launch_tail(const c3b_model *m, const op_t *act, int64_t batch, int bp, float *out, float *z4_tap, cudaStream_t s);
 int c3b_launch_lstm1_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t batch, int tile, cudaStream_t s);
 int c3b_launch_lstm2_tc(const c3b_model *m, const TcPileupBuffers &b, int64_t batch, int tile, cudaStream_t s);

@@ -1,5 +1,8 @@
-// LSTM2 recurrence of Clair3_P (nn.LSTM(256, 160, bidirectional), clair3/model.py:102-107,133; torch semantics: gate rows
-// i,f,g,o, h0 = c0 = 0, the reverse direction walks t = 32..0) on a CTA PAIR (tcgen05 cta_group::2) - the throughput variant.
+// Both recurrent layers of Clair3_P (nn.LSTM(18, 128) and nn.LSTM(256, 160), bidirectional, clair3/model.py:96-107,132-133; torch
+// semantics: gate rows i,f,g,o, h0 = c0 = 0, the reverse direction walks t = 32..0) on a CTA PAIR (tcgen05 cta_group::2).
+// The text below describes LSTM2; LSTM1 is the same kernel with H = 128 (four phases), K = 48 + 128 (the 48 hi | 1 | lo input
+// columns of x_t are bulk-copied into the head of the A operand buffer every step, so the x projection and the bias ride in the
+// same MMAs) and no pre-gates.
 //
 // Why a second kernel.  The round-1 kernel (lstm_tc.cu) puts the gate rows on the TMEM lanes, so its MMAs are 128 x 32 x 16:
 // TMEM (512 columns) holds the ten accumulator blocks of two ping-pong sub-tiles only up to 32 sites each, and a
@@ -32,16 +35,25 @@ namespace {
 
 constexpr int kThreads = 576;
 constexpr int kEpiWarps = 16;
-constexpr int kPhases = 5;
 constexpr int kStages = 3;
-constexpr uint32_t kWPhaseBytes = 20 * 64 * 16;          // one phase of one rank: [20 kg][64 rows][8]
-constexpr uint32_t kWBytes = kPhases * kWPhaseBytes;     // 102,400
-constexpr uint32_t kABytes = 20 * 128 * 16;              // one h operand buffer: [20 kg][128 sites][8]
+
+template <bool L2>
+struct Shape {
+    static constexpr int H = L2 ? 160 : 128;
+    static constexpr int KX = L2 ? 0 : C3B_X1_COLS;                 // x columns at the head of the A operand (LSTM1)
+    static constexpr int KG = (KX + H) / 8;                           // k-groups of the A / B operands: 20 | 22
+    static constexpr int kPhases = H / 32;                            // 5 | 4
+    static constexpr uint32_t kWPhaseBytes = KG * 64 * 16;            // one phase of one rank: [KG][64 rows][8]
+    static constexpr uint32_t kWBytes = kPhases * kWPhaseBytes;       // 102,400 | 90,112
+    static constexpr uint32_t kABytes = KG * 128 * 16;                // one operand buffer: [KG][128 sites][8]
+    static constexpr uint32_t kXBytes = (KX / 8) * 128 * 16;          // its x part (LSTM1): 12,288
+};
 
 struct Lstm2xDev {
-    const op_t *w_img;      // [dir][rank][phase][20][64][8]
-    const __half *pg;       // pg2
-    op_t *hout;             // h2, tile-major [bp/128][1320][128][8]
+    const op_t *w_img;      // [dir][rank][phase][KG][64][8]
+    const __half *pg;       // LSTM2: pg2
+    const op_t *xs;         // LSTM1: xs2 [33][bp/128][6 k-groups][128 sites][8]
+    op_t *hout;             // tile-major: LSTM2 h2 [bp/128][1320][128][8]; LSTM1 h1 [33*bp/128][32][128][8] (row = t*bp + site)
     int bp;                 // padded batch (multiple of 256)
     long long *trace;
 };
@@ -71,14 +83,23 @@ __device__ __forceinline__ uint32_t hfma2u(uint32_t a, uint32_t b, uint32_t c) {
     asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
+// packed pre-activation pair: accumulator (+ fp16 pre-gate pair for LSTM2)
+template <bool L2>
+__device__ __forceinline__ uint32_t preact(float lo, float hi, uint32_t pg) {
+    return L2 ? hadd2u(pack_h2(lo, hi), pg) : pack_h2(lo, hi);
+}
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) {
     const __half2 h = *reinterpret_cast<const __half2 *>(&v);
     return __half22float2(h);
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm2x_kernel(const Lstm2xDev p) {
+template <bool L2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pair_kernel(const Lstm2xDev p) {
+    using S = Shape<L2>;
+    constexpr int kPhases = S::kPhases;
+    constexpr uint32_t kWPhaseBytes = S::kWPhaseBytes, kWBytes = S::kWBytes, kABytes = S::kABytes;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t w_bar, a_ready[2], acc_full[kStages], acc_empty[kStages];
+    __shared__ uint64_t w_bar, a_ready[2], acc_full[kStages], acc_empty[kStages], x_full[2], x_ready[2];
     __shared__ uint32_t tmem_base_smem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -91,7 +112,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm2x_
 
     if (tid == 0) {
         ptx::mbar_init(&w_bar, 1);
-        for (int b = 0; b < 2; ++b) ptx::mbar_init(&a_ready[b], 2 * kEpiWarps);
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(&a_ready[b], 2 * kEpiWarps);
+            ptx::mbar_init(&x_full[b], 1);        // this CTA's x_t bulk copy has landed (LSTM1)
+            ptx::mbar_init(&x_ready[b], 2);       // leader: both CTAs' x_t have landed
+        }
         for (int s = 0; s < kStages; ++s) {
             ptx::mbar_init(&acc_full[s], 1);
             ptx::mbar_init(&acc_empty[s], 2 * kEpiWarps);
@@ -99,7 +124,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm2x_
         ptx::fence_barrier_init();
     }
     if (warp == 17) ptx::tmem_alloc_pair<512>(&tmem_base_smem);
-    // h_{-1} = 0 (buffer 0); buffer 1 is completely written by the epilogue of step 0 before step 1 reads it
+    // h_{-1} = 0 (buffer 0); the h part of buffer 1 is completely written by the epilogue of step 0 before step 1 reads it, the
+    // x parts (LSTM1) are bulk-copied per step
     for (uint32_t i = tid * 16; i < kABytes; i += kThreads * 16) *reinterpret_cast<uint4 *>(a_smem + i) = make_uint4(0, 0, 0, 0);
     ptx::fence_proxy_async_smem();
     ptx::tc_fence_before();
@@ -128,10 +154,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm2x_
             bool first_round = true;
             for (int step = 0; step < C3B_T; ++step) {
                 const int ab = step & 1;
-                if (step > 0) {
-                    ptx::mbar_wait_cluster(&a_ready[ab], (uint32_t)((step - 1) >> 1) & 1u);
-                    ptx::tc_fence_after();
-                }
+                if (step > 0) ptx::mbar_wait_cluster(&a_ready[ab], (uint32_t)((step - 1) >> 1) & 1u);
+                if (!L2) ptx::mbar_wait_cluster(&x_ready[ab], (uint32_t)(step >> 1) & 1u);
+                ptx::tc_fence_after();
                 const uint32_t a_lo = a_lo0 + (uint32_t)ab * a_bstep;
 #pragma unroll 1
                 for (int ph = 0; ph < kPhases; ++ph) {
@@ -142,7 +167,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm2x_
                     const uint32_t d = tmem_base + (uint32_t)(st * 128);
                     uint32_t al = a_lo, bl = b_lo0 + (uint32_t)ph * b_pstep;
 #pragma unroll 1
-                    for (int ks = 0; ks < 10; ++ks) {
+                    for (int ks = 0; ks < S::KG / 2; ++ks) {
                         ptx::umma_f16_pair(d, ((uint64_t)a_hi << 32) | (uint64_t)al, ((uint64_t)b_hi << 32) | (uint64_t)bl, idesc, ks > 0 ? 1u : 0u);
                         al += a_kstep;
                         bl += b_kstep;
@@ -153,6 +178,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm2x_
                         if (first_round) first_round = false; else use_par ^= 1u;
                     }
                 }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 17) {
+        // ===================================================== LSTM1: x_t -> head of the operand buffer of step t (one 12 KB bulk
+        // copy per step and CTA; xs2 is tile-major per time step), then tell the leader that this CTA's copy has landed
+        if (!L2 && lane == 0) {
+            const int ntile = p.bp >> 7;
+            for (int step = 0; step < C3B_T; ++step) {
+                const int t = dir ? (C3B_T - 1 - step) : step;
+                const int ab = step & 1;
+                // buffer ab was last read by the MMAs of step-2: wait for the commit of that step's last phase (steps 0, 1: free).
+                // The issuer cannot be more than one step ahead of this wait (it needs x_ready of this step), so the stage's
+                // barrier is at most one phase past the awaited one: the parity test is unambiguous.
+                if (step >= 2) {
+                    const int g = (step - 2) * kPhases + kPhases - 1;
+                    ptx::mbar_wait(&acc_full[g % kStages], (uint32_t)(g / kStages) & 1u);
+                }
+                ptx::mbar_arrive_expect_tx(&x_full[ab], S::kXBytes);
+                ptx::bulk_g2s(a_addr + (uint32_t)ab * kABytes, (const char *)p.xs + ((size_t)t * ntile + tile128) * S::kXBytes, S::kXBytes, &x_full[ab]);
+                ptx::mbar_wait(&x_full[ab], (uint32_t)(step >> 1) & 1u);
+                ptx::mbar_arrive_cluster(&x_ready[ab], 0);
             }
         }
         __syncwarp();
@@ -167,21 +214,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm2x_
         float c[kPhases * 8];
 #pragma unroll
         for (int i = 0; i < kPhases * 8; ++i) c[i] = 0.f;
+        (void)ntile;
         int st = 0;
         uint32_t full_par = 0;
         const bool tr = p.trace != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
         for (int step = 0; step < C3B_T; ++step) {
             const int t = dir ? (C3B_T - 1 - step) : step;
-            uint8_t *a_next = a_smem + (uint32_t)((step + 1) & 1) * kABytes + (uint32_t)site * 16u;
-            const __half *pg_t = p.pg + ((((size_t)(dir * C3B_T + t) * ntile + tile128) * 80) * 128 + site) * 8;
-            op_t *h_t = p.hout + c3b_tile_major_offset(gsite, t * 40 + dir * 20, 1320);
+            uint8_t *a_next = a_smem + (uint32_t)((step + 1) & 1) * kABytes + (uint32_t)(S::KX / 8) * 2048u + (uint32_t)site * 16u;
+            const __half *pg_t = L2 ? p.pg + ((((size_t)(dir * C3B_T + t) * ntile + tile128) * 80) * 128 + site) * 8 : nullptr;
+            op_t *h_t = p.hout + (L2 ? c3b_tile_major_offset(gsite, t * 40 + dir * 20, 1320)
+                                     : c3b_tile_major_offset((size_t)t * p.bp + gsite, dir * 16, 32));
             if (tr) p.trace[step * 4 + 0] = clock64();
 #pragma unroll
             for (int ph = 0; ph < kPhases; ++ph) {
                 // this phase's pre-gates (four 16-byte loads, coalesced over the warp), issued before the wait on the MMAs
                 uint4 pgv[4];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) pgv[g] = *reinterpret_cast<const uint4 *>(pg_t + (size_t)(16 * ph + 4 * g + wg) * 128 * 8);
+                for (int g = 0; g < 4; ++g)
+                    pgv[g] = L2 ? *reinterpret_cast<const uint4 *>(pg_t + (size_t)(16 * ph + 4 * g + wg) * 128 * 8) : make_uint4(0, 0, 0, 0);
                 ptx::mbar_wait(&acc_full[st], full_par);
                 ptx::tc_fence_after();
                 const uint32_t ta = lane_taddr + (uint32_t)(st * 128);
@@ -193,7 +243,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm2x_
                 {
                     const uint32_t *pp = reinterpret_cast<const uint32_t *>(&pgv[0]);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) si[j] = hfma2u(tanh_h2u(hadd2u(pack_h2(a[2 * j], a[2 * j + 1]), pp[j])), half2_half, half2_half);
+                    for (int j = 0; j < 4; ++j) si[j] = hfma2u(tanh_h2u(preact<L2>(a[2 * j], a[2 * j + 1], pp[j])), half2_half, half2_half);
                 }
                 // gate g
                 ptx::tmem_ld8(ta + 64, a);
@@ -201,7 +251,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm2x_
                 {
                     const uint32_t *pp = reinterpret_cast<const uint32_t *>(&pgv[2]);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) ig[j] = hmul2u(si[j], tanh_h2u(hadd2u(pack_h2(a[2 * j], a[2 * j + 1]), pp[j])));
+                    for (int j = 0; j < 4; ++j) ig[j] = hmul2u(si[j], tanh_h2u(preact<L2>(a[2 * j], a[2 * j + 1], pp[j])));
                 }
                 // gate f
                 ptx::tmem_ld8(ta + 32, a);
@@ -209,7 +259,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm2x_
                 {
                     const uint32_t *pp = reinterpret_cast<const uint32_t *>(&pgv[1]);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) sf[j] = hfma2u(tanh_h2u(hadd2u(pack_h2(a[2 * j], a[2 * j + 1]), pp[j])), half2_half, half2_half);
+                    for (int j = 0; j < 4; ++j) sf[j] = hfma2u(tanh_h2u(preact<L2>(a[2 * j], a[2 * j + 1], pp[j])), half2_half, half2_half);
                 }
                 // gate o
                 ptx::tmem_ld8(ta + 96, a);
@@ -221,7 +271,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm2x_
                 {
                     const uint32_t *pp = reinterpret_cast<const uint32_t *>(&pgv[3]);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) so[j] = hfma2u(tanh_h2u(hadd2u(pack_h2(a[2 * j], a[2 * j + 1]), pp[j])), half2_half, half2_half);
+                    for (int j = 0; j < 4; ++j) so[j] = hfma2u(tanh_h2u(preact<L2>(a[2 * j], a[2 * j + 1], pp[j])), half2_half, half2_half);
                 }
                 // cell update in fp32, h = o * tanh(c) on packed pairs
                 uint4 hv;
@@ -259,15 +309,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm2x_
 
 }  // namespace
 
+template <bool L2>
+static int launch_pair(const c3b_model *m, const Lstm2xDev &p, cudaStream_t s) {
+    const size_t smem = (size_t)Shape<L2>::kWBytes + 2 * Shape<L2>::kABytes;
+    C3B_CUDA(cudaFuncSetAttribute(lstm_pair_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(p.bp / 128, 2);
+    const_cast<c3b_model *>(m)->launches++;
+    lstm_pair_kernel<L2><<<grid, kThreads, smem, s>>>(p);
+    C3B_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int c3b_launch_lstm2x(const c3b_model *m, const op_t *w_img, const __half *pg2, op_t *h2, int bp, long long *trace, cudaStream_t s) {
     if (bp % 256) { c3b_set_error("lstm2x: padded batch %d is not a multiple of 256", bp); return 1; }
     Lstm2xDev p = {};
     p.w_img = w_img; p.pg = pg2; p.hout = h2; p.bp = bp; p.trace = trace;
-    const size_t smem = (size_t)kWBytes + 2 * kABytes;
-    C3B_CUDA(cudaFuncSetAttribute(lstm2x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(bp / 128, 2);
-    const_cast<c3b_model *>(m)->launches++;
-    lstm2x_kernel<<<grid, kThreads, smem, s>>>(p);
-    C3B_CUDA(cudaGetLastError());
-    return 0;
+    return launch_pair<true>(m, p, s);
+}
+
+// LSTM1 on the CTA pair: xs2 = [33][bp/128][6][128][8] (ingest layout 1), h1 tile-major with rows t*bp + site
+int c3b_launch_lstm1x(const c3b_model *m, const op_t *w_img, const op_t *xs2, op_t *h1, int bp, long long *trace, cudaStream_t s) {
+    if (bp % 256) { c3b_set_error("lstm1x: padded batch %d is not a multiple of 256", bp); return 1; }
+    Lstm2xDev p = {};
+    p.w_img = w_img; p.xs = xs2; p.hout = h1; p.bp = bp; p.trace = trace;
+    return launch_pair<false>(m, p, s);
 }

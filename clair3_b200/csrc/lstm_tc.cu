@@ -422,9 +422,11 @@ __device__ __forceinline__ float ingest_to_float(T v) { return (float)v; }
 // rows where a window overhangs the matrix) -> xs[t][bp][48] fp16 with columns [hi(x) | 1 | lo(x) | 0..]: hi = fp16(x)
 // (saturating at +-65504), lo = fp16(x - hi), so hi + lo == x exactly for |x| <= 131 008; column `channels` = constant 1
 // (LSTM1's bias column).
+// tiled = 0: xs[t][bp][48] (lstm_tc_kernel); tiled = 1: xs2[t][bp/128][6 k-groups][128 sites][8] (the CTA-pair kernel bulk-copies one
+// 12 KB run per step and 128-site tile)
 template <typename T>
 __global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, const int64_t *__restrict__ starts, int64_t n_cols,
-                                        op_t *__restrict__ xs, int64_t batch, int bp, int channels) {
+                                        op_t *__restrict__ xs, int64_t batch, int bp, int channels, int tiled) {
     // one thread per (t, site): six 16-byte stores
     const int64_t total = (int64_t)C3B_T * bp;
     for (int64_t tb = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; tb < total; tb += (int64_t)gridDim.x * blockDim.x) {
@@ -452,9 +454,15 @@ __global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, const int64_t *
             }
             v[k] = f2op_sat(f);
         }
-        uint4 *dst = reinterpret_cast<uint4 *>(xs + tb * C3B_X1_COLS);
+        if (tiled) {
+            op_t *dst = xs + (((size_t)t * (bp >> 7) + (b >> 7)) * (C3B_X1_COLS / 8) * 128 + (b & 127)) * 8;
 #pragma unroll
-        for (int k = 0; k < C3B_X1_COLS / 8; ++k) dst[k] = reinterpret_cast<const uint4 *>(v)[k];
+            for (int k = 0; k < C3B_X1_COLS / 8; ++k) *reinterpret_cast<uint4 *>(dst + (size_t)k * 128 * 8) = reinterpret_cast<const uint4 *>(v)[k];
+        } else {
+            uint4 *dst = reinterpret_cast<uint4 *>(xs + tb * C3B_X1_COLS);
+#pragma unroll
+            for (int k = 0; k < C3B_X1_COLS / 8; ++k) dst[k] = reinterpret_cast<const uint4 *>(v)[k];
+        }
     }
 }
 
@@ -480,14 +488,14 @@ int launch_lstm(const LstmDev &p, bool mufu16, int wg, cudaStream_t s) {
 }  // namespace
 
 int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, const int64_t *starts, int64_t n_cols, op_t *xs, int64_t batch,
-                                int bp, cudaStream_t s) {
+                                int bp, int tiled, cudaStream_t s) {
     const int64_t total = (int64_t)C3B_T * bp;
     const int blocks = (int)((total + 127) / 128 < 2048 ? (total + 127) / 128 : 2048);
     switch (dtype) {
-        case C3B_DT_I8: ingest_pileup_tc_kernel<int8_t><<<blocks, 128, 0, s>>>((const int8_t *)x, starts, n_cols, xs, batch, bp, channels); break;
-        case C3B_DT_I32: ingest_pileup_tc_kernel<int32_t><<<blocks, 128, 0, s>>>((const int32_t *)x, starts, n_cols, xs, batch, bp, channels); break;
-        case C3B_DT_I64: ingest_pileup_tc_kernel<int64_t><<<blocks, 128, 0, s>>>((const int64_t *)x, starts, n_cols, xs, batch, bp, channels); break;
-        case C3B_DT_F32: ingest_pileup_tc_kernel<float><<<blocks, 128, 0, s>>>((const float *)x, starts, n_cols, xs, batch, bp, channels); break;
+        case C3B_DT_I8: ingest_pileup_tc_kernel<int8_t><<<blocks, 128, 0, s>>>((const int8_t *)x, starts, n_cols, xs, batch, bp, channels, tiled); break;
+        case C3B_DT_I32: ingest_pileup_tc_kernel<int32_t><<<blocks, 128, 0, s>>>((const int32_t *)x, starts, n_cols, xs, batch, bp, channels, tiled); break;
+        case C3B_DT_I64: ingest_pileup_tc_kernel<int64_t><<<blocks, 128, 0, s>>>((const int64_t *)x, starts, n_cols, xs, batch, bp, channels, tiled); break;
+        case C3B_DT_F32: ingest_pileup_tc_kernel<float><<<blocks, 128, 0, s>>>((const float *)x, starts, n_cols, xs, batch, bp, channels, tiled); break;
         default: c3b_set_error("unsupported input dtype %d", dtype); return 1;
     }
     C3B_CUDA(cudaGetLastError());

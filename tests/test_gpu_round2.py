@@ -118,6 +118,46 @@ def test_pair_lstm2_kernel_matches_reference_goldens(name):
     _assert_tol(_stats("pair_lstm2_golden_%s" % name, y, z["y"]))
 
 
+@pytest.mark.parametrize("name", ["p24", "p90", "p24_int8"])
+def test_pair_lstm1_and_lstm2_kernels_match_reference_goldens(name):
+    """Both recurrent layers on the CTA-pair kernel (options lstm1_impl = lstm2_impl = 1), taps of both layers included."""
+    z, meta, sd, x = golden_case(name)
+    m = _pileup(sd, meta["add_indel_length"], lstm1_impl=1, lstm2_impl=1, taps=1)
+    y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    for tap in ("lstm1", "lstm2"):
+        got = m.tap(tap).reshape(x.shape[0], -1)
+        want = z["tap_" + tap]
+        n = want.shape[0]
+        rel = float(np.linalg.norm(got[:n].reshape(want.shape).astype(np.float64) - want) / np.linalg.norm(want))
+        assert rel < 2e-2, (tap, rel)
+    _assert_tol(_stats("pair_lstm12_golden_%s" % name, y, z["y"]))
+
+
+def test_pair_lstm1_kernel_full_size_deep_and_ragged():
+    from clair3_b200 import synth
+    from oracle import clair3_oracle as orc
+    sd = synth.pileup_state_dict(False, seed=31)
+    x = synth.pileup_inputs(1024, seed=31)
+    m = _pileup(sd, False, lstm1_impl=1, lstm2_impl=1)
+    y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    _assert_tol(_stats("pileup_1024_pair_lstm12", y, orc.pileup_forward(sd, x, False)))
+    for n in (1, 129, 300, 1000):
+        assert np.abs(m(torch.from_numpy(x[:n]).cuda()).cpu().numpy() - y[:n]).max() < 1e-5
+    xs = (x.astype(np.int64) * 75)
+    xs[::2] = x[::2]
+    xs = xs.astype(np.int32)
+    yd = m(torch.from_numpy(xs).cuda()).cpu().numpy()
+    with np.errstate(over="ignore"):
+        _assert_tol(_stats("pileup_1024_pair_lstm12_counts_to_9000", yd, orc.pileup_forward(sd, xs, False)))
+    # window-gather input goes through the same (tiled) ingest
+    cols = x.reshape(-1, 18)[:4000].astype(np.int64)
+    starts = np.arange(0, 3000, 3, dtype=np.int64) - 5
+    from oracle import decode_oracle as dec
+    xw = dec.pileup_windows(cols, starts).astype(np.int32)
+    yw = m.forward_windows(cols, starts).numpy()
+    assert np.abs(yw - m(torch.from_numpy(xw).cuda()).cpu().numpy()).max() < 1e-5
+
+
 def test_pair_lstm2_kernel_full_size_and_streams():
     from clair3_b200 import synth
     from oracle import clair3_oracle as orc

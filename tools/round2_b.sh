@@ -19,6 +19,7 @@ run p_default --workloads pileup
 run p_pair --workloads pileup --opt lstm2_impl=1
 run p_pair_mufu16 --workloads pileup --opt lstm2_impl=1 --opt lstm_mufu16=1
 run p_mufu16 --workloads pileup --opt lstm_mufu16=1
+run p_pair12 --workloads pileup --opt lstm2_impl=1 --opt lstm1_impl=1
 run fa --workloads fa
 SAN=/usr/local/cuda/bin/compute-sanitizer
 for c in "p 256 lstm_tile=64" "p 256 lstm_tile=64 lstm2_impl=1" "p 128 lstm_tile=16"; do
