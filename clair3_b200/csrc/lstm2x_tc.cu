@@ -214,30 +214,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
         float c[kPhases * 8];
 #pragma unroll
         for (int i = 0; i < kPhases * 8; ++i) c[i] = 0.f;
-        (void)ntile;
+        // pre-gate addressing: pg2[dir][t][tile][80][128][8]; this thread's site, first column group
+        const size_t pg_tstride = (size_t)ntile * 80 * 128 * 8;
+        const __half *pg_site = L2 ? p.pg + ((size_t)dir * C3B_T * ntile + tile128) * 80 * 128 * 8 + (size_t)site * 8 : nullptr;
+        uint4 pgv[4];           // this thread's pre-gates of the phase about to be computed (refilled in place one phase ahead)
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            pgv[g] = L2 ? *reinterpret_cast<const uint4 *>(pg_site + (size_t)(dir ? C3B_T - 1 : 0) * pg_tstride + (size_t)(4 * g + wg) * 128 * 8)
+                        : make_uint4(0, 0, 0, 0);
         int st = 0;
         uint32_t full_par = 0;
         const bool tr = p.trace != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
         for (int step = 0; step < C3B_T; ++step) {
             const int t = dir ? (C3B_T - 1 - step) : step;
             uint8_t *a_next = a_smem + (uint32_t)((step + 1) & 1) * kABytes + (uint32_t)(S::KX / 8) * 2048u + (uint32_t)site * 16u;
-            const __half *pg_t = L2 ? p.pg + ((((size_t)(dir * C3B_T + t) * ntile + tile128) * 80) * 128 + site) * 8 : nullptr;
+            const __half *pg_t = L2 ? pg_site + (size_t)t * pg_tstride : nullptr;
+            const __half *pg_tn = L2 ? pg_site + (size_t)(dir ? t - 1 : t + 1) * pg_tstride : nullptr;     // next step (if any)
             op_t *h_t = p.hout + (L2 ? c3b_tile_major_offset(gsite, t * 40 + dir * 20, 1320)
                                      : c3b_tile_major_offset((size_t)t * p.bp + gsite, dir * 16, 32));
             if (tr) p.trace[step * 4 + 0] = clock64();
+            if (L2 && step + 1 < C3B_T && (lane & 7) == 0) {
+                // the pre-gates stream from HBM (86 MB per 1024 sites): pull the NEXT step's lines into L2 now (one prefetch per
+                // 128-byte line), so the register loads one phase ahead below find them there
+#pragma unroll
+                for (int i = 0; i < kPhases * 4; ++i)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pg_tn + (size_t)(16 * (i >> 2) + 4 * (i & 3) + wg) * 128 * 8));
+            }
 #pragma unroll
             for (int ph = 0; ph < kPhases; ++ph) {
-                // this phase's pre-gates (four 16-byte loads, coalesced over the warp), issued before the wait on the MMAs
-                uint4 pgv[4];
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    pgv[g] = L2 ? *reinterpret_cast<const uint4 *>(pg_t + (size_t)(16 * ph + 4 * g + wg) * 128 * 8) : make_uint4(0, 0, 0, 0);
+                // this phase's pre-gates were loaded one phase ago (registers refilled in place as soon as a gate has been consumed)
+                const bool wrap = ph + 1 == kPhases;
+                const bool more = L2 && (!wrap || step + 1 < C3B_T);
+                const __half *pg_nx = (wrap ? pg_tn : pg_t) + (size_t)(16 * (wrap ? 0 : ph + 1) + wg) * 128 * 8;
                 ptx::mbar_wait(&acc_full[st], full_par);
                 ptx::tc_fence_after();
                 const uint32_t ta = lane_taddr + (uint32_t)(st * 128);
                 float a[8];
                 uint32_t si[4], ig[4], sf[4], so[4];
-                // gate i
+                // gate i, then g (tcgen05.ld is a 12-cycle operation: four short round trips cost less than the registers of wider loads)
                 ptx::tmem_ld8(ta + 0, a);
                 ptx::tmem_ld_wait();
                 {
@@ -245,13 +259,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
 #pragma unroll
                     for (int j = 0; j < 4; ++j) si[j] = hfma2u(tanh_h2u(preact<L2>(a[2 * j], a[2 * j + 1], pp[j])), half2_half, half2_half);
                 }
-                // gate g
                 ptx::tmem_ld8(ta + 64, a);
                 ptx::tmem_ld_wait();
                 {
                     const uint32_t *pp = reinterpret_cast<const uint32_t *>(&pgv[2]);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) ig[j] = hmul2u(si[j], tanh_h2u(preact<L2>(a[2 * j], a[2 * j + 1], pp[j])));
+                }
+                if (more) {          // gates i and g of the next phase (four 16-byte loads per phase, coalesced over the warp)
+                    pgv[0] = *reinterpret_cast<const uint4 *>(pg_nx);
+                    pgv[2] = *reinterpret_cast<const uint4 *>(pg_nx + (size_t)8 * 128 * 8);
                 }
                 // gate f
                 ptx::tmem_ld8(ta + 32, a);
@@ -272,6 +289,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
                     const uint32_t *pp = reinterpret_cast<const uint32_t *>(&pgv[3]);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) so[j] = hfma2u(tanh_h2u(preact<L2>(a[2 * j], a[2 * j + 1], pp[j])), half2_half, half2_half);
+                }
+                if (more) {          // gates f and o of the next phase
+                    pgv[1] = *reinterpret_cast<const uint4 *>(pg_nx + (size_t)4 * 128 * 8);
+                    pgv[3] = *reinterpret_cast<const uint4 *>(pg_nx + (size_t)12 * 128 * 8);
                 }
                 // cell update in fp32, h = o * tanh(c) on packed pairs
                 uint4 hv;

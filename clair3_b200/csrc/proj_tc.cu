@@ -16,6 +16,8 @@
 //
 // Roles (320 threads): warps 0-7 epilogue (two warpgroups: lane quadrant = warp & 3, column half = warp >> 2), warp 8 issues
 // tcgen05.mma (one elected thread for the whole loop), warp 9 loads (resident slab once, then the activation ring).
+#include <cstdlib>
+
 #include "c3b_internal.h"
 #include "ptx.cuh"
 
@@ -209,7 +211,12 @@ int c3b_launch_proj2(const c3b_model *m, const op_t *h1, const IgemmW &w, __half
     p.n_tiles = (int)(p.ld_rows / 128);
     p.bp = bp;
     p.trace = trace;
-    int per = m->sm_count / 5;
+    // The kernel is bound by the HBM write of its output (86 MB of pre-gates per 1024 sites at ~3.2 TB/s), not by its MMAs:
+    // 12 CTAs per column group (60 SMs) already write at that rate, and every further SM would only wait on HBM while holding
+    // an SM the recurrent kernels of the other in-flight batches could use.  (C3B_PROJ_CTAS: tuning sweeps only.)
+    static const int per_env = getenv("C3B_PROJ_CTAS") ? atoi(getenv("C3B_PROJ_CTAS")) : 0;
+    int per = per_env > 0 ? per_env : 12;
+    if (per > m->sm_count / 5) per = m->sm_count / 5;
     if (per > p.n_tiles) per = p.n_tiles;
     if (per < 1) per = 1;
     const int grid = 5 * per;
