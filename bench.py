@@ -421,21 +421,31 @@ def profile_kernels(ctx, model, w, xs_dev, value, clocks):
     for i in range(40):
         model(xs_dev[i % len(xs_dev)])
     torch.cuda.synchronize(ctx.device)
-    kernels, tot = {}, 0.0
+    kernels, tot, tot_sm = {}, 0.0, 0.0
+    n_sm = torch.cuda.get_device_properties(ctx.device).multi_processor_count
     for nme in ALL_KERNEL_NAMES:
-        pms, pn = ffi.new("double *"), ffi.new("int64_t *")
+        pms, pn, pc = ffi.new("double *"), ffi.new("int64_t *"), ffi.new("double *")
         check(lib().c3b_get_profile(model._handle, nme.encode(), pms, pn))
         if pn[0]:
-            kernels[nme] = {"ms_per_launch": pms[0] / pn[0], "launches": int(pn[0])}
+            check(lib().c3b_get_profile_ctas(model._handle, nme.encode(), pc))
+            kernels[nme] = {"ms_per_launch": pms[0] / pn[0], "launches": int(pn[0]), "ctas": pc[0]}
             tot += pms[0] / pn[0]
     model.set_option("profile", 0)
     for nme, k in kernels.items():
         k["share"] = k["ms_per_launch"] / tot
+        # SM-time: what the launch costs when several batches share the GPU (tensor-core kernels hold one SM per CTA; the small
+        # CUDA-core kernels - ingest, spp - co-reside with them, their grid is capped at the SM count here)
+        k["sm_time_ms"] = k["ms_per_launch"] * min(k["ctas"], n_sm)
+        tot_sm += k["sm_time_ms"]
         fl = kflops.get(nme)
         if fl:
             k["tflops"] = fl * b / (k["ms_per_launch"] * 1e-3) / 1e12
             k["frac_of_bf16_burst"] = k["tflops"] / pk["bf16_burst"]
-    dom = max((n for n in kernels if n in kflops), key=lambda n: kernels[n]["ms_per_launch"])
+            k["frac_of_occupied_sms"] = k["tflops"] / (pk["bf16_burst"] * min(k["ctas"], n_sm) / n_sm)
+    for k in kernels.values():
+        k["sm_time_share"] = k["sm_time_ms"] / tot_sm
+    # dominant = the tensor-core kernel with the largest SM-time (a 2-CTA launch with a long latency does not bound throughput)
+    dom = max((n for n in kernels if n in kflops), key=lambda n: kernels[n]["sm_time_ms"])
     # DRAM bytes per launch from the committed ncu capture (profiles/traffic.json, written by tools/ncu_summary.py from
     # `ncu --set full`: dram__bytes_read.sum + dram__bytes_write.sum), if it was taken at this workload's batch size
     traffic, traffic_all = None, None
@@ -453,7 +463,9 @@ def profile_kernels(ctx, model, w, xs_dev, value, clocks):
     roofline = {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["tflops"], "peak": pk["bf16_burst"],
                 "unit": "TFLOP/s", "frac": kernels[dom]["tflops"] / pk["bf16_burst"], "traffic": traffic,
                 "peak_source": pk["which"] + ", burst figure (kernel timed alone between CUDA events)",
-                "flop_per_launch": kflops[dom] * b,
+                "flop_per_launch": kflops[dom] * b, "ctas": kernels[dom]["ctas"], "frac_of_occupied_sms": kernels[dom]["frac_of_occupied_sms"],
+                "dominant_by": "SM-time (CTAs x duration; share %.2f of the step's SM-time)" % kernels[dom]["sm_time_share"],
+                "sm_time_ms_per_step": tot_sm,
                 "whole_step": {"achieved": whole, "frac_of_sustained": whole / pk["bf16_sustained"], "frac_of_burst": whole / pk["bf16_burst"],
                                "dram_bytes_per_step_all_kernels": traffic_all,
                                "compulsory_bytes_per_step": b * (site_bytes(w) + model.out_dim * 4)}}
@@ -465,7 +477,7 @@ def profile_kernels(ctx, model, w, xs_dev, value, clocks):
         tile = int(ctx.args.lstm_tile) or 64
         if dom == "lstm2":
             tile = min(tile, 32)        # LSTM2's ten accumulator blocks fit TMEM only up to 32 sites per sub-tile
-        ctas = 2 * ((b + 2 * tile - 1) // (2 * tile))
+        ctas = int(kernels[dom]["ctas"]) or 2 * ((b + 2 * tile - 1) // (2 * tile))
         mufu = 5.0 * 33 * 2 * units * b
         clk_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
         per_clk_sm = mufu / (kernels[dom]["ms_per_launch"] * 1e-3 * clk_hz) / ctas
@@ -560,6 +572,32 @@ def run_forward_workload(ctx, wname, model):
     torch.cuda.synchronize(dev)
     assert y_host.device.type == "cpu"
     sync_ms = ctx.max_over_ranks([s0.elapsed_time(s1)])[0]
+    # (d) pileup only: the window hand-off of c3b_forward_windows - libclair3's per-column count matrix (int64, plp_data.matrix)
+    # plus one window start per candidate go over PCIe instead of one [33,18] tensor per candidate; candidates every 4th column
+    win = None
+    if w["kind"] == "pileup":
+        stride_cols = 4
+        n_cols = b * stride_cols + 33
+        cols_pin = [torch.from_numpy(np.ascontiguousarray(np.resize(x.reshape(-1, 18), (n_cols, 18)).astype(np.int64))).pin_memory()
+                    for x in xs_host[:n_streams]]
+        starts_pin = torch.arange(0, b * stride_cols, stride_cols, dtype=torch.int64).pin_memory()
+        wcount = [0]
+
+        def issue_win(n):
+            k = wcount[0]
+            for i in range(n):
+                st = ctx.streams[(k + i) % n_streams]
+                with torch.cuda.stream(st):
+                    model.forward_windows(cols_pin[(k + i) % len(cols_pin)], starts_pin, ys_pin[(k + i) % n_streams], sync=False)
+            wcount[0] = k + n
+
+        issue_win(2 * n_streams)
+        torch.cuda.synchronize(dev)
+        rw = ctx.calibrated(issue_win, K)
+        win = {"value": b * K * rw["repeats"] * ctx.world / (rw["ms"] * 1e-3), "unit": "sites/s", "steps": K, "repeats": rw["repeats"],
+               "timed_region_s": rw["ms"] * 1e-3, "h2d_bytes_per_step": n_cols * 18 * 8 + b * 8,
+               "mode": "Clair3_P.forward_windows(pinned int64 column matrix [%d,18], pinned window starts) pipelined over %d streams: "
+                       "the 33-row windows are gathered on the GPU (candidates every %dth column)" % (n_cols, n_streams, stride_cols)}
     kind = "P" if w["kind"] == "pileup" else "F"
     rec["e2e"] = {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": b * model.out_dim * 4,
                   "steps": K, "repeats": re["repeats"], "timed_region_s": re["ms"] * 1e-3, "clocks": re["clocks"],
@@ -570,6 +608,8 @@ def run_forward_workload(ctx, wname, model):
                                              "(host wall clock, includes the per-batch result copy)" % n_streams},
                   "synchronous_per_step": {"value": b * n_sync * ctx.world / (sync_ms * 1e-3), "unit": "sites/s", "steps": n_sync,
                                            "mode": "y = model(x_pinned): H2D, forward, D2H, stream sync every step (the _torch_predict shape)"}}
+    if win:
+        rec["e2e"]["forward_windows"] = win
     if ctx.rank == 0:
         rec["kernels"], rec["roofline"] = profile_kernels(ctx, model, w, xs_dev, value, r["clocks"])
     del xs_dev, ys_dev

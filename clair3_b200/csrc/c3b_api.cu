@@ -19,6 +19,8 @@ void c3b_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 extern "C" const char *c3b_last_error(void) { return g_err; }
+static thread_local long long g_last_grid = 0;
+void c3b_note_grid(long long ctas) { g_last_grid = ctas; }
 extern "C" const char *c3b_version(void) { return "clair3_b200 0.1 (sm_100a)"; }
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -248,6 +250,7 @@ extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
     } else if (!strcmp(name, "profile")) {
         m->profile = value ? 1 : 0;
         m->prof_total.clear();
+        m->prof_ctas.clear();
         for (Workspace *w : m->ws) {
             for (auto &r : w->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
             w->prof.clear();
@@ -681,12 +684,13 @@ struct ProfScope {
             cudaEventCreate(&e0);
             cudaEventCreate(&e1);
             cudaEventRecord(e0, s);
+            g_last_grid = 0;
         }
     }
     ~ProfScope() {
         if (m->profile) {
             cudaEventRecord(e1, s);
-            w->prof.push_back({name, e0, e1});
+            w->prof.push_back({name, e0, e1, g_last_grid});
         }
     }
 };
@@ -704,6 +708,7 @@ extern "C" int c3b_get_profile(c3b_model *m, const char *kernel, double *total_m
                 auto &t = m->prof_total[r.name];
                 t.first += ms;
                 t.second += 1;
+                m->prof_ctas[r.name] += (double)r.ctas;
             }
             cudaEventDestroy(r.e0);
             cudaEventDestroy(r.e1);
@@ -713,6 +718,15 @@ extern "C" int c3b_get_profile(c3b_model *m, const char *kernel, double *total_m
     auto it = m->prof_total.find(kernel);
     if (total_ms) *total_ms = it == m->prof_total.end() ? 0.0 : it->second.first;
     if (launches) *launches = it == m->prof_total.end() ? 0 : it->second.second;
+    return 0;
+}
+
+extern "C" int c3b_get_profile_ctas(c3b_model *m, const char *kernel, double *ctas_per_launch) {
+    double ms = 0.0;
+    int64_t n = 0;
+    if (c3b_get_profile(m, kernel, &ms, &n)) return 1;
+    auto it = m->prof_ctas.find(kernel);
+    if (ctas_per_launch) *ctas_per_launch = (n > 0 && it != m->prof_ctas.end()) ? it->second / (double)n : 0.0;
     return 0;
 }
 

@@ -19,6 +19,7 @@
 #define C3B_MAX_PILEUP_CHANNELS ((C3B_X1_COLS - 1) / 2)
 
 void c3b_set_error(const char *fmt, ...);
+void c3b_note_grid(long long ctas);      // launchers report their grid size (CTAs) for the per-kernel profile (SM-time = CTAs x duration)
 
 // Tensor-core operand type.  fp16 (11-bit significand) rather than bf16 (8-bit): same tcgen05 rate, 8x smaller rounding
 // error; every operand on this path is bounded (counts <= 2048 exact, |h| <= 1, BN-normalised feature maps) and stores
@@ -180,7 +181,7 @@ struct Workspace {
     bool fa_zeroed = false;
     std::map<std::string, Tap> taps;   // per workspace, filled only while option "taps" is on
     // per-kernel CUDA-event pairs recorded while option "profile" is on (resolved lazily by c3b_get_profile)
-    struct ProfRec { const char *name; cudaEvent_t e0, e1; };
+    struct ProfRec { const char *name; cudaEvent_t e0, e1; long long ctas; };
     std::vector<ProfRec> prof;
 };
 
@@ -201,6 +202,7 @@ struct c3b_model {
     long long *lstm_trace = nullptr;   // device [2][33][4] clock stamps (debug option "lstm_trace")
     int trace_conv = 1;            // which Clair3_F conv (0..8) stamps the trace buffer (option lstm_trace = 10 + index)
     std::map<std::string, std::pair<double, int64_t>> prof_total;   // name -> (ms, launches)
+    std::map<std::string, double> prof_ctas;                         // name -> sum of CTAs launched
     int sm_count = 148;
     bool finalized = false;
     std::map<std::string, HostParam> params;

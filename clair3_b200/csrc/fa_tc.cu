@@ -124,6 +124,7 @@ int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, op
     if (channels > cpad) { c3b_set_error("full-alignment input has %d channels, at most %d supported", channels, cpad); return 1; }
     const int64_t total = batch * 4 * (g1.h + 1) * (g1.w + 1) * ((channels + 7) / 8);
     const int blocks = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
+    c3b_note_grid(blocks);
     switch (dtype) {
         case C3B_DT_I8: ingest_fa_tc_kernel<int8_t><<<blocks, 256, 0, s>>>((const int8_t *)x, out, batch, channels, cpad, depth, g1); break;
         case C3B_DT_I32: ingest_fa_tc_kernel<int32_t><<<blocks, 256, 0, s>>>((const int32_t *)x, out, batch, channels, cpad, depth, g1); break;
@@ -136,6 +137,7 @@ int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, op
 
 int c3b_launch_spp_tc(const op_t *x, const PlanarGeom &g, op_t *out, int64_t batch, int c, int bp, cudaStream_t s) {
     if (batch == 0) return 0;
+    c3b_note_grid(batch);
     spp_tc_kernel<<<(unsigned)batch, 448, 0, s>>>(x, g, out, c, bp);
     C3B_CUDA(cudaGetLastError());
     return 0;

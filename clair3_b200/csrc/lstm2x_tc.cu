@@ -123,12 +123,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 17) ptx::tmem_alloc_pair<512>(&tmem_base_smem);
     // h_{-1} = 0 (buffer 0); the h part of buffer 1 is completely written by the epilogue of step 0 before step 1 reads it, the
     // x parts (LSTM1) are bulk-copied per step
     for (uint32_t i = tid * 16; i < kABytes; i += kThreads * 16) *reinterpret_cast<uint4 *>(a_smem + i) = make_uint4(0, 0, 0, 0);
     ptx::fence_proxy_async_smem();
-    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 17) ptx::tmem_alloc_pair<512>(&tmem_base_smem);     // after the barrier: the allocation's shared-memory write is the
+    ptx::tc_fence_before();                                         // only access between the two barriers (racecheck-clean)
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
@@ -336,6 +337,7 @@ static int launch_pair(const c3b_model *m, const Lstm2xDev &p, cudaStream_t s) {
     C3B_CUDA(cudaFuncSetAttribute(lstm_pair_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(p.bp / 128, 2);
     const_cast<c3b_model *>(m)->launches++;
+    c3b_note_grid((long long)grid.x * grid.y);
     lstm_pair_kernel<L2><<<grid, kThreads, smem, s>>>(p);
     C3B_CUDA(cudaGetLastError());
     return 0;

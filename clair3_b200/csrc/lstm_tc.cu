@@ -473,6 +473,7 @@ int launch_lstm_impl(const LstmDev &p, cudaStream_t s) {
     auto kern = lstm_tc_kernel<NB, LAYER2, MUFU16, WG>;
     C3B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(p.bp / (2 * NB), 2);
+    c3b_note_grid((long long)grid.x * grid.y);
     kern<<<grid, 2 * 128 * WG + 32, smem, s>>>(p);
     C3B_CUDA(cudaGetLastError());
     return 0;
@@ -491,6 +492,7 @@ int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, const in
                                 int bp, int tiled, cudaStream_t s) {
     const int64_t total = (int64_t)C3B_T * bp;
     const int blocks = (int)((total + 127) / 128 < 2048 ? (total + 127) / 128 : 2048);
+    c3b_note_grid(blocks);
     switch (dtype) {
         case C3B_DT_I8: ingest_pileup_tc_kernel<int8_t><<<blocks, 128, 0, s>>>((const int8_t *)x, starts, n_cols, xs, batch, bp, channels, tiled); break;
         case C3B_DT_I32: ingest_pileup_tc_kernel<int32_t><<<blocks, 128, 0, s>>>((const int32_t *)x, starts, n_cols, xs, batch, bp, channels, tiled); break;

@@ -446,6 +446,7 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
     const size_t smem = (p.w_resident ? (size_t)p.nchunks * w_bytes : (size_t)p.w_stages * w_bytes) + p.img_bufs * img_bytes + 256;
     const int grid = p.n_macro < m->sm_count ? p.n_macro : m->sm_count;
     const_cast<c3b_model *>(m)->launches++;
+    c3b_note_grid(grid);
     switch (p.MT) {
         case 1:
             C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));

@@ -222,6 +222,7 @@ int c3b_launch_proj2(const c3b_model *m, const op_t *h1, const IgemmW &w, __half
     const int grid = 5 * per;
     const size_t smem = kSlabBytes + kStages * kStageBytes + 128;
     const_cast<c3b_model *>(m)->launches++;
+    c3b_note_grid(grid);
     if (nbl == 32) {
         C3B_CUDA(cudaFuncSetAttribute(proj2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         proj2_kernel<32><<<grid, kThreads, smem, s>>>(p);

@@ -18,10 +18,12 @@
 
 namespace {
 
-constexpr int kThreads = 192;                 // warps 0-3 epilogue (thread = site), warp 4 MMA, warp 5 loader
+constexpr int kThreads = 320;                 // warps 0-7 epilogue (thread = site, two warpgroups split the columns), warp 8 MMA, warp 9 loader
 constexpr float kSeluAlpha = 1.6732632423543772f;
 constexpr float kSeluScale = 1.0507009873554805f;
-__device__ __forceinline__ float selu(float x) { return kSeluScale * (x > 0.f ? x : kSeluAlpha * expm1f(x)); }
+// SELU with the hardware exponential: the result is rounded to fp16 (operand images) or fed to a softmax right after, so the
+// ~1e-7 absolute error of exp(x) - 1 near zero is far below what survives; expm1f costs ~40 instructions per element.
+__device__ __forceinline__ float selu(float x) { return kSeluScale * (x > 0.f ? x : kSeluAlpha * (__expf(x) - 1.f)); }
 
 struct TailDev {
     const op_t *act;          // tile-major k-group-planar [bp/128][K/8][128][8]
@@ -65,15 +67,15 @@ __global__ void __launch_bounds__(kThreads, 1) tail_kernel(const TailDev p) {
     if (tid == 0) {
         for (int s = 0; s < 8; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
         ptx::mbar_init(&l4_done, 1);
-        ptx::mbar_init(&a4_ready, 128);
+        ptx::mbar_init(&a4_ready, 256);
         ptx::mbar_init(&w5_full, 1);
         ptx::mbar_init(&wy_full, 1);
         ptx::mbar_init(&l5_done, 1);
-        ptx::mbar_init(&a5_ready, 128);
+        ptx::mbar_init(&a5_ready, 256);
         ptx::mbar_init(&y_done, 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 4) ptx::tmem_alloc<512>(&tmem_base_smem);
+    if (warp == 8) ptx::tmem_alloc<512>(&tmem_base_smem);
     for (int i = tid; i < D4; i += kThreads) b4_s[i] = p.b4[i];
     for (int i = tid; i < p.nheads * 128; i += kThreads) b5_s[i >> 7][i & 127] = p.b5[i >> 7][i & 127];
     for (int i = tid; i < p.nheads * 48; i += kThreads) by_s[i / 48][i % 48] = (i % 48) < p.npad[i / 48] ? p.by[i / 48][i % 48] : 0.f;
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_kernel(const TailDev p) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp == 5) {
+    if (warp == 9) {
         // ===================================================== loader
         // activations are tile-major: k-chunk c of this CTA's 128-site tile is one contiguous 16 KB run
         if (lane == 0) {
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_kernel(const TailDev p) {
                 ptx::bulk_g2s(w5_addr, p.w5[h], kW5Bytes, &w5_full);
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ===================================================== MMA issuer
         if (ptx::elect_one()) {
             const uint32_t idesc4 = ptx::umma_idesc_f16(128, D4);
@@ -164,16 +166,18 @@ __global__ void __launch_bounds__(kThreads, 1) tail_kernel(const TailDev p) {
         }
         __syncwarp();
     } else {
-        // ===================================================== epilogue: thread = site
-        const int r = tid;                                  // TMEM lane = site within the tile
+        // ===================================================== epilogue: thread = site; warpgroup wg takes half of the L4 / L5
+        // columns, warpgroup 0 alone the (tiny) output layer + softmax
+        const int wg = warp >> 2, q = warp & 3;
+        const int r = q * 32 + lane;                        // TMEM lane = site within the tile
         const long long site = (long long)at * 128 + r;
         const bool valid = site < p.batch;
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         ptx::mbar_wait(&l4_done, 0);
         ptx::tc_fence_after();
         // a4 = SELU(z4 + b4) -> fp16 operand image [k-group][site][8]
 #pragma unroll 1
-        for (int j0 = 0; j0 < D4; j0 += 16) {
+        for (int j0 = wg * (D4 / 2); j0 < (wg + 1) * (D4 / 2); j0 += 16) {
             float v[16];
             ptx::tmem_ld16(taddr + (uint32_t)j0, v);
             ptx::tmem_ld_wait();
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_kernel(const TailDev p) {
             ptx::mbar_wait(&l5_done, (uint32_t)h & 1u);
             ptx::tc_fence_after();
 #pragma unroll 1
-            for (int j0 = 0; j0 < 128; j0 += 16) {
+            for (int j0 = wg * 64; j0 < (wg + 1) * 64; j0 += 16) {
                 float v[16];
                 ptx::tmem_ld16(taddr + L5_COL + (uint32_t)j0, v);
                 ptx::tmem_ld_wait();
@@ -212,6 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_kernel(const TailDev p) {
             ptx::fence_proxy_async_smem();
             ptx::tc_fence_before();
             ptx::mbar_arrive(&a5_ready);
+            if (wg != 0) continue;          // the second warpgroup goes straight to the next head's L5 accumulator
             ptx::mbar_wait(&y_done, (uint32_t)h & 1u);
             ptx::tc_fence_after();
             // SELU(y + by) -> softmax over the head's n outputs (<= 48 columns, three 16-column TMEM loads)
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_kernel(const TailDev p) {
 #pragma unroll
             for (int o = 0; o < 48; ++o) {
                 if (o < n) {
-                    y[o] = expf(y[o] - mx);
+                    y[o] = __expf(y[o] - mx);
                     sum += y[o];
                 }
             }
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_kernel(const TailDev p) {
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<512>(tmem_base);
     }
@@ -277,6 +282,7 @@ int c3b_launch_tail(const c3b_model *m, const op_t *act, int64_t batch, int bp, 
     smem += 128;
     const int grid = (int)((batch + 127) / 128);
     const_cast<c3b_model *>(m)->launches++;
+    c3b_note_grid(grid);
     if (d4 == 128) {
         C3B_CUDA(cudaFuncSetAttribute(tail_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tail_kernel<128><<<grid, kThreads, smem, s>>>(p);

@@ -127,6 +127,9 @@ int c3b_bcast_weights(c3b_model *m, void *nccl_comm, int root, void *cuda_stream
 /* Per-kernel device time accumulated while option "profile" is on.  kernel names: pileup "ingest" "lstm1" "proj2" "lstm2"
  * "tail" (L4 + heads); full-alignment "ingest" "conv0".."conv8" "spp" "tail".  Synchronises the streams it recorded on. */
 int c3b_get_profile(c3b_model *m, const char *kernel, double *total_ms, int64_t *launches);
+/* Average grid size (CTAs, one per SM for the tensor-core kernels) of that kernel's launches: SM-time = CTAs x duration is what a
+ * kernel costs when several batches share the GPU. */
+int c3b_get_profile_ctas(c3b_model *m, const char *kernel, double *ctas_per_launch);
 
 /* Number of this library's kernels launched on behalf of m so far (bench.py's gpu_launches). */
 int64_t c3b_launch_count(const c3b_model *m);
