@@ -142,7 +142,7 @@ const std::vector<float> &P(const c3b_model *m, const std::string &k) { return m
 // UMMA SWIZZLE_NONE K-major operand image of a [rows][k] matrix: [chunk][rowblock][8 kgroups][rb rows][8] fp16.
 // get(row, k) supplies the (already folded / permuted) element; out-of-range k is zero.
 template <typename F>
-std::vector<uint16_t> pack_igemm(int rows, int kgroups, int rb, F get) {
+std::vector<uint16_t> pack_operand(int rows, int kgroups, int rb, F get) {
     const int nchunks = (kgroups + 7) / 8;
     const int nrb = rows / rb;
     std::vector<uint16_t> img((size_t)nchunks * nrb * 8 * rb * 8, 0);
@@ -348,7 +348,7 @@ static int finalize_impl(c3b_model *m) {
         const int kg = m->l4_in / 8;
         const int l4_in = m->l4_in, d4 = m->d4;
         m->tail = TailW();
-        std::vector<uint16_t> img = pack_igemm(d4, kg, d4, [&](int r, int k) { return w4[(size_t)r * l4_in + k]; });
+        std::vector<uint16_t> img = pack_operand(d4, kg, d4, [&](int r, int k) { return w4[(size_t)r * l4_in + k]; });
         put(blob, img.data(), img.size() * 2, (const void **)&m->tail.w4, false);
         put(blob, P(m, "L4.bias").data(), (size_t)d4 * 4, (const void **)&m->tail.b4, false);
         int toff = 0;
@@ -357,8 +357,8 @@ static int finalize_impl(c3b_model *m) {
             const std::vector<float> &wy = P(m, std::string(kHeadNames[h][1]) + ".weight");   // [n][128]
             const std::vector<float> &byv = P(m, std::string(kHeadNames[h][1]) + ".bias");
             const int n = kHeadDims[h], npad = (n + 15) / 16 * 16;
-            std::vector<uint16_t> i5 = pack_igemm(128, d4 / 8, 128, [&](int r, int k) { return w5[(size_t)r * d4 + k]; });
-            std::vector<uint16_t> iy = pack_igemm(npad, 16, npad, [&](int r, int k) { return r < n ? wy[(size_t)r * 128 + k] : 0.f; });
+            std::vector<uint16_t> i5 = pack_operand(128, d4 / 8, 128, [&](int r, int k) { return w5[(size_t)r * d4 + k]; });
+            std::vector<uint16_t> iy = pack_operand(npad, 16, npad, [&](int r, int k) { return r < n ? wy[(size_t)r * 128 + k] : 0.f; });
             std::vector<float> byp(npad, 0.f);
             for (int o = 0; o < n; ++o) byp[o] = byv[o];
             put(blob, i5.data(), i5.size() * 2, (const void **)&m->tail.w5[h], false);
@@ -468,7 +468,7 @@ static int finalize_impl(c3b_model *m) {
             put(blob, img.data(), img.size() * 2, (const void **)&m->lstm_tc[1][0].w_img, false);
             m->lstm_tc[1][0].bias = nullptr;
             // one 256-row slab per column group of the projection kernel (proj_tc.cu): [chunk 4][group 5][8 kg][256 rows][8]
-            std::vector<uint16_t> pimg = pack_igemm(1280, 32, 256, [&](int R, int k) {
+            std::vector<uint16_t> pimg = pack_operand(1280, 32, 256, [&](int R, int k) {
                 const int d = R / 640;
                 const int row = lstm2_torch_row(R % 640);
                 return (*wih_d[d])[(size_t)row * 256 + k] * ((row / C3B_H2 == 2) ? 1.0f : 0.5f);
@@ -489,7 +489,7 @@ static int finalize_impl(c3b_model *m) {
                 const std::vector<float> &bih = P(m, "LSTM2.bias_ih" + sfx), &bhh = P(m, "LSTM2.bias_hh" + sfx);
                 for (int R2 = 0; R2 < 640; ++R2) pbias2[(size_t)d * 640 + R2] = (bih[x_row(R2)] + bhh[x_row(R2)]) * x_gs(R2);
             }
-            std::vector<uint16_t> pimg2 = pack_igemm(1280, 32, 256, [&](int R, int k) {
+            std::vector<uint16_t> pimg2 = pack_operand(1280, 32, 256, [&](int R, int k) {
                 return (*wih_d[R / 640])[(size_t)x_row(R % 640) * 256 + k] * x_gs(R % 640);
             });
             m->proj2x = m->proj2;
@@ -535,7 +535,7 @@ static int finalize_impl(c3b_model *m) {
             // tensor-core image: k = tap*cin_pad + ci; conv1's input channels are padded to one UMMA k-step (16)
             const int cin_pad = (i == 0) ? 16 : cin;
             const int kg = 9 * cin_pad / 8;
-            std::vector<uint16_t> img = pack_igemm(cout, kg, cout, [&](int co, int k) {
+            std::vector<uint16_t> img = pack_operand(cout, kg, cout, [&](int co, int k) {
                 const int t = k / cin_pad, ci = k % cin_pad;
                 return ci < cin ? wf[((size_t)t * cin + ci) * cout + co] : 0.f;
             });
@@ -1182,78 +1182,6 @@ extern "C" int c3b_debug_lstm_trace(c3b_model *m, int64_t *out264) {
     C3B_CUDA(cudaDeviceSynchronize());
     C3B_CUDA(cudaMemcpy(out264, m->lstm_trace, sizeof(long long) * 2 * C3B_T * 4, cudaMemcpyDeviceToHost));
     return 0;
-}
-
-// ------------------------------------------------------------------------------------------------ kernel unit-test hooks
-// Exercise the tcgen05 implicit-GEMM kernel on caller-provided matrices (tests/test_igemm.py); not part of the drop-in API.
-extern "C" int c3b_debug_gemm(c3b_model *m, int swapped, int64_t M, int N, int K, const float *a, const float *wmat,
-                              const float *bias, int relu, int ksplit, float *out) {
-    if (!m) { c3b_set_error("c3b_debug_gemm: null model"); return 1; }
-    if (K % 8) { c3b_set_error("c3b_debug_gemm: K must be a multiple of 8"); return 1; }
-    C3B_CUDA(cudaSetDevice(m->device));
-    // swapped orientation = the k-group-planar bulk-copy operand path ([K/8][Mp][8]); standard = row-major gather path
-    const int64_t Mp = (M + 127) / 128 * 128;
-    std::vector<uint16_t> ab(swapped ? (size_t)Mp * K : (size_t)M * K, 0);
-    if (swapped) {
-        for (int64_t r = 0; r < M; ++r)
-            for (int k = 0; k < K; ++k) ab[((size_t)(k >> 3) * Mp + r) * 8 + (k & 7)] = c3b_f2op(a[(size_t)r * K + k]);
-    } else {
-        for (size_t i = 0; i < ab.size(); ++i) ab[i] = c3b_f2op(a[i]);
-    }
-    const int rb = swapped ? 128 : N;
-    std::vector<uint16_t> img = pack_igemm(N, K / 8, rb, [&](int r, int k) { return wmat[(size_t)r * K + k]; });
-    void *da = nullptr, *dw = nullptr, *db = nullptr, *dout = nullptr;
-    C3B_CUDA(cudaMalloc(&da, ab.size() * 2));
-    C3B_CUDA(cudaMalloc(&dw, img.size() * 2));
-    C3B_CUDA(cudaMalloc(&db, (size_t)N * 4));
-    const int nsp = swapped ? c3b_effective_ksplit((K / 8 + 7) / 8, ksplit > 0 ? ksplit : 1) : 1;
-    const size_t out_bytes = swapped ? (size_t)nsp * M * N * 4 : (size_t)M * N * 2;
-    C3B_CUDA(cudaMalloc(&dout, out_bytes));
-    C3B_CUDA(cudaMemcpy(da, ab.data(), ab.size() * 2, cudaMemcpyHostToDevice));
-    C3B_CUDA(cudaMemcpy(dw, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
-    std::vector<float> zb((size_t)N, 0.f);
-    C3B_CUDA(cudaMemcpy(db, bias ? bias : zb.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
-    C3B_CUDA(cudaMemset(dout, 0, out_bytes));
-    IgemmArgs ga = {};
-    ga.a = (const op_t *)da;
-    ga.m = M;
-    ga.taps = swapped ? 0 : 1;
-    ga.ld_rows = Mp;
-    ga.cin = K;
-    ga.lda = K;
-    ga.w.w_img = (const op_t *)dw;
-    ga.w.bias = (const float *)db;
-    ga.w.n = N;
-    ga.w.kgroups = K / 8;
-    ga.w.nchunks = (K / 8 + 7) / 8;
-    ga.out = dout;
-    ga.ldo = N;
-    ga.relu = relu;
-    ga.epilogue = swapped ? IGEMM_EPI_F32_ATOMIC : IGEMM_EPI_BF16_BIAS_RELU;
-    ga.ksplit = ksplit;
-    ga.split_stride = (int64_t)M * N;
-    int rc = c3b_launch_igemm(m, ga, 0);
-    if (!rc) {
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { c3b_set_error("igemm kernel failed: %s", cudaGetErrorString(e)); rc = 1; }
-    }
-    if (!rc) {
-        if (swapped) {
-            std::vector<float> part((size_t)nsp * M * N);
-            C3B_CUDA(cudaMemcpy(part.data(), dout, out_bytes, cudaMemcpyDeviceToHost));
-            for (size_t i = 0; i < (size_t)M * N; ++i) {
-                float acc = 0.f;
-                for (int sp = 0; sp < nsp; ++sp) acc += part[(size_t)sp * M * N + i];
-                out[i] = acc;
-            }
-        } else {
-            std::vector<uint16_t> raw((size_t)M * N);
-            C3B_CUDA(cudaMemcpy(raw.data(), dout, out_bytes, cudaMemcpyDeviceToHost));
-            for (size_t i = 0; i < raw.size(); ++i) out[i] = c3b_op2f(raw[i]);
-        }
-    }
-    cudaFree(da); cudaFree(dw); cudaFree(db); cudaFree(dout);
-    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ destroy

@@ -242,10 +242,6 @@ int c3b_launch_ingest_pileup_f32(const void *x, int dtype, float *out, int64_t n
 int c3b_launch_ingest_fa_f32(const void *x, int dtype, float *out, int64_t n_elems, cudaStream_t s);
 // z4: nsplit partial sums [nsplit][split_stride] of the L4 pre-activation (no bias); the kernel adds them
 int c3b_launch_heads(const float *z4, int nsplit, int64_t split_stride, const HeadsParams &hp, float *out, int64_t batch, cudaStream_t s);
-inline int c3b_effective_ksplit(int nchunks, int ksplit) {
-    const int cps = (nchunks + ksplit - 1) / ksplit;
-    return (nchunks + cps - 1) / cps;
-}
 
 // ---- decode.cu ----
 int c3b_launch_decode_stage1(const float *y, const uint8_t *ref_gt21, int64_t batch, int out_dim, uint8_t *is_ref, float *ref_prob,
@@ -259,7 +255,7 @@ int c3b_launch_conv_f32(const float *x, const ConvF32 &w, const float *residual,
                         int win, int hout, int wout, cudaStream_t s);
 int c3b_launch_spp_f32(const float *x, float *out, int64_t batch, int h, int w, int c, cudaStream_t s);
 
-// ---- tensor-core path (lstm_tc.cu / igemm_tc.cu) ----
+// ---- tensor-core path ----
 struct TcPileupBuffers {
     op_t *xs;     // [33][B][48] fp16, time-major: hi(x) | 1 | lo(x) columns
     op_t *h1;     // tile-major k-group-planar, 32 k-groups: row = t*Bp + b, k = dir*128 + j  (projection GEMM operand)
@@ -298,37 +294,6 @@ inline size_t c3b_parity_offset(const PlanarGeom &g, int c, int64_t b, int hp, i
     return (size_t)((hp & 1) * 2 + (wp & 1)) * ((size_t)(c / 8) * g.p * 8) + ((size_t)g.g + b * g.s + (size_t)((hp >> 1) + 1) * g.wp + ((wp >> 1) + 1)) * 8;
 }
 int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s);
-
-// Generic implicit GEMM on tcgen05:  D[M x N] = A[M x K] * W[N x K]^T with fused epilogues.
-enum IgemmEpilogue {
-    IGEMM_EPI_BF16_BIAS_RELU = 0,   // fp16 NHWC store (name kept), + bias, optional residual add, ReLU      (convs)
-    IGEMM_EPI_F16_BIAS = 1,         // fp16 row-major store, + bias                              (LSTM2 pre-gates)
-    IGEMM_EPI_F32_ATOMIC = 2,       // fp32 split-K partial sums partial[ks][M][N] (plain stores; name kept)   (L4)
-};
-struct IgemmArgs {
-    const op_t *a;   // activations
-    int64_t m;                // GEMM rows (pixels / positions / sites)
-    // row addressing: conv mode (taps = 9) or plain (taps = 1)
-    int taps;                 // 9 conv gather | 1 plain row-major gather | 0 plain k-group-planar [K/8][ld_rows][8]
-    int64_t ld_rows;          // planar: rows per k-group plane
-    int hin, win, cin;        // conv input geometry (NHWC); plain: cin = K, hin = win = 1
-    int hout, wout, stride;   // conv output geometry
-    int64_t lda;              // plain mode: row stride in elements
-    IgemmW w;
-    void *out;                // f16 / f32
-    int64_t ldo;              // output row stride in elements
-    const op_t *residual;   // optional (same layout as out, fp16)
-    int relu;
-    int epilogue;
-    int ksplit;               // >1: split the K chunks over `ksplit` CTAs per tile (partial-sum epilogue only)
-    int64_t split_stride;     // elements between the ks slices of the partial-sum output
-    // conv mode with planar padded tensors on either side (strided stem convs between pconv layers)
-    int in_planar, out_planar;
-    PlanarGeom gin, gout;
-    long long *trace;         // debug: clock stamps of CTA 0 ([tile][8]: MMA thread 0..3, epilogue thread 4..6)
-};
-int c3b_launch_igemm(const c3b_model *m, const IgemmArgs &a, cudaStream_t s);
-
 
 int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, op_t *out, int64_t batch, int depth, const PlanarGeom &g1,
                             cudaStream_t s);

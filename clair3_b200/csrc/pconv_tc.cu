@@ -12,7 +12,7 @@
 //   * border slots are computed like any other row but never stored: they keep the zeros of the one-time workspace clear,
 //     so the output is again a valid planar padded tensor for the next convolution (and the residual add reads the same
 //     slot of its own input).
-// Weights: the host-packed per-chunk images of igemm_tc.cu ([tap*C/64 + kc][8 k-groups][N][8]); resident when they fit
+// Weights: the host-packed per-chunk operand images (pack_operand, c3b_api.cu) ([tap*C/64 + kc][8 k-groups][N][8]); resident when they fit
 // (res_block1: 72 KB), otherwise streamed through a ring with each piece applied to MT accumulators.
 //
 // Roles (320 threads): warp 9 lane 0 issues all bulk copies, warp 8 issues tcgen05.mma (one elected lane), warps 0-7 run

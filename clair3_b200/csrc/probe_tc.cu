@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __half *a, const __
     const uint64_t a_desc = ptx::umma_desc_nosw(ptx::smem_u32(a_smem), 2048, 128);
     const uint64_t b_desc = ptx::umma_desc_nosw(ptx::smem_u32(b_smem), (uint32_t)n * 16u, 128);
     uint32_t phase = 0;
-    // ---- numerics: D_ts at columns [0,n), D_ss at columns [n, 2n) is skipped (SS is validated by the igemm tests)
+    // ---- numerics: D_ts at columns [0,n), D_ss at columns [n, 2n) is skipped (SS is what every production kernel uses)
     if (tid == 0) {
         ptx::umma_f16_ts(tmem_base, tmem_base + 256, b_desc, idesc, 0);
         ptx::umma_commit(&bar);

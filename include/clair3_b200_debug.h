@@ -1,6 +1,6 @@
 /*
  * clair3_b200_debug.h - debug / measurement hooks of libclair3b200.so.  NOT part of the drop-in surface (clair3_b200.h):
- * activation taps for the parity tests, a kernel unit-test entry, clock-stamp traces and hardware probes (tools/diag.py).
+ * activation taps for the parity tests, clock-stamp traces and hardware probes (tools/diag.py).
  *
  * Extra c3b_set_option names that exist only for these hooks: "tap_ws" (which stream workspace c3b_get_tap reads, -1 = first
  * that has the tap), "lstm_trace" (clock stamps of one CTA: 1 = LSTM kernels, 10+i = Clair3_F conv i, 30 = LSTM2 projection),
@@ -19,13 +19,6 @@ extern "C" {
  * names: pileup "lstm1"[B,33,256] "lstm2"[B,33,320] "l4_pre"[B,128]; full-alignment "conv1" "res_block1" "conv3" "res_block2"
  * "conv5" "res_block3" (NHWC) "spp"[B,3584] "l4_pre"[B,256].  *count_inout: capacity in / elements out. */
 int c3b_get_tap(c3b_model *m, const char *name, float *host_out, int64_t *count_inout);
-
-/* Kernel unit-test hook (tests/test_gpu_parity.py::test_igemm_kernel_against_numpy): run the tcgen05 implicit-GEMM kernel on
- * caller matrices.  out[M][N] = a[M][K] * w[N][K]^T; swapped=0: standard orientation, +bias, optional ReLU, fp16-rounded;
- * swapped=1: weights on the TMEM lanes, split-K (ksplit) fp32 partial sums, no bias.  K % 8 == 0; N % 16 == 0
- * (N % 128 == 0 when swapped). */
-int c3b_debug_gemm(c3b_model *m, int swapped, int64_t M, int N, int K, const float *a, const float *w, const float *bias,
-                   int relu, int ksplit, float *out);
 
 /* With option "lstm_trace" on, CTA (0,0) of each LSTM kernel stamps clock64 at four points of every step (operands ready,
  * MMAs issued, accumulator ready, epilogue done); copies [2 layers][33 steps][4] stamps out. */

@@ -92,38 +92,6 @@ def test_tensor_core_conv_taps_match_reference():
         assert _relerr(got, want) < 2e-2, tap
 
 
-@pytest.mark.parametrize("swapped,M,N,K,ksplit", [
-    (0, 128, 64, 64, 1), (0, 300, 64, 72, 1), (0, 1000, 128, 576, 1), (0, 257, 256, 1152, 1), (0, 130, 16, 16, 1),
-    (1, 128, 128, 64, 1), (1, 200, 256, 256, 1), (1, 77, 128, 1072, 3), (1, 1024, 128, 10560, 11),
-    # enough tiles for the W-stationary mode (weights resident in shared memory; two row blocks per CTA when swapped)
-    (0, 40000, 64, 576, 1), (1, 40000, 256, 256, 1), (1, 20000, 128, 80, 1),
-])
-def test_igemm_kernel_against_numpy(swapped, M, N, K, ksplit):
-    from clair3_b200._ffi import check, ffi, lib
-    r = np.random.default_rng(M + N + K)
-    a = r.standard_normal((M, K)).astype(np.float32)
-    w = (r.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
-    bias = r.standard_normal(N).astype(np.float32)
-    out = np.zeros((M, N), dtype=np.float32)
-    h = ffi.new("c3b_model **")
-    check(lib().c3b_create(h, 0, 18, 0, 0))
-    try:
-        check(lib().c3b_debug_gemm(h[0], swapped, M, N, K, ffi.cast("float *", a.ctypes.data),
-                                   ffi.cast("float *", w.ctypes.data), ffi.cast("float *", bias.ctypes.data), 1, ksplit,
-                                   ffi.cast("float *", out.ctypes.data)))
-    finally:
-        lib().c3b_destroy(h[0])
-    a16 = torch.from_numpy(a).half().float().numpy().astype(np.float64)
-    w16 = torch.from_numpy(w).half().float().numpy().astype(np.float64)
-    ref = a16 @ w16.T
-    if not swapped:
-        ref = np.maximum(ref + bias, 0)
-        tol = 2e-3                      # output is fp16-rounded
-    else:
-        tol = 1e-3
-    assert np.abs(out - ref).max() <= tol * max(1.0, np.abs(ref).max())
-
-
 def test_ragged_empty_and_host_buffers():
     z, meta, sd, x = golden_case("p24")
     m = _model(meta, sd, TC)

@@ -1,6 +1,6 @@
 """GPU diagnostics: per-case, per-tap error report for both precisions (prints, never asserts).
 
-    python tools/diag.py fp32|tc|igemm [case ...]
+    python tools/diag.py fp32|tc [case ...]
 """
 import os
 import sys
@@ -56,42 +56,6 @@ def run_case(name, precision, opts):
             got = got[:want.shape[0]].reshape(want.shape)
         print(f"    tap {tap:11s} rel-L2 {relerr(got, want):.3e}  max|d| {np.abs(got - want).max():.3e}  "
               f"(|ref| max {np.abs(want).max():.2f})", flush=True)
-
-
-def run_igemm():
-    from clair3_b200._ffi import check, ffi, lib
-    shapes = [(0, 128, 64, 64, 1), (0, 128, 16, 16, 1), (0, 300, 64, 72, 1), (0, 1000, 128, 576, 1), (0, 257, 256, 1152, 1),
-              (1, 128, 128, 64, 1), (1, 200, 256, 256, 1), (1, 77, 128, 1072, 3), (1, 1024, 128, 10560, 11),
-              (0, 40000, 64, 576, 1), (1, 40000, 256, 256, 1), (1, 20000, 128, 80, 1)]
-    for swapped, M, N, K, ks in shapes:
-        r = np.random.default_rng(M + N + K)
-        a = r.standard_normal((M, K)).astype(np.float32)
-        w = (r.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
-        bias = r.standard_normal(N).astype(np.float32)
-        out = np.zeros((M, N), dtype=np.float32)
-        h = ffi.new("c3b_model **")
-        check(lib().c3b_create(h, 0, 18, 0, 0))
-        try:
-            check(lib().c3b_debug_gemm(h[0], swapped, M, N, K, ffi.cast("float *", a.ctypes.data),
-                                       ffi.cast("float *", w.ctypes.data), ffi.cast("float *", bias.ctypes.data), 0, ks,
-                                       ffi.cast("float *", out.ctypes.data)))
-        except Exception as e:  # noqa: BLE001
-            print(f"igemm swapped={swapped} M={M} N={N} K={K}: ERROR {e}", flush=True)
-            continue
-        finally:
-            lib().c3b_destroy(h[0])
-        a16 = torch.from_numpy(a).half().float().numpy().astype(np.float64)
-        w16 = torch.from_numpy(w).half().float().numpy().astype(np.float64)
-        ref = a16 @ w16.T + (0 if swapped else bias)
-        err = np.abs(out - ref)
-        print(f"igemm swapped={swapped} M={M} N={N} K={K} ks={ks}: max err {err.max():.3e} (|ref| max {np.abs(ref).max():.2f}) "
-              f"rel {relerr(out, ref):.3e}", flush=True)
-        if err.max() > 0.1:
-            # help localise layout bugs: error by row block / column block
-            rb = err.reshape(-1, N)[:128].max(axis=1)
-            cb = err[:128].max(axis=0)
-            print("    row err (first 16):", np.round(rb[:16], 2), " col err (first 16):", np.round(cb[:16], 2))
-            print("    out[0,:8]", np.round(out[0, :8], 3), " ref[0,:8]", np.round(ref[0, :8], 3))
 
 
 def run_ptrace(conv=1):
@@ -295,8 +259,6 @@ if __name__ == "__main__":
         else:
             cases2.append(c)
     cases = cases2 or (GOLDEN_PILEUP + GOLDEN_FA)
-    if mode == "igemm":
-        run_igemm()
     elif mode == "ptrace":
         for c in ([int(d) for d in str(opts["convs"])] if "convs" in opts else [1]):
             run_ptrace(c)
