@@ -99,7 +99,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
     constexpr int kPhases = S::kPhases;
     constexpr uint32_t kWPhaseBytes = S::kWPhaseBytes, kWBytes = S::kWBytes, kABytes = S::kABytes;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t w_bar, a_ready[2], acc_full[kStages], acc_empty[kStages], x_full[2], x_ready[2];
+    __shared__ uint64_t w_bar, a_ready[2], acc_full[kStages], acc_empty[kStages], x_full[2], x_ready[2], x_free[2];
     __shared__ uint32_t tmem_base_smem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -116,6 +116,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
             ptx::mbar_init(&a_ready[b], 2 * kEpiWarps);
             ptx::mbar_init(&x_full[b], 1);        // this CTA's x_t bulk copy has landed (LSTM1)
             ptx::mbar_init(&x_ready[b], 2);       // leader: both CTAs' x_t have landed
+            ptx::mbar_init(&x_free[b], 1);        // every MMA that read operand buffer b has completed (multicast commit, once per step)
         }
         for (int s = 0; s < kStages; ++s) {
             ptx::mbar_init(&acc_full[s], 1);
@@ -179,6 +180,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
                         if (first_round) first_round = false; else use_par ^= 1u;
                     }
                 }
+                if (!L2) ptx::umma_commit_pair(&x_free[ab]);      // LSTM1: the loaders may refill this buffer's x columns (step + 2)
             }
         }
         __syncwarp();
@@ -190,13 +192,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
             for (int step = 0; step < C3B_T; ++step) {
                 const int t = dir ? (C3B_T - 1 - step) : step;
                 const int ab = step & 1;
-                // buffer ab was last read by the MMAs of step-2: wait for the commit of that step's last phase (steps 0, 1: free).
-                // The issuer cannot be more than one step ahead of this wait (it needs x_ready of this step), so the stage's
-                // barrier is at most one phase past the awaited one: the parity test is unambiguous.
-                if (step >= 2) {
-                    const int g = (step - 2) * kPhases + kPhases - 1;
-                    ptx::mbar_wait(&acc_full[g % kStages], (uint32_t)(g / kStages) & 1u);
-                }
+                // buffer ab was last read by the MMAs of step-2: their completion arrives on x_free[ab] exactly once per step, and
+                // the issuer cannot start step `step` before this thread has delivered x_step - producer and consumer advance in
+                // lockstep, so the parity wait is unambiguous (steps 0, 1: the buffers are free)
+                if (step >= 2) ptx::mbar_wait(&x_free[ab], (uint32_t)((step - 2) >> 1) & 1u);
                 ptx::mbar_arrive_expect_tx(&x_full[ab], S::kXBytes);
                 ptx::bulk_g2s(a_addr + (uint32_t)ab * kABytes, (const char *)p.xs + ((size_t)t * ntile + tile128) * S::kXBytes, S::kXBytes, &x_full[ab]);
                 ptx::mbar_wait(&x_full[ab], (uint32_t)(step >> 1) & 1u);
