@@ -232,7 +232,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
             const __half *pg_tn = L2 ? pg_site + (size_t)(dir ? t - 1 : t + 1) * pg_tstride : nullptr;     // next step (if any)
             op_t *h_t = p.hout + (L2 ? c3b_tile_major_offset(gsite, t * 40 + dir * 20, 1320)
                                      : c3b_tile_major_offset((size_t)t * p.bp + gsite, dir * 16, 32));
-            if (tr) p.trace[step * 4 + 0] = clock64();
             if (L2 && step + 1 < C3B_T && (lane & 7) == 0) {
                 // the pre-gates stream from HBM (86 MB per 1024 sites): pull the NEXT step's lines into L2 now (one prefetch per
                 // 128-byte line), so the register loads one phase ahead below find them there
@@ -246,8 +245,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
                 const bool wrap = ph + 1 == kPhases;
                 const bool more = L2 && (!wrap || step + 1 < C3B_T);
                 const __half *pg_nx = (wrap ? pg_tn : pg_t) + (size_t)(16 * (wrap ? 0 : ph + 1) + wg) * 128 * 8;
+                const bool trp = tr && step >= 8 && step < 8 + 6;
+                if (trp) p.trace[((step - 8) * kPhases + ph) * 4 + 0] = clock64();
                 ptx::mbar_wait(&acc_full[st], full_par);
                 ptx::tc_fence_after();
+                if (trp) p.trace[((step - 8) * kPhases + ph) * 4 + 1] = clock64();
                 const uint32_t ta = lane_taddr + (uint32_t)(st * 128);
                 float a[8];
                 uint32_t si[4], ig[4], sf[4], so[4];
@@ -284,7 +286,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
                 // the stage has been read: hand it back to the MMA issuer (one arrival per warp, to the leader CTA)
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_cluster(&acc_empty[st], 0);
+                if (lane == 0) ptx::mbar_arrive_cluster_relaxed(&acc_empty[st], 0);
+                if (trp) p.trace[((step - 8) * kPhases + ph) * 4 + 2] = clock64();
                 {
                     const uint32_t *pp = reinterpret_cast<const uint32_t *>(&pgv[3]);
 #pragma unroll
@@ -307,7 +310,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
                 }
                 // h_t[site][units 32 ph + 8 wg .. + 8): next step's A operand (k-group 4 ph + wg) and the layer output
                 *reinterpret_cast<uint4 *>(a_next + (uint32_t)(4 * ph + wg) * 2048u) = hv;
-                *reinterpret_cast<uint4 *>(h_t + (size_t)(4 * ph + wg) * 128 * 8) = hv;
+                if (trp) p.trace[((step - 8) * kPhases + ph) * 4 + 3] = clock64();
                 if (++st == kStages) { st = 0; full_par ^= 1u; }
             }
             // every h_t value of this warp's sites and unit groups is in the operand buffer: tell the MMA issuer
@@ -316,7 +319,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive_cluster(&a_ready[(step + 1) & 1], 0);
             }
-            if (tr) p.trace[step * 4 + 3] = clock64();
+            // the layer output leaves AFTER the release above (a cluster-scope release waits for the arriving thread's earlier
+            // global stores: issued before it, they would put one HBM write latency on the recurrence's critical path every
+            // step): each thread copies its own 16-byte chunks back out of the operand buffer while the next step's MMAs run
+#pragma unroll
+            for (int ph = 0; ph < kPhases; ++ph)
+                *reinterpret_cast<uint4 *>(h_t + (size_t)(4 * ph + wg) * 128 * 8) = *reinterpret_cast<const uint4 *>(a_next + (uint32_t)(4 * ph + wg) * 2048u);
         }
     }
     // teardown: both CTAs have finished every TMEM read / MMA before the pair's allocation is returned

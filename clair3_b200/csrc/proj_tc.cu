@@ -211,11 +211,12 @@ int c3b_launch_proj2(const c3b_model *m, const op_t *h1, const IgemmW &w, __half
     p.n_tiles = (int)(p.ld_rows / 128);
     p.bp = bp;
     p.trace = trace;
-    // The kernel is bound by the HBM write of its output (86 MB of pre-gates per 1024 sites at ~3.2 TB/s), not by its MMAs:
-    // 12 CTAs per column group (60 SMs) already write at that rate, and every further SM would only wait on HBM while holding
-    // an SM the recurrent kernels of the other in-flight batches could use.  (C3B_PROJ_CTAS: tuning sweeps only.)
+    // The kernel is bound by the write of its output (86 MB of pre-gates per 1024 sites): ~3.2 TB/s of HBM writes with 145 CTAs
+    // (31 us), and ~16 B/clk of store bandwidth per SM with fewer (60 CTAs: 63 us) - its SM-time is ~4 ms per launch either way,
+    // so 16 CTAs per column group trade a little latency for SMs the recurrent kernels of the other in-flight batches can use.
+    // (C3B_PROJ_CTAS: tuning sweeps only.)
     static const int per_env = getenv("C3B_PROJ_CTAS") ? atoi(getenv("C3B_PROJ_CTAS")) : 0;
-    int per = per_env > 0 ? per_env : 12;
+    int per = per_env > 0 ? per_env : 16;
     if (per > m->sm_count / 5) per = m->sm_count / 5;
     if (per > p.n_tiles) per = p.n_tiles;
     if (per < 1) per = 1;

@@ -179,6 +179,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *local_bar, uint32_
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_bar)), "r"(rank));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
+// Same without memory ordering: for arrivals that only signal "my tcgen05.ld reads of this TMEM stage are done" (the ordering is
+// tcgen05.fence::before_thread_sync + the barrier itself).  A release at cluster scope would make the arriving warp wait for
+// every earlier global store of its threads - measured: ~3 k cycles per arrival in the LSTM epilogue.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t *local_bar, uint32_t rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
 // Wait with acquire at cluster scope (the arrivals come from both CTAs)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
     uint32_t ok;

@@ -18,11 +18,12 @@ if [ $? -ne 0 ]; then echo "GATE FAILED"; tail -40 gpurun_out/${R}_gate.log; exi
 echo "gate ok"
 timeout 200 python -m pytest tests/test_gpu_round2.py -m gpu -q -x --timeout=60 -k "pair_lstm2_kernel" > gpurun_out/${R}_gate_pair2.log 2>&1; P2=$?; tail -2 gpurun_out/${R}_gate_pair2.log
 timeout 200 python -m pytest tests/test_gpu_round2.py -m gpu -q -x --timeout=60 -k "pair_lstm1" > gpurun_out/${R}_gate_pair1.log 2>&1; P1=$?; tail -12 gpurun_out/${R}_gate_pair1.log
+if [ $P2 -eq 0 ] && [ $P1 -eq 0 ]; then timeout 120 python tools/pair_trace.py 1024 > gpurun_out/${R}_pair_trace.txt 2>&1; cat gpurun_out/${R}_pair_trace.txt | tail -16; fi
 run p_default --workloads pileup
 if [ $P2 -eq 0 ]; then run p_pair2 --workloads pileup --opt lstm2_impl=1; fi
 if [ $P2 -eq 0 ] && [ $P1 -eq 0 ]; then
   run p_pair12 --workloads pileup --opt lstm2_impl=1 --opt lstm1_impl=1
-  for n in 6 20; do C3B_PROJ_CTAS=$n run p_pair12_proj$n --workloads pileup --opt lstm2_impl=1 --opt lstm1_impl=1; done
+  for n in 29; do C3B_PROJ_CTAS=$n run p_pair12_proj$n --workloads pileup --opt lstm2_impl=1 --opt lstm1_impl=1; done
 fi
 run fa --workloads fa
 DESEL=""
