@@ -26,8 +26,11 @@
 //
 // Roles (576 threads per CTA): warps 0-15 epilogue (warpgroup w = 8-unit group of each phase, warp & 3 = TMEM lane quadrant),
 // warp 16: one elected thread of the LEADER CTA issues every MMA, warp 17: weights loader + TMEM allocation.
-// Cross-CTA barriers live in the leader: a_ready[2] (the pair's h_t operands are complete: 32 warp arrivals) and acc_empty[3]
-// (a TMEM stage has been read by both CTAs); acc_full[3] is multicast to both CTAs by tcgen05.commit.
+// Barriers: acc_full[3] is multicast to both CTAs by tcgen05.commit; acc_empty[3] lives in the leader (a TMEM stage has been read
+// by both CTAs: 32 relaxed warp arrivals); "h_t operands complete" is collected per CTA on a LOCAL barrier (a_ready[2], 16 warp
+// arrivals with cheap CTA-scope release) and the peer's completion is forwarded to the leader (a_peer[2]) by one otherwise idle
+// thread - a cluster-scope release by every epilogue warp would wait for that warp's outstanding global loads / stores every
+// step (measured: ~3 k cycles of the ~11 k cycle step).
 #include "c3b_internal.h"
 #include "ptx.cuh"
 
@@ -99,7 +102,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
     constexpr int kPhases = S::kPhases;
     constexpr uint32_t kWPhaseBytes = S::kWPhaseBytes, kWBytes = S::kWBytes, kABytes = S::kABytes;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t w_bar, a_ready[2], acc_full[kStages], acc_empty[kStages], x_full[2], x_ready[2], x_free[2];
+    __shared__ uint64_t w_bar, a_ready[2], a_peer[2], acc_full[kStages], acc_empty[kStages], x_full[2], x_ready[2], x_free[2];
     __shared__ uint32_t tmem_base_smem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -113,7 +116,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
     if (tid == 0) {
         ptx::mbar_init(&w_bar, 1);
         for (int b = 0; b < 2; ++b) {
-            ptx::mbar_init(&a_ready[b], 2 * kEpiWarps);
+            ptx::mbar_init(&a_ready[b], kEpiWarps);     // this CTA's 16 epilogue warps have written their h_t values
+            ptx::mbar_init(&a_peer[b], 1);              // leader: the peer CTA's a_ready has completed
             ptx::mbar_init(&x_full[b], 1);        // this CTA's x_t bulk copy has landed (LSTM1)
             ptx::mbar_init(&x_ready[b], 2);       // leader: both CTAs' x_t have landed
             ptx::mbar_init(&x_free[b], 1);        // every MMA that read operand buffer b has completed (multicast commit, once per step)
@@ -156,7 +160,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
             bool first_round = true;
             for (int step = 0; step < C3B_T; ++step) {
                 const int ab = step & 1;
-                if (step > 0) ptx::mbar_wait_cluster(&a_ready[ab], (uint32_t)((step - 1) >> 1) & 1u);
+                if (step > 0) {
+                    ptx::mbar_wait(&a_ready[ab], (uint32_t)((step - 1) >> 1) & 1u);
+                    ptx::mbar_wait_cluster(&a_peer[ab], (uint32_t)((step - 1) >> 1) & 1u);
+                }
                 if (!L2) ptx::mbar_wait_cluster(&x_ready[ab], (uint32_t)(step >> 1) & 1u);
                 ptx::tc_fence_after();
                 const uint32_t a_lo = a_lo0 + (uint32_t)ab * a_bstep;
@@ -181,6 +188,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
                     }
                 }
                 if (!L2) ptx::umma_commit_pair(&x_free[ab]);      // LSTM1: the loaders may refill this buffer's x columns (step + 2)
+            }
+        } else if (rank == 1 && ptx::elect_one()) {
+            // peer CTA: forward "my epilogue warps have all written h_t" to the leader (this thread has no memory traffic of its
+            // own, so its cluster-scope release costs nothing)
+            for (int step = 1; step < C3B_T; ++step) {
+                ptx::mbar_wait(&a_ready[step & 1], (uint32_t)((step - 1) >> 1) & 1u);
+                ptx::mbar_arrive_cluster(&a_peer[step & 1], 0);
             }
         }
         __syncwarp();
@@ -317,7 +331,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lstm_pa
             if (step + 1 < C3B_T) {
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_cluster(&a_ready[(step + 1) & 1], 0);
+                if (lane == 0) ptx::mbar_arrive(&a_ready[(step + 1) & 1]);
             }
             // the layer output leaves AFTER the release above (a cluster-scope release waits for the arriving thread's earlier
             // global stores: issued before it, they would put one HBM write latency on the recurrence's critical path every
