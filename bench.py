@@ -470,14 +470,12 @@ def profile_kernels(ctx, model, w, xs_dev, value, clocks):
                                "dram_bytes_per_step_all_kernels": traffic_all,
                                "compulsory_bytes_per_step": b * (site_bytes(w) + model.out_dim * 4)}}
     if dom in ("lstm1", "lstm2"):
-        # The recurrent kernels are not tensor-bound: their epilogue needs 5 MUFU.TANH per (site, step, direction, unit)
-        # and the SFU pipe issues 16 lanes/clk/SM.  One launch occupies 2 * ceil(B / (2*tile)) CTAs (one per SM), so the
-        # honest ceiling for THIS launch is those SMs' SFU rate; the other SMs are filled by the other streams.
+        # The recurrent kernels are not tensor-bound: their epilogue needs 5 tanh evaluations per (site, step, direction, unit)
+        # and the SFU pipe delivers 16 per clock and SM (tanh.approx.f32: 16 lanes/clk; the packed f16x2 form: two results per
+        # lane at half the issue rate - measured, no net gain).  One launch occupies `ctas` SMs, so the honest ceiling for THIS
+        # launch is those SMs' SFU rate; the other SMs are filled by the other streams.
         units = 128 if dom == "lstm1" else 160
-        tile = int(ctx.args.lstm_tile) or 64
-        if dom == "lstm2":
-            tile = min(tile, 32)        # LSTM2's ten accumulator blocks fit TMEM only up to 32 sites per sub-tile
-        ctas = int(kernels[dom]["ctas"]) or 2 * ((b + 2 * tile - 1) // (2 * tile))
+        ctas = int(kernels[dom]["ctas"])
         mufu = 5.0 * 33 * 2 * units * b
         clk_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
         per_clk_sm = mufu / (kernels[dom]["ms_per_launch"] * 1e-3 * clk_hz) / ctas

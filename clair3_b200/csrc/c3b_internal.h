@@ -193,8 +193,8 @@ struct c3b_model {
     int lstm_tile = 0;
     int profile = 0;
     int lstm_wg = 2;                   // epilogue warpgroups per LSTM sub-tile (option "lstm_wg": 1 or 2)
-    int lstm1_impl = 0;                // the same choice for LSTM1
-    int lstm2_impl = 0;                // 0: gate rows on the TMEM lanes (lstm_tc.cu), 1: CTA-pair kernel with the sites on the lanes (lstm2x_tc.cu)
+    int lstm1_impl = 0;                // the same choice for LSTM1 (default 0: measured equal SM-time, lower latency)
+    int lstm2_impl = 1;                // 1 (default): CTA-pair kernel with the sites on the lanes (lstm2x_tc.cu), 0: gate rows on the lanes (lstm_tc.cu)
     int lstm_mufu16 = 0;               // 1: packed tanh.approx.f16x2 gate activations, 0 (default, faster: the epilogue is issue-bound): fp32 tanh.approx
     int tap_ws = -1;                   // debug: workspace index c3b_get_tap reads
     int taps = 0;                      // debug option "taps": record where the intermediate activations of a forward live

@@ -158,6 +158,20 @@ def test_pair_lstm1_kernel_full_size_deep_and_ragged():
     assert np.abs(yw - m(torch.from_numpy(xw).cuda()).cpu().numpy()).max() < 1e-5
 
 
+@pytest.mark.parametrize("tile", [16, 32])
+def test_rows_on_lanes_lstm2_kernel_still_matches(tile):
+    """The round-1 LSTM2 kernel (option lstm2_impl = 0: gate rows on the TMEM lanes, 16- or 32-site sub-tiles) stays covered now
+    that the CTA-pair kernel is the default."""
+    z, meta, sd, x = golden_case("p24")
+    m = _pileup(sd, False, lstm2_impl=0, lstm_tile=tile, taps=1)
+    y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    got = m.tap("lstm2").reshape(x.shape[0], -1)
+    want = z["tap_lstm2"]
+    rel = float(np.linalg.norm(got[:want.shape[0]].reshape(want.shape).astype(np.float64) - want) / np.linalg.norm(want))
+    assert rel < 2e-2, rel
+    _assert_tol(_stats("rows_on_lanes_lstm2_tile%d" % tile, y, z["y"]))
+
+
 def test_pair_lstm2_kernel_full_size_and_streams():
     from clair3_b200 import synth
     from oracle import clair3_oracle as orc
