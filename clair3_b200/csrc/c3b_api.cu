@@ -586,7 +586,10 @@ extern "C" int c3b_bcast_weights(c3b_model *m, void *nccl_comm, int root, void *
     typedef int (*bcast_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
     static bcast_fn fn = nullptr;
     if (!fn) {
-        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        // the communicator was created by whatever libnccl the caller has loaded (e.g. the one bundled with torch): bind to THAT
+        // copy first (RTLD_NOLOAD matches an already-loaded object by soname), only then fall back to the system library
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (!h) { c3b_set_error("c3b_bcast_weights: cannot dlopen libnccl: %s", dlerror()); return 1; }
         fn = (bcast_fn)dlsym(h, "ncclBroadcast");

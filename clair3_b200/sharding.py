@@ -61,21 +61,27 @@ class NcclComm:
 
     def __init__(self, device, group=None):
         import ctypes
+
+        class _UniqueId(ctypes.Structure):                 # ncclUniqueId: 128 opaque bytes, passed BY VALUE to ncclCommInitRank
+            _fields_ = [("internal", ctypes.c_byte * 128)]
+
         self._lib = _libnccl()
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-        uid = (ctypes.c_byte * 128)()
+        uid = _UniqueId()
         if rank == 0:
+            self._lib.ncclGetUniqueId.argtypes = [ctypes.POINTER(_UniqueId)]
+            self._lib.ncclGetUniqueId.restype = ctypes.c_int
             rc = self._lib.ncclGetUniqueId(ctypes.byref(uid))
             if rc != 0:
                 raise RuntimeError("ncclGetUniqueId failed: %d" % rc)
         t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device=device if dist.get_backend(group) == "nccl" else "cpu")
         dist.broadcast(t, src=0, group=group)
-        raw = bytes(t.cpu().tolist())
-        uid = (ctypes.c_byte * 128).from_buffer_copy(raw)
+        ctypes.memmove(ctypes.byref(uid), bytes(t.cpu().tolist()), 128)
         self.comm = ctypes.c_void_p()
         torch.cuda.set_device(device)
         # ncclResult_t ncclCommInitRank(ncclComm_t* comm, int nranks, ncclUniqueId commId /* by value */, int rank)
-        self._lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_byte * 128, ctypes.c_int]
+        self._lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _UniqueId, ctypes.c_int]
+        self._lib.ncclCommInitRank.restype = ctypes.c_int
         rc = self._lib.ncclCommInitRank(ctypes.byref(self.comm), world, uid, rank)
         if rc != 0:
             raise RuntimeError("ncclCommInitRank failed: %d" % rc)
@@ -83,6 +89,7 @@ class NcclComm:
     def destroy(self):
         if self.comm:
             self._lib.ncclCommDestroy.argtypes = [__import__("ctypes").c_void_p]
+            self._lib.ncclCommDestroy.restype = __import__("ctypes").c_int
             self._lib.ncclCommDestroy(self.comm)
             self.comm = None
 
