@@ -444,15 +444,31 @@ __global__ void ingest_pileup_tc_kernel(const T *__restrict__ x, const int64_t *
             }
         }
         __align__(16) op_t v[C3B_X1_COLS];
+        if (channels == 18) {
+            // the reference's pileup shape (shared/param_p.py:32-36): every index is a compile-time constant, one load per count
+            float xv[18];
 #pragma unroll
-        for (int k = 0; k < C3B_X1_COLS; ++k) {          // static indices: v stays in registers
-            float f = (k == channels) ? 1.f : 0.f;
-            if (have && k != channels && k <= 2 * channels) {
-                const float xv = ingest_to_float(src[k < channels ? k : k - channels - 1]);
-                const op_t hi = f2op_sat(xv);
-                f = k < channels ? op2f(hi) : xv - op2f(hi);
+            for (int c = 0; c < 18; ++c) xv[c] = have ? ingest_to_float(src[c]) : 0.f;
+#pragma unroll
+            for (int c = 0; c < 18; ++c) {
+                const op_t hi = f2op_sat(xv[c]);
+                v[c] = hi;
+                v[19 + c] = f2op_sat(xv[c] - op2f(hi));
             }
-            v[k] = f2op_sat(f);
+            v[18] = f2op(1.f);
+#pragma unroll
+            for (int k = 37; k < C3B_X1_COLS; ++k) v[k] = f2op(0.f);
+        } else {
+#pragma unroll
+            for (int k = 0; k < C3B_X1_COLS; ++k) {          // static indices: v stays in registers
+                float f = (k == channels) ? 1.f : 0.f;
+                if (have && k != channels && k <= 2 * channels) {
+                    const float xvv = ingest_to_float(src[k < channels ? k : k - channels - 1]);
+                    const op_t hi = f2op_sat(xvv);
+                    f = k < channels ? op2f(hi) : xvv - op2f(hi);
+                }
+                v[k] = f2op_sat(f);
+            }
         }
         if (tiled) {
             op_t *dst = xs + (((size_t)t * (bp >> 7) + (b >> 7)) * (C3B_X1_COLS / 8) * 128 + (b & 127)) * 8;
