@@ -42,9 +42,7 @@ struct ProjDev {
 // NBL > 0: pgT layout for the round-1 recurrent kernel with NBL-site sub-tiles (2-byte stores, 64 contiguous bytes per warp
 // instruction); NBL == 0: pg2 layout for the CTA-pair kernel (lstm2x_tc.cu): [dir][t][128-site tile][80 column groups][128][8],
 // two 16-byte stores per 16 columns, 512 contiguous bytes per warp instruction.
-// TMA (pg2 layout only): the epilogue stages 8 KB pieces of the output (four column groups x 128 sites, contiguous in pg2) in
-// shared memory and hands them to the TMA engine (cp.async.bulk shared -> global) instead of storing through the LSU.
-template <int NBL, bool TMA = false>
+template <int NBL>
 __global__ void __launch_bounds__(kThreads, 1) proj2_kernel(const ProjDev p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tmem_full[2], tmem_empty[2], w_bar;
@@ -56,11 +54,9 @@ __global__ void __launch_bounds__(kThreads, 1) proj2_kernel(const ProjDev p) {
     const int at0 = blockIdx.x / 5, at_step = gridDim.x / 5;
     const uint32_t slab = ptx::smem_u32(smem);
     const uint32_t ring = slab + kSlabBytes;
-    constexpr int kRing = TMA ? 4 : kStages;              // the staging buffers (2 warpgroups x 2 x 8 KB) take two ring stages' room
-    uint8_t *stg_base = smem + kSlabBytes + kRing * kStageBytes;
 
     if (tid == 0) {
-        for (int s = 0; s < kRing; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 256); }
         ptx::mbar_init(&w_bar, 1);
         ptx::fence_barrier_init();
@@ -89,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, 1) proj2_kernel(const ProjDev p) {
                     ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
                     ptx::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
                     ptx::bulk_g2s(ring + (uint32_t)s * kStageBytes, src, kStageBytes, &full_bar[s]);
-                    if (++s == kRing) { s = 0; ph ^= 1u; }
+                    if (++s == kStages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -126,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) proj2_kernel(const ProjDev p) {
                                       ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)k * b_kstep), idesc, (c > 0 || k > 0) ? 1u : 0u);
                     ptx::umma_commit(&empty_bar[s]);
                     if (c == 3) ptx::umma_commit(&tmem_full[acc]);
-                    if (++s == kRing) { s = 0; ph ^= 1u; }
+                    if (++s == kStages) { s = 0; ph ^= 1u; }
                 }
                 if (tr) p.trace[tcount * 8 + 3] = clock64();
             }
@@ -181,41 +177,6 @@ __global__ void __launch_bounds__(kThreads, 1) proj2_kernel(const ProjDev p) {
                     *reinterpret_cast<uint4 *>(dst + (size_t)(2 * ch + 1) * 128 * 8) = pk[1];
                 }
             };
-            if (TMA) {
-                const int wt = (q << 5) | lane;                       // thread within the warpgroup = site within the tile
-                uint8_t *stg_g = stg_base + g * 16384;
-#pragma unroll
-                for (int cp = 0; cp < 4; ++cp) {                       // chunk pair = 32 columns = four column groups = one 8 KB piece
-                    uint8_t *buf = stg_g + (cp & 1) * 8192;
-                    if (wt == 0) ptx::bulk_wait_read<1>();              // the piece stored from this buffer two pairs ago has been read
-                    ptx::named_bar_sync(1 + g, 128);
-#pragma unroll
-                    for (int hc = 0; hc < 2; ++hc) {
-                        const int ch = 2 * cp + hc;
-                        float *v = hc ? v1 : v0;
-                        ptx::tmem_ld_wait();
-                        if (hc == 0) ptx::tmem_ld16(taddr + (uint32_t)(16 * (ch + 1)), v1);
-                        else if (ch + 1 < 8) ptx::tmem_ld16(taddr + (uint32_t)(16 * (ch + 1)), v0);
-                        uint4 pk[2];
-                        uint32_t *pw = reinterpret_cast<uint32_t *>(pk);
-#pragma unroll
-                        for (int i4 = 0; i4 < 4; ++i4) {
-                            const float4 bb = b4[ch * 4 + i4];
-                            pw[2 * i4] = f2op2_sat(v[i4 * 4 + 0] + bb.x, v[i4 * 4 + 1] + bb.y);
-                            pw[2 * i4 + 1] = f2op2_sat(v[i4 * 4 + 2] + bb.z, v[i4 * 4 + 3] + bb.w);
-                        }
-                        *reinterpret_cast<uint4 *>(buf + (2 * hc) * 2048 + wt * 16) = pk[0];
-                        *reinterpret_cast<uint4 *>(buf + (2 * hc + 1) * 2048 + wt * 16) = pk[1];
-                    }
-                    ptx::fence_proxy_async_smem();
-                    ptx::named_bar_sync(1 + g, 128);
-                    if (wt == 0) {
-                        __half *piece = p.out + ((((size_t)(dir * C3B_T + t) * (p.bp >> 7) + ((int)(pos0 % p.bp) >> 7)) * 80 + (size_t)blk * 16 + 4 * cp) * 128) * 8;
-                        ptx::bulk_s2g(piece, ptx::smem_u32(buf), 8192u);
-                        ptx::bulk_commit();
-                    }
-                }
-            } else {
 #pragma unroll
             for (int ch = 0; ch < 8; ch += 2) {
                 ptx::tmem_ld_wait();
@@ -225,12 +186,10 @@ __global__ void __launch_bounds__(kThreads, 1) proj2_kernel(const ProjDev p) {
                 if (ch + 2 < 8) ptx::tmem_ld16(taddr + (uint32_t)(16 * (ch + 2)), v0);
                 emit(v1, ch + 1);
             }
-            }
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tmem_empty[acc]);
             if (tr) p.trace[tcount * 8 + 6] = clock64();
         }
-        if (TMA && ((q << 5) | lane) == 0) ptx::bulk_wait_read0();        // the last pieces have left shared memory
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -255,6 +214,8 @@ int c3b_launch_proj2(const c3b_model *m, const op_t *h1, const IgemmW &w, __half
     // The kernel is bound by the write of its output (86 MB of pre-gates per 1024 sites): ~3.2 TB/s of HBM writes with 145 CTAs
     // (31 us), and ~16 B/clk of store bandwidth per SM with fewer (60 CTAs: 63 us) - its SM-time is ~4 ms per launch either way,
     // so 16 CTAs per column group trade a little latency for SMs the recurrent kernels of the other in-flight batches can use.
+    // Handing the output to the TMA engine instead (8 KB pieces staged in shared memory, cp.async.bulk shared -> global) was
+    // measured slower: 55 us against 45 us at 80 CTAs, 79 us at 50, 36 us at 145 - the ~13 B/clk per SM is not an LSU limit.
     // (C3B_PROJ_CTAS: tuning sweeps only.)
     static const int per_env = getenv("C3B_PROJ_CTAS") ? atoi(getenv("C3B_PROJ_CTAS")) : 0;
     int per = per_env > 0 ? per_env : 16;
@@ -272,15 +233,8 @@ int c3b_launch_proj2(const c3b_model *m, const op_t *h1, const IgemmW &w, __half
         C3B_CUDA(cudaFuncSetAttribute(proj2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         proj2_kernel<16><<<grid, kThreads, smem, s>>>(p);
     } else {
-        static const bool tma = getenv("C3B_PROJ_TMA") && atoi(getenv("C3B_PROJ_TMA")) != 0;     // experiment: TMA-engine stores
-        if (tma) {
-            const size_t smem_t = kSlabBytes + 4 * kStageBytes + 2 * 16384 + 128;
-            C3B_CUDA(cudaFuncSetAttribute((proj2_kernel<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-            proj2_kernel<0, true><<<grid, kThreads, smem_t, s>>>(p);
-        } else {
-            C3B_CUDA(cudaFuncSetAttribute((proj2_kernel<0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            proj2_kernel<0, false><<<grid, kThreads, smem, s>>>(p);
-        }
+        C3B_CUDA(cudaFuncSetAttribute(proj2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        proj2_kernel<0><<<grid, kThreads, smem, s>>>(p);
     }
     C3B_CUDA(cudaGetLastError());
     return 0;

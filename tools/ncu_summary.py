@@ -55,10 +55,12 @@ def traffic(path, workload, batch, out_json):
         name = r[idx["Kernel Name"]]
         byts = sum(float(r[idx[k]]) * scale[units[idx[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         key = None
-        if "lstm_tc_kernel" in name:
+        if "lstm_pair_kernel" in name:
+            key = "lstm2" if "1>" in name.replace("(bool)", "") else "lstm1"
+        elif "lstm_tc_kernel" in name:
             key = "lstm2" if ", 1, " in name.replace("(bool)", "") or ",1," in name else "lstm1"
-        elif "lstm2x_kernel" in name:
-            key = "lstm2"
+        elif "lstm_pair_kernel" in name:
+            key = "lstm2" if "1>" in name.replace("(bool)", "") else "lstm1"
         elif "proj2_kernel" in name:
             key = "proj2"
         elif "tail_kernel" in name:
