@@ -32,9 +32,9 @@ def main():
     print("Static instruction counts per kernel: `UTCHMMA` = tcgen05.mma (`gdesc,gdesc` = both operands in shared memory; the LSTM2")
     print("kernel also has the `tmem,gdesc` A-in-TMEM form), `UTCBAR` = tcgen05.commit, `UBLKCP` = cp.async.bulk (TMA engine),")
     print("`LDTM`/`STTM` = tcgen05.ld/st, `SYNCS` = mbarrier ops, `LDGSTS` = cp.async (only the fp32 debug heads kernel's")
-    print("weight ring uses it).  The CTA-pair LSTM kernel (`lstm_pair_kernel`) issues `UTCHMMA.2CTA`, commits with `UTCBAR.2CTA.MULTICAST`
-and allocates TMEM with `UTCATOMSWS.2CTA` (`cuobjdump -sass clair3_b200/csrc/_obj/lstm2x_tc.o | grep -o "UTC[A-Z0-9_.]*" | sort | uniq -c`:
-2 x `UTCHMMA.2CTA`, 3 x `UTCBAR.2CTA.MULTICAST`, 4 x `UTCATOMSWS.2CTA.FIND_AND_SET.ALIGN`).\n")
+    print("weight ring uses it).  The CTA-pair LSTM kernel (`lstm_pair_kernel`) issues `UTCHMMA.2CTA`, commits with")
+    print("`UTCBAR.2CTA.MULTICAST` and allocates TMEM with `UTCATOMSWS.2CTA` (cuobjdump -sass clair3_b200/csrc/_obj/lstm2x_tc.o |")
+    print("grep -o 'UTC[A-Z0-9_.]*' | sort | uniq -c: 2 x `UTCHMMA.2CTA`, 3 x `UTCBAR.2CTA.MULTICAST`, 4 x `UTCATOMSWS.2CTA.FIND_AND_SET.ALIGN`).\n")
     print("| kernel | instrs | " + " | ".join(MN) + " |")
     print("|---|---|" + "---|" * len(MN))
     for (k, c), name in zip(counts.items(), names):
