@@ -262,11 +262,15 @@ __global__ void __launch_bounds__(2 * 128 * WG + 32, 1) lstm_tc_kernel(const Lst
         const int t = dir ? (C3B_T - 1 - step) : step;
 
         if constexpr (!LAYER2) {
-            // stage x_t: xs[t][b0+n][0..47] -> operand k-groups 0..5
-            for (int idx = gt; idx < NB * (KX / 8); idx += kGroupThreads) {
-                const int n = idx / (KX / 8), kg = idx % (KX / 8);
-                const uint4 v = *reinterpret_cast<const uint4 *>(p.xs + ((size_t)t * p.bp + b0 + n) * KX + kg * 8);
-                *reinterpret_cast<uint4 *>(b_smem + kg * LBO_B + n * 16) = v;
+            // stage x_0: xs[t][b0+n][0..47] -> operand k-groups 0..5.  Later steps find x_t already there: it was fetched into
+            // registers while the previous step's MMAs ran and stored once they had finished reading the operand buffer (below) -
+            // a global load on the step's critical path cost ~700 cycles of L2 latency per step.
+            if (step == 0) {
+                for (int idx = gt; idx < NB * (KX / 8); idx += kGroupThreads) {
+                    const int n = idx / (KX / 8), kg = idx % (KX / 8);
+                    const uint4 v = *reinterpret_cast<const uint4 *>(p.xs + ((size_t)t * p.bp + b0 + n) * KX + kg * 8);
+                    *reinterpret_cast<uint4 *>(b_smem + kg * LBO_B + n * 16) = v;
+                }
             }
         }
         ptx::fence_proxy_async_smem();
@@ -279,6 +283,20 @@ __global__ void __launch_bounds__(2 * 128 * WG + 32, 1) lstm_tc_kernel(const Lst
         if (tr) p.trace[step * 4 + 0] = clock64();
         if (tr) p.trace[step * 4 + 1] = clock64();
 
+        // LSTM1: fetch x_{t+1} now (in flight while the MMAs run), store it after the accumulator barrier
+        constexpr int XN = LAYER2 ? 1 : (NB * (KX / 8) + kGroupThreads - 1) / kGroupThreads;
+        uint4 xnext[XN];
+        if constexpr (!LAYER2) {
+            if (step + 1 < C3B_T) {
+                const int tn = dir ? t - 1 : t + 1;
+#pragma unroll
+                for (int i = 0; i < XN; ++i) {
+                    const int idx = gt + i * kGroupThreads;
+                    if (idx < NB * (KX / 8))
+                        xnext[i] = *reinterpret_cast<const uint4 *>(p.xs + ((size_t)tn * p.bp + b0 + idx / (KX / 8)) * KX + (idx % (KX / 8)) * 8);
+                }
+            }
+        }
         // while the MMAs run: ship h_{t_prev} (still in the operand buffer) to global memory
         if (step > 0) {
             for (int idx = gt; idx < NB * (H / 8); idx += kGroupThreads) {
@@ -314,6 +332,15 @@ __global__ void __launch_bounds__(2 * 128 * WG + 32, 1) lstm_tc_kernel(const Lst
         ptx::tc_fence_after();
         if (tr) p.trace[step * 4 + 2] = clock64();
         ptx::named_bar_sync(bar_id, kGroupThreads);                         // S2: the sub-tile's threads are done reading h_{t_prev}
+        if constexpr (!LAYER2) {
+            if (step + 1 < C3B_T) {       // this step's MMAs have completed: the x columns of the operand buffer may take x_{t+1}
+#pragma unroll
+                for (int i = 0; i < XN; ++i) {
+                    const int idx = gt + i * kGroupThreads;
+                    if (idx < NB * (KX / 8)) *reinterpret_cast<uint4 *>(b_smem + (idx % (KX / 8)) * LBO_B + (idx / (KX / 8)) * 16) = xnext[i];
+                }
+            }
+        }
 
         if (LAYER2) {
             // tail block (units 128..159): warp q holds gate q; activate and publish to the exchange buffer

@@ -259,7 +259,7 @@ if __name__ == "__main__":
         else:
             cases2.append(c)
     cases = cases2 or (GOLDEN_PILEUP + GOLDEN_FA)
-    elif mode == "ptrace":
+    if mode == "ptrace":
         for c in ([int(d) for d in str(opts["convs"])] if "convs" in opts else [1]):
             run_ptrace(c)
     elif mode == "stress":
