@@ -5,7 +5,7 @@ import re
 import sys
 
 print("# compute-sanitizer evidence\n")
-print("One small forward of each network per run (`tools/sanitize_case.py`; `tools/sanitize_round.sh`, `tools/round2_b.sh`), B200, "
+print("One small forward of each network per run (`tools/sanitize_case.py`; `tools/sanitize_round.sh`, `tools/round2_f.sh`), B200, "
       "`compute-sanitizer --tool <tool>`.  `ok (B, out)` is the script's own success line (the forward completed and returned).\n")
 print("| log | tool | case | result |")
 print("|---|---|---|---|")
