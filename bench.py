@@ -517,7 +517,7 @@ def run_forward_workload(ctx, wname, model):
     rec = {"value": value, "unit": "sites/s", "scaling": "weak", "steps": K, "repeats": r["repeats"],
            "timed_region_s": r["ms"] * 1e-3, "ms_per_step": r["ms"] / (K * r["repeats"]), "clocks": r["clocks"],
            "gpu_launches": int(launches), "parity_max_abs_dp": parity, "config": config_of(wname),
-           "run": {"streams_in_flight": n_streams, "lstm_subtile_sites": args.lstm_tile if w["kind"] == "pileup" else None,
+           "run": {"streams_in_flight": n_streams, "lstm_subtile_sites": (args.lstm_tile or "auto (64 stream-ordered / 16 synchronous)") if w["kind"] == "pileup" else None,
                    "l2_policy": "inputs rotated over %d distinct device-resident batches (> 126 MB L2)" % pool}}
 
     # ---- e2e: pinned host tensors in and out through the module API, H2D and D2H inside the timed region
@@ -545,7 +545,7 @@ def run_forward_workload(ctx, wname, model):
     def run_stream(n):
         it = (xs_pin[i % len(xs_pin)] for i in range(n))
         cnt = 0
-        for y in model.predict_stream(it, streams=n_streams, lstm_tile=args.lstm_tile):
+        for y in model.predict_stream(it, streams=n_streams):
             cnt += len(y)
         return cnt
     run_stream(2 * n_streams)
@@ -699,8 +699,9 @@ def main():
     ap.add_argument("--workload", default=None, help="alias: run a single workload")
     ap.add_argument("--streams", type=int, default=12)
     ap.add_argument("--lstm-wg", type=int, default=0, help="epilogue warpgroups per LSTM sub-tile (0 = library default)")
-    ap.add_argument("--lstm-tile", type=int, default=64,
-                    help="sites per LSTM sub-tile (16|32|64; 0 = library auto = latency-oriented 16 at this batch)")
+    ap.add_argument("--lstm-tile", type=int, default=0,
+                    help="sites per LSTM1 sub-tile (16|32|64; 0 = library choice by call shape: 64 for stream-ordered calls, the "
+                         "smallest GPU-filling tile for synchronous host-buffer calls)")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value for the pileup model (tuning runs), repeatable")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--min-region-s", type=float, default=2.0,

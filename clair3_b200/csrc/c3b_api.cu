@@ -743,7 +743,10 @@ struct PileupSrc {
     int64_t n_cols;
 };
 
-static int forward_pileup_chunk(c3b_model *m, Workspace *w, const PileupSrc &src, int64_t n, float *y, bool tap,
+// latency: the call is a synchronous host-buffer forward (the reference's _torch_predict shape: one batch in flight, the caller
+// waits) -> kernel variants that finish ONE batch soonest (many short CTAs); otherwise the variants with the smallest SM-time,
+// for callers that keep several batches in flight (forward_async / predict_stream / device-resident calls on several streams).
+static int forward_pileup_chunk(c3b_model *m, Workspace *w, const PileupSrc &src, int64_t n, float *y, bool tap, bool latency,
                                 cudaStream_t s) {
     const void *x = src.x;
     const int x_dtype = src.dtype;
@@ -779,12 +782,15 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const PileupSrc &src
     b.z4 = cv.take<float>((size_t)16 * bp * 128 * 4);
     b.bp = (int)bp;
     // sub-tile width (sites per MMA column block); a CTA ping-pongs two sub-tiles -> 2 directions x bp / (2*tile) CTAs
-    int tile1 = m->lstm_tile, tile2 = m->lstm_tile;
-    if (tile1 == 0) {
-        tile1 = (bp / 64 >= m->sm_count) ? 64 : (bp / 32 >= m->sm_count) ? 32 : 16;
-        tile2 = tile1;
-    }
-    if (tile2 > 32) tile2 = 32;
+    // sub-tile width of lstm_tc_kernel (sites per MMA column block; a CTA ping-pongs two sub-tiles -> 2 directions x bp / (2*tile)
+    // CTAs): 64 = fewest SM-microseconds per site, the smallest tile that still fills the GPU = shortest single-batch latency
+    int tile1 = m->lstm_tile, tile2;
+    if (tile1 == 0) tile1 = !latency ? 64 : (bp / 64 >= m->sm_count) ? 64 : (bp / 32 >= m->sm_count) ? 32 : 16;
+    tile2 = tile1 > 32 ? 32 : tile1;
+    // LSTM2: always the CTA-pair kernel unless forced (the two kernels round differently - packed fp16 gate activations - and
+    // the answer must not depend on the call shape); the latency / throughput choice only picks bit-identical variants
+    // (LSTM1 tile width, the projection's grid)
+    const int lstm2_impl = m->lstm2_impl;
     { PROF("ingest"); if (c3b_launch_ingest_pileup_tc(x, x_dtype, m->channels, src.starts, src.n_cols, b.xs, n, (int)bp, m->lstm1_impl, s)) return 1; }
     m->launches += 1;
     if (m->lstm1_impl == 1) {
@@ -795,12 +801,12 @@ static int forward_pileup_chunk(c3b_model *m, Workspace *w, const PileupSrc &src
         if (c3b_launch_lstm1_tc(m, b, n, tile1, s)) return 1;
     }
     long long *ptrace = (m->lstm_trace && m->trace_conv == 20) ? m->lstm_trace : nullptr;
-    if (m->lstm2_impl == 1) {
-        { PROF("proj2"); if (c3b_launch_proj2(m, b.h1, m->proj2x, b.pg, (int)bp, 0, ptrace, s)) return 1; }
+    if (lstm2_impl == 1) {
+        { PROF("proj2"); if (c3b_launch_proj2(m, b.h1, m->proj2x, b.pg, (int)bp, 0, latency, ptrace, s)) return 1; }
         { PROF("lstm2");
           if (c3b_launch_lstm2x(m, m->lstm2x_w, b.pg, b.h2, (int)bp, (m->lstm_trace && m->trace_conv == 1) ? m->lstm_trace + C3B_T * 4 : nullptr, s)) return 1; }
     } else {
-        { PROF("proj2"); if (c3b_launch_proj2(m, b.h1, m->proj2, b.pg, (int)bp, tile2, ptrace, s)) return 1; }
+        { PROF("proj2"); if (c3b_launch_proj2(m, b.h1, m->proj2, b.pg, (int)bp, tile2, latency, ptrace, s)) return 1; }
         { PROF("lstm2"); if (c3b_launch_lstm2_tc(m, b, n, tile2, s)) return 1; }
     }
     { PROF("tail"); if (c3b_launch_tail(m, b.h2, n, (int)bp, y, tap ? b.z4 : nullptr, s)) return 1; }
@@ -1019,7 +1025,7 @@ static int forward_impl(c3b_model *m, const void *x, int x_dtype, int x_on_devic
             src.n_cols = n_cols;
             src.starts = starts ? sd + b0 : nullptr;
             src.x = starts ? xd : (const void *)((const char *)xd + (size_t)b0 * site_elems * esz);
-            rc = forward_pileup_chunk(m, w, src, n, yc, b0 == 0, s);
+            rc = forward_pileup_chunk(m, w, src, n, yc, b0 == 0, sync_host && (!x_on_device || !y_on_device), s);
         } else {
             rc = forward_fa_chunk(m, w, (const char *)xd + (size_t)b0 * site_elems * esz, x_dtype, n, depth, yc, b0 == 0, s);
         }

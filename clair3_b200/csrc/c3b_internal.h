@@ -270,7 +270,8 @@ int c3b_launch_ingest_pileup_tc(const void *x, int dtype, int channels, const in
                                 int bp, int tiled, cudaStream_t s);
 int c3b_launch_gather_windows_f32(const void *cols, int dtype, int channels, const int64_t *starts, int64_t n_cols, float *out,
                                   int64_t batch, cudaStream_t s);
-int c3b_launch_proj2(const c3b_model *m, const op_t *h1, const IgemmW &w, __half *pg, int bp, int nbl, long long *trace, cudaStream_t s);
+int c3b_launch_proj2(const c3b_model *m, const op_t *h1, const IgemmW &w, __half *pg, int bp, int nbl, bool latency, long long *trace,
+                     cudaStream_t s);
 int c3b_launch_lstm2x(const c3b_model *m, const op_t *w_img, const __half *pg2, op_t *h2, int bp, long long *trace, cudaStream_t s);
 int c3b_launch_lstm1x(const c3b_model *m, const op_t *w_img, const op_t *xs2, op_t *h1, int bp, long long *trace, cudaStream_t s);
 int c3b_launch_tail(const c3b_model *m, const op_t *act, int64_t batch, int bp, float *out, float *z4_tap, cudaStream_t s);

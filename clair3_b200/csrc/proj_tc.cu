@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(kThreads, 1) proj2_kernel(const ProjDev p) {
 
 // h1: k-group-planar [32][33*bp][8]; w_img: pack_igemm(1280, 32, 256) image; pg: pgT for LSTM2 sub-tiles of `nbl` sites
 // nbl = 16 | 32: pgT for the round-1 recurrent kernel; nbl = 0: pg2 for the CTA-pair kernel
-int c3b_launch_proj2(const c3b_model *m, const op_t *h1, const IgemmW &w, __half *pg, int bp, int nbl, long long *trace, cudaStream_t s) {
+int c3b_launch_proj2(const c3b_model *m, const op_t *h1, const IgemmW &w, __half *pg, int bp, int nbl, bool latency, long long *trace,
+                     cudaStream_t s) {
     if (bp % 128 || (nbl != 0 && nbl != 16 && nbl != 32)) { c3b_set_error("proj2: bad geometry bp=%d nbl=%d", bp, nbl); return 1; }
     ProjDev p = {};
     p.act = h1; p.w_img = w.w_img; p.bias = w.bias; p.out = pg;
@@ -218,7 +219,7 @@ int c3b_launch_proj2(const c3b_model *m, const op_t *h1, const IgemmW &w, __half
     // measured slower: 55 us against 45 us at 80 CTAs, 79 us at 50, 36 us at 145 - the ~13 B/clk per SM is not an LSU limit.
     // (C3B_PROJ_CTAS: tuning sweeps only.)
     static const int per_env = getenv("C3B_PROJ_CTAS") ? atoi(getenv("C3B_PROJ_CTAS")) : 0;
-    int per = per_env > 0 ? per_env : 16;
+    int per = per_env > 0 ? per_env : latency ? m->sm_count / 5 : 16;       // one batch in flight: every SM (32 us instead of 45)
     if (per > m->sm_count / 5) per = m->sm_count / 5;
     if (per > p.n_tiles) per = p.n_tiles;
     if (per < 1) per = 1;

@@ -248,7 +248,7 @@ class _C3BModule:
                                       c("void *", stream)))
         return out
 
-    def predict_stream(self, batches, streams=8, lstm_tile=64):
+    def predict_stream(self, batches, streams=8):
         """Pipelined ``_torch_predict`` (``clair3/CallVariantsFromCffi.py:48-52,300-331``): consume an iterable of host batches
         (numpy arrays or CPU tensors, ragged sizes allowed) and yield one float32 numpy ``Y`` per batch, in order, while up to
         ``streams`` batches are in flight - H2D, kernels and D2H of consecutive batches overlap on as many CUDA streams, each
@@ -257,8 +257,6 @@ class _C3BModule:
         if self._handle is None:
             raise C3BError("model has no device/weights yet: call .to(device) and .load_state_dict() first")
         n = max(1, int(streams))
-        if self._kind == K["C3B_PILEUP"] and lstm_tile:
-            self.set_option("lstm_tile", lstm_tile)      # throughput-oriented LSTM tiles (several batches share the GPU)
         with torch.cuda.device(self._device):
             cu = [torch.cuda.Stream(self._device) for _ in range(n)]
         slots = [{"x": None, "y": None, "ev": None, "batch": 0} for _ in range(n)]

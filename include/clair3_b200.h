@@ -64,7 +64,9 @@ int c3b_finalize(c3b_model *m);
 /* name: "precision" (C3B_PREC_*), "chunk_sites" (sites per internal pass), "lstm_tile" (batch columns per LSTM CTA sub-tile:
  * 16|32|64, 0 = auto), "lstm_wg" (epilogue warpgroups per LSTM sub-tile: 1|2),
  * "lstm1_impl" / "lstm2_impl" (recurrent kernel of each layer: 0 = gate rows on the TMEM lanes, lstm_tc.cu; 1 = CTA-pair kernel with the
- * sites on the lanes, lstm2x_tc.cu; defaults 0 / 1),
+ * sites on the lanes, lstm2x_tc.cu; defaults 0 / 1).  With lstm_tile 0 the library picks by call shape between bit-identical
+ * variants: synchronous host-buffer calls (one batch in flight) get the LSTM1 tile and projection grid with the shortest latency,
+ * stream-ordered calls the ones with the least SM-time,
  * "profile" (1: bracket every kernel launch with CUDA events on its stream and accumulate per-kernel time; setting it resets the
  * totals), "taps" (1: remember where the intermediate activations of a forward live, for c3b_get_tap in clair3_b200_debug.h).
  * Debug-only options are listed in clair3_b200_debug.h. */

@@ -48,7 +48,7 @@ class _StubModel:
     """Module-protocol stand-in: deterministic 'probabilities' from the tensor, decode via the oracle restatement."""
     out_dim = 24
 
-    def predict_stream(self, batches, streams=8, lstm_tile=64):
+    def predict_stream(self, batches, streams=8):
         for x in batches:
             x = np.asarray(x).astype(np.float32)
             z = np.stack([x[:, 3 + (k % 30), k % 18] * 0.05 + 0.01 * k for k in range(24)], axis=1)
@@ -116,7 +116,6 @@ def test_launcher_single_rank_end_to_end(tmp_path, monkeypatch):
     m = Clair3_P(False, True, 18)
     m.to(torch.device("cuda"))
     m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
-    m.set_option("lstm_tile", 64)
     x = np.concatenate([np.load(p + ".npy") for p in prefixes])
     y = m(torch.from_numpy(x)).numpy()
     gt = launcher.center_ref_gt21(all_pos)
