@@ -545,6 +545,14 @@ static int finalize_impl(c3b_model *m) {
             m->conv_tc[i].nchunks = (kg + 7) / 8;
             put(blob, img.data(), img.size() * 2, (const void **)&m->conv_tc[i].w_img, false);
             put(blob, bf.data(), bf.size() * 4, (const void **)&m->conv_tc[i].bias, false);
+            if (cout >= 128) {
+                // the streamed-weight convs run on CTA pairs (pconv_tc.cu): each CTA's half of a piece's output channels contiguous
+                std::vector<uint16_t> img2 = pack_operand(cout, kg, cout / 2, [&](int co, int k) {
+                    const int t = k / cin_pad, ci = k % cin_pad;
+                    return ci < cin ? wf[((size_t)t * cin + ci) * cout + co] : 0.f;
+                });
+                put(blob, img2.data(), img2.size() * 2, (const void **)&m->conv_tc[i].w_img_pair, false);
+            }
         }
     }
 

@@ -110,6 +110,7 @@ struct LstmTC {
 };
 struct IgemmW {
     const op_t *w_img;   // UMMA B-operand image per k-chunk: [nchunks][8 kgroups][N rows][8] fp16
+    const op_t *w_img_pair;       // convs with N >= 128: the same as [nchunks][2 halves of N][8 kgroups][N/2 rows][8] (CTA-pair form)
     const float *bias;            // [N]
     int n;                        // output columns (Cout / gate rows / dense units)
     int kgroups;                  // K/8 (16-byte k-groups), real
