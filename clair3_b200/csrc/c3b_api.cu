@@ -261,6 +261,9 @@ extern "C" int c3b_set_option(c3b_model *m, const char *name, int value) {
     } else if (!strcmp(name, "lstm1_impl")) {
         if (value != 0 && value != 1) { c3b_set_error("lstm1_impl must be 0 (gate rows on the lanes) or 1 (CTA-pair kernel)"); return 1; }
         m->lstm1_impl = value;
+    } else if (!strcmp(name, "pconv_impl")) {
+        if (value != 0 && value != 1) { c3b_set_error("pconv_impl must be 0 (one CTA per tile) or 1 (block-pipelined / CTA-pair form)"); return 1; }
+        m->pconv_impl = value;
     } else if (!strcmp(name, "lstm2_impl")) {
         if (value != 0 && value != 1) { c3b_set_error("lstm2_impl must be 0 (gate rows on the lanes) or 1 (CTA-pair kernel)"); return 1; }
         m->lstm2_impl = value;
@@ -911,17 +914,17 @@ static int forward_fa_chunk(c3b_model *m, Workspace *w, const void *x, int x_dty
         pa.in = stem_in[l]; pa.out = a0; pa.residual = nullptr; pa.w = m->conv_tc[3 * l];
         auto trace_of = [&](int ci) { return (m->lstm_trace && m->trace_conv == ci) ? m->lstm_trace : nullptr; };
         pa.trace = trace_of(3 * l);
-        { PROF(cn[3 * l]); if (c3b_launch_pconv(m, pa, s)) return 1; }
+        { PROF(cn[3 * l]); if ((m->pconv_impl ? c3b_launch_pconv2(m, pa, s) : c3b_launch_pconv(m, pa, s))) return 1; }
         // residual block: two stride-1 shifted-view convolutions; the second one scatters its output into the next stem's
         // parity planes (levels 0, 1) or writes the plain planar map SPP reads (level 2)
         pa.c = co; pa.stride2 = 0;
         pa.trace = trace_of(3 * l + 1);
         pa.in = a0; pa.out = a1; pa.w = m->conv_tc[3 * l + 1];
-        { PROF(cn[3 * l + 1]); if (c3b_launch_pconv(m, pa, s)) return 1; }
+        { PROF(cn[3 * l + 1]); if ((m->pconv_impl ? c3b_launch_pconv2(m, pa, s) : c3b_launch_pconv(m, pa, s))) return 1; }
         pa.trace = trace_of(3 * l + 2);
         pa.in = a1; pa.out = a2; pa.residual = a0; pa.w = m->conv_tc[3 * l + 2];
         if (l < 2) { pa.out_parity = 1; pa.next = geo[l + 1]; }
-        { PROF(cn[3 * l + 2]); if (c3b_launch_pconv(m, pa, s)) return 1; }
+        { PROF(cn[3 * l + 2]); if ((m->pconv_impl ? c3b_launch_pconv2(m, pa, s) : c3b_launch_pconv(m, pa, s))) return 1; }
     }
     { PROF("spp"); if (c3b_launch_spp_tc(act[2][2], geo[2], sp, n, 256, (int)bp, s)) return 1; }
     { PROF("tail"); if (c3b_launch_tail(m, sp, n, (int)bp, y, tap ? z4 : nullptr, s)) return 1; }

@@ -195,6 +195,7 @@ struct c3b_model {
     int profile = 0;
     int lstm_wg = 2;                   // epilogue warpgroups per LSTM sub-tile (option "lstm_wg": 1 or 2)
     int lstm1_impl = 0;                // the same choice for LSTM1 (default 0: measured equal SM-time, lower latency)
+    int pconv_impl = 0;                // 0 (default): pconv_tc.cu; 1: the block-pipelined / CTA-pair form (pconv2_tc.cu)
     int lstm2_impl = 1;                // 1 (default): CTA-pair kernel with the sites on the lanes (lstm2x_tc.cu), 0: gate rows on the lanes (lstm_tc.cu)
     int lstm_mufu16 = 0;               // 1: packed tanh.approx.f16x2 gate activations, 0 (default, faster: the epilogue is issue-bound): fp32 tanh.approx
     int tap_ws = -1;                   // debug: workspace index c3b_get_tap reads
@@ -296,6 +297,7 @@ inline size_t c3b_parity_offset(const PlanarGeom &g, int c, int64_t b, int hp, i
     return (size_t)((hp & 1) * 2 + (wp & 1)) * ((size_t)(c / 8) * g.p * 8) + ((size_t)g.g + b * g.s + (size_t)((hp >> 1) + 1) * g.wp + ((wp >> 1) + 1)) * 8;
 }
 int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s);
+int c3b_launch_pconv2(const c3b_model *m, const PconvArgs &a, cudaStream_t s);   // block-pipelined / CTA-pair form (pconv2_tc.cu)
 
 int c3b_launch_ingest_fa_tc(const void *x, int dtype, int channels, int cpad, op_t *out, int64_t batch, int depth, const PlanarGeom &g1,
                             cudaStream_t s);

@@ -32,7 +32,7 @@ constexpr int kMetaSlots = 1024;
 
 struct PconvDev {
     const op_t *in;
-    const op_t *w_img;       // pair form: the [chunk][rank][8 kg][N/2][8] image (each CTA's half of a piece is one contiguous run)
+    const op_t *w_img;
     const float *bias;
     const op_t *residual;
     op_t *out;
@@ -56,7 +56,6 @@ struct PconvDev {
     int nS, nWp, nG;       // next level: slots per site, padded width, guard
     long long nP;          // next level: plane pitch
     long long *trace;      // optional: CTA 0 stamps [macro][8] (debug option "lstm_trace")
-    int dbg_skip_w;        // timing experiments only (env C3B_PCONV_SKIPW): never load / wait for streamed weights (wrong results)
 };
 
 // Border mask and parity-scatter target of slot l of a site (the epilogue looks this up instead of dividing per tile).
@@ -151,17 +150,11 @@ __device__ __forceinline__ void epilogue_tiles(const PconvDev &p, uint32_t tbase
     }
 }
 
-// PAIR = the CTA-pair form for STREAMED weights (cluster of two, tcgen05 cta_group::2, M = 256): every MMA covers tile ti of
-// BOTH CTAs' macro-tiles (each CTA's own image as the A operand) against a B operand of which each CTA holds HALF the output
-// channels, so each SM streams half the weight bytes per MMA cycle - the per-SM L2 -> shared-memory stream (about 35 B/clk),
-// not the tensor pipe, bounds the non-resident convs (a 32 KB piece feeds 2 x 4 MMAs of 129 cycles at N = 256).  The leader's
-// elected thread issues every MMA and commits (multicast) to both CTAs' barriers; the peer's otherwise idle MMA warp forwards
-// "my image / my weight half has landed" to the leader; both CTAs' epilogue warps return accumulator stages to the leader.
-template <int MT, bool PAIR>
+template <int MT>
 __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t w_full[kMaxWStages], w_empty[kMaxWStages], w_peer[kMaxWStages];
-    __shared__ uint64_t img_full[2], img_empty[2], img_peer[2], tmem_full[2], tmem_empty[2], w_res_bar;
+    __shared__ uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
+    __shared__ uint64_t img_full[2], img_empty[2], tmem_full[2], tmem_empty[2], w_res_bar;
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float bias_s[256];
     __shared__ uint32_t a_off_s[144];
@@ -170,42 +163,32 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
-    const uint32_t w_bytes = PAIR ? (uint32_t)p.N * 64u : (uint32_t)p.N * 128u;     // one ring stage (this CTA's part of a piece)
+    const uint32_t w_bytes = (uint32_t)p.N * 128u;
     const uint32_t img_bytes = (uint32_t)p.nplanes * (uint32_t)(p.C / 8) * (uint32_t)p.n_in * 16u;
     const uint32_t lbo_img = (uint32_t)p.n_in * 16u;
-    const uint32_t lbo_w = PAIR ? (uint32_t)p.N * 8u : (uint32_t)p.N * 16u;         // k-group pitch of the B image in shared memory
+    const uint32_t lbo_w = (uint32_t)p.N * 16u;
     const uint32_t smem_base = ptx::smem_u32(smem);
     const uint32_t w_region = p.w_resident ? (uint32_t)p.nchunks * w_bytes : (uint32_t)p.w_stages * w_bytes;
     const uint32_t img_base = smem_base + w_region;
 
     if (tid == 0) {
-        for (int s = 0; s < kMaxWStages; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); ptx::mbar_init(&w_peer[s], 1); }
+        for (int s = 0; s < kMaxWStages; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&img_full[s], 1);
             ptx::mbar_init(&img_empty[s], 1);
-            ptx::mbar_init(&img_peer[s], 1);
             ptx::mbar_init(&tmem_full[s], 1);
-            ptx::mbar_init(&tmem_empty[s], PAIR ? 16 : 256);     // pair: one arrival per epilogue warp of both CTAs, at the leader
+            ptx::mbar_init(&tmem_empty[s], 256);
         }
         ptx::mbar_init(&w_res_bar, 1);
         ptx::fence_barrier_init();
     }
-    if (!PAIR && warp == 8) ptx::tmem_alloc<512>(&tmem_base_smem);
+    if (warp == 8) ptx::tmem_alloc<512>(&tmem_base_smem);
     for (int i = tid; i < p.N; i += kThreads) bias_s[i] = p.bias ? p.bias[i] : 0.f;
     for (int l = tid; l < p.S && l < kMetaSlots; l += kThreads) meta_s[l] = slot_meta(p, l);
-    if (PAIR) {
-        __syncthreads();                            // the pair allocation's shared-memory write is the only access between two barriers
-        if (warp == 8) ptx::tmem_alloc_pair<512>(&tmem_base_smem);
-    }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
-    if (PAIR) ptx::cluster_sync_all();            // the peer's barriers are initialised before any multicast commit / remote arrival
-    // macro-tiles of this CTA: mb + rank for mb = first, first + gridDim.x, ... (pair: both CTAs run the leader's trip count; a
-    // peer tile past the end is computed on the last valid image and never stored)
-    const int mb0 = (int)blockIdx.x - (int)rank;
 
     if (warp == 9) {
         // ===================================================== loader (one thread): image chunks + weight pieces
@@ -220,7 +203,6 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                 const uint32_t ph = (uint32_t)(li / p.img_bufs) & 1u;
                 ptx::mbar_wait(&img_empty[buf], ph ^ 1u);
                 ptx::mbar_arrive_expect_tx(&img_full[buf], img_bytes);
-                if (PAIR && macro >= p.n_macro) macro = p.n_macro - 1;
                 const long long slot0 = (long long)p.G + 128LL * MT * macro - p.halo_lo;
                 const uint32_t dst = img_base + (uint32_t)buf * img_bytes;
                 for (int pl = 0; pl < p.nplanes; ++pl)
@@ -231,38 +213,27 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
             };
             int li = 0, w_stage = 0;
             uint32_t w_phase = 0;
-            if (mb0 < p.n_macro) load_img(mb0 + (int)rank, 0);
-            for (int mb = mb0; mb < p.n_macro; mb += gridDim.x, ++li) {
-                const int next = mb + gridDim.x;
-                if (p.img_bufs == 2 && next < p.n_macro) load_img(next + (int)rank, li + 1);      // prefetch while this tile computes
-                if (!p.w_resident && !p.dbg_skip_w) {
+            if ((int)blockIdx.x < p.n_macro) load_img(blockIdx.x, 0);
+            for (int macro = blockIdx.x; macro < p.n_macro; macro += gridDim.x, ++li) {
+                const int next = macro + gridDim.x;
+                if (p.img_bufs == 2 && next < p.n_macro) load_img(next, li + 1);      // prefetch while this tile computes
+                if (!p.w_resident) {
                     for (int c = 0; c < p.nchunks; ++c) {
                         ptx::mbar_wait(&w_empty[w_stage], w_phase ^ 1u);
                         ptx::mbar_arrive_expect_tx(&w_full[w_stage], w_bytes);
-                        const uint32_t dst = smem_base + (uint32_t)w_stage * w_bytes;
-                        // pair: this CTA's half of the piece's output channels (rows [rank*N/2, (rank+1)*N/2) of each k-group), packed
-                        // contiguously on the host - eight 1-2 KB copies per piece instead of one cost 9-13 k cycles per macro-tile
-                        ptx::bulk_g2s(dst, (const char *)p.w_img + ((size_t)c * (PAIR ? 2 : 1) + rank) * w_bytes, w_bytes, &w_full[w_stage]);
+                        ptx::bulk_g2s(smem_base + (uint32_t)w_stage * w_bytes, (const char *)p.w_img + (size_t)c * w_bytes, w_bytes, &w_full[w_stage]);
                         if (++w_stage == p.w_stages) { w_stage = 0; w_phase ^= 1u; }
                     }
                 }
-                if (p.img_bufs == 1 && next < p.n_macro) load_img(next + (int)rank, li + 1);      // single buffer: after this tile's MMAs
+                if (p.img_bufs == 1 && next < p.n_macro) load_img(next, li + 1);      // single buffer: after this tile's MMAs
             }
         }
     } else if (warp == 8) {
         // ===================================================== MMA issuer
-        const uint32_t idesc = ptx::umma_idesc_f16(PAIR ? 256 : 128, (uint32_t)p.N);
-        auto mma = [&](uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
-            if (PAIR) ptx::umma_f16_pair(d, a_desc, b_desc, idesc, accumulate);
-            else ptx::umma_f16(d, a_desc, b_desc, idesc, accumulate);
-        };
-        auto commit = [&](uint64_t *bar) {          // pair: the arrival is delivered to the barrier at this offset in BOTH CTAs
-            if (PAIR) ptx::umma_commit_pair(bar);
-            else ptx::umma_commit(bar);
-        };
+        const uint32_t idesc = ptx::umma_idesc_f16(128, (uint32_t)p.N);
         // per-k-step A-view offsets (descriptor start-address units of 16 B): tap (dh,dw), channel block kk ->
         // plane (stride 2 only), k-group pair 2*kk, slot shift
-        for (int q = lane; q < p.nksteps && p.kpt_shift < 2; q += 32) {        // (only the C = 16 path reads the table)
+        for (int q = lane; q < p.nksteps; q += 32) {
             const int tap = q >> p.kpt_shift, kk = q - (tap << p.kpt_shift);
             const int dh = tap / 3, dw = tap - dh * 3;
             const int plane = p.nplanes == 4 ? ((dh & 1) * 2 + (dw & 1)) : 0;
@@ -277,10 +248,9 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
         int li = 0, w_stage = 0;
         uint32_t w_phase = 0;
         // ONE elected thread runs the whole loop (barrier waits included): no per-chunk elect / reconvergence / warp sync
-        const bool elected = ptx::elect_one();
-        if (elected && rank == 0) {
+        if (ptx::elect_one()) {
         if (p.w_resident) ptx::mbar_wait(&w_res_bar, 0);
-        for (int mb = mb0; mb < p.n_macro; mb += gridDim.x, ++li) {
+        for (int macro = blockIdx.x; macro < p.n_macro; macro += gridDim.x, ++li) {
             const int buf = li % p.img_bufs;
             const uint32_t iph = (uint32_t)(li / p.img_bufs) & 1u;
             const int acc = li % p.acc_stages;
@@ -288,10 +258,8 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
             const bool tr = p.trace != nullptr && blockIdx.x == 0 && li < 8;
             if (tr) p.trace[li * 8 + 0] = clock64();
             ptx::mbar_wait(&img_full[buf], iph);
-            if (PAIR) ptx::mbar_wait_cluster(&img_peer[buf], iph);
             if (tr) p.trace[li * 8 + 1] = clock64();
-            if (PAIR) ptx::mbar_wait_cluster(&tmem_empty[acc], aph ^ 1u);
-            else ptx::mbar_wait(&tmem_empty[acc], aph ^ 1u);
+            ptx::mbar_wait(&tmem_empty[acc], aph ^ 1u);
             ptx::tc_fence_after();
             if (tr) p.trace[li * 8 + 2] = clock64();
             const uint32_t img = img_base + (uint32_t)buf * img_bytes;
@@ -304,17 +272,15 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
             const uint32_t a_lo = a_desc_lo + (img >> 4);
             auto acquire_w = [&](int c) -> uint32_t {
                 if (p.w_resident) return smem_base + (uint32_t)c * w_bytes;
-                if (p.dbg_skip_w) return smem_base + (uint32_t)w_stage * w_bytes;
                 ptx::mbar_wait(&w_full[w_stage], w_phase);
-                if (PAIR) ptx::mbar_wait_cluster(&w_peer[w_stage], w_phase);
                 ptx::tc_fence_after();
                 return smem_base + (uint32_t)w_stage * w_bytes;
             };
             auto release_w = [&](bool last) {
-                if (!p.w_resident && !p.dbg_skip_w) commit(&w_empty[w_stage]);
+                if (!p.w_resident) ptx::umma_commit(&w_empty[w_stage]);
                 if (last) {
-                    commit(&tmem_full[acc]);
-                    commit(&img_empty[buf]);
+                    ptx::umma_commit(&tmem_full[acc]);
+                    ptx::umma_commit(&img_empty[buf]);
                 }
             };
             auto advance_w = [&]() {
@@ -339,9 +305,9 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                             const uint64_t b_desc = ((uint64_t)w_desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)ks * b_step);
 #pragma unroll
                             for (int ti = 0; ti < MT; ++ti)
-                                mma(d0 + (uint32_t)(ti * p.N),
-                                    ((uint64_t)a_desc_hi << 32) | (uint64_t)(a_c + (uint32_t)ks * kstep_a + (uint32_t)(ti * 128)), b_desc,
-                                    (tap > 0 || ks > 0 || kc > 0) ? 1u : 0u);
+                                ptx::umma_f16(d0 + (uint32_t)(ti * p.N),
+                                              ((uint64_t)a_desc_hi << 32) | (uint64_t)(a_c + (uint32_t)ks * kstep_a + (uint32_t)(ti * 128)), b_desc, idesc,
+                                              (tap > 0 || ks > 0 || kc > 0) ? 1u : 0u);
                         }
                         release_w(tap == 8 && kc + 1 == p.cpt);
                         advance_w();
@@ -360,7 +326,8 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                             const uint64_t b_desc = ((uint64_t)w_desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)ks * b_step);
 #pragma unroll
                             for (int ti = 0; ti < MT; ++ti)
-                                mma(d0 + (uint32_t)(ti * p.N), ((uint64_t)a_desc_hi << 32) | (uint64_t)(ao + (uint32_t)(ti * 128)), b_desc, q > 0 ? 1u : 0u);
+                                ptx::umma_f16(d0 + (uint32_t)(ti * p.N), ((uint64_t)a_desc_hi << 32) | (uint64_t)(ao + (uint32_t)(ti * 128)), b_desc,
+                                              idesc, q > 0 ? 1u : 0u);
                         }
                     }
                     release_w(c + 1 == p.nchunks);
@@ -369,25 +336,6 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
             }
             if (tr) p.trace[li * 8 + 3] = clock64();
         }
-        } else if (PAIR && elected) {
-            // peer CTA: forward "my image / my half of weight piece c has landed" to the leader, in the order the leader consumes
-            // them.  Producer, forwarder and consumer advance in lockstep: a ring stage is refilled only after the leader's commit
-            // for its previous use.  The arrivals are RELAXED: the bytes were written by the TMA engine (complete before the local
-            // barrier flips) and are read by the tensor core straight from this CTA's shared memory - nothing of this thread's
-            // needs publishing, and a release at cluster scope costs about 1000 cycles per arrival (measured: 18 forwards per
-            // macro-tile made the pair form's MMA phase 17-20 k cycles instead of 8.6 k).
-            for (int mb = mb0; mb < p.n_macro; mb += gridDim.x, ++li) {
-                const int buf = li % p.img_bufs;
-                ptx::mbar_wait(&img_full[buf], (uint32_t)(li / p.img_bufs) & 1u);
-                ptx::mbar_arrive_cluster_relaxed(&img_peer[buf], 0);
-                if (!p.w_resident && !p.dbg_skip_w) {
-                    for (int c = 0; c < p.nchunks; ++c) {
-                        ptx::mbar_wait(&w_full[w_stage], w_phase);
-                        ptx::mbar_arrive_cluster_relaxed(&w_peer[w_stage], 0);
-                        if (++w_stage == p.w_stages) { w_stage = 0; w_phase ^= 1u; }
-                    }
-                }
-            }
         }
         __syncwarp();
     } else if (warp < 8) {
@@ -397,8 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
         const int eg = warp >> 2;
         const int r = q * 32 + lane;
         int li = 0;
-        for (int mb = mb0; mb < p.n_macro; mb += gridDim.x, ++li) {
-            const int macro = mb + (int)rank;         // pair: the peer's tile past the end has no slot < T, nothing is stored
+        for (int macro = blockIdx.x; macro < p.n_macro; macro += gridDim.x, ++li) {
             const int acc = li % p.acc_stages;
             const uint32_t aph = (uint32_t)(li / p.acc_stages) & 1u;
             const bool tr = p.trace != nullptr && blockIdx.x == 0 && tid == 128 && li < 8;
@@ -416,45 +363,19 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const PconvDev p) {
                 else epilogue_tiles<MT, false, false>(p, tbase, g0, eg, bias_s, meta_s);
             }
             ptx::tc_fence_before();
-            if (PAIR) {
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_cluster_relaxed(&tmem_empty[acc], 0);
-            } else {
-                ptx::mbar_arrive(&tmem_empty[acc]);
-            }
+            ptx::mbar_arrive(&tmem_empty[acc]);
             if (tr) p.trace[li * 8 + 6] = clock64();
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (PAIR) ptx::cluster_sync_all();           // both CTAs are done with TMEM, each other's barriers and operand halves
     if (warp == 8) {
         ptx::tc_fence_after();
-        if (PAIR) ptx::tmem_dealloc_pair<512>(tmem_base);
-        else ptx::tmem_dealloc<512>(tmem_base);
+        ptx::tmem_dealloc<512>(tmem_base);
     }
 }
 
 }  // namespace
-
-static int launch_pconv(void (*kern)(const PconvDev), int grid, int cluster, size_t smem, const PconvDev &p, cudaStream_t s) {
-    C3B_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = cluster > 1 ? 1 : 0;
-    C3B_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
-    C3B_CUDA(cudaGetLastError());
-    return 0;
-}
 
 int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
     const PlanarGeom &g = a.geom;
@@ -467,8 +388,6 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
     p.H = g.h; p.W = g.w; p.Wp = g.wp; p.S = g.s; p.G = g.g; p.T = g.t; p.P = g.p;
     p.relu = a.relu;
     p.trace = a.trace;
-    static const int skip_w = getenv("C3B_PCONV_SKIPW") ? atoi(getenv("C3B_PCONV_SKIPW")) : 0;
-    p.dbg_skip_w = skip_w;
     p.nksteps = 9 * a.c / 16;
     p.nchunks = (p.nksteps + 3) / 4;
     p.cpt = a.c / 64;
@@ -489,26 +408,20 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
     // balances the tile count over the SMs); streamed weights want MT >= 2 (every piece feeds MT accumulators) and a deep
     // ring, so the image is single-buffered there.  Cost model = rounds of macro-tiles x MMAs per macro-tile.
     long long best_cost = -1;
-    int pair = 0;
-    // streamed weights can run on the CTA pair (each SM streams half of every piece): C3B_PCONV_PAIR=1 (A/B runs; off by default
-    // until it measures faster end to end)
-    static const bool allow_pair = getenv("C3B_PCONV_PAIR") && atoi(getenv("C3B_PCONV_PAIR")) != 0;
     static const int force_mt = getenv("C3B_PCONV_MT") ? atoi(getenv("C3B_PCONV_MT")) : 0;   // tuning sweeps only
-    for (int mt = ((a.n <= 64 || force_mt == 4) ? 4 : 2); mt >= 1; mt >>= 1) {
+    for (int mt = (a.n <= 64 ? 4 : 2); mt >= 1; mt >>= 1) {
         if (mt * a.n > 512) continue;
         const int n_in = a.stride2 ? (128 * mt + g.wp + 1 + 7) / 8 * 8 : 128 * mt + 2 * (g.wp + 1);
         const size_t img_bytes = (size_t)p.nplanes * (a.c / 8) * n_in * 16;
-        int resident = 0, bufs = 0, stages = 0, pr = 0;
-        const long long n_macro = (g.t + 128LL * mt - 1) / (128LL * mt);
+        int resident = 0, bufs = 0, stages = 0;
         if (w_all + 2 * img_bytes <= budget) { resident = 1; bufs = 2; }
         else if (w_all + img_bytes <= budget) { resident = 1; bufs = 1; }
         else if (mt >= 2 || a.n <= 64 || a.stride2) {
-            pr = (allow_pair && n_macro >= 2 && a.w.w_img_pair != nullptr) ? 1 : 0;
-            const size_t st_bytes = pr ? w_bytes / 2 : w_bytes;          // one ring stage
-            if (img_bytes + 2 * st_bytes <= budget) { bufs = 1; stages = (int)((budget - img_bytes) / st_bytes); }
-            if (2 * img_bytes + 6 * st_bytes <= budget) { bufs = 2; stages = (int)((budget - 2 * img_bytes) / st_bytes); }
+            if (img_bytes + 2 * w_bytes <= budget) { bufs = 1; stages = (int)((budget - img_bytes) / w_bytes); }
+            if (2 * img_bytes + 6 * w_bytes <= budget) { bufs = 2; stages = (int)((budget - 2 * img_bytes) / w_bytes); }
             if (!bufs) continue;
         } else continue;
+        const long long n_macro = (g.t + 128LL * mt - 1) / (128LL * mt);
         const long long rounds = (n_macro + m->sm_count - 1) / m->sm_count;
         // + a fixed per-macro-tile cost: measured, MT = 1 is 1.2-1.5x slower than MT = 2/4 on every level even with resident
         // weights (each macro-tile pays an image-chunk round trip that only several tiles of MMAs hide)
@@ -516,35 +429,39 @@ int c3b_launch_pconv(const c3b_model *m, const PconvArgs &a, cudaStream_t s) {
         if (force_mt > 0) cost = (mt == force_mt) ? 1 : 1000000 + cost;
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
-            p.MT = mt; p.n_in = n_in; p.w_resident = resident; p.img_bufs = bufs; p.w_stages = stages; pair = pr;
+            p.MT = mt; p.n_in = n_in; p.w_resident = resident; p.img_bufs = bufs; p.w_stages = stages;
             p.acc_stages = (mt * a.n * 2 <= 512) ? 2 : 1;
         }
     }
     if (best_cost < 0) { c3b_set_error("pconv: feature map does not fit shared memory"); return 1; }
     static const bool dbg = getenv("C3B_DEBUG_PCONV") != nullptr;
     if (dbg)
-        fprintf(stderr, "[pconv] C=%d N=%d stride2=%d T=%lld: MT=%d resident=%d pair=%d img_bufs=%d w_stages=%d cost=%lld\n", a.c, a.n, a.stride2,
-                (long long)g.t, p.MT, p.w_resident, pair, p.img_bufs, p.w_stages, best_cost);
+        fprintf(stderr, "[pconv] C=%d N=%d stride2=%d T=%lld: MT=%d resident=%d img_bufs=%d w_stages=%d cost=%lld\n", a.c, a.n, a.stride2,
+                (long long)g.t, p.MT, p.w_resident, p.img_bufs, p.w_stages, best_cost);
     if (p.w_stages > kMaxWStages) p.w_stages = kMaxWStages;
     const long long per_macro = 128LL * p.MT;
     p.n_macro = (int)((g.t + per_macro - 1) / per_macro);
     if ((long long)p.n_macro * per_macro + g.g > g.p - g.g + per_macro) { /* plane pitch covers the rounded-up slot range by construction */ }
     const size_t img_bytes = (size_t)p.nplanes * (a.c / 8) * p.n_in * 16;
-    const size_t st_bytes = pair ? w_bytes / 2 : w_bytes;
-    const size_t smem = (p.w_resident ? (size_t)p.nchunks * w_bytes : (size_t)p.w_stages * st_bytes) + p.img_bufs * img_bytes + 256;
-    int grid = p.n_macro < m->sm_count ? p.n_macro : m->sm_count;
-    if (pair) grid = (grid + 1) & ~1;            // whole pairs (sm_count is even; an odd tile count gets one never-stored peer tile)
-    if (pair && grid > m->sm_count) grid = m->sm_count & ~1;
+    const size_t smem = (p.w_resident ? (size_t)p.nchunks * w_bytes : (size_t)p.w_stages * w_bytes) + p.img_bufs * img_bytes + 256;
+    const int grid = p.n_macro < m->sm_count ? p.n_macro : m->sm_count;
     const_cast<c3b_model *>(m)->launches++;
     c3b_note_grid(grid);
-    if (pair) p.w_img = a.w.w_img_pair;
-    switch (p.MT * 2 + pair) {
-        case 2: return launch_pconv(pconv_kernel<1, false>, grid, 1, smem, p, s);
-        case 3: return launch_pconv(pconv_kernel<1, true>, grid, 2, smem, p, s);
-        case 4: return launch_pconv(pconv_kernel<2, false>, grid, 1, smem, p, s);
-        case 5: return launch_pconv(pconv_kernel<2, true>, grid, 2, smem, p, s);
-        case 8: return launch_pconv(pconv_kernel<4, false>, grid, 1, smem, p, s);
-        case 9: return launch_pconv(pconv_kernel<4, true>, grid, 2, smem, p, s);
+    switch (p.MT) {
+        case 1:
+            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
+            pconv_kernel<1><<<grid, kThreads, smem, s>>>(p);
+            break;
+        case 2:
+            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
+            pconv_kernel<2><<<grid, kThreads, smem, s>>>(p);
+            break;
+        case 4:
+            C3B_CUDA(cudaFuncSetAttribute(pconv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
+            pconv_kernel<4><<<grid, kThreads, smem, s>>>(p);
+            break;
         default: c3b_set_error("pconv: unsupported MT %d", p.MT); return 1;
     }
+    C3B_CUDA(cudaGetLastError());
+    return 0;
 }

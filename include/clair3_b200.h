@@ -67,6 +67,8 @@ int c3b_finalize(c3b_model *m);
  * sites on the lanes, lstm2x_tc.cu; defaults 0 / 1).  With lstm_tile 0 the library picks by call shape between bit-identical
  * variants: synchronous host-buffer calls (one batch in flight) get the LSTM1 tile and projection grid with the shortest latency,
  * stream-ordered calls the ones with the least SM-time,
+ * "pconv_impl" (Clair3_F convolutions: 0 = one CTA per macro-tile, pconv_tc.cu, default; 1 = block-pipelined loads and CTA pairs
+ * (tcgen05 cta_group::2) for the streamed-weight convs, pconv2_tc.cu),
  * "profile" (1: bracket every kernel launch with CUDA events on its stream and accumulate per-kernel time; setting it resets the
  * totals), "taps" (1: remember where the intermediate activations of a forward live, for c3b_get_tap in clair3_b200_debug.h).
  * Debug-only options are listed in clair3_b200_debug.h. */

@@ -393,6 +393,51 @@ def test_predict_stream_yields_in_order_and_matches_sync():
         assert np.abs(g - w).max() < 1e-5
 
 
+# ---------------------------------------------------------------------------------------------- pconv_impl = 1
+@pytest.mark.parametrize("name", ["f8", "f9_dwell", "f55", "f8_24"])
+def test_pair_convolutions_match_reference_goldens(name):
+    """Option pconv_impl = 1 (block-pipelined image loads, rolled piece schedule, CTA pairs with cta_group::2 MMAs for the
+    streamed-weight convs; pconv2_tc.cu) against the goldens minted from the reference module, conv taps included."""
+    z, meta, sd, x = golden_case(name)
+    m = _fa(sd, meta["channels"], meta["add_indel_length"], pconv_impl=1, taps=1)
+    y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    for tap in ("conv1", "res_block1", "conv3", "res_block2", "conv5", "res_block3"):
+        if "tap_" + tap not in z.files:
+            continue
+        want = z["tap_" + tap]                         # [1,C,H,W]
+        got = m.tap(tap).reshape(x.shape[0], want.shape[2], want.shape[3], want.shape[1])[:1].transpose(0, 3, 1, 2)
+        rel = float(np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want))
+        assert rel < 2e-2, (tap, rel)
+    _assert_tol(_stats("pair_conv_golden_%s" % name, y, z["y"]))
+
+
+def test_pair_convolutions_full_size_ragged_and_streams():
+    """pconv_impl = 1 at BASELINE's full-alignment size against the oracle, against the default kernels, on ragged batches (odd
+    macro-tile counts exercise the never-stored peer tile of the last pair) and on concurrent streams."""
+    from clair3_b200 import synth
+    from oracle import clair3_oracle as orc
+    sd = synth.fa_state_dict(True, channels=8, seed=81)
+    x = synth.fa_inputs(300, depth=89, channels=8, seed=81)
+    xd = torch.from_numpy(x).cuda()
+    m0, m1 = _fa(sd), _fa(sd, pconv_impl=1)
+    y0, y1 = m0(xd).cpu().numpy(), m1(xd).cpu().numpy()
+    ref = np.concatenate([orc.fa_forward(sd, x[i:i + 100], True) for i in range(0, 300, 100)])
+    _assert_tol(_stats("pair_conv_300", y1, ref))
+    assert np.abs(y1 - y0).max() < 5e-3            # same fp16 operands, different fp32 accumulation order (taps by parity plane)
+    for n in (1, 3, 44, 129, 256, 257):
+        assert np.abs(m1(xd[:n]).cpu().numpy() - y1[:n]).max() < 1e-5, n
+    streams = [torch.cuda.Stream() for _ in range(6)]
+    xs = [xd[: (256 if i % 2 else 77)] for i in range(6)]
+    for rep in range(3):
+        outs = [None] * 6
+        for i in range(6):
+            with torch.cuda.stream(streams[i]):
+                outs[i] = m1(xs[i])
+        torch.cuda.synchronize()
+        for i in range(6):
+            assert np.abs(outs[i].cpu().numpy() - y1[: xs[i].shape[0]]).max() < 1e-4
+
+
 # ---------------------------------------------------------------------------------------------- full-alignment edges
 def test_full_alignment_ragged_chunks_and_alternating_batches():
     """300 sites = 256 + 44: the tail chunk reuses the 256-site layout (no re-clear); alternating batch sizes and depths on one

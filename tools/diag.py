@@ -81,7 +81,11 @@ def run_ptrace(conv=1):
         r = tr[li]
         if r[0] == 0:
             continue
-        print(f"macro {li}: MMA warp: start {r[0]-t0:7d} img_wait {r[1]-r[0]:6d} tmem_wait {r[2]-r[1]:6d} mma_issue+run {r[3]-r[2]:6d} | "
+        if li == 0 and buf[64]:
+            x = buf[64:72]
+            print(f"  ring: piece0 issued+commit queued {x[0]-t0}; loader: first refill released {x[1]-t0}; MMA thread: starts waiting for it "
+                  f"{x[5]-t0}, own half landed {x[3]-t0}, peer half forwarded {x[4]-t0}", flush=True)
+        print(f"macro {li}: MMA warp: start {r[0]-t0:7d} tmem_wait {r[2]-r[0]:6d} first_block_wait {r[1]-r[2]:6d} mma_issue+run {r[3]-r[1]:6d} | "
               f"epilogue: start {r[4]-t0:7d} wait_full {r[5]-r[4]:6d} work {r[6]-r[5]:6d}", flush=True)
 
 

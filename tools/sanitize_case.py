@@ -13,8 +13,14 @@ if which == "p":
 else:
     sd = synth.fa_state_dict(True, channels=8, seed=0); x = synth.fa_inputs(B, seed=1)
     m = Clair3_F(True, True, 8)
+reps = 1
 for a in sys.argv[3:]:
-    k, v = a.split("="); m.set_option(k, int(v))
+    k, v = a.split("=")
+    if k == "reps":
+        reps = int(v)          # extra forwards (ncu captures skip the first one)
+    else:
+        m.set_option(k, int(v))
 m.to(torch.device("cuda")); m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
-y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+for _ in range(reps):
+    y = m(torch.from_numpy(x).cuda()).cpu().numpy()
 print("ok", y.shape, float(y.sum()))
