@@ -13,6 +13,8 @@ sub-record per configuration:
     cascade   configs[3]  >= 1 M pileup sites then >= 100 k full-alignment sites (the ~10:1 ratio of
               run_clair3.py:303-313), fed from pinned HOST memory, split into N contiguous site ranges
               (clair3/CallVariantsFromCffiGPU.py:141-156)                            STRONG-scaled over ranks
+    pileup_counts  SURVEY.md 8f row N4: the pileup feature counter (calculate_clair3_pileup, src/clair3_pileup.c:142-476) on
+              decoded alignment records, aligned bases/s (its own metric; HBM-bound integer work)          weak
 
 A *step* is one forward of the hot path over one synthetic candidate-site batch.  Every timed region issues the K steps
 ``repeats`` times back to back so that it lasts >= 2 s whatever K is (``timed_region_s``, ``repeats`` in the record;
@@ -689,13 +691,112 @@ def run_cascade(ctx, model_p, model_f):
     return rec
 
 
+
+# ------------------------------------------------------------------------------------------------------- pileup feature counting
+PLP_CFG = dict(region=1 << 20, depth=40, read_len=8000, indel_rate=0.04, origin=10000, seed=5)
+
+
+def run_pileup_counts(ctx):
+    """SURVEY.md 8f row N4 (pileup half): calculate_clair3_pileup (src/clair3_pileup.c:142-476) on the GPU from decoded alignment
+    records.  A step = one c3b_plp_count over one synthetic region; value = device-resident records, e2e = pinned host records
+    in, count matrix / candidates out (H2D + 8 kernels + D2H inside the region).  Unit: aligned bases/s, a base = one
+    (read, covered column) pair that the reference's inner loop visits (sum of the per-column depths)."""
+    from clair3_b200 import pileup_counts as pc, synth_reads as sr
+    from oracle import pileup_oracle as po      # checker + CPU baseline only
+    args, dev, cfg = ctx.args, ctx.device, PLP_CFG
+    rec, ref, rs = sr.random_alignment(cfg["region"], depth=cfg["depth"], read_len=cfg["read_len"], seed=cfg["seed"],          # the same records on every rank (weak scaling)
+                                      
+                                       indel_rate=cfg["indel_rate"], origin=cfg["origin"])
+    start, end = cfg["origin"], cfg["origin"] + cfg["region"]
+    host = pc.BamRecords.from_dict(rec)
+    # parity on the bench input (a 65,536-column prefix keeps the CPU side bounded), then the CPU baseline on the same prefix
+    n_ctr = min(4, len(ctx.streams))
+    counters = [pc.PileupCounter(dev) for _ in range(n_ctr)]
+    sample_end = start + 65536
+    got = counters[0].count(host, start, sample_end, ref, rs).fetch()
+    t0 = time.perf_counter()
+    want = po.clair3_pileup(rec, start, sample_end, ref, rs)
+    cpu_s = time.perf_counter() - t0
+    exact = all(got[k].shape == want[k].shape and np.array_equal(got[k], want[k]) for k in ("matrix", "major", "stats", "cand_cols", "cand_ok"))
+    sample_bases = int(want["stats"][:, 0].sum())
+    if not exact:
+        raise RuntimeError("pileup_counts: GPU result differs from the oracle on the bench input")
+
+    drec = host.to_device(dev, ref)
+    full = counters[0].count(drec, start, end, None, rs).fetch()
+    bases = int(full["stats"][:, 0].sum())
+    n_cols, n_cand = len(full["major"]), len(full["cand_cols"])
+    ms_alone, launches_per_call = counters[0].last_ms()
+    K = args.steps
+    cnt = [0]
+
+    def issue_dev(n):
+        k = cnt[0]
+        for i in range(n):
+            j = (k + i) % n_ctr
+            with torch.cuda.stream(ctx.streams[j]):
+                counters[j].count(drec, start, end, None, rs)
+        cnt[0] = k + n
+
+    issue_dev(2 * n_ctr)
+    torch.cuda.synchronize(dev)
+    issue_dev(args.warmup)
+    r = ctx.calibrated(issue_dev, K)
+    value = bases * K * r["repeats"] * ctx.world / (r["ms"] * 1e-3)
+
+    # e2e: pinned host records in, results out, synchronous per call (the shape of the reference's per-chunk call)
+    pin = pc.BamRecords(**{k: torch.from_numpy(getattr(host, k).view({"uint16": np.int16, "uint32": np.int32}.get(getattr(host, k).dtype.name, getattr(host, k).dtype))).pin_memory().numpy().view(getattr(host, k).dtype)
+                           for k, _ in pc._FIELDS})
+    ecnt = [0]
+
+    def issue_e2e(n):
+        for i in range(n):
+            with torch.cuda.stream(ctx.streams[0]):
+                counters[0].count(pin, start, end, ref, rs).fetch()
+        ecnt[0] += n
+
+    issue_e2e(2)
+    re = ctx.calibrated(issue_e2e, max(2, K // 4), est_calls=2)
+    e2e_value = bases * max(2, K // 4) * re["repeats"] * ctx.world / (re["ms"] * 1e-3)
+    h2d = host.nbytes() + len(ref)
+    d2h = n_cols * (18 * 8 + 8 + 24) + n_cand * 9
+    pk = peaks()
+    # compulsory bytes of one call: the records and reference read once, the emitted arrays written once
+    alg_bytes = h2d + d2h + n_cand * 8
+    ach = alg_bytes / (ms_alone * 1e-3) / 1e9
+    out = {"metric": "aligned-bases/sec", "value": value, "unit": "bases/s", "scaling": "weak", "steps": K, "repeats": r["repeats"],
+           "timed_region_s": r["ms"] * 1e-3, "ms_per_step": r["ms"] / (K * r["repeats"]), "clocks": r["clocks"],
+           "columns_per_s": n_cols * K * r["repeats"] * ctx.world / (r["ms"] * 1e-3),
+           "gpu_launches": int(launches_per_call * K * r["repeats"]), "parity": "bit-exact vs oracle/pileup_oracle.c on the first 65536 columns of the bench input",
+           "config": {"workload": "pileup feature counting (calculate_clair3_pileup) over a synthetic %d-column region, mean depth %d, "
+                                  "%d reads of ~%d bases (%d CIGAR words), %d aligned bases, %d candidates; %d calls in flight"
+                                  % (cfg["region"], cfg["depth"], host.n_reads, cfg["read_len"], len(host.cigar), bases, n_cand, n_ctr)},
+           "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": max(2, K // 4),
+                   "repeats": re["repeats"], "timed_region_s": re["ms"] * 1e-3,
+                   "mode": "PileupCounter.count(pinned host records).fetch(): H2D of the records, 8 kernels, D2H of matrix / major / stats / candidates, synchronous per call"},
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
+                        "peak_source": pk["which"], "kernel": "all 8 kernels of one call, timed alone with CUDA events on its stream (c3b_plp_last_ms): %.3f ms" % ms_alone,
+                        "algorithmic_bytes_per_call": alg_bytes,
+                        "note": "compulsory bytes only (records + reference in, emitted arrays out); the count kernel is bound by dependent L2 "
+                                "loads (a binary search over the CIGAR prefix sums per read and column), not by bandwidth"}}
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = {"value": sample_bases / cpu_s, "unit": "bases/s", "cores": 1, "kind": "port",
+                               "sample": "oracle/pileup_oracle.c (plain-C restatement of calculate_clair3_pileup, single thread like the reference's "
+                                         "per-chunk call) on the first 65536 columns of the same records: %d aligned bases in %.3f s" % (sample_bases, cpu_s)}
+    for c in counters:
+        c.close()
+    del drec
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20, help="K: steps per repeat (every timed region repeats the K steps until it lasts >= 2 s)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workloads", default="pileup,fa,fa_dwell,cascade")
+    ap.add_argument("--workloads", default="pileup,fa,fa_dwell,cascade,pileup_counts")
     ap.add_argument("--workload", default=None, help="alias: run a single workload")
     ap.add_argument("--streams", type=int, default=12)
     ap.add_argument("--lstm-wg", type=int, default=0, help="epilogue warpgroups per LSTM sub-tile (0 = library default)")
@@ -762,6 +863,12 @@ def main():
     for wname in args.workloads:
         if wname == "cascade":
             subs[wname] = run_cascade(ctx, models["pileup"], models["fa"])
+        elif wname == "pileup_counts":
+            try:                                                      # a widening row: it must not be able to take the headline down
+                subs[wname] = run_pileup_counts(ctx)
+            except Exception as e:                                    # noqa: BLE001
+                subs[wname] = {"error": "%s: %s" % (type(e).__name__, e)}
+                torch.cuda.synchronize(device)
         else:
             subs[wname] = run_forward_workload(ctx, wname, models[wname])
 
@@ -785,7 +892,7 @@ def main():
         sampler.stop()
 
     if rank == 0:
-        head_name = "pileup" if "pileup" in subs else args.workloads[0]
+        head_name = "pileup" if "pileup" in subs else [n for n in args.workloads if "error" not in subs.get(n, {})][0]
         head = subs[head_name]
         e2e = dict(head["e2e"])
         if "h2d_bytes_per_step" not in e2e:                           # cascade as the head (single-workload runs)

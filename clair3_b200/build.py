@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libclair3b200.so")
 OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
-SOURCES = ["c3b_api.cu", "kernels_common.cu", "kernels_fp32.cu", "lstm_tc.cu", "fa_tc.cu", "pconv_tc.cu", "pconv2_tc.cu", "probe_tc.cu", "decode.cu", "proj_tc.cu", "tail_tc.cu", "lstm2x_tc.cu"]
+SOURCES = ["c3b_api.cu", "kernels_common.cu", "kernels_fp32.cu", "lstm_tc.cu", "fa_tc.cu", "pconv_tc.cu", "pconv2_tc.cu", "probe_tc.cu", "decode.cu", "proj_tc.cu", "tail_tc.cu", "lstm2x_tc.cu", "plp_counts.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
@@ -37,7 +37,8 @@ def _stale(target, deps):
 
 def build_library(force=False, verbose=False):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
-    headers.append(os.path.join(os.path.dirname(HERE), "include", "clair3_b200.h"))
+    for h in ("clair3_b200.h", "clair3_b200_debug.h", "clair3_b200_pileup.h"):
+        headers.append(os.path.join(os.path.dirname(HERE), "include", h))
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
     jobs = []

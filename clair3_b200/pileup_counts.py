@@ -1,0 +1,214 @@
+"""Host side of the GPU pileup feature counter (``include/clair3_b200_pileup.h``; SURVEY.md 8f row N4, pileup half).
+
+Mirrors the reference's binding of ``calculate_clair3_pileup`` (HKU-BAL/Clair3 ``preprocess/CreateTensorPileupFromCffi.py:30-85,
+127-180``: ``pileup_counts_clair3`` -> ``lib.calculate_clair3_pileup`` -> ``_plp_data_to_numpy``) from the point where htslib has
+decoded the alignment records: the caller hands over the ``bam1_t`` fields as arrays (``BamRecords``), the counting, candidate
+selection and - optionally - the Clair3_P forward over the candidates' windows run on the B200 without the count matrix ever
+leaving HBM.  No CPU fallback: everything here calls ``libclair3b200.so``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._ffi import C3BError, check, ffi, lib
+
+FLANKING = 16                 # shared/param_p.py flankingBaseNum; pileup_flanking_base_num src/clair3_pileup.h:93
+CHANNELS = 18
+
+_FIELDS = (("pos", np.int64), ("flag", np.uint16), ("mapq", np.uint8), ("cigar_off", np.int64), ("cigar", np.uint32),
+           ("seq_off", np.int64), ("seq", np.uint8), ("l_qseq", np.int32))
+
+
+class BamRecords:
+    """A coordinate-sorted run of alignment records of one contig in htslib's in-memory layout (``c3b_bam_records``):
+    pos / flag / mapq / l_qseq per read, CIGAR words ``len << 4 | op`` and 4-bit packed sequences addressed through
+    ``cigar_off`` / ``seq_off`` (n + 1 offsets each)."""
+
+    def __init__(self, **arrays):
+        missing = [k for k, _ in _FIELDS if k not in arrays]
+        if missing:
+            raise C3BError("BamRecords: missing %s" % ", ".join(missing))
+        for k, dt in _FIELDS:
+            setattr(self, k, np.ascontiguousarray(arrays[k], dtype=dt))
+        n = len(self.pos)
+        if not (len(self.flag) == len(self.mapq) == len(self.l_qseq) == n):
+            raise C3BError("BamRecords: per-read arrays differ in length")
+        if len(self.cigar_off) != n + 1 or len(self.seq_off) != n + 1:
+            raise C3BError("BamRecords: cigar_off / seq_off need n_reads + 1 entries")
+        if n:
+            if self.cigar_off[0] != 0 or self.seq_off[0] != 0 or self.cigar_off[-1] != len(self.cigar) or self.seq_off[-1] != len(self.seq):
+                raise C3BError("BamRecords: offsets do not span cigar / seq")
+            if (np.diff(self.cigar_off) < 0).any() or (np.diff(self.seq_off) < 0).any():
+                raise C3BError("BamRecords: offsets must not decrease")
+            if (np.diff(self.pos) < 0).any():
+                raise C3BError("BamRecords: records must be sorted by pos (a coordinate-sorted BAM)")
+            if ((self.l_qseq.astype(np.int64) + 1) // 2 > np.diff(self.seq_off)).any():
+                raise C3BError("BamRecords: a packed sequence is shorter than (l_qseq + 1) / 2 bytes")
+        self.n_reads = n
+
+    @classmethod
+    def from_dict(cls, d):
+        return d if isinstance(d, cls) else cls(**{k: d[k] for k, _ in _FIELDS})
+
+    def _struct(self):
+        s = ffi.new("c3b_bam_records *")
+        s.n_reads = self.n_reads
+        for k, dt in _FIELDS:
+            setattr(s, k, ffi.cast("const %s *" % _CTYPE[np.dtype(dt).name], getattr(self, k).ctypes.data))
+        return s
+
+    def nbytes(self):
+        return int(sum(getattr(self, k).nbytes for k, _ in _FIELDS))
+
+    def to_device(self, device, ref_seq=None):
+        """The same records as device tensors (``c3b_plp_count(..., on_device = 1)``): for callers whose decoder already writes
+        into HBM, and for timing the counter without the host copies."""
+        return DeviceBamRecords(self, device, ref_seq)
+
+
+_CTYPE = {"int64": "int64_t", "uint16": "uint16_t", "uint8": "uint8_t", "uint32": "uint32_t", "int32": "int32_t"}
+_TORCH_VIEW = {"uint16": np.int16, "uint32": np.int32}          # torch has no unsigned 16/32-bit tensors: same bits, signed view
+
+
+class DeviceBamRecords:
+    def __init__(self, rec, device, ref_seq=None):
+        self.n_reads = rec.n_reads
+        self.device = torch.device(device)
+        self.t = {}
+        for k, dt in _FIELDS:
+            a = getattr(rec, k)
+            v = a.view(_TORCH_VIEW.get(np.dtype(dt).name, a.dtype)) if a.size else a.astype(_TORCH_VIEW.get(np.dtype(dt).name, a.dtype))
+            self.t[k] = torch.from_numpy(np.ascontiguousarray(v)).to(self.device)
+        self.ref = None
+        if ref_seq is not None:
+            b = ref_seq.encode() if isinstance(ref_seq, str) else bytes(ref_seq)
+            self.ref = torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy()).to(self.device)
+
+    def _struct(self):
+        s = ffi.new("c3b_bam_records *")
+        s.n_reads = self.n_reads
+        for k, dt in _FIELDS:
+            setattr(s, k, ffi.cast("const %s *" % _CTYPE[np.dtype(dt).name], self.t[k].data_ptr()))
+        return s
+
+
+class PileupCounter:
+    """One counting workspace on one B200 (``c3b_plp``).  ``count()`` is asynchronous on the current torch stream of the device;
+    ``sizes()`` / ``fetch()`` wait for it."""
+
+    def __init__(self, device=0):
+        dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        if dev.type != "cuda":
+            raise C3BError("PileupCounter needs a CUDA device (no CPU fallback)")
+        self._device = dev
+        out = ffi.new("c3b_plp **")
+        check(lib().c3b_plp_create(out, dev.index or 0))
+        self._h = out[0]
+        self._keep = None
+        self._shape = None
+
+    def count(self, records, start, end, ref_seq, ref_start, min_depth=2, min_snp_af=0.08, min_indel_af=0.15, min_mq=5,
+              call_snp_only=False, call_ht=False, gvcf=False):
+        """Arguments as ``calculate_clair3_pileup`` takes them (src/clair3_pileup.c:142) with the region as 0-based
+        [start, end) and the reference bases of [ref_start, ref_start + len(ref_seq))."""
+        on_dev = isinstance(records, DeviceBamRecords)
+        rec = records if on_dev else BamRecords.from_dict(records)
+        prm = ffi.new("c3b_plp_params *")
+        prm.min_depth, prm.min_snp_af, prm.min_indel_af, prm.min_mq = int(min_depth), float(min_snp_af), float(min_indel_af), int(min_mq)
+        prm.call_snp_only, prm.call_ht, prm.gvcf = int(bool(call_snp_only)), int(bool(call_ht)), int(bool(gvcf))
+        st = rec._struct()
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        if on_dev:
+            if ref_seq is None:
+                ref_seq = rec.ref
+            if not (isinstance(ref_seq, torch.Tensor) and ref_seq.dtype == torch.uint8 and ref_seq.device == rec.device):
+                raise C3BError("count: device records need the reference bases as a uint8 tensor on the same device")
+            ref, refbuf = ref_seq.contiguous(), None
+            refptr, reflen = ffi.cast("const char *", ref.data_ptr()), ref.numel()
+        else:
+            ref = ref_seq.encode() if isinstance(ref_seq, str) else bytes(ref_seq)
+            refbuf = ffi.from_buffer(ref)
+            refptr, reflen = ffi.cast("const char *", refbuf), len(ref)
+        check(lib().c3b_plp_count(self._h, st, int(on_dev), int(start), int(end), refptr, int(ref_start), reflen, prm,
+                                  ffi.cast("void *", stream)))
+        self._keep = (rec, ref, refbuf, st)          # buffers stay alive while the copies / kernels are in flight
+        self._shape = (int(end) - int(start), bool(gvcf))
+        return self
+
+    def sizes(self):
+        a, b = ffi.new("int64_t *"), ffi.new("int64_t *")
+        check(lib().c3b_plp_sizes(self._h, a, b))
+        return int(a[0]), int(b[0])
+
+    def fetch(self):
+        """dict: matrix [n_cols,18] int64, major [n_cols], stats [n_cols,6] int32 (depth, ref, alt, del, ins, flags), cand_cols,
+        cand_ok (+ pos_ref_count / pos_total_count [end - start] after ``gvcf=True``)."""
+        nc, nk = self.sizes()
+        W, gvcf = self._shape
+        out = {"matrix": np.zeros((nc, CHANNELS), np.int64), "major": np.zeros(nc, np.int64), "stats": np.zeros((nc, 6), np.int32),
+               "cand_cols": np.zeros(nk, np.int64), "cand_ok": np.zeros(nk, np.uint8)}
+        c = ffi.cast
+        prc = ptc = ffi.NULL
+        if gvcf:
+            out["pos_ref_count"] = np.zeros(W, np.int64)
+            out["pos_total_count"] = np.zeros(W, np.int64)
+            prc, ptc = c("int64_t *", out["pos_ref_count"].ctypes.data), c("int64_t *", out["pos_total_count"].ctypes.data)
+        check(lib().c3b_plp_fetch(self._h, c("int64_t *", out["matrix"].ctypes.data), c("int64_t *", out["major"].ctypes.data),
+                                  c("int32_t *", out["stats"].ctypes.data), c("int64_t *", out["cand_cols"].ctypes.data),
+                                  c("uint8_t *", out["cand_ok"].ctypes.data), prc, ptc))
+        return out
+
+    def forward(self, model):
+        """Clair3_P over the 33-column window of EVERY candidate of the last count, straight from the device-resident matrix
+        (``c3b_forward_windows`` with ``on_device = 1``).  Returns (probabilities float32 [n_cand, 24|90] on the device, cand_ok
+        uint8 [n_cand] on the host): rows whose window is incomplete (``cand_ok == 0`` - the reference drops those candidates,
+        ``preprocess/CreateTensorPileupFromCffi.py:362-369``) are computed on zero-padded windows and must be ignored."""
+        nc, nk = self.sizes()
+        y = torch.empty((nk, model.out_dim), dtype=torch.float32, device=self._device)
+        ok = np.zeros(nk, np.uint8)
+        if nk == 0:
+            return y, ok
+        pm, ps, pk = ffi.new("const int64_t **"), ffi.new("const int64_t **"), ffi.new("const uint8_t **")
+        check(lib().c3b_plp_device(self._h, pm, ffi.NULL, ffi.NULL, ps, pk))
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        check(lib().c3b_forward_windows(model._handle, ffi.cast("void *", pm[0]), lib_const("C3B_DT_I64"), nc, ps[0], 1, nk,
+                                        ffi.cast("float *", y.data_ptr()), 1, 0, ffi.cast("void *", stream)))
+        check(lib().c3b_plp_fetch(self._h, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.cast("uint8_t *", ok.ctypes.data), ffi.NULL, ffi.NULL))
+        return y, ok
+
+    def last_ms(self):
+        ms, n = ffi.new("float *"), ffi.new("int *")
+        check(lib().c3b_plp_last_ms(self._h, ms, n))
+        return float(ms[0]), int(n[0])
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            lib().c3b_plp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def lib_const(name):
+    from ._ffi import CONSTANTS
+    return CONSTANTS[name]
+
+
+def pileup_counts_clair3(records, start, end, ref_seq, ref_start, counter=None, device=0, **params):
+    """The shape ``_plp_data_to_numpy`` returns (``preprocess/CreateTensorPileupFromCffi.py:127-180``): (np_counts [n_cols, 18],
+    positions structured array with 'major' / 'minor', candidate column indices, stats) - alt_info strings excepted."""
+    own = counter is None
+    counter = counter or PileupCounter(device)
+    try:
+        r = counter.count(records, start, end, ref_seq, ref_start, **params).fetch()
+    finally:
+        if own:
+            counter.close()
+    positions = np.zeros(len(r["major"]), dtype=[("major", int), ("minor", int)])
+    positions["major"] = r["major"]
+    return r["matrix"], positions, r["cand_cols"], r

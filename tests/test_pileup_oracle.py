@@ -1,0 +1,172 @@
+"""CPU checks of the pileup feature counter's oracle (oracle/pileup_oracle.c, the plain-C restatement of
+``calculate_clair3_pileup``, HKU-BAL/Clair3 src/clair3_pileup.c:142-476) and of the host side of the GPU counter.
+
+The reference ships no golden vectors for this function and neither libclair3 nor htslib can be built here, so the oracle is
+pinned by hand-worked known-answer cases (every expected number below is derived in the comments from the reference's source
+lines) and cross-checked against an independent random-access Python model (tests/plp_model.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from clair3_b200 import synth_reads as sr
+from oracle import pileup_oracle as po
+from plp_model import model_pileup
+
+KEYS = ("matrix", "major", "stats", "cand_cols", "cand_ok")
+
+
+def case_indels():
+    """ref 0..19 = AACCGGTTAACCGGTTAACC, region [0, 20).
+    r1 pos 2 fwd 5M       CCGGT          matches ref 2..6
+    r2 pos 2 rev 3M2D2M   CCG--AA        deletion of ref 5,6; A (mismatch) on ref 7, A on ref 8
+    r3 pos 4 fwd 2M1I2M   GG[T]TT        insertion 'T' after ref 5
+    r4 secondary (flag 256): dropped by the reader (src/medaka_bamiter.c:22)
+    r5 mapq 3 < min_mq 5: dropped (:24)"""
+    ref = "AACCGGTTAACCGGTTAACC"
+    rec = sr.records_from_lists([
+        (2, 0, 60, [("M", 5)], "CCGGT"),
+        (2, 16, 60, [("M", 3), ("D", 2), ("M", 2)], "CCGAA"),
+        (4, 0, 60, [("M", 2), ("I", 1), ("M", 2)], "GGTTT"),
+        (3, 256, 60, [("M", 6)], "CCGGTT"),
+        (3, 0, 3, [("M", 6)], "TTTTTT"),
+    ])
+    #            A   C   G   T  Ia  Ib  Da  Db   D | a   c   g   t  ia  ib  da  db   d
+    matrix = np.array([
+        [0, -1, 0, 0, 0, 0, 0, 0, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0],      # pos 2, ref C: C+ 1, c- 1 -> -sum on both strands (:368-369)
+        [0, -1, 0, 0, 0, 0, 0, 0, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0],      # pos 3, ref C
+        [0, 0, -2, 0, 0, 0, 0, 0, 0, 0, 0, -1, 0, 0, 0, 1, 1, 0],      # pos 4, ref G: r1,r3 G+, r2 g- and its 2D starts next: da=db=1
+        [0, 0, -2, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1],       # pos 5, ref G: r1,r3 G+ (r3 + insertion T: Ia=Ib=1), r2 deleted: d- 1
+        [0, 0, 0, -2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1],       # pos 6, ref T: r1,r3 T+, r2 deleted
+        [0, 0, 0, -1, 0, 0, 0, 0, 0, 1, 0, 0, -1, 0, 0, 0, 0, 0],      # pos 7, ref T: r3 T+, r2 a-: T+ = -fwd sum, t- = -rev sum (= -1!)
+        [0, 0, 0, 0, 0, 0, 0, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0],       # pos 8, ref A: r2 a- only
+    ], dtype=np.int64)
+    major = np.arange(2, 9, dtype=np.int64)
+    #                 depth ref alt del ins
+    stats5 = np.array([[2, 2, 0, 0, 0], [2, 2, 0, 0, 0], [3, 3, 0, 1, 0], [3, 2, 0, 0, 1], [3, 2, 0, 0, 0], [2, 1, 1, 0, 0],
+                       [1, 1, 0, 0, 0]], dtype=np.int32)
+    # call_ht (no flanking requirement), min_depth 2, snp 0.08, indel 0.15: pos 4 (del 1/3), pos 5 (ins 1/3), pos 7 (alt 1/2)
+    cand = np.array([2, 3, 5], dtype=np.int64)
+    return rec, ref, matrix, major, stats5, cand
+
+
+def case_quirks():
+    """ref 0..11 = ACGTACGTACGT, region [0, 12).
+    rA pos 0 fwd 4M      ANGT   N on column 1: feature index -1 -> the PREVIOUS column's feature 17 (src/clair3_pileup.c:280)
+    rB pos 0 fwd 2M3N2M  ACCG   reference skip over 2,3,4 (is_refskip: counted by htslib as covering, skipped by :251)"""
+    ref = "ACGTACGTACGT"
+    rec = sr.records_from_lists([
+        (0, 0, 60, [("M", 4)], "ANGT"),
+        (0, 0, 60, [("M", 2), ("N", 3), ("M", 2)], "ACCG"),
+    ])
+    matrix = np.zeros((7, 18), dtype=np.int64)
+    matrix[0, 0] = -2          # pos 0 ref A: two A+
+    matrix[0, 17] = 1          # ... plus column 1's N
+    matrix[1, 1] = -1          # pos 1 ref C: rB C+ (rA's N went to column 0)
+    matrix[2, 2] = -1          # pos 2 ref G: rA G+, rB skipped
+    matrix[3, 3] = -1          # pos 3 ref T
+    #       pos 4: only rB, reference-skipped: covered, all features zero
+    matrix[5, 1] = -1          # pos 5 ref C: rB C+
+    matrix[6, 2] = -1          # pos 6 ref G
+    major = np.arange(0, 7, dtype=np.int64)
+    stats5 = np.array([[2, 2, 0, 0, 0], [2, 1, 0, 0, 0], [1, 1, 0, 0, 0], [1, 1, 0, 0, 0], [1, 0, 0, 0, 0], [1, 1, 0, 0, 0],
+                       [1, 1, 0, 0, 0]], dtype=np.int32)      # depth counts the N base (:287); an all-skip column has depth max(1, 0)
+    zero_rows = np.array([0, 0, 0, 0, 1, 0, 0], dtype=bool)
+    return rec, ref, matrix, major, stats5, zero_rows
+
+
+def test_known_answer_indels():
+    rec, ref, matrix, major, stats5, cand = case_indels()
+    r = po.clair3_pileup(rec, 0, 20, ref, 0, call_ht=True)
+    assert np.array_equal(r["major"], major)
+    assert np.array_equal(r["matrix"], matrix)
+    assert np.array_equal(r["stats"][:, :5], stats5)
+    assert np.array_equal(r["cand_cols"], cand)
+    assert not r["cand_ok"].any()                     # 7 columns: no candidate has 16 columns on each side
+    # without call_ht nothing has 16 contiguous columns before it (:385-387)
+    assert len(po.clair3_pileup(rec, 0, 20, ref, 0)["cand_cols"]) == 0
+
+
+def test_known_answer_quirks():
+    rec, ref, matrix, major, stats5, zero_rows = case_quirks()
+    r = po.clair3_pileup(rec, 0, 12, ref, 0, call_ht=True, min_depth=1)
+    assert np.array_equal(r["major"], major)
+    assert np.array_equal(r["matrix"], matrix)
+    assert np.array_equal(r["stats"][:, :5], stats5)
+    assert np.array_equal((r["stats"][:, 5] & 2) != 0, zero_rows)
+
+
+def test_adjacent_deletions_merge_and_insertion_after_deletion():
+    """resolve_cigar2: '1D2D' is one 3-base deletion seen from the preceding base; an insertion right after a deletion is reported
+    on the deletion's last column with the inserted bases starting at qpos (first = 0, src/clair3_pileup.c:294)."""
+    ref = "ACGTACGTACGTACGT"
+    rec = sr.records_from_lists([
+        (0, 0, 60, [("M", 2), ("D", 1), ("D", 2), ("M", 2)], "ACCG"),           # deletion of 2,3,4
+        (0, 0, 60, [("M", 2), ("D", 3), ("M", 2)], "ACCG"),                     # the same deletion as one operation
+        (0, 16, 60, [("M", 3), ("D", 2), ("I", 2), ("M", 1)], "ACGTTG"),        # deletion of 3,4 then insertion TT, then ref 5
+    ])
+    r = po.clair3_pileup(rec, 0, 16, ref, 0, call_ht=True)
+    m = r["matrix"]
+    assert m[1, 6] == 2 and m[1, 7] == 2              # both forward reads: ONE deletion length (3) -> all 2, best 2
+    assert m[2, 15] == 1 and m[2, 16] == 1            # reverse read's 2D seen from column 2
+    assert m[4, 13] == 1 and m[4, 14] == 1            # its insertion is on the deletion's last column (4), reverse strand
+    assert m[2, 8] == 2 and m[3, 8] == 2 and m[4, 8] == 2 and m[3, 17] == 1 and m[4, 17] == 1
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_oracle_matches_random_access_model(seed):
+    wild = seed % 2 == 0
+    origin = [1000, 0, 5, 300][seed % 4]
+    gaps = [(origin + 100, origin + 160)] if seed % 3 == 0 else ()
+    rec, ref, rs = sr.random_alignment(260, depth=[3, 10, 25][seed % 3], read_len=[60, 150, 300][seed % 3], seed=seed, wild=wild,
+                                       origin=origin, gaps=gaps, indel_rate=0.08, n_rate=0.01)
+    kw = dict(min_depth=[2, 4][seed % 2], min_mq=[5, 20][seed % 2], call_snp_only=seed % 5 == 0, call_ht=seed % 7 == 0)
+    a = po.clair3_pileup(rec, origin, origin + 260, ref, rs, **kw)
+    b = model_pileup(rec, origin, origin + 260, ref, rs, **kw)
+    for k in KEYS:
+        assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), k
+
+
+def test_properties_on_a_larger_region():
+    rec, ref, rs = sr.random_alignment(6000, depth=30, read_len=1500, seed=11)
+    r = po.clair3_pileup(rec, 1000, 7000, ref, rs, gvcf=True)
+    m, st = r["matrix"], r["stats"]
+    assert len(r["major"]) == 6000 and (np.diff(r["major"]) == 1).all()
+    assert (m[:, [5, 7, 14, 16]] <= m[:, [4, 6, 13, 15]]).all()                 # best <= all
+    assert (st[:, 3] == m[:, 6] + m[:, 15]).all() and (st[:, 4] == m[:, 4] + m[:, 13]).all()
+    up = np.frombuffer(ref.upper().encode(), np.uint8)[r["major"] - rs]
+    idx = np.select([up == ord("C"), up == ord("G"), up == ord("T")], [1, 2, 3], 0)
+    rows = np.arange(len(m))
+    # the reference-base feature holds minus the strand's A+C+G+T total (:368-369): the four base features of a strand sum to
+    # 2 * (that feature) ... i.e. others - total = -ref count
+    for base in (0, 9):
+        four = m[:, base:base + 4].copy()
+        refcol = four[rows, idx].copy()
+        four[rows, idx] = 0
+        assert (refcol <= 0).all() and (-refcol >= four.sum(axis=1)).all()
+    assert len(r["cand_cols"]) > 10 and (np.diff(r["cand_cols"]) > 0).all()
+    assert (r["pos_total_count"] >= r["pos_ref_count"]).all()
+
+
+def test_host_side_validation_and_symbols():
+    from clair3_b200 import _ffi, pileup_counts as pc
+    rec, ref, rs = sr.random_alignment(300, 5, 100, seed=1)
+    b = pc.BamRecords.from_dict(rec)
+    assert b.n_reads == len(rec["pos"]) and b.nbytes() > 0
+    bad = dict(rec)
+    bad["pos"] = rec["pos"][::-1].copy()
+    with pytest.raises(_ffi.C3BError, match="sorted"):
+        pc.BamRecords.from_dict(bad)
+    bad = dict(rec)
+    bad["cigar_off"] = rec["cigar_off"][:-1]
+    with pytest.raises(_ffi.C3BError, match="n_reads \\+ 1"):
+        pc.BamRecords.from_dict(bad)
+    for name in ("c3b_plp_create", "c3b_plp_count", "c3b_plp_sizes", "c3b_plp_fetch", "c3b_plp_device", "c3b_plp_last_ms", "c3b_plp_destroy"):
+        assert name in _ffi.DECLARED_FUNCTIONS
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(_ffi.C3BError, match="no CUDA device|no CPU"):
+            pc.PileupCounter(0)

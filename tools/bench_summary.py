@@ -20,11 +20,14 @@ def main(path):
     print("| workload | scaling | value (device-resident) | e2e pipelined | e2e predict_stream | e2e sync per step | region s | SM MHz (reasons) | CPU baseline (cores) | parity max dp |")
     print("|---|---|---|---|---|---|---|---|---|---|")
     for name, w in d["workloads"].items():
+        if "error" in w:
+            print("| %s | failed: %s |" % (name, w["error"]))
+            continue
         e = w.get("e2e", {})
         ck = w.get("clocks") or {}
         cpu = w.get("cpu_baseline") or {}
         print("| %s | %s | %s | %s | %s | %s | %.2f | %s (%s) | %s (%s) | %s |" % (
-            name, w.get("scaling"), f(w["value"], " sites/s"), f(e.get("value"), ""), f((e.get("predict_stream") or {}).get("value"), ""),
+            name, w.get("scaling"), f(w["value"], " " + w.get("unit", "sites/s")), f(e.get("value"), ""), f((e.get("predict_stream") or {}).get("value"), ""),
             f((e.get("synchronous_per_step") or {}).get("value"), ""), w.get("timed_region_s", 0), ck.get("sm_mhz"), ",".join(ck.get("reasons") or []) or "none",
             f(cpu.get("value"), ""), cpu.get("cores"), ("%.1e" % w["parity_max_abs_dp"]) if w.get("parity_max_abs_dp") is not None else "n/a"))
     for name, w in d["workloads"].items():
@@ -47,6 +50,13 @@ def main(path):
         if "forward_windows" in w.get("e2e", {}):
             fw = w["e2e"]["forward_windows"]
             print("\nforward_windows e2e: %s (%s; %s H2D per step)" % (f(fw["value"], " sites/s"), fw["mode"], f(fw["h2d_bytes_per_step"], "B")))
+    pcw = d["workloads"].get("pileup_counts")
+    if pcw and "error" not in pcw:
+        r = pcw["roofline"]
+        print("\n## pileup_counts (SURVEY 8f N4): %s\n" % pcw["config"]["workload"])
+        print("%s device-resident, %s columns/s, e2e %s (%s); parity: %s; roofline (HBM): %.1f GB/s of %.0f = %.4f (%s); %s"
+              % (f(pcw["value"], " bases/s"), f(pcw["columns_per_s"]), f(pcw["e2e"]["value"], " bases/s"), pcw["e2e"]["mode"], pcw["parity"],
+                 r["achieved"], r["peak"], r["frac"], r["kernel"], r["note"]))
     wb = d.get("weight_broadcast") or {}
     if wb.get("bytes"):
         print("\nweight broadcast: %s via %s" % (f(wb["bytes"], "B"), wb.get("how")))
