@@ -752,7 +752,7 @@ def run_pileup_counts(ctx):
     def issue_e2e(n):
         for i in range(n):
             with torch.cuda.stream(ctx.streams[0]):
-                counters[0].count(pin, start, end, ref, rs).fetch()
+                counters[0].count(pin, start, end, ref, rs).fetch(pinned=True)
         ecnt[0] += n
 
     issue_e2e(2)
@@ -773,7 +773,7 @@ def run_pileup_counts(ctx):
                                   % (cfg["region"], cfg["depth"], host.n_reads, cfg["read_len"], len(host.cigar), bases, n_cand, n_ctr)},
            "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": max(2, K // 4),
                    "repeats": re["repeats"], "timed_region_s": re["ms"] * 1e-3,
-                   "mode": "PileupCounter.count(pinned host records).fetch(): H2D of the records, 8 kernels, D2H of matrix / major / stats / candidates, synchronous per call"},
+                   "mode": "PileupCounter.count(pinned host records).fetch(pinned=True): H2D of the records, 8 kernels, D2H of matrix / major / stats / candidates into page-locked buffers, synchronous per call"},
            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
                         "peak_source": pk["which"], "kernel": "all 8 kernels of one call, timed alone with CUDA events on its stream (c3b_plp_last_ms): %.3f ms" % ms_alone,
                         "algorithmic_bytes_per_call": alg_bytes,

@@ -28,6 +28,7 @@
 // written and re-read), 0.5 B per aligned base (packed sequence), ~27 B per read, and per column 72 + 24 + 4 B dense (written, read
 // once) + 144 + 8 + 24 B emitted: see DESIGN.md 3.8.
 #include <limits.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "c3b_internal.h"
@@ -158,17 +159,125 @@ struct CountArgs {
     int *status;
 };
 
-#define NODE(arr, i) (*((i) < NP ? &s_##arr[(i)] : &A.g_##arr[(i) - NP]))
+struct Pool {          // the tile's shared-memory indel nodes
+    uint32_t *meta;    // bit 31 insertion, bit 30 reverse strand, length
+    uint32_t *read;    // representative read
+    uint32_t *qpos;    // first inserted base in that read
+    uint32_t *cnt;
+    int32_t *next;
+    int *used;
+};
 
-__global__ void __launch_bounds__(TILE) plp_count_tile_kernel(CountArgs A) {
+#define NODE(arr, i) (*((i) < NP ? &P.arr[(i)] : &A.g_##arr[(i) - NP]))
+
+// What ONE read shows on ONE column (htslib's resolve_cigar2 as a pure function of the operation k that covers the column) and
+// what the reference's inner loop does with it (src/clair3_pileup.c:249-308).  cw / xend / y0 are operation k's CIGAR word, end
+// offset and query start; nb is the read base at qpos (prefetched by the caller when the operation is a match).
+__device__ __forceinline__ void plp_visit(const CountArgs &A, const Pool &P, int32_t *cnt, const int tid, const int64_t r,
+                                          const int64_t cb, const int nc, const int off, const int k, const uint32_t cw,
+                                          const int xend, const int y0, const int rev, const uint8_t *sq, const int lq, const int nb,
+                                          int &depth, int &head) {
+    const uint32_t op = cw & 15u;
+    const int l = (int)(cw >> 4);
+    if (op == 3u) return;                                                    // is_refskip, src/clair3_pileup.c:251
+    long long indel = 0;
+    if (off == xend - 1 && k + 1 < nc) {                                     // resolve_cigar2: peek the next operation
+        uint32_t c2 = __ldg(A.R.cigar + cb + k + 1);
+        const uint32_t op2 = c2 & 15u;
+        if (op2 == 2u && op != 2u) {
+            indel = -(long long)(c2 >> 4);
+            for (int j = k + 2; j < nc; ++j) {
+                c2 = __ldg(A.R.cigar + cb + j);
+                if ((c2 & 15u) == 2u) indel -= (long long)(c2 >> 4); else break;
+            }
+        } else if (op2 == 1u) {
+            indel = (long long)(c2 >> 4);
+            for (int j = k + 2; j < nc; ++j) {
+                c2 = __ldg(A.R.cigar + cb + j);
+                const uint32_t o = c2 & 15u;
+                if (o == 1u) indel += (long long)(c2 >> 4); else if (o != 6u) break;
+            }
+        } else if (op2 == 6u && k + 2 < nc) {
+            long long l3 = 0;
+            for (int j = k + 2; j < nc; ++j) {
+                c2 = __ldg(A.R.cigar + cb + j);
+                const uint32_t o = c2 & 15u;
+                if (o == 1u) l3 += (long long)(c2 >> 4); else if (ref_cons(o)) break;
+            }
+            if (l3 > 0) indel = l3;
+        }
+    }
+    const bool is_del = (op == 2u);
+    const long long qpos = is_del ? (long long)y0 : (long long)y0 + (off - (xend - l));
+
+    // the column's base / deletion counters, src/clair3_pileup.c:276-290
+    int base_i;
+    if (is_del) {
+        base_i = rev ? 17 : 8;
+    } else {
+        const int t = nb == 1 ? 0 : nb == 2 ? 1 : nb == 4 ? 2 : nb == 8 ? 3 : -1;
+        base_i = t < 0 ? -1 : t + 9 * rev;
+    }
+    ++depth;
+    cnt[(base_i >= 0 ? base_i : NFEAT) * TILE + tid] += 1;
+
+    if (indel != 0) {                                                        // :253-272 (deletion table), :293-307 (insertion strings)
+        const int kind = indel > 0 ? 1 : 0;
+        long long len = indel > 0 ? indel : -indel;
+        if (len >= (1ll << 30)) { atomicOr(A.status, 4); len = (1ll << 30) - 1; }
+        const uint32_t meta = ((uint32_t)kind << 31) | ((uint32_t)rev << 30) | (uint32_t)len;
+        const long long q0 = qpos + (is_del ? 0 : 1);
+        int c = 0;
+        bool found = false;
+        for (int i = head; i >= 0; i = NODE(next, i)) {
+            if (NODE(meta, i) != meta) continue;
+            bool same = true;
+            if (kind) {
+                const uint32_t rr = NODE(read, i);
+                const long long rq = (long long)NODE(qpos, i);
+                const uint8_t *s2 = A.R.seq + __ldg(A.R.seq_off + rr);
+                const int lq2 = __ldg(A.R.l_qseq + rr);
+                for (long long j = 0; j < len; ++j)
+                    if (nib_at(sq, lq, q0 + j) != nib_at(s2, lq2, rq + j)) { same = false; break; }
+            }
+            if (same) { c = (int)(NODE(cnt, i) += 1u); found = true; break; }
+        }
+        if (!found) {
+            int slot = atomicAdd(P.used, 1);
+            if (slot >= NP) {
+                const int g = atomicAdd(A.g_used, 1);
+                if (g >= G_POOL) { atomicOr(A.status, 1); slot = -1; } else slot = NP + g;
+            }
+            if (slot >= 0) {
+                NODE(meta, slot) = meta;
+                NODE(read, slot) = (uint32_t)r;
+                NODE(qpos, slot) = (uint32_t)q0;
+                NODE(cnt, slot) = 1u;
+                NODE(next, slot) = head;
+                head = slot;
+            }
+            c = 1;
+        }
+        const int f_all = kind ? (rev ? 13 : 4) : (rev ? 15 : 6);
+        cnt[f_all * TILE + tid] += 1;                                        // stats.sum / all_count
+        if (c > cnt[(f_all + 1) * TILE + tid]) cnt[(f_all + 1) * TILE + tid] = c;   // stats.max / best_count
+    }
+}
+
+// ILP reads are resolved side by side: their binary searches (about 12 dependent L2 loads each for a 5,000-word CIGAR) and the
+// loads that follow are independent chains, so the latency that bounds this kernel is paid once per ILP reads (measured: §7).
+template <int ILP>
+__global__ void __launch_bounds__(TILE, ILP == 4 ? 3 : 4) plp_count_tile_kernel(CountArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t *cnt = reinterpret_cast<int32_t *>(smem_raw);                       // [NCNT][TILE]
-    uint32_t *s_meta = reinterpret_cast<uint32_t *>(cnt + NCNT * TILE);          // [NP] bit 31 insertion, bit 30 reverse, length
-    uint32_t *s_read = s_meta + NP;                                              // representative read
-    uint32_t *s_qpos = s_read + NP;                                              // first inserted base in that read
-    uint32_t *s_cnt = s_qpos + NP;
-    int32_t *s_next = reinterpret_cast<int32_t *>(s_cnt + NP);
     __shared__ int s_used;
+    Pool P;
+    P.meta = reinterpret_cast<uint32_t *>(cnt + NCNT * TILE);
+    P.read = P.meta + NP;
+    P.qpos = P.read + NP;
+    P.cnt = P.qpos + NP;
+    P.next = reinterpret_cast<int32_t *>(P.cnt + NP);
+    P.used = &s_used;
     const int tid = threadIdx.x;
     const int64_t tile_start = A.start + (int64_t)blockIdx.x * TILE;
     const int64_t tile_end = tile_start + TILE < A.end ? tile_start + TILE : A.end;
@@ -192,107 +301,67 @@ __global__ void __launch_bounds__(TILE) plp_count_tile_kernel(CountArgs A) {
 
     int depth = 0, head = -1;
     bool covered = false;
-    for (int64_t r = lo; r < hi; ++r) {
-        const int64_t rp = __ldg(A.R.pos + r), re = __ldg(A.rend + r);
-        if (!active || p < rp || p >= re) continue;
-        covered = true;                                                          // n_plp > 0: htslib reports the column
-        const int64_t cb = __ldg(A.R.cigar_off + r);
-        const int nc = (int)(__ldg(A.R.cigar_off + r + 1) - cb);
-        const int off = (int)(p - rp);
-        int a = 0, b = nc;
-        while (a < b) { const int m = (a + b) >> 1; if (__ldg(A.opx_end + cb + m) > off) b = m; else a = m + 1; }
-        const int k = a;
-        const uint32_t cw = __ldg(A.R.cigar + cb + k);
-        const uint32_t op = cw & 15u;
-        const int l = (int)(cw >> 4);
-        if (op == 3u) continue;                                                  // is_refskip, src/clair3_pileup.c:251
-        const int xend = __ldg(A.opx_end + cb + k);
-        long long indel = 0;
-        if (off == xend - 1 && k + 1 < nc) {                                     // resolve_cigar2: peek the next operation
-            uint32_t c2 = __ldg(A.R.cigar + cb + k + 1);
-            const uint32_t op2 = c2 & 15u;
-            if (op2 == 2u && op != 2u) {
-                indel = -(long long)(c2 >> 4);
-                for (int j = k + 2; j < nc; ++j) {
-                    c2 = __ldg(A.R.cigar + cb + j);
-                    if ((c2 & 15u) == 2u) indel -= (long long)(c2 >> 4); else break;
+    for (int64_t r0 = lo; r0 < hi; r0 += ILP) {
+        int64_t cb[ILP];
+        int nc[ILP], off[ILP], a[ILP], b[ILP];
+        bool in[ILP];
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) {
+            const int64_t r = r0 + j;
+            in[j] = false;
+            a[j] = b[j] = 0;
+            cb[j] = 0; nc[j] = 0; off[j] = 0;
+            if (r < hi) {
+                const int64_t rp = __ldg(A.R.pos + r), re = __ldg(A.rend + r);
+                if (active && p >= rp && p < re) {
+                    in[j] = true;
+                    cb[j] = __ldg(A.R.cigar_off + r);
+                    nc[j] = (int)(__ldg(A.R.cigar_off + r + 1) - cb[j]);
+                    off[j] = (int)(p - rp);
+                    b[j] = nc[j];
                 }
-            } else if (op2 == 1u) {
-                indel = (long long)(c2 >> 4);
-                for (int j = k + 2; j < nc; ++j) {
-                    c2 = __ldg(A.R.cigar + cb + j);
-                    const uint32_t o = c2 & 15u;
-                    if (o == 1u) indel += (long long)(c2 >> 4); else if (o != 6u) break;
-                }
-            } else if (op2 == 6u && k + 2 < nc) {
-                long long l3 = 0;
-                for (int j = k + 2; j < nc; ++j) {
-                    c2 = __ldg(A.R.cigar + cb + j);
-                    const uint32_t o = c2 & 15u;
-                    if (o == 1u) l3 += (long long)(c2 >> 4); else if (ref_cons(o)) break;
-                }
-                if (l3 > 0) indel = l3;
             }
         }
-        const bool is_del = (op == 2u);
-        const int y0 = __ldg(A.opy + cb + k);
-        const long long qpos = is_del ? (long long)y0 : (long long)y0 + (off - (xend - l));
-        const int rev = (__ldg(A.R.flag + r) >> 4) & 1;
-        const uint8_t *sq = A.R.seq + __ldg(A.R.seq_off + r);
-        const int lq = __ldg(A.R.l_qseq + r);
-
-        // the column's base / deletion counters, src/clair3_pileup.c:276-290
-        int base_i;
-        if (is_del) {
-            base_i = rev ? 17 : 8;
-        } else {
-            const int nb = nib_at(sq, lq, qpos);
-            const int t = nb == 1 ? 0 : nb == 2 ? 1 : nb == 4 ? 2 : nb == 8 ? 3 : -1;
-            base_i = t < 0 ? -1 : t + 9 * rev;
+        bool more = true;                                   // the operation on this column: first one whose end offset exceeds off
+        while (more) {
+            more = false;
+#pragma unroll
+            for (int j = 0; j < ILP; ++j) {
+                if (a[j] < b[j]) {
+                    const int m = (a[j] + b[j]) >> 1;
+                    if (__ldg(A.opx_end + cb[j] + m) > off[j]) b[j] = m; else a[j] = m + 1;
+                    more = true;
+                }
+            }
         }
-        ++depth;
-        cnt[(base_i >= 0 ? base_i : NFEAT) * TILE + tid] += 1;
-
-        if (indel != 0) {                                                        // :253-272 (deletion table), :293-307 (insertion strings)
-            const int kind = indel > 0 ? 1 : 0;
-            long long len = indel > 0 ? indel : -indel;
-            if (len >= (1ll << 30)) { atomicOr(A.status, 4); len = (1ll << 30) - 1; }
-            const uint32_t meta = ((uint32_t)kind << 31) | ((uint32_t)rev << 30) | (uint32_t)len;
-            const long long q0 = qpos + (is_del ? 0 : 1);
-            int c = 0;
-            bool found = false;
-            for (int i = head; i >= 0; i = NODE(next, i)) {
-                if (NODE(meta, i) != meta) continue;
-                bool same = true;
-                if (kind) {
-                    const uint32_t rr = NODE(read, i);
-                    const long long rq = (long long)NODE(qpos, i);
-                    const uint8_t *s2 = A.R.seq + __ldg(A.R.seq_off + rr);
-                    const int lq2 = __ldg(A.R.l_qseq + rr);
-                    for (long long j = 0; j < len; ++j)
-                        if (nib_at(sq, lq, q0 + j) != nib_at(s2, lq2, rq + j)) { same = false; break; }
-                }
-                if (same) { c = (int)(NODE(cnt, i) += 1u); found = true; break; }
+        uint32_t cw[ILP];
+        int xend[ILP], y0[ILP], rev[ILP], lq[ILP], nb[ILP];
+        const uint8_t *sq[ILP];
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) {
+            cw[j] = 0; xend[j] = 0; y0[j] = 0; rev[j] = 0; lq[j] = 0; sq[j] = A.R.seq;
+            if (in[j]) {
+                const int64_t r = r0 + j;
+                cw[j] = __ldg(A.R.cigar + cb[j] + a[j]);
+                xend[j] = __ldg(A.opx_end + cb[j] + a[j]);
+                y0[j] = __ldg(A.opy + cb[j] + a[j]);
+                rev[j] = (__ldg(A.R.flag + r) >> 4) & 1;
+                sq[j] = A.R.seq + __ldg(A.R.seq_off + r);
+                lq[j] = __ldg(A.R.l_qseq + r);
             }
-            if (!found) {
-                int slot = atomicAdd(&s_used, 1);
-                if (slot >= NP) {
-                    const int g = atomicAdd(A.g_used, 1);
-                    if (g >= G_POOL) { atomicOr(A.status, 1); slot = -1; } else slot = NP + g;
-                }
-                if (slot >= 0) {
-                    NODE(meta, slot) = meta;
-                    NODE(read, slot) = (uint32_t)r;
-                    NODE(qpos, slot) = (uint32_t)q0;
-                    NODE(cnt, slot) = 1u;
-                    NODE(next, slot) = head;
-                    head = slot;
-                }
-                c = 1;
+        }
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) {
+            nb[j] = 0;
+            const uint32_t op = cw[j] & 15u;
+            if (in[j] && op != 2u && op != 3u) nb[j] = nib_at(sq[j], lq[j], (long long)y0[j] + (off[j] - (xend[j] - (int)(cw[j] >> 4))));
+        }
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) {
+            if (in[j]) {
+                covered = true;                              // n_plp > 0: htslib reports the column
+                plp_visit(A, P, cnt, tid, r0 + j, cb[j], nc[j], off[j], a[j], cw[j], xend[j], y0[j], rev[j], sq[j], lq[j], nb[j], depth, head);
             }
-            const int f_all = kind ? (rev ? 13 : 4) : (rev ? 15 : 6);
-            cnt[f_all * TILE + tid] += 1;                                        // stats.sum / all_count
-            if (c > cnt[(f_all + 1) * TILE + tid]) cnt[(f_all + 1) * TILE + tid] = c;   // stats.max / best_count
         }
     }
 
@@ -558,6 +627,7 @@ struct c3b_plp {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int launches = 0;
+    int ilp = 4;                        // reads resolved side by side in the count kernel (1 | 2 | 4; env C3B_PLP_ILP for A/B runs)
     int64_t *host_counters = nullptr;   // pinned: n_cols, n_cand, (g_used | status << 32)
     int64_t n_cols = -1, n_cand = -1;
 };
@@ -583,6 +653,10 @@ int c3b_plp_create(c3b_plp **out, int device_ordinal) {
     C3B_CUDA(cudaSetDevice(device_ordinal));
     c3b_plp *w = new c3b_plp();
     w->device = device_ordinal;
+    if (const char *e = getenv("C3B_PLP_ILP")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4) w->ilp = v;
+    }
     if (cudaEventCreate(&w->ev0) != cudaSuccess || cudaEventCreate(&w->ev1) != cudaSuccess ||
         cudaMallocHost((void **)&w->host_counters, 4 * sizeof(int64_t)) != cudaSuccess) {
         c3b_set_error("c3b_plp_create: event / pinned allocation failed");
@@ -694,7 +768,11 @@ int c3b_plp_count(c3b_plp *w, const c3b_bam_records *reads, int on_device, int64
         A.g_meta = w->g_meta.as<uint32_t>(); A.g_read = w->g_read.as<uint32_t>(); A.g_qpos = w->g_qpos.as<uint32_t>();
         A.g_cnt = w->g_cnt.as<uint32_t>(); A.g_next = w->g_next.as<int32_t>(); A.g_used = g_used; A.status = status;
         const size_t smem = (size_t)NCNT * TILE * 4 + (size_t)NP * 20;
-        plp_count_tile_kernel<<<tiles, TILE, smem, s>>>(A);
+        switch (w->ilp) {
+            case 1: plp_count_tile_kernel<1><<<tiles, TILE, smem, s>>>(A); break;
+            case 2: plp_count_tile_kernel<2><<<tiles, TILE, smem, s>>>(A); break;
+            default: plp_count_tile_kernel<4><<<tiles, TILE, smem, s>>>(A); break;
+        }
         plp_scan_tiles_kernel<<<1, 1024, 0, s>>>(w->tile_cov.as<int32_t>(), w->tile_off.as<int64_t>(), tiles, n_cols_dev);
         EmitArgs E;
         E.start = start; E.end = end; E.call_ht = params->call_ht;

@@ -107,6 +107,7 @@ class PileupCounter:
         self._h = out[0]
         self._keep = None
         self._shape = None
+        self._pin = {}
 
     def count(self, records, start, end, ref_seq, ref_start, min_depth=2, min_snp_af=0.08, min_indel_af=0.15, min_mq=5,
               call_snp_only=False, call_ht=False, gvcf=False):
@@ -141,18 +142,34 @@ class PileupCounter:
         check(lib().c3b_plp_sizes(self._h, a, b))
         return int(a[0]), int(b[0])
 
-    def fetch(self):
+    def _pinned(self, name, shape, dtype):
+        """A reusable page-locked host buffer (grown on demand): D2H into pinned memory runs at the PCIe rate, into a fresh
+        pageable numpy array at a fraction of it (page faults + staging)."""
+        n = int(np.prod(shape))
+        t = self._pin.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1) + max(n, 1) // 4, dtype=dtype).pin_memory()
+            self._pin[name] = t
+        return t[:n].view(*shape).numpy()
+
+    def fetch(self, pinned=False):
         """dict: matrix [n_cols,18] int64, major [n_cols], stats [n_cols,6] int32 (depth, ref, alt, del, ins, flags), cand_cols,
-        cand_ok (+ pos_ref_count / pos_total_count [end - start] after ``gvcf=True``)."""
+        cand_ok (+ pos_ref_count / pos_total_count [end - start] after ``gvcf=True``).  ``pinned=True``: the arrays are views of
+        the counter's page-locked staging buffers - no allocation, full PCIe rate - valid until the next ``fetch``."""
         nc, nk = self.sizes()
         W, gvcf = self._shape
-        out = {"matrix": np.zeros((nc, CHANNELS), np.int64), "major": np.zeros(nc, np.int64), "stats": np.zeros((nc, 6), np.int32),
-               "cand_cols": np.zeros(nk, np.int64), "cand_ok": np.zeros(nk, np.uint8)}
+        if pinned:
+            out = {"matrix": self._pinned("matrix", (nc, CHANNELS), torch.int64), "major": self._pinned("major", (nc,), torch.int64),
+                   "stats": self._pinned("stats", (nc, 6), torch.int32), "cand_cols": self._pinned("cand_cols", (nk,), torch.int64),
+                   "cand_ok": self._pinned("cand_ok", (nk,), torch.uint8)}
+        else:
+            out = {"matrix": np.zeros((nc, CHANNELS), np.int64), "major": np.zeros(nc, np.int64), "stats": np.zeros((nc, 6), np.int32),
+                   "cand_cols": np.zeros(nk, np.int64), "cand_ok": np.zeros(nk, np.uint8)}
         c = ffi.cast
         prc = ptc = ffi.NULL
         if gvcf:
-            out["pos_ref_count"] = np.zeros(W, np.int64)
-            out["pos_total_count"] = np.zeros(W, np.int64)
+            out["pos_ref_count"] = self._pinned("prc", (W,), torch.int64) if pinned else np.zeros(W, np.int64)
+            out["pos_total_count"] = self._pinned("ptc", (W,), torch.int64) if pinned else np.zeros(W, np.int64)
             prc, ptc = c("int64_t *", out["pos_ref_count"].ctypes.data), c("int64_t *", out["pos_total_count"].ctypes.data)
         check(lib().c3b_plp_fetch(self._h, c("int64_t *", out["matrix"].ctypes.data), c("int64_t *", out["major"].ctypes.data),
                                   c("int32_t *", out["stats"].ctypes.data), c("int64_t *", out["cand_cols"].ctypes.data),
@@ -192,6 +209,29 @@ class PileupCounter:
             self.close()
         except Exception:
             pass
+
+
+def chunk_region(contig_length, chunk_id, chunk_num):
+    """The 1-based contig slice [ctg_start, ctg_end] of chunk ``chunk_id`` (1-based, as ``--chunk_id``) of ``chunk_num``:
+    ``preprocess/CreateTensorPileupFromCffi.py:249,281-292`` (no BED / VCF restriction)."""
+    if not 1 <= chunk_id <= chunk_num:
+        raise C3BError("chunk_region: chunk_id %d outside 1..%d" % (chunk_id, chunk_num))
+    cid = chunk_id - 1
+    chunk_size = contig_length // chunk_num + 1 if contig_length % chunk_num else contig_length // chunk_num
+    ctg_start = chunk_size * cid
+    return ctg_start, ctg_start + chunk_size
+
+
+def counting_region(ctg_start, ctg_end, no_of_positions=2 * FLANKING + 1):
+    """The 0-based, end-exclusive [start, end) that reaches ``calculate_clair3_pileup`` for a 1-based contig slice: the slice is
+    widened by ``no_of_positions`` (``:305-311``), written as the region string ``name:{max(0, start - 1)}-{end}`` (``:55``) and
+    parsed by ``hts_parse_reg``, which turns the 1-based start into ``start - 1`` (clipped at 0) and keeps the end
+    (``src/clair3_pileup.c:148-151``)."""
+    ctg_start = max(1, ctg_start)
+    extend_start = max(1, ctg_start - no_of_positions)
+    extend_end = ctg_end + no_of_positions
+    s = max(0, extend_start - 1)
+    return max(0, s - 1), extend_end
 
 
 def lib_const(name):

@@ -81,6 +81,9 @@ def test_long_reads_large_region(counter):
     got = counter.count(rec, 1000, 41000, ref, rs, gvcf=True).fetch()
     want = po.clair3_pileup(rec, 1000, 41000, ref, rs, gvcf=True)
     _compare("long_reads_40k", got, want, gvcf=True)
+    pinned = counter.fetch(pinned=True)              # the page-locked staging path returns the same arrays
+    for k in got:
+        assert np.array_equal(pinned[k], got[k]), k
     ms, launches = counter.last_ms()
     assert launches == 8 and ms > 0
     _STATS["long_reads_40k"]["device_ms"] = ms

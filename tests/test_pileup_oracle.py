@@ -170,3 +170,17 @@ def test_host_side_validation_and_symbols():
     if not torch.cuda.is_available():
         with pytest.raises(_ffi.C3BError, match="no CUDA device|no CPU"):
             pc.PileupCounter(0)
+
+
+def test_chunk_and_counting_regions():
+    """preprocess/CreateTensorPileupFromCffi.py:281-292,305-311,55 restated: the chunks tile the contig, the counting region is the
+    slice widened by 33 positions on each side, shifted by the two 1-based -> 0-based conversions on its way into C."""
+    from clair3_b200 import _ffi, pileup_counts as pc
+    L, n = 1_000_003, 7
+    cuts = [pc.chunk_region(L, i, n) for i in range(1, n + 1)]
+    assert cuts[0][0] == 0 and cuts[-1][1] >= L and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+    assert pc.chunk_region(700, 2, 7) == (100, 200)
+    assert pc.counting_region(0, 100) == (0, 133)                 # start clipped at 1, then at 0 twice
+    assert pc.counting_region(1000, 2000) == (965, 2033)          # 1000 - 33 = 967 (1-based) -> "966" -> 965 (0-based)
+    with pytest.raises(_ffi.C3BError):
+        pc.chunk_region(100, 0, 4)

@@ -40,10 +40,15 @@ def main():
         region = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 18
         rec, ref, rs = sr.random_alignment(region, depth=40, read_len=8000, seed=5, indel_rate=0.04, origin=10000)
         d = pc.BamRecords.from_dict(rec).to_device(torch.device("cuda:0"), ref)
-        for _ in range(3):
+        reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+        ms = []
+        for _ in range(reps):
             ctr.count(d, 10000, 10000 + region, None, rs)
             torch.cuda.synchronize()
-            print("count: %.3f ms, %d launches" % ctr.last_ms(), ctr.sizes())
+            ms.append(ctr.last_ms()[0])
+        nc, nk = ctr.sizes()
+        print("ILP=%s region %d: count %s ms (median %.3f), %d columns, %d candidates"
+              % (os.environ.get("C3B_PLP_ILP", "default"), region, ["%.3f" % m for m in ms[:8]], float(np.median(ms[1:] or ms)), nc, nk))
         return
     from test_pileup_oracle import case_indels, case_quirks
     ok = True
