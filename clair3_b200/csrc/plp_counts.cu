@@ -39,7 +39,7 @@ namespace {
 constexpr int TILE = 256;
 constexpr int NFEAT = 18;
 constexpr int NCNT = 19;          // 18 features + the index -1 counter
-constexpr int NP = 1408;          // shared-memory indel nodes per tile (20 B each)
+constexpr int NP = 704;           // shared-memory indel nodes per tile (20 B each): 33.5 KB per CTA with the counters -> 6 CTAs per SM
 constexpr int FLANK = 16;         // pileup_flanking_base_num, src/clair3_pileup.h:93
 constexpr int G_POOL = 1 << 21;   // global overflow nodes per workspace
 
@@ -267,7 +267,7 @@ __device__ __forceinline__ void plp_visit(const CountArgs &A, const Pool &P, int
 // ILP reads are resolved side by side: their binary searches (about 12 dependent L2 loads each for a 5,000-word CIGAR) and the
 // loads that follow are independent chains, so the latency that bounds this kernel is paid once per ILP reads (measured: §7).
 template <int ILP>
-__global__ void __launch_bounds__(TILE, ILP == 4 ? 3 : 4) plp_count_tile_kernel(CountArgs A) {
+__global__ void __launch_bounds__(TILE, ILP == 4 ? 3 : ILP == 2 ? 4 : 6) plp_count_tile_kernel(CountArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t *cnt = reinterpret_cast<int32_t *>(smem_raw);                       // [NCNT][TILE]
     __shared__ int s_used;
@@ -288,14 +288,17 @@ __global__ void __launch_bounds__(TILE, ILP == 4 ? 3 : 4) plp_count_tile_kernel(
     if (tid == 0) s_used = 0;
     __syncthreads();
 
-    // reads that can touch the tile
+    // reads that can touch this WARP's 32 columns (per tile the loop ran 1.7x as many warp iterations: a 256-column tile sees
+    // reads that end before or start after most of its warps)
     int64_t lo, hi;
     {
-        int64_t a = 0, b = A.R.n;
-        while (a < b) { const int64_t m = (a + b) >> 1; if (__ldg(A.pmax + m) > tile_start) b = m; else a = m + 1; }
+        const int64_t w_start = tile_start + (tid & ~31);
+        const int64_t w_end = w_start + 32 < tile_end ? w_start + 32 : tile_end;
+        int64_t a = 0, b = w_start < tile_end ? A.R.n : 0;
+        while (a < b) { const int64_t m = (a + b) >> 1; if (__ldg(A.pmax + m) > w_start) b = m; else a = m + 1; }
         lo = a;
-        a = lo; b = A.R.n;
-        while (a < b) { const int64_t m = (a + b) >> 1; if (__ldg(A.R.pos + m) >= tile_end) b = m; else a = m + 1; }
+        b = w_start < tile_end ? A.R.n : 0;
+        while (a < b) { const int64_t m = (a + b) >> 1; if (__ldg(A.R.pos + m) >= w_end) b = m; else a = m + 1; }
         hi = a;
     }
 
@@ -627,7 +630,10 @@ struct c3b_plp {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int launches = 0;
-    int ilp = 4;                        // reads resolved side by side in the count kernel (1 | 2 | 4; env C3B_PLP_ILP for A/B runs)
+    int ilp = 1;                        // reads resolved side by side in the count kernel (1 | 2 | 4; env C3B_PLP_ILP for A/B runs).
+                                        // Measured (1,048,576 columns, depth 40): 1.109 / 1.106 / 1.386 ms - the kernel is issue-bound, not
+                                        // latency-bound (ncu: 470 warp instructions per read and warp, 22 of 32 lanes active), so the extra
+                                        // registers of ILP 4 only cost occupancy
     int64_t *host_counters = nullptr;   // pinned: n_cols, n_cand, (g_used | status << 32)
     int64_t n_cols = -1, n_cand = -1;
 };
@@ -769,9 +775,9 @@ int c3b_plp_count(c3b_plp *w, const c3b_bam_records *reads, int on_device, int64
         A.g_cnt = w->g_cnt.as<uint32_t>(); A.g_next = w->g_next.as<int32_t>(); A.g_used = g_used; A.status = status;
         const size_t smem = (size_t)NCNT * TILE * 4 + (size_t)NP * 20;
         switch (w->ilp) {
-            case 1: plp_count_tile_kernel<1><<<tiles, TILE, smem, s>>>(A); break;
             case 2: plp_count_tile_kernel<2><<<tiles, TILE, smem, s>>>(A); break;
-            default: plp_count_tile_kernel<4><<<tiles, TILE, smem, s>>>(A); break;
+            case 4: plp_count_tile_kernel<4><<<tiles, TILE, smem, s>>>(A); break;
+            default: plp_count_tile_kernel<1><<<tiles, TILE, smem, s>>>(A); break;
         }
         plp_scan_tiles_kernel<<<1, 1024, 0, s>>>(w->tile_cov.as<int32_t>(), w->tile_off.as<int64_t>(), tiles, n_cols_dev);
         EmitArgs E;

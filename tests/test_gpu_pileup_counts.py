@@ -92,7 +92,7 @@ def test_long_reads_large_region(counter):
 
 
 def test_deep_indel_rich_tile_spills_to_the_global_pool(counter):
-    """More distinct indel alleles in one 256-column tile than its shared-memory pool holds (1408 nodes)."""
+    """More distinct indel alleles in one 256-column tile than its shared-memory pool holds (704 nodes)."""
     from clair3_b200 import synth_reads as sr
     from oracle import pileup_oracle as po
     rec, ref, rs = sr.random_alignment(600, depth=300, read_len=300, seed=9, indel_rate=0.12, wild=False)
