@@ -764,6 +764,13 @@ def run_pileup_counts(ctx):
     # compulsory bytes of one call: the records and reference read once, the emitted arrays written once
     alg_bytes = h2d + d2h + n_cand * 8
     ach = alg_bytes / (ms_alone * 1e-3) / 1e9
+    traffic = None
+    try:
+        ent = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["pileup_counts"]["count_tile"]
+        if ent.get("region_columns") == cfg["region"] and ent.get("depth") == cfg["depth"]:
+            traffic = ent["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
     out = {"metric": "aligned-bases/sec", "value": value, "unit": "bases/s", "scaling": "weak", "steps": K, "repeats": r["repeats"],
            "timed_region_s": r["ms"] * 1e-3, "ms_per_step": r["ms"] / (K * r["repeats"]), "clocks": r["clocks"],
            "columns_per_s": n_cols * K * r["repeats"] * ctx.world / (r["ms"] * 1e-3),
@@ -774,11 +781,13 @@ def run_pileup_counts(ctx):
            "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": max(2, K // 4),
                    "repeats": re["repeats"], "timed_region_s": re["ms"] * 1e-3,
                    "mode": "PileupCounter.count(pinned host records).fetch(pinned=True): H2D of the records, 8 kernels, D2H of matrix / major / stats / candidates into page-locked buffers, synchronous per call"},
-           "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic,
                         "peak_source": pk["which"], "kernel": "all 8 kernels of one call, timed alone with CUDA events on its stream (c3b_plp_last_ms): %.3f ms" % ms_alone,
                         "algorithmic_bytes_per_call": alg_bytes,
-                        "note": "compulsory bytes only (records + reference in, emitted arrays out); the count kernel is bound by dependent L2 "
-                                "loads (a binary search over the CIGAR prefix sums per read and column), not by bandwidth"}}
+                        "note": "achieved = compulsory bytes (records + reference in, emitted arrays out) / the call's device time; traffic = DRAM bytes "
+                                "of the dominant kernel (plp_count_tile, 86 % of the call) from the committed ncu capture.  That kernel is issue-bound "
+                                "(ncu: 76 % of the issue slots busy, ~470 warp instructions per read and warp: a binary search over the CIGAR prefix "
+                                "sums per read and column, single-lane indel bookkeeping), not bandwidth-bound"}}
     if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = {"value": sample_bases / cpu_s, "unit": "bases/s", "cores": 1, "kind": "port",
                                "sample": "oracle/pileup_oracle.c (plain-C restatement of calculate_clair3_pileup, single thread like the reference's "
