@@ -817,7 +817,12 @@ def main():
     ap.add_argument("--min-region-s", type=float, default=2.0,
                     help="minimum length of every timed region (profiling runs under ncu pass 0: one pass of the K steps)")
     args = ap.parse_args()
+    explicit = args.workload is not None or any(a.startswith("--workloads") for a in sys.argv[1:])
     args.workloads = [x for x in (args.workload or args.workloads).split(",") if x]
+    if not explicit and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # the feature counter shards by region with no exchange at all (replicas only); the multi-rank line stays the measured
+        # round-2 shape (networks + cascade), the counter is a single-GPU sub-record unless asked for by name
+        args.workloads = [x for x in args.workloads if x != "pileup_counts"]
     global MIN_REGION_S
     MIN_REGION_S = max(0.0, args.min_region_s)
     if args.steps <= 0:

@@ -170,16 +170,65 @@ struct Pool {          // the tile's shared-memory indel nodes
 
 #define NODE(arr, i) (*((i) < NP ? &P.arr[(i)] : &A.g_##arr[(i) - NP]))
 
+// One indel allele seen on this thread's column (src/clair3_pileup.c:253-272 deletion table, :293-307 insertion strings): find it
+// in the column's list (strings compared base by base against the representative read) or append it; update all / best.
+// meta = insertion << 31 | reverse << 30 | length, q0 = first inserted base in read r (insertions).
+__device__ __forceinline__ void plp_event(const CountArgs &A, const Pool &P, int32_t *cnt, const int tid, const uint32_t meta,
+                                          const long long q0, const uint32_t r, int &head) {
+    const int kind = (int)(meta >> 31), rev = (int)((meta >> 30) & 1u);
+    const long long len = (long long)(meta & 0x3fffffffu);
+    const uint8_t *sq = A.R.seq;
+    int lq = 0;
+    if (kind) {
+        sq = A.R.seq + __ldg(A.R.seq_off + r);
+        lq = __ldg(A.R.l_qseq + r);
+    }
+    int c = 0;
+    bool found = false;
+    for (int i = head; i >= 0; i = NODE(next, i)) {
+        if (NODE(meta, i) != meta) continue;
+        bool same = true;
+        if (kind) {
+            const uint32_t rr = NODE(read, i);
+            const long long rq = (long long)NODE(qpos, i);
+            const uint8_t *s2 = A.R.seq + __ldg(A.R.seq_off + rr);
+            const int lq2 = __ldg(A.R.l_qseq + rr);
+            for (long long j = 0; j < len; ++j)
+                if (nib_at(sq, lq, q0 + j) != nib_at(s2, lq2, rq + j)) { same = false; break; }
+        }
+        if (same) { c = (int)(NODE(cnt, i) += 1u); found = true; break; }
+    }
+    if (!found) {
+        int slot = atomicAdd(P.used, 1);
+        if (slot >= NP) {
+            const int g = atomicAdd(A.g_used, 1);
+            if (g >= G_POOL) { atomicOr(A.status, 1); slot = -1; } else slot = NP + g;
+        }
+        if (slot >= 0) {
+            NODE(meta, slot) = meta;
+            NODE(read, slot) = r;
+            NODE(qpos, slot) = (uint32_t)q0;
+            NODE(cnt, slot) = 1u;
+            NODE(next, slot) = head;
+            head = slot;
+        }
+        c = 1;
+    }
+    const int f_all = kind ? (rev ? 13 : 4) : (rev ? 15 : 6);
+    cnt[f_all * TILE + tid] += 1;                                            // stats.sum / all_count
+    if (c > cnt[(f_all + 1) * TILE + tid]) cnt[(f_all + 1) * TILE + tid] = c;       // stats.max / best_count
+}
+
 // What ONE read shows on ONE column (htslib's resolve_cigar2 as a pure function of the operation k that covers the column) and
 // what the reference's inner loop does with it (src/clair3_pileup.c:249-308).  cw / xend / y0 are operation k's CIGAR word, end
-// offset and query start; nb is the read base at qpos (prefetched by the caller when the operation is a match).
-__device__ __forceinline__ void plp_visit(const CountArgs &A, const Pool &P, int32_t *cnt, const int tid, const int64_t r,
-                                          const int64_t cb, const int nc, const int off, const int k, const uint32_t cw,
-                                          const int xend, const int y0, const int rev, const uint8_t *sq, const int lq, const int nb,
-                                          int &depth, int &head) {
+// offset and query start; nb is the read base at qpos.  Returns the indel allele that starts after this base, if any, in
+// (ev_meta, ev_q0) instead of recording it (the caller records it at once, or batches it across the warp).
+__device__ __forceinline__ bool plp_visit(const CountArgs &A, int32_t *cnt, const int tid, const int64_t cb, const int nc,
+                                          const int off, const int k, const uint32_t cw, const int xend, const int y0, const int rev,
+                                          const int nb, int &depth, uint32_t &ev_meta, long long &ev_q0) {
     const uint32_t op = cw & 15u;
     const int l = (int)(cw >> 4);
-    if (op == 3u) return;                                                    // is_refskip, src/clair3_pileup.c:251
+    if (op == 3u) return false;                                              // is_refskip, src/clair3_pileup.c:251
     long long indel = 0;
     if (off == xend - 1 && k + 1 < nc) {                                     // resolve_cigar2: peek the next operation
         uint32_t c2 = __ldg(A.R.cigar + cb + k + 1);
@@ -220,54 +269,22 @@ __device__ __forceinline__ void plp_visit(const CountArgs &A, const Pool &P, int
     }
     ++depth;
     cnt[(base_i >= 0 ? base_i : NFEAT) * TILE + tid] += 1;
-
-    if (indel != 0) {                                                        // :253-272 (deletion table), :293-307 (insertion strings)
-        const int kind = indel > 0 ? 1 : 0;
-        long long len = indel > 0 ? indel : -indel;
-        if (len >= (1ll << 30)) { atomicOr(A.status, 4); len = (1ll << 30) - 1; }
-        const uint32_t meta = ((uint32_t)kind << 31) | ((uint32_t)rev << 30) | (uint32_t)len;
-        const long long q0 = qpos + (is_del ? 0 : 1);
-        int c = 0;
-        bool found = false;
-        for (int i = head; i >= 0; i = NODE(next, i)) {
-            if (NODE(meta, i) != meta) continue;
-            bool same = true;
-            if (kind) {
-                const uint32_t rr = NODE(read, i);
-                const long long rq = (long long)NODE(qpos, i);
-                const uint8_t *s2 = A.R.seq + __ldg(A.R.seq_off + rr);
-                const int lq2 = __ldg(A.R.l_qseq + rr);
-                for (long long j = 0; j < len; ++j)
-                    if (nib_at(sq, lq, q0 + j) != nib_at(s2, lq2, rq + j)) { same = false; break; }
-            }
-            if (same) { c = (int)(NODE(cnt, i) += 1u); found = true; break; }
-        }
-        if (!found) {
-            int slot = atomicAdd(P.used, 1);
-            if (slot >= NP) {
-                const int g = atomicAdd(A.g_used, 1);
-                if (g >= G_POOL) { atomicOr(A.status, 1); slot = -1; } else slot = NP + g;
-            }
-            if (slot >= 0) {
-                NODE(meta, slot) = meta;
-                NODE(read, slot) = (uint32_t)r;
-                NODE(qpos, slot) = (uint32_t)q0;
-                NODE(cnt, slot) = 1u;
-                NODE(next, slot) = head;
-                head = slot;
-            }
-            c = 1;
-        }
-        const int f_all = kind ? (rev ? 13 : 4) : (rev ? 15 : 6);
-        cnt[f_all * TILE + tid] += 1;                                        // stats.sum / all_count
-        if (c > cnt[(f_all + 1) * TILE + tid]) cnt[(f_all + 1) * TILE + tid] = c;   // stats.max / best_count
-    }
+    if (indel == 0) return false;
+    const int kind = indel > 0 ? 1 : 0;
+    long long len = indel > 0 ? indel : -indel;
+    if (len >= (1ll << 30)) { atomicOr(A.status, 4); len = (1ll << 30) - 1; }
+    ev_meta = ((uint32_t)kind << 31) | ((uint32_t)rev << 30) | (uint32_t)len;
+    ev_q0 = qpos + (is_del ? 0 : 1);
+    return true;
 }
 
-// ILP reads are resolved side by side: their binary searches (about 12 dependent L2 loads each for a 5,000-word CIGAR) and the
-// loads that follow are independent chains, so the latency that bounds this kernel is paid once per ILP reads (measured: §7).
-template <int ILP>
-__global__ void __launch_bounds__(TILE, ILP == 4 ? 3 : ILP == 2 ? 4 : 6) plp_count_tile_kernel(CountArgs A) {
+// MODE bit 0: the operation under a column is found with a fixed-trip search (the trip count depends only on the read's CIGAR
+//             length, so the warp never diverges in it and each step is 8 instructions instead of 12);
+// MODE bit 1: indel alleles are recorded in batches: a lane keeps its allele pending until six lanes of the warp have one (or a
+//             lane gets a second one), so the ~150-instruction list walk runs with several lanes active instead of one - in the
+//             profile of MODE 0 it ran on 91 % of the warp iterations with a single lane (30 % of all instructions issued).
+template <int MODE>
+__global__ void __launch_bounds__(TILE, 6) plp_count_tile_kernel(CountArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t *cnt = reinterpret_cast<int32_t *>(smem_raw);                       // [NCNT][TILE]
     __shared__ int s_used;
@@ -304,69 +321,55 @@ __global__ void __launch_bounds__(TILE, ILP == 4 ? 3 : ILP == 2 ? 4 : 6) plp_cou
 
     int depth = 0, head = -1;
     bool covered = false;
-    for (int64_t r0 = lo; r0 < hi; r0 += ILP) {
-        int64_t cb[ILP];
-        int nc[ILP], off[ILP], a[ILP], b[ILP];
-        bool in[ILP];
-#pragma unroll
-        for (int j = 0; j < ILP; ++j) {
-            const int64_t r = r0 + j;
-            in[j] = false;
-            a[j] = b[j] = 0;
-            cb[j] = 0; nc[j] = 0; off[j] = 0;
-            if (r < hi) {
-                const int64_t rp = __ldg(A.R.pos + r), re = __ldg(A.rend + r);
-                if (active && p >= rp && p < re) {
-                    in[j] = true;
-                    cb[j] = __ldg(A.R.cigar_off + r);
-                    nc[j] = (int)(__ldg(A.R.cigar_off + r + 1) - cb[j]);
-                    off[j] = (int)(p - rp);
-                    b[j] = nc[j];
+    bool pend = false;                                       // MODE bit 1: this lane's allele waiting to be recorded
+    uint32_t p_meta = 0, p_r = 0;
+    long long p_q0 = 0;
+    for (int64_t r = lo; r < hi; ++r) {                      // warp-uniform trip count
+        const int64_t rp = __ldg(A.R.pos + r), re = __ldg(A.rend + r);
+        const bool in = active && p >= rp && p < re;
+        bool new_ev = false;
+        uint32_t e_meta = 0;
+        long long e_q0 = 0;
+        if (in) {
+            covered = true;                                  // n_plp > 0: htslib reports the column
+            const int64_t cb = __ldg(A.R.cigar_off + r);
+            const int nc = (int)(__ldg(A.R.cigar_off + r + 1) - cb);
+            const int off = (int)(p - rp);
+            const int32_t *ox = A.opx_end + cb;
+            int k;                                           // the operation on this column: first one whose end offset exceeds off
+            if (MODE & 1) {
+                k = 0;
+                for (int s = 1 << (31 - __clz(nc)); s > 0; s >>= 1) {
+                    const int j = k + s;
+                    if (j <= nc && __ldg(ox + j - 1) <= off) k = j;
                 }
+            } else {
+                int a = 0, b = nc;
+                while (a < b) { const int m = (a + b) >> 1; if (__ldg(ox + m) > off) b = m; else a = m + 1; }
+                k = a;
             }
+            const uint32_t cw = __ldg(A.R.cigar + cb + k);
+            const int xend = __ldg(ox + k);
+            const int y0 = __ldg(A.opy + cb + k);
+            const int rev = (__ldg(A.R.flag + r) >> 4) & 1;
+            const uint32_t op = cw & 15u;
+            int nb = 0;
+            if (op != 2u && op != 3u)
+                nb = nib_at(A.R.seq + __ldg(A.R.seq_off + r), __ldg(A.R.l_qseq + r), (long long)y0 + (off - (xend - (int)(cw >> 4))));
+            new_ev = plp_visit(A, cnt, tid, cb, nc, off, k, cw, xend, y0, rev, nb, depth, e_meta, e_q0);
+            if (!(MODE & 2) && new_ev) plp_event(A, P, cnt, tid, e_meta, e_q0, (uint32_t)r, head);
         }
-        bool more = true;                                   // the operation on this column: first one whose end offset exceeds off
-        while (more) {
-            more = false;
-#pragma unroll
-            for (int j = 0; j < ILP; ++j) {
-                if (a[j] < b[j]) {
-                    const int m = (a[j] + b[j]) >> 1;
-                    if (__ldg(A.opx_end + cb[j] + m) > off[j]) b[j] = m; else a[j] = m + 1;
-                    more = true;
-                }
+        if (MODE & 2) {
+            const unsigned pb = __ballot_sync(0xffffffffu, pend);
+            const bool clash = __any_sync(0xffffffffu, pend && new_ev);
+            if ((clash || __popc(pb) >= 6) && pend) {
+                plp_event(A, P, cnt, tid, p_meta, p_q0, p_r, head);
+                pend = false;
             }
-        }
-        uint32_t cw[ILP];
-        int xend[ILP], y0[ILP], rev[ILP], lq[ILP], nb[ILP];
-        const uint8_t *sq[ILP];
-#pragma unroll
-        for (int j = 0; j < ILP; ++j) {
-            cw[j] = 0; xend[j] = 0; y0[j] = 0; rev[j] = 0; lq[j] = 0; sq[j] = A.R.seq;
-            if (in[j]) {
-                const int64_t r = r0 + j;
-                cw[j] = __ldg(A.R.cigar + cb[j] + a[j]);
-                xend[j] = __ldg(A.opx_end + cb[j] + a[j]);
-                y0[j] = __ldg(A.opy + cb[j] + a[j]);
-                rev[j] = (__ldg(A.R.flag + r) >> 4) & 1;
-                sq[j] = A.R.seq + __ldg(A.R.seq_off + r);
-                lq[j] = __ldg(A.R.l_qseq + r);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < ILP; ++j) {
-            nb[j] = 0;
-            const uint32_t op = cw[j] & 15u;
-            if (in[j] && op != 2u && op != 3u) nb[j] = nib_at(sq[j], lq[j], (long long)y0[j] + (off[j] - (xend[j] - (int)(cw[j] >> 4))));
-        }
-#pragma unroll
-        for (int j = 0; j < ILP; ++j) {
-            if (in[j]) {
-                covered = true;                              // n_plp > 0: htslib reports the column
-                plp_visit(A, P, cnt, tid, r0 + j, cb[j], nc[j], off[j], a[j], cw[j], xend[j], y0[j], rev[j], sq[j], lq[j], nb[j], depth, head);
-            }
+            if (new_ev) { pend = true; p_meta = e_meta; p_q0 = e_q0; p_r = (uint32_t)r; }
         }
     }
+    if ((MODE & 2) && pend) plp_event(A, P, cnt, tid, p_meta, p_q0, p_r, head);
 
     // the column's statistics and allele-frequency test, src/clair3_pileup.c:349-387
     if (active) {
@@ -630,10 +633,7 @@ struct c3b_plp {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int launches = 0;
-    int ilp = 1;                        // reads resolved side by side in the count kernel (1 | 2 | 4; env C3B_PLP_ILP for A/B runs).
-                                        // Measured (1,048,576 columns, depth 40): 1.109 / 1.106 / 1.386 ms - the kernel is issue-bound, not
-                                        // latency-bound (ncu: 470 warp instructions per read and warp, 22 of 32 lanes active), so the extra
-                                        // registers of ILP 4 only cost occupancy
+    int mode = 0;                       // count kernel variant (template MODE bits; env C3B_PLP_MODE for A/B runs)
     int64_t *host_counters = nullptr;   // pinned: n_cols, n_cand, (g_used | status << 32)
     int64_t n_cols = -1, n_cand = -1;
 };
@@ -659,9 +659,9 @@ int c3b_plp_create(c3b_plp **out, int device_ordinal) {
     C3B_CUDA(cudaSetDevice(device_ordinal));
     c3b_plp *w = new c3b_plp();
     w->device = device_ordinal;
-    if (const char *e = getenv("C3B_PLP_ILP")) {
+    if (const char *e = getenv("C3B_PLP_MODE")) {
         const int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4) w->ilp = v;
+        if (v >= 0 && v <= 3) w->mode = v;
     }
     if (cudaEventCreate(&w->ev0) != cudaSuccess || cudaEventCreate(&w->ev1) != cudaSuccess ||
         cudaMallocHost((void **)&w->host_counters, 4 * sizeof(int64_t)) != cudaSuccess) {
@@ -774,10 +774,11 @@ int c3b_plp_count(c3b_plp *w, const c3b_bam_records *reads, int on_device, int64
         A.g_meta = w->g_meta.as<uint32_t>(); A.g_read = w->g_read.as<uint32_t>(); A.g_qpos = w->g_qpos.as<uint32_t>();
         A.g_cnt = w->g_cnt.as<uint32_t>(); A.g_next = w->g_next.as<int32_t>(); A.g_used = g_used; A.status = status;
         const size_t smem = (size_t)NCNT * TILE * 4 + (size_t)NP * 20;
-        switch (w->ilp) {
+        switch (w->mode) {
+            case 1: plp_count_tile_kernel<1><<<tiles, TILE, smem, s>>>(A); break;
             case 2: plp_count_tile_kernel<2><<<tiles, TILE, smem, s>>>(A); break;
-            case 4: plp_count_tile_kernel<4><<<tiles, TILE, smem, s>>>(A); break;
-            default: plp_count_tile_kernel<1><<<tiles, TILE, smem, s>>>(A); break;
+            case 3: plp_count_tile_kernel<3><<<tiles, TILE, smem, s>>>(A); break;
+            default: plp_count_tile_kernel<0><<<tiles, TILE, smem, s>>>(A); break;
         }
         plp_scan_tiles_kernel<<<1, 1024, 0, s>>>(w->tile_cov.as<int32_t>(), w->tile_off.as<int64_t>(), tiles, n_cols_dev);
         EmitArgs E;
