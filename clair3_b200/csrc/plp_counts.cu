@@ -222,7 +222,7 @@ __device__ __forceinline__ void plp_event(const CountArgs &A, const Pool &P, int
 // What ONE read shows on ONE column (htslib's resolve_cigar2 as a pure function of the operation k that covers the column) and
 // what the reference's inner loop does with it (src/clair3_pileup.c:249-308).  cw / xend / y0 are operation k's CIGAR word, end
 // offset and query start; nb is the read base at qpos.  Returns the indel allele that starts after this base, if any, in
-// (ev_meta, ev_q0) instead of recording it (the caller records it at once, or batches it across the warp).
+// (ev_meta, ev_q0) instead of recording it (the caller records it).
 __device__ __forceinline__ bool plp_visit(const CountArgs &A, int32_t *cnt, const int tid, const int64_t cb, const int nc,
                                           const int off, const int k, const uint32_t cw, const int xend, const int y0, const int rev,
                                           const int nb, int &depth, uint32_t &ev_meta, long long &ev_q0) {
@@ -278,12 +278,10 @@ __device__ __forceinline__ bool plp_visit(const CountArgs &A, int32_t *cnt, cons
     return true;
 }
 
-// MODE bit 0: the operation under a column is found with a fixed-trip search (the trip count depends only on the read's CIGAR
-//             length, so the warp never diverges in it and each step is 8 instructions instead of 12);
-// MODE bit 1: indel alleles are recorded in batches: a lane keeps its allele pending until six lanes of the warp have one (or a
-//             lane gets a second one), so the ~150-instruction list walk runs with several lanes active instead of one - in the
-//             profile of MODE 0 it ran on 91 % of the warp iterations with a single lane (30 % of all instructions issued).
-template <int MODE>
+// Measured alternatives that did NOT pay (1,048,576 columns, depth 40, all bit-exact; profiles/r2_plp_ab.md): resolving 2 / 4 reads
+// side by side (1.106 / 1.386 ms against 1.109: the extra registers cost occupancy), a fixed-trip branch-free search (0.934 ms
+// against 0.894) and batching the indel bookkeeping across the warp until six lanes have an allele pending (0.903 ms).  What did
+// pay: per-warp instead of per-tile read ranges and six CTAs per SM (1.109 -> 0.894 ms).
 __global__ void __launch_bounds__(TILE, 6) plp_count_tile_kernel(CountArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t *cnt = reinterpret_cast<int32_t *>(smem_raw);                       // [NCNT][TILE]
@@ -321,13 +319,9 @@ __global__ void __launch_bounds__(TILE, 6) plp_count_tile_kernel(CountArgs A) {
 
     int depth = 0, head = -1;
     bool covered = false;
-    bool pend = false;                                       // MODE bit 1: this lane's allele waiting to be recorded
-    uint32_t p_meta = 0, p_r = 0;
-    long long p_q0 = 0;
     for (int64_t r = lo; r < hi; ++r) {                      // warp-uniform trip count
         const int64_t rp = __ldg(A.R.pos + r), re = __ldg(A.rend + r);
         const bool in = active && p >= rp && p < re;
-        bool new_ev = false;
         uint32_t e_meta = 0;
         long long e_q0 = 0;
         if (in) {
@@ -336,18 +330,9 @@ __global__ void __launch_bounds__(TILE, 6) plp_count_tile_kernel(CountArgs A) {
             const int nc = (int)(__ldg(A.R.cigar_off + r + 1) - cb);
             const int off = (int)(p - rp);
             const int32_t *ox = A.opx_end + cb;
-            int k;                                           // the operation on this column: first one whose end offset exceeds off
-            if (MODE & 1) {
-                k = 0;
-                for (int s = 1 << (31 - __clz(nc)); s > 0; s >>= 1) {
-                    const int j = k + s;
-                    if (j <= nc && __ldg(ox + j - 1) <= off) k = j;
-                }
-            } else {
-                int a = 0, b = nc;
-                while (a < b) { const int m = (a + b) >> 1; if (__ldg(ox + m) > off) b = m; else a = m + 1; }
-                k = a;
-            }
+            int a = 0, b = nc;                               // the operation on this column: first one whose end offset exceeds off
+            while (a < b) { const int m = (a + b) >> 1; if (__ldg(ox + m) > off) b = m; else a = m + 1; }
+            const int k = a;
             const uint32_t cw = __ldg(A.R.cigar + cb + k);
             const int xend = __ldg(ox + k);
             const int y0 = __ldg(A.opy + cb + k);
@@ -356,20 +341,10 @@ __global__ void __launch_bounds__(TILE, 6) plp_count_tile_kernel(CountArgs A) {
             int nb = 0;
             if (op != 2u && op != 3u)
                 nb = nib_at(A.R.seq + __ldg(A.R.seq_off + r), __ldg(A.R.l_qseq + r), (long long)y0 + (off - (xend - (int)(cw >> 4))));
-            new_ev = plp_visit(A, cnt, tid, cb, nc, off, k, cw, xend, y0, rev, nb, depth, e_meta, e_q0);
-            if (!(MODE & 2) && new_ev) plp_event(A, P, cnt, tid, e_meta, e_q0, (uint32_t)r, head);
-        }
-        if (MODE & 2) {
-            const unsigned pb = __ballot_sync(0xffffffffu, pend);
-            const bool clash = __any_sync(0xffffffffu, pend && new_ev);
-            if ((clash || __popc(pb) >= 6) && pend) {
-                plp_event(A, P, cnt, tid, p_meta, p_q0, p_r, head);
-                pend = false;
-            }
-            if (new_ev) { pend = true; p_meta = e_meta; p_q0 = e_q0; p_r = (uint32_t)r; }
+            if (plp_visit(A, cnt, tid, cb, nc, off, k, cw, xend, y0, rev, nb, depth, e_meta, e_q0))
+                plp_event(A, P, cnt, tid, e_meta, e_q0, (uint32_t)r, head);
         }
     }
-    if ((MODE & 2) && pend) plp_event(A, P, cnt, tid, p_meta, p_q0, p_r, head);
 
     // the column's statistics and allele-frequency test, src/clair3_pileup.c:349-387
     if (active) {
@@ -633,7 +608,6 @@ struct c3b_plp {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int launches = 0;
-    int mode = 0;                       // count kernel variant (template MODE bits; env C3B_PLP_MODE for A/B runs)
     int64_t *host_counters = nullptr;   // pinned: n_cols, n_cand, (g_used | status << 32)
     int64_t n_cols = -1, n_cand = -1;
 };
@@ -659,10 +633,6 @@ int c3b_plp_create(c3b_plp **out, int device_ordinal) {
     C3B_CUDA(cudaSetDevice(device_ordinal));
     c3b_plp *w = new c3b_plp();
     w->device = device_ordinal;
-    if (const char *e = getenv("C3B_PLP_MODE")) {
-        const int v = atoi(e);
-        if (v >= 0 && v <= 3) w->mode = v;
-    }
     if (cudaEventCreate(&w->ev0) != cudaSuccess || cudaEventCreate(&w->ev1) != cudaSuccess ||
         cudaMallocHost((void **)&w->host_counters, 4 * sizeof(int64_t)) != cudaSuccess) {
         c3b_set_error("c3b_plp_create: event / pinned allocation failed");
@@ -774,12 +744,7 @@ int c3b_plp_count(c3b_plp *w, const c3b_bam_records *reads, int on_device, int64
         A.g_meta = w->g_meta.as<uint32_t>(); A.g_read = w->g_read.as<uint32_t>(); A.g_qpos = w->g_qpos.as<uint32_t>();
         A.g_cnt = w->g_cnt.as<uint32_t>(); A.g_next = w->g_next.as<int32_t>(); A.g_used = g_used; A.status = status;
         const size_t smem = (size_t)NCNT * TILE * 4 + (size_t)NP * 20;
-        switch (w->mode) {
-            case 1: plp_count_tile_kernel<1><<<tiles, TILE, smem, s>>>(A); break;
-            case 2: plp_count_tile_kernel<2><<<tiles, TILE, smem, s>>>(A); break;
-            case 3: plp_count_tile_kernel<3><<<tiles, TILE, smem, s>>>(A); break;
-            default: plp_count_tile_kernel<0><<<tiles, TILE, smem, s>>>(A); break;
-        }
+        plp_count_tile_kernel<<<tiles, TILE, smem, s>>>(A);
         plp_scan_tiles_kernel<<<1, 1024, 0, s>>>(w->tile_cov.as<int32_t>(), w->tile_off.as<int64_t>(), tiles, n_cols_dev);
         EmitArgs E;
         E.start = start; E.end = end; E.call_ht = params->call_ht;

@@ -47,8 +47,8 @@ def main():
             torch.cuda.synchronize()
             ms.append(ctr.last_ms()[0])
         nc, nk = ctr.sizes()
-        print("MODE=%s region %d: count %s ms (median %.3f), %d columns, %d candidates"
-              % (os.environ.get("C3B_PLP_MODE", "default"), region, ["%.3f" % m for m in ms[:8]], float(np.median(ms[1:] or ms)), nc, nk))
+        print("kernel %s, region %d: count %s ms (median %.3f), %d columns, %d candidates"
+              % ("shipped", region, ["%.3f" % m for m in ms[:8]], float(np.median(ms[1:] or ms)), nc, nk))
         return
     from test_pileup_oracle import case_indels, case_quirks
     ok = True
