@@ -234,6 +234,15 @@ def counting_region(ctg_start, ctg_end, no_of_positions=2 * FLANKING + 1):
     return max(0, s - 1), extend_end
 
 
+def chunks_for_rank(chunk_num, rank, world):
+    """The 1-based chunk ids rank ``rank`` of ``world`` counts: contiguous runs, like the reference's per-GPU file lists
+    (``clair3/CallVariantsFromCffiGPU.py:141-156``), so every rank's candidates stay in contig order.  Regions are independent:
+    the counter shards with no exchange step at all (one ``PileupCounter`` per process / GPU)."""
+    from .sharding import site_range
+    lo, hi = site_range(chunk_num, rank, world)
+    return list(range(lo + 1, hi + 1))
+
+
 def lib_const(name):
     from ._ffi import CONSTANTS
     return CONSTANTS[name]

@@ -151,3 +151,24 @@ def test_device_resident_records_and_chained_forward(counter):
     assert float(np.abs(y[sel] - yref).max()) < 1e-5            # same kernels, same per-site arithmetic (cf. test_forward_windows_equals_host_sliced_tensors)
     _STATS["chained_forward"] = {"candidates": int(len(ok)), "complete_windows": int(ok.sum()), "identical_to_host_sliced_forward": True}
     _dump()
+
+
+def test_additivity_at_bench_size(counter):
+    """The bench region (1,048,576 columns, depth 40) is too large for the oracle to be the comparison of record in a test, so the
+    full size is checked through a size-independent property: linearity of the counts in the set of reads (see
+    tests/test_pileup_oracle.py::check_additivity), plus the oracle itself on a 32,768-column window of the same call."""
+    from clair3_b200 import synth_reads as sr
+    from oracle import pileup_oracle as po
+    from test_pileup_oracle import check_additivity
+    region, origin = 1 << 20, 10000
+    rec, ref, rs = sr.random_alignment(region, depth=40, read_len=8000, seed=5, indel_rate=0.04, origin=origin, n_rate=0.0,
+                                       filtered_frac=0.0)
+    rec["mapq"][:] = 60
+    n = check_additivity(lambda r: counter.count(r, origin, origin + region, ref, rs).fetch(), rec, origin, origin + region, ref, rs)
+    whole = counter.count(rec, origin, origin + region, ref, rs).fetch()
+    want = po.clair3_pileup(rec, origin, origin + 32768, ref, rs)
+    k = len(want["major"]) - 40            # the window's last columns see no right-hand neighbours in the oracle's shorter region
+    assert np.array_equal(whole["major"][:k], want["major"][:k]) and np.array_equal(whole["matrix"][:k], want["matrix"][:k])
+    assert np.array_equal(whole["stats"][:k, :5], want["stats"][:k, :5])
+    _STATS["additivity_1M"] = {"columns_compared": n, "linear_features_additive": True, "oracle_window_columns": int(k)}
+    _dump()

@@ -184,3 +184,46 @@ def test_chunk_and_counting_regions():
     assert pc.counting_region(1000, 2000) == (965, 2033)          # 1000 - 33 = 967 (1-based) -> "966" -> 965 (0-based)
     with pytest.raises(_ffi.C3BError):
         pc.chunk_region(100, 0, 4)
+
+
+LINEAR = [f for f in range(18) if f not in (5, 7, 14, 16)]           # every feature but the four "best allele" maxima
+
+
+def split_by_parity(rec):
+    """Two record sets: the even-numbered and the odd-numbered reads."""
+    from clair3_b200 import synth_reads as sr
+    out = []
+    for par in (0, 1):
+        idx = np.arange(par, len(rec["pos"]), 2)
+        cig = [rec["cigar"][rec["cigar_off"][i]:rec["cigar_off"][i + 1]] for i in idx]
+        seq = [rec["seq"][rec["seq_off"][i]:rec["seq_off"][i + 1]] for i in idx]
+        out.append({"pos": rec["pos"][idx], "flag": rec["flag"][idx], "mapq": rec["mapq"][idx], "l_qseq": rec["l_qseq"][idx],
+                    "cigar_off": np.concatenate([[0], np.cumsum([len(c) for c in cig])]).astype(np.int64),
+                    "cigar": np.concatenate(cig) if cig else np.zeros(0, np.uint32),
+                    "seq_off": np.concatenate([[0], np.cumsum([len(q) for q in seq])]).astype(np.int64),
+                    "seq": np.concatenate(seq) if seq else np.zeros(0, np.uint8)})
+    return out
+
+
+def check_additivity(count, rec, start, end, ref, rs):
+    """Size-independent property of the counter: with no non-ACGT read bases (no index -1 spill-over between columns), every
+    feature except the best-allele maxima is LINEAR in the set of reads - on the columns both halves cover, counts(all reads) =
+    counts(even reads) + counts(odd reads), minus-the-strand-total reference features included; the maxima are sub-additive."""
+    a, b = split_by_parity(rec)
+    whole, ra, rb = count(rec), count(a), count(b)
+    common = np.intersect1d(ra["major"], rb["major"])
+    assert len(common) > 0.9 * (end - start)
+    iw, ia, ib = (np.searchsorted(r["major"], common) for r in (whole, ra, rb))
+    mw, ma, mb = whole["matrix"][iw], ra["matrix"][ia], rb["matrix"][ib]
+    assert np.array_equal(mw[:, LINEAR], ma[:, LINEAR] + mb[:, LINEAR])
+    best = [5, 7, 14, 16]
+    assert (mw[:, best] <= ma[:, best] + mb[:, best]).all() and (mw[:, best] >= np.maximum(ma[:, best], mb[:, best])).all()
+    sw, sa, sb = whole["stats"][iw], ra["stats"][ia], rb["stats"][ib]
+    assert np.array_equal(sw[:, [0, 3, 4]], sa[:, [0, 3, 4]] + sb[:, [0, 3, 4]])          # depth, del_count, ins_count
+    return int(len(common))
+
+
+def test_counts_are_additive_over_read_subsets():
+    rec, ref, rs = sr.random_alignment(3000, depth=30, read_len=700, seed=13, n_rate=0.0, filtered_frac=0.0)
+    rec["mapq"][:] = 60
+    check_additivity(lambda r: po.clair3_pileup(r, 1000, 4000, ref, rs), rec, 1000, 4000, ref, rs)
