@@ -42,6 +42,7 @@ constexpr int NCNT = 19;          // 18 features + the index -1 counter
 constexpr int NP = 704;           // shared-memory indel nodes per tile (20 B each): 33.5 KB per CTA with the counters -> 6 CTAs per SM
 constexpr int FLANK = 16;         // pileup_flanking_base_num, src/clair3_pileup.h:93
 constexpr int G_POOL = 1 << 21;   // global overflow nodes per workspace
+constexpr int AL_CAP = 1 << 22;   // exported allele records per call (16 B each)
 
 struct DevReads {
     int64_t n;
@@ -157,6 +158,11 @@ struct CountArgs {
     int32_t *g_next;
     int *g_used;
     int *status;
+    // optional export of the candidate columns' allele lists (for the all_alt_info text): null = off
+    uint32_t *al_meta, *al_read, *al_qpos, *al_cnt;
+    int32_t *al_off, *al_n;   // [W] first record / number of records of a column
+    int *al_used;
+    int al_cap;
 };
 
 struct Pool {          // the tile's shared-memory indel nodes
@@ -389,12 +395,29 @@ __global__ void __launch_bounds__(TILE, 6) plp_count_tile_kernel(CountArgs A) {
             pass = pass && (int64_t)d >= A.prm.min_depth && ref_acgt;
             ds[0] = d; ds[1] = ref_count; ds[2] = alt_count; ds[3] = del_count; ds[4] = ins_count;
             ds[5] = (pass ? 1 : 0) | 4;
+            if (A.al_meta) {               // the column's distinct alleles, oldest first (the list is newest first)
+                int n = 0;
+                if (pass)
+                    for (int i = head; i >= 0; i = NODE(next, i)) ++n;
+                int base = n ? atomicAdd(A.al_used, n) : 0;
+                if (base + n > A.al_cap) { atomicOr(A.status, 8); n = 0; base = 0; }
+                A.al_off[p - A.start] = base;
+                A.al_n[p - A.start] = n;
+                int wr = base + n - 1;
+                for (int i = head; i >= 0 && wr >= base; i = NODE(next, i), --wr) {
+                    A.al_meta[wr] = NODE(meta, i);
+                    A.al_read[wr] = NODE(read, i);
+                    A.al_qpos[wr] = NODE(qpos, i);
+                    A.al_cnt[wr] = NODE(cnt, i);
+                }
+            }
             if (A.gv_ref) {
                 A.gv_ref[p - A.start] = ref_count;
                 A.gv_tot[p - A.start] = (int64_t)ref_count + all_alt + del_count + ins_count;
             }
         } else {
             ds[0] = ds[1] = ds[2] = ds[3] = ds[4] = ds[5] = 0;
+            if (A.al_meta) { A.al_off[p - A.start] = 0; A.al_n[p - A.start] = 0; }
         }
         A.nquirk[p - A.start] = cnt[NFEAT * TILE + tid];
     }
@@ -600,11 +623,12 @@ struct c3b_plp {
     // scratch
     DBuf opx, opy, rend, pmax, rows32, dstats, nquirk, dci, tile_cov, tile_off, tile_cand, tile_coff;
     DBuf g_meta, g_read, g_qpos, g_cnt, g_next;
+    DBuf al_meta, al_read, al_qpos, al_cnt, al_off, al_n;   // allele export (params.alt_info)
     DBuf counters;      // int64 n_cols, int64 n_cand, int g_used, int status
     // outputs
     DBuf matrix, major, stats, cand_cols, wstart, cand_ok, gv_ref, gv_tot;
     int64_t W = 0;
-    bool gvcf = false, counted = false;
+    bool gvcf = false, counted = false, alleles = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int launches = 0;
@@ -713,6 +737,10 @@ int c3b_plp_count(c3b_plp *w, const c3b_bam_records *reads, int on_device, int64
         w->cand_ok.ensure(Wz))
         return 1;
     if (w->gvcf && (w->gv_ref.ensure(Wz * 8) || w->gv_tot.ensure(Wz * 8))) return 1;
+    w->alleles = params->alt_info != 0;
+    if (w->alleles && (w->al_meta.ensure((size_t)AL_CAP * 4) || w->al_read.ensure((size_t)AL_CAP * 4) || w->al_qpos.ensure((size_t)AL_CAP * 4) ||
+                       w->al_cnt.ensure((size_t)AL_CAP * 4) || w->al_off.ensure(Wz * 4) || w->al_n.ensure(Wz * 4)))
+        return 1;
     C3B_CUDA(cudaMemsetAsync(w->counters.p, 0, 32, s));
     if (w->gvcf && W > 0) {
         C3B_CUDA(cudaMemsetAsync(w->gv_ref.p, 0, (size_t)W * 8, s));
@@ -722,6 +750,7 @@ int c3b_plp_count(c3b_plp *w, const c3b_bam_records *reads, int on_device, int64
     int64_t *n_cand_dev = n_cols_dev + 1;
     int *g_used = reinterpret_cast<int *>(n_cols_dev + 2);
     int *status = g_used + 1;
+    int *al_used = reinterpret_cast<int *>(n_cols_dev + 3);
 
     w->launches = 0;
     C3B_CUDA(cudaEventRecord(w->ev0, s));
@@ -743,6 +772,8 @@ int c3b_plp_count(c3b_plp *w, const c3b_bam_records *reads, int on_device, int64
         A.tile_cov = w->tile_cov.as<int32_t>();
         A.g_meta = w->g_meta.as<uint32_t>(); A.g_read = w->g_read.as<uint32_t>(); A.g_qpos = w->g_qpos.as<uint32_t>();
         A.g_cnt = w->g_cnt.as<uint32_t>(); A.g_next = w->g_next.as<int32_t>(); A.g_used = g_used; A.status = status;
+        A.al_meta = w->alleles ? w->al_meta.as<uint32_t>() : nullptr; A.al_read = w->al_read.as<uint32_t>(); A.al_qpos = w->al_qpos.as<uint32_t>();
+        A.al_cnt = w->al_cnt.as<uint32_t>(); A.al_off = w->al_off.as<int32_t>(); A.al_n = w->al_n.as<int32_t>(); A.al_used = al_used; A.al_cap = AL_CAP;
         const size_t smem = (size_t)NCNT * TILE * 4 + (size_t)NP * 20;
         plp_count_tile_kernel<<<tiles, TILE, smem, s>>>(A);
         plp_scan_tiles_kernel<<<1, 1024, 0, s>>>(w->tile_cov.as<int32_t>(), w->tile_off.as<int64_t>(), tiles, n_cols_dev);
@@ -778,6 +809,7 @@ int c3b_plp_sizes(c3b_plp *w, int64_t *n_cols, int64_t *n_candidates) {
     if (status & 1) { c3b_set_error("c3b_plp_count: more than %d distinct indel alleles spilled from the tiles' shared-memory pools", G_POOL); return 1; }
     if (status & 2) { c3b_set_error("c3b_plp_count: a read spans more than 2^31 reference or query bases"); return 1; }
     if (status & 4) { c3b_set_error("c3b_plp_count: an indel of 2^30 bases or more"); return 1; }
+    if (status & 8) { c3b_set_error("c3b_plp_count: more than %d allele records to export (params.alt_info); count a smaller region", AL_CAP); return 1; }
     w->n_cols = w->host_counters[0];
     w->n_cand = w->host_counters[1];
     if (n_cols) *n_cols = w->n_cols;
@@ -799,6 +831,29 @@ int c3b_plp_fetch(c3b_plp *w, int64_t *matrix, int64_t *major, int32_t *stats, i
     if ((pos_ref_count || pos_total_count) && !w->gvcf) { c3b_set_error("c3b_plp_fetch: the count ran without params.gvcf"); return 1; }
     if (pos_ref_count && w->W) C3B_CUDA(cudaMemcpyAsync(pos_ref_count, w->gv_ref.p, (size_t)w->W * 8, cudaMemcpyDeviceToHost, s));
     if (pos_total_count && w->W) C3B_CUDA(cudaMemcpyAsync(pos_total_count, w->gv_tot.p, (size_t)w->W * 8, cudaMemcpyDeviceToHost, s));
+    C3B_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int c3b_plp_fetch_alleles(c3b_plp *w, int32_t *al_off, int32_t *al_n, uint32_t *meta, uint32_t *read, uint32_t *qpos, uint32_t *cnt,
+                          int64_t capacity, int64_t *n_alleles) {
+    if (!w) { c3b_set_error("c3b_plp_fetch_alleles: null workspace"); return 1; }
+    if (w->n_cols < 0 && c3b_plp_sizes(w, nullptr, nullptr)) return 1;
+    if (!w->alleles) { c3b_set_error("c3b_plp_fetch_alleles: the count ran without params.alt_info"); return 1; }
+    const int64_t n = (int64_t)(int)(w->host_counters[3] & 0xffffffffll);
+    if (n_alleles) *n_alleles = n;
+    cudaStream_t s = w->stream;
+    if (al_off && w->W) C3B_CUDA(cudaMemcpyAsync(al_off, w->al_off.p, (size_t)w->W * 4, cudaMemcpyDeviceToHost, s));
+    if (al_n && w->W) C3B_CUDA(cudaMemcpyAsync(al_n, w->al_n.p, (size_t)w->W * 4, cudaMemcpyDeviceToHost, s));
+    if (meta || read || qpos || cnt) {
+        if (capacity < n) { c3b_set_error("c3b_plp_fetch_alleles: capacity %lld < %lld records", (long long)capacity, (long long)n); return 1; }
+        if (n) {
+            if (meta) C3B_CUDA(cudaMemcpyAsync(meta, w->al_meta.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+            if (read) C3B_CUDA(cudaMemcpyAsync(read, w->al_read.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+            if (qpos) C3B_CUDA(cudaMemcpyAsync(qpos, w->al_qpos.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+            if (cnt) C3B_CUDA(cudaMemcpyAsync(cnt, w->al_cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        }
+    }
     C3B_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
@@ -831,7 +886,8 @@ void c3b_plp_destroy(c3b_plp *w) {
     DBuf *all[] = {&w->in_pos, &w->in_flag, &w->in_mapq, &w->in_coff, &w->in_cigar, &w->in_soff, &w->in_seq, &w->in_lq, &w->in_ref,
                    &w->opx, &w->opy, &w->rend, &w->pmax, &w->rows32, &w->dstats, &w->nquirk, &w->dci, &w->tile_cov, &w->tile_off,
                    &w->tile_cand, &w->tile_coff, &w->g_meta, &w->g_read, &w->g_qpos, &w->g_cnt, &w->g_next, &w->counters,
-                   &w->matrix, &w->major, &w->stats, &w->cand_cols, &w->wstart, &w->cand_ok, &w->gv_ref, &w->gv_tot};
+                   &w->matrix, &w->major, &w->stats, &w->cand_cols, &w->wstart, &w->cand_ok, &w->gv_ref, &w->gv_tot,
+                   &w->al_meta, &w->al_read, &w->al_qpos, &w->al_cnt, &w->al_off, &w->al_n};
     for (DBuf *b : all) b->release();
     if (w->ev0) cudaEventDestroy(w->ev0);
     if (w->ev1) cudaEventDestroy(w->ev1);

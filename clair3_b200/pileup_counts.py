@@ -110,14 +110,16 @@ class PileupCounter:
         self._pin = {}
 
     def count(self, records, start, end, ref_seq, ref_start, min_depth=2, min_snp_af=0.08, min_indel_af=0.15, min_mq=5,
-              call_snp_only=False, call_ht=False, gvcf=False):
+              call_snp_only=False, call_ht=False, gvcf=False, alt_info=False, max_indel_length=50):
         """Arguments as ``calculate_clair3_pileup`` takes them (src/clair3_pileup.c:142) with the region as 0-based
-        [start, end) and the reference bases of [ref_start, ref_start + len(ref_seq))."""
+        [start, end) and the reference bases of [ref_start, ref_start + len(ref_seq)).  ``alt_info=True`` also exports the
+        candidates' allele lists so that ``alt_info_strings()`` can format the reference's ``all_alt_info`` text."""
         on_dev = isinstance(records, DeviceBamRecords)
         rec = records if on_dev else BamRecords.from_dict(records)
         prm = ffi.new("c3b_plp_params *")
         prm.min_depth, prm.min_snp_af, prm.min_indel_af, prm.min_mq = int(min_depth), float(min_snp_af), float(min_indel_af), int(min_mq)
         prm.call_snp_only, prm.call_ht, prm.gvcf = int(bool(call_snp_only)), int(bool(call_ht)), int(bool(gvcf))
+        prm.alt_info = int(bool(alt_info))
         st = rec._struct()
         stream = torch.cuda.current_stream(self._device).cuda_stream
         if on_dev:
@@ -135,6 +137,7 @@ class PileupCounter:
                                   ffi.cast("void *", stream)))
         self._keep = (rec, ref, refbuf, st)          # buffers stay alive while the copies / kernels are in flight
         self._shape = (int(end) - int(start), bool(gvcf))
+        self._alt = (bool(alt_info), int(start), int(ref_start), int(max_indel_length))
         return self
 
     def sizes(self):
@@ -176,6 +179,38 @@ class PileupCounter:
                                   c("uint8_t *", out["cand_ok"].ctypes.data), prc, ptc))
         return out
 
+    def alt_info_strings(self, fetched=None):
+        """The ``all_alt_info`` strings of ``calculate_clair3_pileup`` (src/clair3_pileup.c:391-450), one per candidate in
+        candidate order: ``"<pos+1>-<depth>-<ref base>-X<b> n D<ref bases> n I<ref base><inserted bases> n R<ref base> n "`` -
+        SNP alleles in A C G T order, deletions by length, insertions in the iteration order of the reference's khash string
+        counter, the remaining reference depth last.  The GPU supplies the allele lists (``c3b_plp_fetch_alleles``), the text is
+        formatted here from the HOST records of the count (the inserted bases are read from the representative reads)."""
+        want, start, ref_start, max_indel = self._alt
+        if not want:
+            raise C3BError("alt_info_strings: count(..., alt_info=True) first")
+        rec, ref = self._keep[0], self._keep[1]
+        if isinstance(rec, DeviceBamRecords):
+            raise C3BError("alt_info_strings needs host records (the inserted bases are read on the host)")
+        r = fetched if fetched is not None else self.fetch()
+        W = self._shape[0]
+        n = ffi.new("int64_t *")
+        check(lib().c3b_plp_fetch_alleles(self._h, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, 0, n))
+        na = int(n[0])
+        al_off, al_n = np.zeros(W, np.int32), np.zeros(W, np.int32)
+        meta, rd, qp, cn = (np.zeros(max(na, 1), np.uint32) for _ in range(4))
+        c = ffi.cast
+        check(lib().c3b_plp_fetch_alleles(self._h, c("int32_t *", al_off.ctypes.data), c("int32_t *", al_n.ctypes.data),
+                                          c("uint32_t *", meta.ctypes.data), c("uint32_t *", rd.ctypes.data),
+                                          c("uint32_t *", qp.ctypes.data), c("uint32_t *", cn.ctypes.data), len(meta), n))
+        out = []
+        for ci in r["cand_cols"]:
+            p = int(r["major"][ci])
+            a0 = int(al_off[p - start])
+            sl = slice(a0, a0 + int(al_n[p - start]))
+            out.append(format_alt_info(p, r["matrix"][ci], r["stats"][ci], ref, ref_start, max_indel,
+                                       meta[sl], rd[sl], qp[sl], cn[sl], rec))
+        return out
+
     def forward(self, model):
         """Clair3_P over the 33-column window of EVERY candidate of the last count, straight from the device-resident matrix
         (``c3b_forward_windows`` with ``on_device = 1``).  Returns (probabilities float32 [n_cand, 24|90] on the device, cand_ok
@@ -209,6 +244,114 @@ class PileupCounter:
             self.close()
         except Exception:
             pass
+
+
+_NT16 = "=ACMGRSVTWYHKDBN"                      # htslib seq_nt16_str
+_B2I = {2: 1, 6: 2, 19: 3}                     # base2index (src/clair3_pileup.h:57-62): 'C' - 'A', 'G' - 'A', 'T' - 'A'
+
+
+def khash_iteration_order(keys):
+    """Bucket order of klib's khash (vendored by the reference as src/khash.h) after inserting the distinct byte strings ``keys`` in
+    this order - the order in which the reference prints a column's insertion alleles (``kh_begin .. kh_end`` over
+    ``ins_counts_all``, src/clair3_pileup.c:427-441).  Restated for an insert-only table: X31 string hash (khash.h:395-400),
+    power-of-two buckets from 4, triangular probing (:329), growth whenever n_occupied >= 0.77 n_buckets at the start of a put
+    (:312-320), and kh_resize's in-place kick-out rehash (:268-292)."""
+    hashes = []
+    for k in keys:
+        h = k[0] if k else 0
+        for ch in k[1:]:
+            h = (h * 31 + ch) & 0xFFFFFFFF
+        hashes.append(h)
+    n, size, upper, slot = 0, 0, 0, []
+    for key in range(len(keys)):
+        if size >= upper:
+            nn = 4
+            while nn < n + 1:
+                nn <<= 1
+            if size < int(nn * 0.77 + 0.5):
+                new, taken = slot + [-1] * (nn - n), [False] * nn
+                occ = [s >= 0 for s in slot] + [False] * (nn - n)
+                mask = nn - 1
+                for j in range(n):
+                    if not occ[j]:
+                        continue
+                    cur, occ[j], new[j] = new[j], False, -1
+                    while True:
+                        i, step = hashes[cur] & mask, 0
+                        while taken[i]:
+                            step += 1
+                            i = (i + step) & mask
+                        taken[i] = True
+                        if i < n and occ[i]:
+                            new[i], cur = cur, new[i]
+                            occ[i] = False
+                        else:
+                            new[i] = cur
+                            break
+                slot, n, upper = new, nn, int(nn * 0.77 + 0.5)
+        mask, step = n - 1, 0
+        i = hashes[key] & mask
+        while slot[i] >= 0:
+            step += 1
+            i = (i + step) & mask
+        slot[i] = key
+        size += 1
+    return [s for s in slot if s >= 0]
+
+
+def _insertion_bytes(rec, read, q0, length):
+    so, lq = int(rec.seq_off[read]), int(rec.l_qseq[read])
+    out = bytearray()
+    for i in range(q0, q0 + length):
+        nib = 0
+        if 0 <= i < lq:
+            b = int(rec.seq[so + (i >> 1)])
+            nib = (b >> 4) if (i & 1) == 0 else (b & 15)
+        out.append(ord(_NT16[nib]))
+    return bytes(out)
+
+
+def format_alt_info(pos, row, stats, ref, ref_start, max_indel_length, meta, read, qpos, cnt, rec):
+    """One ``all_alt_info`` string (src/clair3_pileup.c:391-450) from a candidate's matrix row, its stats and its allele records."""
+    off = pos - ref_start
+    rb = ref[off:off + 1].upper() if 0 <= off < len(ref) else b"N"
+    rbc = rb.decode("latin-1")
+    rf = _B2I.get(rb[0] - 65, 0)
+    depth, ref_depth = int(stats[0]), int(stats[1])
+    parts = ["%d-%d-%s-" % (pos + 1, depth, rbc)]
+    for i in range(4):
+        alt_sum = int(row[i]) + int(row[i + 9])
+        if alt_sum > 0 and i != rf:
+            parts.append("X%s %d " % ("ACGT"[i], alt_sum))
+    dels, ins_order, ins_cnt = {}, [], {}
+    for m, r, q, c in zip(meta.tolist(), read.tolist(), qpos.tolist(), cnt.tolist()):
+        length = m & 0x3FFFFFFF
+        if m >> 31:
+            key = _insertion_bytes(rec, r, q, length)
+            if key not in ins_cnt:
+                ins_cnt[key] = [0, r]
+                ins_order.append(key)
+            ins_cnt[key][0] += c
+            ins_cnt[key][1] = min(ins_cnt[key][1], r)
+        else:
+            dels[length] = dels.get(length, 0) + c
+    for length in sorted(dels):
+        d = dels[length]
+        ref_depth -= d
+        if d > 0 and length <= max_indel_length:
+            tail = ref[off + 1:off + 1 + length]
+            nul = tail.find(b"\0")
+            parts.append("D%s %d " % ((tail if nul < 0 else tail[:nul]).decode("latin-1"), d))
+    ins_order.sort(key=lambda k: ins_cnt[k][1])           # first occurrence over both strands = the reference's insertion order
+    for j in khash_iteration_order(ins_order):
+        key = ins_order[j]
+        val = ins_cnt[key][0]
+        ref_depth -= val
+        if len(key) <= max_indel_length:
+            parts.append("I%s%s %d " % (rbc, key.decode("latin-1"), val))
+    if ref_depth > 0:
+        parts.append("R%s %d " % (rbc, ref_depth))
+    return "".join(parts)
 
 
 def chunk_region(contig_length, chunk_id, chunk_num):

@@ -10,8 +10,8 @@
  * image), the caller hands over what bam1_t carries.  What is counted, column by column, is exactly what the reference's loop
  * over bam_mplp_auto() counts (see oracle/pileup_oracle.c for the line-by-line restatement, quirks included).
  *
- * Not produced here: the all_alt_info strings (src/clair3_pileup.c:391-450, text formatting of per-candidate allele counts) - the
- * candidate columns, their depths and allele-class counts are returned as integers instead.
+ * The all_alt_info strings (src/clair3_pileup.c:391-450) are text: the GPU exports the per-candidate allele lists
+ * (c3b_plp_fetch_alleles) and the host shim formats them, byte for byte as the reference does.
  *
  * Same conventions as clair3_b200.h: int status, 0 = ok, message via c3b_last_error(); no CPU fallback.
  */
@@ -52,6 +52,8 @@ typedef struct c3b_plp_params {
     int32_t call_snp_only;
     int32_t call_ht;            /* 1: no 16-column flanking requirement (src/clair3_pileup.c:385-387) */
     int32_t gvcf;               /* 1: also fill pos_ref_count / pos_total_count (:205-210, :453-456) */
+    int32_t alt_info;           /* 1: also export every pre-candidate column's distinct indel alleles (c3b_plp_fetch_alleles), from
+                                   which the host formats the all_alt_info text of :391-450 */
 } c3b_plp_params;
 
 /* A counting workspace on one device (scratch grows on demand; one call in flight per workspace). */
@@ -79,6 +81,18 @@ int c3b_plp_sizes(c3b_plp *w, int64_t *n_cols, int64_t *n_candidates);
  *   pos_ref_count / pos_total_count [end - start] int64 (only with params.gvcf)                                  */
 int c3b_plp_fetch(c3b_plp *w, int64_t *matrix, int64_t *major, int32_t *stats, int64_t *cand_cols, uint8_t *cand_ok,
                   int64_t *pos_ref_count, int64_t *pos_total_count);
+
+/* The distinct indel alleles of every column that passed the allele-frequency test (needs params.alt_info), in order of first
+ * occurrence - what the reference keeps per column in dels_f / dels_r and its three insertion-string counters:
+ *   al_off / al_n [end - start] int32   first record and number of records of the column at position start + i (0 elsewhere)
+ *   meta  [n]  uint32   insertion << 31 | reverse strand << 30 | length
+ *   read  [n]  uint32   index (into the records of the count) of the first read that showed the allele
+ *   qpos  [n]  uint32   query offset of its first inserted base in that read (insertions)
+ *   cnt   [n]  uint32   reads of that strand showing it
+ * Any pointer may be NULL; n_alleles alone sizes the buffers.  clair3_b200/pileup_counts.py formats the all_alt_info strings
+ * (src/clair3_pileup.c:391-450, insertion alleles in the reference's khash bucket order) from these on the host. */
+int c3b_plp_fetch_alleles(c3b_plp *w, int32_t *al_off, int32_t *al_n, uint32_t *meta, uint32_t *read, uint32_t *qpos, uint32_t *cnt,
+                          int64_t capacity, int64_t *n_alleles);
 
 /* Device views of the same results, valid until the next c3b_plp_count on w: matrix and window_starts
  * (= cand_cols - 16, the first row of every candidate's 33-row window) are exactly the `cols` / `starts` arguments of

@@ -30,6 +30,7 @@
  * Build: oracle/build_oracle.py (gcc -O2 -shared) -> oracle/_build/libpileup_oracle.so
  */
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -161,10 +162,97 @@ typedef struct {
     int64_t cnt_f, cnt_r;
 } ins_t;
 
+
+/* ---- all_alt_info text (src/clair3_pileup.c:391-450) ----------------------------------------------------------------------------
+ * The insertion alleles are printed in the ITERATION ORDER of the reference's khash string counter ins_counts_all, i.e. by bucket.
+ * khash (klib, vendored as src/khash.h) restated for an insert-only table: X31 string hash (:395-400), n_buckets a power of two >= 4,
+ * triangular probing i = (i + ++step) & mask (:329), growth to the next power of two whenever n_occupied >= 0.77 * n_buckets at the
+ * START of a put (:312-320), and the in-place "kick-out" rehash of kh_resize (:268-292).  Only the order of first occurrence of the
+ * distinct keys matters (a put of a present key never moves anything). */
+typedef struct {
+    uint32_t n, size, upper;
+    int *slot;              /* bucket -> key index, -1 = empty */
+} khs_t;
+
+static uint32_t x31(const uint8_t *nibs, int64_t len) {
+    static const char nt16[] = "=ACMGRSVTWYHKDBN";
+    if (len == 0) return 0;
+    uint32_t h = (uint32_t)nt16[nibs[0]];
+    for (int64_t i = 1; i < len; ++i) h = (h << 5) - h + (uint32_t)nt16[nibs[i]];
+    return h;
+}
+
+static void khs_resize(khs_t *h, uint32_t want, const uint32_t *hashes) {
+    uint32_t nn = want;
+    --nn; nn |= nn >> 1; nn |= nn >> 2; nn |= nn >> 4; nn |= nn >> 8; nn |= nn >> 16; ++nn;
+    if (nn < 4) nn = 4;
+    if (h->size >= (uint32_t)(nn * 0.77 + 0.5)) return;
+    int *slot = (int *)malloc(sizeof(int) * nn);
+    uint8_t *newf = (uint8_t *)calloc(nn, 1);                 /* new_flags: 1 = taken */
+    uint8_t *oldocc = (uint8_t *)calloc(nn, 1);               /* old flags: 1 = still holds an element to move */
+    for (uint32_t j = 0; j < nn; ++j) slot[j] = -1;
+    for (uint32_t j = 0; j < h->n; ++j) { slot[j] = h->slot[j]; oldocc[j] = h->slot[j] >= 0; }
+    uint32_t mask = nn - 1;
+    for (uint32_t j = 0; j < h->n; ++j) {
+        if (!oldocc[j]) continue;
+        int key = slot[j];
+        oldocc[j] = 0;
+        slot[j] = -1;
+        for (;;) {
+            uint32_t i = hashes[key] & mask, step = 0;
+            while (newf[i]) i = (i + (++step)) & mask;
+            newf[i] = 1;
+            if (i < h->n && oldocc[i]) {                      /* kick out the element that still sits there */
+                int tmp = slot[i];
+                slot[i] = key;
+                key = tmp;
+                oldocc[i] = 0;
+            } else {
+                slot[i] = key;
+                break;
+            }
+        }
+    }
+    free(h->slot); free(newf); free(oldocc);
+    h->slot = slot;
+    h->n = nn;
+    h->upper = (uint32_t)(nn * 0.77 + 0.5);
+}
+
+/* order[0..n_keys): the key indices (first-occurrence order in, bucket order out) */
+static void khash_iteration_order(const uint32_t *hashes, int n_keys, int *order) {
+    khs_t h = {0, 0, 0, NULL};
+    for (int key = 0; key < n_keys; ++key) {
+        if (h.size >= h.upper) khs_resize(&h, h.n + 1, hashes);
+        uint32_t mask = h.n - 1, i = hashes[key] & mask, step = 0;
+        while (h.slot[i] >= 0) i = (i + (++step)) & mask;     /* distinct keys: never equal to a present one */
+        h.slot[i] = key;
+        ++h.size;
+    }
+    int k = 0;
+    for (uint32_t j = 0; j < h.n; ++j)
+        if (h.slot[j] >= 0) order[k++] = h.slot[j];
+    free(h.slot);
+}
+
+typedef struct {
+    char *buf;
+    int64_t len, cap;
+} text_t;
+
+static void text_add(text_t *t, const char *s, int64_t n) {
+    if (!t->buf) return;
+    if (t->len + n + 1 > t->cap) { t->len = t->cap + 1; return; }        /* overflow: reported through the returned length */
+    memcpy(t->buf + t->len, s, (size_t)n);
+    t->len += n;
+    t->buf[t->len] = 0;
+}
+
 typedef struct {
     int64_t min_depth;
     float min_snp_af, min_indel_af;
     int32_t min_mq, call_snp_only, call_ht, gvcf;
+    int64_t max_indel_length;       /* only shapes the all_alt_info text (:411, :428) */
 } plp_params_t;
 
 /* Outputs (caller-allocated for W = end - start columns): matrix [W][18], major [W], stats [W][6] = depth, ref_count, alt_count,
@@ -175,7 +263,10 @@ int oracle_clair3_pileup(int64_t n_reads, const int64_t *rpos, const uint16_t *f
                          const int32_t *l_qseq, int64_t start, int64_t end, const char *ref_seq, int64_t ref_start, int64_t ref_len,
                          const plp_params_t *prm, int64_t *n_cols_out, int64_t *matrix, int64_t *major, int32_t *stats,
                          int64_t *cand_cols, uint8_t *cand_ok, int64_t *n_cand_out, int64_t *pos_ref_count,
-                         int64_t *pos_total_count) {
+                         int64_t *pos_total_count, char *alt_text, int64_t alt_cap, int64_t *alt_len) {
+    /* alt_text (optional): the all_alt_info strings of the candidates, one per line, in candidate order */
+    text_t txt = {alt_text, 0, alt_cap};
+    if (alt_text && alt_cap > 0) alt_text[0] = 0;
     int64_t W = end - start;
     *n_cols_out = 0;
     *n_cand_out = 0;
@@ -324,6 +415,52 @@ int oracle_clair3_pileup(int64_t n_reads, const int64_t *rpos, const uint16_t *f
         }
         pass_af = pass_af && pass_min_depth && ref_acgt;
         if (!prm->call_ht) pass_af = pass_af && contiguous >= FLANK;
+        if (pass_af && txt.buf) {                                               /* :391-450 */
+            char tmp[96];
+            int64_t ref_depth = ref_count;
+            int n = snprintf(tmp, sizeof tmp, "%lld-%lld-%c-", (long long)(pos + 1), (long long)depth, ref_base);
+            text_add(&txt, tmp, n);
+            for (int i = 0; i < 4; ++i) {
+                int64_t alt_sum = m[i] + m[i + 9];
+                if (alt_sum > 0 && i != rf) { n = snprintf(tmp, sizeof tmp, "X%c %lld ", plp_bases[i], (long long)alt_sum); text_add(&txt, tmp, n); }
+            }
+            for (int64_t i = 0; i < del_cap; ++i) {
+                int64_t d = dels_f[i] + dels_r[i];
+                ref_depth -= d;
+                if (d > 0 && i + 1 <= prm->max_indel_length) {
+                    text_add(&txt, "D", 1);
+                    for (int64_t q = 0; q <= i; ++q) {                          /* "%.*s" of ref_seq + offset + 1: raw case, stops at the end */
+                        int64_t o = off + 1 + q;
+                        if (o < 0 || o >= ref_len || ref_seq[o] == 0) break;
+                        text_add(&txt, ref_seq + o, 1);
+                    }
+                    n = snprintf(tmp, sizeof tmp, " %lld ", (long long)d);
+                    text_add(&txt, tmp, n);
+                }
+            }
+            if (n_ins > 0) {
+                uint32_t *hs = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n_ins);
+                int *order = (int *)malloc(sizeof(int) * (size_t)n_ins);
+                for (int64_t i = 0; i < n_ins; ++i) hs[i] = x31(ins[i].nibs, ins[i].len);
+                khash_iteration_order(hs, (int)n_ins, order);
+                for (int64_t q = 0; q < n_ins; ++q) {
+                    const ins_t *e = &ins[order[q]];
+                    int64_t val = e->cnt_f + e->cnt_r;
+                    ref_depth -= val;
+                    if (e->len <= prm->max_indel_length) {
+                        static const char nt16[] = "=ACMGRSVTWYHKDBN";
+                        tmp[0] = 'I'; tmp[1] = ref_base;
+                        text_add(&txt, tmp, 2);
+                        for (int64_t b = 0; b < e->len; ++b) text_add(&txt, &nt16[e->nibs[b]], 1);
+                        n = snprintf(tmp, sizeof tmp, " %lld ", (long long)val);
+                        text_add(&txt, tmp, n);
+                    }
+                }
+                free(hs); free(order);
+            }
+            if (ref_depth > 0) { n = snprintf(tmp, sizeof tmp, "R%c %lld ", ref_base, (long long)ref_depth); text_add(&txt, tmp, n); }
+            text_add(&txt, "\n", 1);
+        }
         int zero = 1;
         for (int i = 0; i < FEAT; ++i) { matrix[n_cols * FEAT + i] = m[i]; if (m[i]) zero = 0; }
         major[n_cols] = pos;
@@ -359,6 +496,7 @@ int oracle_clair3_pileup(int64_t n_reads, const int64_t *rpos, const uint16_t *f
     }
     *n_cols_out = n_cols;
     *n_cand_out = n_cand;
+    if (alt_len) *alt_len = txt.len;
     free(cur); free(rend); free(keep);
     return 0;
 }

@@ -27,7 +27,7 @@ def build(force=False):
 class _Params(ctypes.Structure):
     _fields_ = [("min_depth", ctypes.c_int64), ("min_snp_af", ctypes.c_float), ("min_indel_af", ctypes.c_float),
                 ("min_mq", ctypes.c_int32), ("call_snp_only", ctypes.c_int32), ("call_ht", ctypes.c_int32),
-                ("gvcf", ctypes.c_int32)]
+                ("gvcf", ctypes.c_int32), ("max_indel_length", ctypes.c_int64)]
 
 
 _lib = None
@@ -46,10 +46,10 @@ def _p(a):
 
 
 def clair3_pileup(reads, start, end, ref_seq, ref_start, min_depth=2, min_snp_af=0.08, min_indel_af=0.15, min_mq=5,
-                  call_snp_only=False, call_ht=False, gvcf=False):
+                  call_snp_only=False, call_ht=False, gvcf=False, max_indel_length=50, alt_info=False):
     """reads: dict of numpy arrays with the keys of ``clair3_b200.pileup_counts.BamRecords`` (pos, flag, mapq, cigar_off, cigar,
     seq_off, seq, l_qseq).  Returns a dict: matrix [n_cols,18] int64, major [n_cols] int64, stats [n_cols,6] int32, cand_cols,
-    cand_ok, pos_ref_count, pos_total_count."""
+    cand_ok, pos_ref_count, pos_total_count (+ alt_info: the all_alt_info strings of the candidates, with ``alt_info=True``)."""
     L = _load()
     n = int(len(reads["pos"]))
     W = max(int(end - start), 0)
@@ -63,7 +63,7 @@ def clair3_pileup(reads, start, end, ref_seq, ref_start, min_depth=2, min_snp_af
     l_qseq = np.ascontiguousarray(reads["l_qseq"], dtype=np.int32)
     ref = np.frombuffer(ref_seq.encode() if isinstance(ref_seq, str) else bytes(ref_seq), dtype=np.uint8).copy()
     prm = _Params(int(min_depth), float(min_snp_af), float(min_indel_af), int(min_mq), int(bool(call_snp_only)),
-                  int(bool(call_ht)), int(bool(gvcf)))
+                  int(bool(call_ht)), int(bool(gvcf)), int(max_indel_length))
     matrix = np.zeros((W, 18), dtype=np.int64)
     major = np.zeros(W, dtype=np.int64)
     stats = np.zeros((W, 6), dtype=np.int32)
@@ -73,13 +73,21 @@ def clair3_pileup(reads, start, end, ref_seq, ref_start, min_depth=2, min_snp_af
     ptc = np.zeros(W, dtype=np.int64)
     n_cols = ctypes.c_int64(0)
     n_cand = ctypes.c_int64(0)
+    alt_cap = 64 * 1024 * 1024 if alt_info else 0
+    alt_buf = ctypes.create_string_buffer(alt_cap) if alt_info else None
+    alt_len = ctypes.c_int64(0)
     rc = L.oracle_clair3_pileup(ctypes.c_int64(n), _p(pos), _p(flag), _p(mapq), _p(cigar_off), _p(cigar), _p(seq_off), _p(seq),
                                 _p(l_qseq), ctypes.c_int64(int(start)), ctypes.c_int64(int(end)), _p(ref),
                                 ctypes.c_int64(int(ref_start)), ctypes.c_int64(len(ref)), ctypes.byref(prm),
                                 ctypes.byref(n_cols), _p(matrix), _p(major), _p(stats), _p(cand), _p(ok), ctypes.byref(n_cand),
-                                _p(prc), _p(ptc))
+                                _p(prc), _p(ptc), alt_buf, ctypes.c_int64(alt_cap), ctypes.byref(alt_len))
     if rc != 0:
         raise MemoryError("oracle_clair3_pileup failed")
     nc, nk = n_cols.value, n_cand.value
-    return {"matrix": matrix[:nc].copy(), "major": major[:nc].copy(), "stats": stats[:nc].copy(), "cand_cols": cand[:nk].copy(),
+    extra = {}
+    if alt_info:
+        if alt_len.value > alt_cap:
+            raise MemoryError("alt_info text buffer too small")
+        extra["alt_info"] = alt_buf.raw[:alt_len.value].decode().split("\n")[:-1]
+    return {**extra, "matrix": matrix[:nc].copy(), "major": major[:nc].copy(), "stats": stats[:nc].copy(), "cand_cols": cand[:nk].copy(),
             "cand_ok": ok[:nk].copy(), "pos_ref_count": prc, "pos_total_count": ptc}

@@ -26,6 +26,7 @@ def model_pileup(rec, start, end, ref_seq, ref_start, min_depth=2, min_snp_af=0.
     covered = np.zeros(W, bool)
     dels = [dict() for _ in range(W)]          # (strand, length) -> count
     ins = [dict() for _ in range(W)]           # (strand, string) -> count
+    alle = [dict() for _ in range(W)]          # allele -> [first read, first inserted base in it, count], in order of first occurrence
     n = len(rec["pos"])
     for r in range(n):
         fl = int(rec["flag"][r])
@@ -79,6 +80,7 @@ def model_pileup(rec, start, end, ref_seq, ref_start, min_depth=2, min_snp_af=0.
             c = p - start
             if indel < 0:
                 dels[c][(rev, -indel)] = dels[c].get((rev, -indel), 0) + 1
+                alle[c].setdefault((0, rev, -indel, None), [r, 0, 0])[2] += 1
             bi = (17 if rev else 8) if is_del else N2C[_nib(rec["seq"], so, lq, qpos) + 16 * rev]
             depth[c] += 1
             if bi >= 0:
@@ -89,7 +91,8 @@ def model_pileup(rec, start, end, ref_seq, ref_start, min_depth=2, min_snp_af=0.
                 f0 = 0 if is_del else 1
                 s = tuple(_nib(rec["seq"], so, lq, qpos + f0 + i) for i in range(indel))
                 ins[c][(rev, s)] = ins[c].get((rev, s), 0) + 1
-    rows, major, stats = [], [], []
+                alle[c].setdefault((1, rev, indel, s), [r, qpos + f0, 0])[2] += 1
+    rows, major, stats, alleles = [], [], [], []
     prev_emitted = None
     for c in range(W):
         if not covered[c]:
@@ -135,6 +138,7 @@ def model_pileup(rec, start, end, ref_seq, ref_start, min_depth=2, min_snp_af=0.
             rows[-1][17] += quirk[c]
         rows.append(m)
         major.append(p)
+        alleles.append([((k[0] << 31) | (k[1] << 30) | k[2], v[0], v[1], v[2]) for k, v in alle[c].items()])
         stats.append([d, ref_count, alt, del_count, ins_count, 1 if ok else 0])
     matrix = np.array(rows, np.int64).reshape(-1, 18)
     stats = np.array(stats, np.int32).reshape(-1, 6)
@@ -147,4 +151,5 @@ def model_pileup(rec, start, end, ref_seq, ref_start, min_depth=2, min_snp_af=0.
         g = c - 16 >= 0 and c + 16 < len(major) and major[c + 16] - major[c - 16] == 32
         g = g and not (stats[c - 16:c + 17, 5] & 2).any()
         okw.append(1 if g else 0)
-    return {"matrix": matrix, "major": major, "stats": stats, "cand_cols": cand, "cand_ok": np.array(okw, np.uint8)}
+    return {"matrix": matrix, "major": major, "stats": stats, "cand_cols": cand, "cand_ok": np.array(okw, np.uint8),
+            "alleles": alleles}        # per emitted column: (meta, first read, query offset, count) as c3b_plp_fetch_alleles exports them

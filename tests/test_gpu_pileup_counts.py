@@ -172,3 +172,25 @@ def test_additivity_at_bench_size(counter):
     assert np.array_equal(whole["stats"][:k, :5], want["stats"][:k, :5])
     _STATS["additivity_1M"] = {"columns_compared": n, "linear_features_additive": True, "oracle_window_columns": int(k)}
     _dump()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_all_alt_info_text(counter, seed):
+    """calculate_clair3_pileup's all_alt_info strings (src/clair3_pileup.c:391-450): allele lists exported by the count kernel,
+    text formatted on the host - byte for byte the oracle's text, insertion alleles in khash bucket order."""
+    from clair3_b200 import synth_reads as sr
+    from oracle import pileup_oracle as po
+    rec, ref, rs = sr.random_alignment([700, 3000, 513, 20000][seed], depth=[15, 40, 300, 30][seed], read_len=[100, 600, 300, 3000][seed],
+                                       seed=60 + seed, wild=seed == 0, indel_rate=[0.08, 0.06, 0.12, 0.05][seed], n_rate=0.01)
+    width = [700, 3000, 513, 20000][seed]
+    max_indel = [50, 5, 50, 50][seed]
+    kw = dict(call_ht=seed == 0, gvcf=seed == 1)
+    want = po.clair3_pileup(rec, 1000, 1000 + width, ref, rs, alt_info=True, max_indel_length=max_indel, **kw)
+    got = counter.count(rec, 1000, 1000 + width, ref, rs, alt_info=True, max_indel_length=max_indel, **kw).fetch()
+    _compare("alt_info_%d" % seed, got, want, gvcf=kw["gvcf"])
+    text = counter.alt_info_strings(got)
+    assert len(text) == len(want["alt_info"]) == len(want["cand_cols"])
+    for a, b in zip(text, want["alt_info"]):
+        assert a == b, (a, b)
+    _STATS["alt_info_%d" % seed]["alt_info_strings_identical"] = len(text)
+    _dump()

@@ -227,3 +227,68 @@ def test_counts_are_additive_over_read_subsets():
     rec, ref, rs = sr.random_alignment(3000, depth=30, read_len=700, seed=13, n_rate=0.0, filtered_frac=0.0)
     rec["mapq"][:] = 60
     check_additivity(lambda r: po.clair3_pileup(r, 1000, 4000, ref, rs), rec, 1000, 4000, ref, rs)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_alt_info_text_host_formatter_matches_oracle(seed):
+    """The all_alt_info strings (src/clair3_pileup.c:391-450): the product's host formatter (clair3_b200.pileup_counts.format_alt_info,
+    with its own restatement of khash's bucket order), fed with allele lists in the layout the GPU exports (taken here from the
+    random-access model), against the C oracle's text (which restates khash separately)."""
+    from clair3_b200 import pileup_counts as pc
+    wild = seed % 2 == 0
+    rec, ref, rs = sr.random_alignment(400, depth=[15, 40, 28][seed % 3], read_len=[100, 300, 200][seed % 3], seed=40 + seed, wild=wild,
+                                       indel_rate=[0.08, 0.15][seed % 2], n_rate=0.01)
+    max_indel = [50, 5][seed % 2]
+    want = po.clair3_pileup(rec, 1000, 1400, ref, rs, alt_info=True, max_indel_length=max_indel, call_ht=seed == 5)
+    m = model_pileup(rec, 1000, 1400, ref, rs, call_ht=seed == 5)
+    assert np.array_equal(m["cand_cols"], want["cand_cols"]) and len(want["alt_info"]) == len(want["cand_cols"]) >= 1
+    host = pc.BamRecords.from_dict(rec)
+    refb = ref.encode()
+    got = []
+    for ci in m["cand_cols"]:
+        al = m["alleles"][ci]
+        cols = [np.array([a[j] for a in al], dtype=np.uint32) for j in range(4)]
+        got.append(pc.format_alt_info(int(m["major"][ci]), m["matrix"][ci], m["stats"][ci], refb, rs, max_indel, *cols, host))
+    assert got == want["alt_info"]
+
+
+def test_alt_info_known_answer():
+    rec, ref, *_ = case_indels()
+    r = po.clair3_pileup(rec, 0, 20, ref, 0, call_ht=True, alt_info=True)
+    # pos 4 (1-based 5): depth 3, ref G, r2's deletion of ref 5,6 = "GT" once, reference depth 3 - 1; pos 5: r3's insertion T after G;
+    # pos 7: one A against ref T
+    assert r["alt_info"] == ["5-3-G-DGT 1 RG 2 ", "6-3-G-IGT 1 RG 1 ", "8-2-T-XA 1 RT 1 "]
+
+
+def test_alt_info_many_insertion_alleles_follow_khash_bucket_order():
+    """40 distinct insertion alleles on one column take the reference's string counter through its 4 -> 8 -> 16 -> 32 -> 64 bucket
+    growth (kick-out rehash each time): the text lists them in bucket order, identically in the oracle (C restatement of khash) and
+    in the product's host formatter (Python restatement)."""
+    from clair3_b200 import pileup_counts as pc
+    rng = np.random.default_rng(3)
+    ref = "ACGTACGTACGTACGTACGTACGT"
+    items, seen = [], set()
+    while len(items) < 60:
+        k = int(rng.integers(1, 7))
+        insert = "".join("ACGT"[i] for i in rng.integers(0, 4, k))
+        if len(seen) >= 40 and insert not in seen:
+            continue
+        seen.add(insert)
+        items.append((0, 16 if rng.random() < 0.4 else 0, 60, [("M", 4), ("I", k), ("M", 4)], "ACGT" + insert + "ACGT"))
+    rec = sr.records_from_lists(items)
+    want = po.clair3_pileup(rec, 0, 24, ref, 0, call_ht=True, alt_info=True)
+    m = model_pileup(rec, 0, 24, ref, 0, call_ht=True)
+    ci = int(np.nonzero(m["major"] == 3)[0][0])
+    assert ci in m["cand_cols"].tolist()
+    al = m["alleles"][ci]
+    assert len({a[0] & 0x3FFFFFFF for a in al}) >= 5 and len(seen) == 40
+    cols = [np.array([a[j] for a in al], dtype=np.uint32) for j in range(4)]
+    text = pc.format_alt_info(3, m["matrix"][ci], m["stats"][ci], ref.encode(), 0, 50, *cols, pc.BamRecords.from_dict(rec))
+    assert text == want["alt_info"][m["cand_cols"].tolist().index(ci)]
+    assert text.count(" IT") + text.startswith("4-60-T-IT") == 40
+    first_seen = []
+    for it in items:
+        if it[4][4:-4] not in first_seen:
+            first_seen.append(it[4][4:-4])
+    printed = [tok[2:] for tok in text.split("-", 3)[3].split(" ") if tok.startswith("IT")]
+    assert sorted(printed) == sorted(first_seen) and printed != first_seen            # bucket order, not insertion order

@@ -60,6 +60,14 @@ def main():
     for seed, (width, depth, rl, wild) in enumerate([(700, 4, 60, True), (256, 12, 150, False), (1025, 35, 400, True), (5000, 30, 2000, False)]):
         rec, ref, rs = sr.random_alignment(width, depth=depth, read_len=rl, seed=200 + seed, wild=wild, indel_rate=0.08, n_rate=0.01)
         ok &= report("random_%d" % seed, ctr.count(rec, 1000, 1000 + width, ref, rs).fetch(), po.clair3_pileup(rec, 1000, 1000 + width, ref, rs))
+    rec, ref, rs = sr.random_alignment(3000, depth=40, read_len=600, seed=61, indel_rate=0.06, n_rate=0.01)
+    want = po.clair3_pileup(rec, 1000, 4000, ref, rs, alt_info=True)
+    got = ctr.count(rec, 1000, 4000, ref, rs, alt_info=True).fetch()
+    ok &= report("alt_info_counts", got, want)
+    text = ctr.alt_info_strings(got)
+    bad = [(a, b) for a, b in zip(text, want["alt_info"]) if a != b]
+    print("alt_info text: %d strings, %d differ%s" % (len(text), len(bad) + abs(len(text) - len(want["alt_info"])), (" first: %r vs %r" % bad[0]) if bad else ""))
+    ok &= not bad and len(text) == len(want["alt_info"])
     print("DIAG", "ALL BIT-EXACT" if ok else "HAS MISMATCHES")
 
 
