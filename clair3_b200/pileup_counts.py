@@ -391,16 +391,51 @@ def lib_const(name):
     return CONSTANTS[name]
 
 
-def pileup_counts_clair3(records, start, end, ref_seq, ref_start, counter=None, device=0, **params):
-    """The shape ``_plp_data_to_numpy`` returns (``preprocess/CreateTensorPileupFromCffi.py:127-180``): (np_counts [n_cols, 18],
-    positions structured array with 'major' / 'minor', candidate column indices, stats) - alt_info strings excepted."""
+def enforce_chunk_contiguity(counts, positions):
+    """``__enforce_pileup_chunk_contiguity`` (preprocess/CreateTensorPileupFromCffi.py:180-236) for ONE region: the counter reports
+    covered columns only, so a coverage hole shows up as a jump > 1 in ``positions['major']``; the reference cuts the matrix there
+    and hands the caller a list of contiguous (counts, positions) chunks."""
+    if len(positions) == 0:
+        return []
+    gaps = np.where(np.ediff1d(positions["major"]) > 1)[0] + 1
+    out, first = [], 0
+    for g in list(gaps) + [len(positions)]:
+        if g > first:
+            out.append((counts[first:g], positions[first:g]))
+        first = g
+    return out
+
+
+def alt_info_list(strings, ref_name):
+    """The tuples ``_process_region`` builds from the C strings (preprocess/CreateTensorPileupFromCffi.py:66-73):
+    (1-based position, "ctg:pos:ref_base", "depth-alt text")."""
+    out = []
+    for s in strings:
+        f = s.rstrip().split("-")
+        if len(f) < 4:
+            continue
+        pos, depth, center_ref_base, alt = f[:4]
+        out.append((int(pos), ref_name + ":" + pos + ":" + center_ref_base, depth + "-" + alt))
+    return out
+
+
+def pileup_counts_clair3(records, ref_name, start, end, ref_seq, ref_start, counter=None, device=0, **params):
+    """``pileup_counts_clair3`` of the reference (preprocess/CreateTensorPileupFromCffi.py:30-85) on decoded records: returns
+    (chunk_results, all_alt_info_list, gvcf_output) - contiguous (counts [n,18] int64, positions with 'major' / 'minor') chunks,
+    the (pos, "ctg:pos:ref", "depth-alt") tuples of every candidate and, with ``gvcf=True``, [pos_ref_count, pos_total_count] -
+    for the 0-based [start, end) that reaches ``calculate_clair3_pileup`` (see ``counting_region``).  Keyword arguments as
+    ``PileupCounter.count``; the allele text needs host records."""
     own = counter is None
     counter = counter or PileupCounter(device)
     try:
+        params = dict(params)
+        params["alt_info"] = True
         r = counter.count(records, start, end, ref_seq, ref_start, **params).fetch()
+        strings = counter.alt_info_strings(r)
     finally:
         if own:
             counter.close()
     positions = np.zeros(len(r["major"]), dtype=[("major", int), ("minor", int)])
     positions["major"] = r["major"]
-    return r["matrix"], positions, r["cand_cols"], r
+    gvcf_output = [r["pos_ref_count"], r["pos_total_count"]] if "pos_ref_count" in r else []
+    return enforce_chunk_contiguity(r["matrix"], positions), alt_info_list(strings, ref_name), gvcf_output

@@ -194,3 +194,16 @@ def test_all_alt_info_text(counter, seed):
         assert a == b, (a, b)
     _STATS["alt_info_%d" % seed]["alt_info_strings_identical"] = len(text)
     _dump()
+
+
+def test_pileup_counts_clair3_shape_of_the_reference_caller(counter):
+    """pileup_counts_clair3 (preprocess/CreateTensorPileupFromCffi.py:30-85): contiguous chunks, candidate tuples, gVCF arrays."""
+    from clair3_b200 import pileup_counts as pc, synth_reads as sr
+    from oracle import pileup_oracle as po
+    rec, ref, rs = sr.random_alignment(900, depth=8, read_len=120, seed=17, gaps=[(1300, 1420), (1700, 1760)])
+    want = po.clair3_pileup(rec, 1000, 1900, ref, rs, alt_info=True, gvcf=True)
+    chunks, tuples, gv = pc.pileup_counts_clair3(rec, "chr20", 1000, 1900, ref, rs, counter=counter, gvcf=True)
+    assert np.array_equal(np.concatenate([c for c, _ in chunks]), want["matrix"])
+    assert np.array_equal(np.concatenate([p["major"] for _, p in chunks]), want["major"]) and len(chunks) >= 3
+    assert tuples == pc.alt_info_list(want["alt_info"], "chr20") and len(tuples) > 0
+    assert np.array_equal(gv[0], want["pos_ref_count"]) and np.array_equal(gv[1], want["pos_total_count"])

@@ -292,3 +292,24 @@ def test_alt_info_many_insertion_alleles_follow_khash_bucket_order():
             first_seen.append(it[4][4:-4])
     printed = [tok[2:] for tok in text.split("-", 3)[3].split(" ") if tok.startswith("IT")]
     assert sorted(printed) == sorted(first_seen) and printed != first_seen            # bucket order, not insertion order
+
+
+def test_host_post_processing_mirrors_the_reference_caller():
+    """enforce_chunk_contiguity / alt_info_list restate preprocess/CreateTensorPileupFromCffi.py:180-236 and :66-73 on the counter's
+    outputs (fed here from the oracle): chunks split at coverage holes, one tuple per candidate string."""
+    from clair3_b200 import pileup_counts as pc
+    rec, ref, rs = sr.random_alignment(900, depth=8, read_len=120, seed=17, gaps=[(1300, 1420), (1700, 1760)])
+    r = po.clair3_pileup(rec, 1000, 1900, ref, rs, alt_info=True)
+    positions = np.zeros(len(r["major"]), dtype=[("major", int), ("minor", int)])
+    positions["major"] = r["major"]
+    chunks = pc.enforce_chunk_contiguity(r["matrix"], positions)
+    assert len(chunks) >= 3 and sum(len(c[1]) for c in chunks) == len(positions)
+    for counts, pos in chunks:
+        assert len(counts) == len(pos) and (np.diff(pos["major"]) == 1).all()
+    for (_, a), (_, b) in zip(chunks, chunks[1:]):
+        assert b["major"][0] - a["major"][-1] > 1
+    tup = pc.alt_info_list(r["alt_info"], "chr20")
+    assert len(tup) == len(r["alt_info"]) > 0
+    p0, name, alt = tup[0]
+    assert p0 == int(r["major"][r["cand_cols"][0]]) + 1 and name.startswith("chr20:%d:" % p0) and alt.split("-")[0].isdigit()
+    assert pc.enforce_chunk_contiguity(r["matrix"][:0], positions[:0]) == []
