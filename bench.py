@@ -799,6 +799,16 @@ def run_pileup_counts(ctx):
     return out
 
 
+def select_workloads(spec, explicit, world):
+    """The sub-records one run measures.  The feature counter shards by region with no exchange at all (replicas only), so the
+    multi-rank line stays the measured round-2 shape (networks + cascade) and the counter is a single-GPU sub-record unless it is
+    asked for by name."""
+    names = [x for x in spec.split(",") if x]
+    if not explicit and world > 1:
+        names = [x for x in names if x != "pileup_counts"]
+    return names
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -818,11 +828,7 @@ def main():
                     help="minimum length of every timed region (profiling runs under ncu pass 0: one pass of the K steps)")
     args = ap.parse_args()
     explicit = args.workload is not None or any(a.startswith("--workloads") for a in sys.argv[1:])
-    args.workloads = [x for x in (args.workload or args.workloads).split(",") if x]
-    if not explicit and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        # the feature counter shards by region with no exchange at all (replicas only); the multi-rank line stays the measured
-        # round-2 shape (networks + cascade), the counter is a single-GPU sub-record unless asked for by name
-        args.workloads = [x for x in args.workloads if x != "pileup_counts"]
+    args.workloads = select_workloads(args.workload or args.workloads, explicit, int(os.environ.get("WORLD_SIZE", "1")))
     global MIN_REGION_S
     MIN_REGION_S = max(0.0, args.min_region_s)
     if args.steps <= 0:

@@ -101,6 +101,8 @@ class PileupCounter:
         dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
         if dev.type != "cuda":
             raise C3BError("PileupCounter needs a CUDA device (no CPU fallback)")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         self._device = dev
         out = ffi.new("c3b_plp **")
         check(lib().c3b_plp_create(out, dev.index or 0))
@@ -216,6 +218,12 @@ class PileupCounter:
         (``c3b_forward_windows`` with ``on_device = 1``).  Returns (probabilities float32 [n_cand, 24|90] on the device, cand_ok
         uint8 [n_cand] on the host): rows whose window is incomplete (``cand_ok == 0`` - the reference drops those candidates,
         ``preprocess/CreateTensorPileupFromCffi.py:362-369``) are computed on zero-padded windows and must be ignored."""
+        if getattr(model, "_handle", None) is None:
+            raise C3BError("forward: the model has no device / weights yet (.to(device), .load_state_dict())")
+        if getattr(model, "input_channels", CHANNELS) != CHANNELS or model._kind != lib_const("C3B_PILEUP"):
+            raise C3BError("forward: needs the pileup network (Clair3_P, 18 channels)")
+        if torch.device(model._device) != self._device:
+            raise C3BError("forward: the model lives on %s, the counter on %s" % (model._device, self._device))
         nc, nk = self.sizes()
         y = torch.empty((nk, model.out_dim), dtype=torch.float32, device=self._device)
         ok = np.zeros(nk, np.uint8)

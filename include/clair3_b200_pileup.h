@@ -28,7 +28,9 @@ extern "C" {
 typedef struct c3b_plp c3b_plp;
 
 /* A coordinate-sorted run of alignment records of ONE contig, fields as htslib lays them out in bam1_t
- * (the vendored public header src/sam.h: bam1_core_t, bam_get_cigar, bam_get_seq). */
+ * (the vendored public header src/sam.h: bam1_core_t, bam_get_cigar, bam_get_seq).  The library trusts the offsets: cigar_off and
+ * seq_off must be non-decreasing, start at 0 and address cigar[] / seq[] in bounds, every packed sequence must hold
+ * (l_qseq + 1) / 2 bytes (clair3_b200/pileup_counts.py: BamRecords checks all of this on the host). */
 typedef struct c3b_bam_records {
     int64_t n_reads;
     const int64_t *pos;         /* [n]   bam1_core_t.pos: 0-based leftmost coordinate, ascending                         */

@@ -31,3 +31,14 @@ def test_reference_arm_prints_one_contract_line():
 
 def test_reference_arm_other_ranks_exit_quietly():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--steps", "1", "--warmup", "1", "--gpus", "2") == []
+
+
+def test_workload_selection():
+    """Default line: everything on one GPU; under a multi-rank launch the feature counter (replicas only, no exchange) is left out
+    unless asked for by name."""
+    sys.path.insert(0, ROOT)
+    import bench
+    default = "pileup,fa,fa_dwell,cascade,pileup_counts"
+    assert bench.select_workloads(default, False, 1) == default.split(",")
+    assert bench.select_workloads(default, False, 8) == ["pileup", "fa", "fa_dwell", "cascade"]
+    assert bench.select_workloads("pileup_counts", True, 2) == ["pileup_counts"]

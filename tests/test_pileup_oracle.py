@@ -313,3 +313,22 @@ def test_host_post_processing_mirrors_the_reference_caller():
     p0, name, alt = tup[0]
     assert p0 == int(r["major"][r["cand_cols"][0]]) + 1 and name.startswith("chr20:%d:" % p0) and alt.split("-")[0].isdigit()
     assert pc.enforce_chunk_contiguity(r["matrix"][:0], positions[:0]) == []
+
+
+def test_forward_argument_checks_without_a_gpu():
+    """PileupCounter.forward refuses a model without weights, the full-alignment network and a model on another device before it
+    touches the library (the checks themselves need no GPU)."""
+    import types
+    import torch
+    from clair3_b200 import _ffi, pileup_counts as pc
+    ctr = object.__new__(pc.PileupCounter)
+    ctr._device = torch.device("cuda", 0)
+    ok = types.SimpleNamespace(_handle=object(), _kind=_ffi.CONSTANTS["C3B_PILEUP"], input_channels=18, _device=torch.device("cuda:0"), out_dim=24)
+    for bad, msg in ((dict(_handle=None), "no device"), (dict(_kind=_ffi.CONSTANTS["C3B_FULL_ALIGNMENT"]), "pileup network"),
+                     (dict(input_channels=8), "pileup network"), (dict(_device=torch.device("cuda", 1)), "lives on")):
+        m = types.SimpleNamespace(**{**vars(ok), **bad})
+        with pytest.raises(_ffi.C3BError, match=msg):
+            pc.PileupCounter.forward(ctr, m)
+    with pytest.raises(AttributeError):            # a valid model passes every check and only then reaches the (absent) workspace
+        pc.PileupCounter.forward(ctr, ok)
+    ctr._h = None                                  # so that __del__ has nothing to release
