@@ -792,11 +792,55 @@ def run_pileup_counts(ctx):
         out["cpu_baseline"] = {"value": sample_bases / cpu_s, "unit": "bases/s", "cores": 1, "kind": "port",
                                "sample": "oracle/pileup_oracle.c (plain-C restatement of calculate_clair3_pileup, single thread like the reference's "
                                          "per-chunk call) on the first 65536 columns of the same records: %d aligned bases in %.3f s" % (sample_bases, cpu_s)}
+        try:                                          # the reference's deployment shape: one process per chunk on all host cores
+            ncores = len(os.sched_getaffinity(0))
+            dep = cpu_counts_all_cores(rec, ref, rs, start, end, max(1, min(ncores * 3 // 4, 64)))
+            out["cpu_baseline"]["single_thread"] = {"value": out["cpu_baseline"]["value"], "cores": 1}
+            out["cpu_baseline"]["deployment_shape"] = dep
+            if dep["processes"] > 0 and dep["value"] > out["cpu_baseline"]["value"]:
+                out["cpu_baseline"].update({"value": dep["value"], "cores": dep["processes"],
+                                            "sample": dep["sample"] + " (oracle/pileup_oracle.c; single thread on the first 65536 columns: %.1f M bases/s)"
+                                                      % (sample_bases / cpu_s / 1e6)})
+        except Exception as e:                        # noqa: BLE001 - the one-core figure stands
+            out["cpu_baseline"]["deployment_shape"] = {"error": "%s: %s" % (type(e).__name__, e)}
     for c in counters:
         c.close()
     del drec
     torch.cuda.empty_cache()
     return out
+
+
+def cpu_counts_all_cores(rec, ref, rs, start, end, nproc, min_seconds=1.5):
+    """The feature counter's CPU baseline in the reference's deployment shape: the region cut into `nproc` chunks, one
+    single-threaded oracle process per chunk, all running at once (the reference: one CreateTensorPileupFromCffi process per chunk
+    under GNU parallel); each worker counts its chunk repeatedly for >= min_seconds; rate = sum of the workers' rates."""
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="c3b_plp_cpu_")
+    path = os.path.join(tmp, "records.npz")
+    np.savez(path, ref=np.frombuffer(ref.encode() if isinstance(ref, str) else ref, dtype=np.uint8), ref_start=np.int64(rs), **rec)
+    cuts = [start + (end - start) * i // nproc for i in range(nproc + 1)]
+    env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    procs = [subprocess.Popen([sys.executable, "-m", "oracle.pileup_oracle", path, str(cuts[i]), str(cuts[i + 1]), str(min_seconds)],
+                              cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for i in range(nproc)]
+    total, ok, secs = 0.0, 0, 0.0
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=min_seconds * 20 + 120)
+            r = json.loads(out.strip().splitlines()[-1])
+            if r["seconds"] > 0:
+                total += r["bases"] / r["seconds"]
+                secs = max(secs, r["seconds"])
+                ok += 1
+        except Exception:
+            p.kill()
+    try:
+        os.remove(path)
+        os.rmdir(tmp)
+    except OSError:
+        pass
+    return {"value": total, "unit": "bases/s", "processes": ok, "threads_each": 1, "seconds": secs,
+            "sample": "%d single-thread oracle processes, one contiguous chunk of the bench region each, counted repeatedly for >= %.1f s, rates summed"
+                      % (ok, min_seconds)}
 
 
 def select_workloads(spec, explicit, world):

@@ -91,3 +91,46 @@ def clair3_pileup(reads, start, end, ref_seq, ref_start, min_depth=2, min_snp_af
         extra["alt_info"] = alt_buf.raw[:alt_len.value].decode().split("\n")[:-1]
     return {**extra, "matrix": matrix[:nc].copy(), "major": major[:nc].copy(), "stats": stats[:nc].copy(), "cand_cols": cand[:nk].copy(),
             "cand_ok": ok[:nk].copy(), "pos_ref_count": prc, "pos_total_count": ptc}
+
+
+def _reads_overlapping(rec, lo, hi):
+    """The records an indexed fetch of [lo, hi) would return (what sam_itr_querys hands the reference for its region string)."""
+    ops = rec["cigar"] & 15
+    lens = (rec["cigar"] >> 4).astype(np.int64)
+    refl = np.where(np.isin(ops, (0, 2, 3, 7, 8)), lens, 0)
+    csum = np.concatenate([[0], np.cumsum(refl)])
+    span = csum[rec["cigar_off"][1:]] - csum[rec["cigar_off"][:-1]]
+    keep = np.nonzero((rec["pos"] < hi) & (rec["pos"] + span > lo))[0]
+    if len(keep) == 0:
+        return None
+    a, b = int(keep[0]), int(keep[-1]) + 1            # sorted by pos: a contiguous run is a superset and keeps the order
+    c0, s0 = int(rec["cigar_off"][a]), int(rec["seq_off"][a])
+    return {"pos": rec["pos"][a:b], "flag": rec["flag"][a:b], "mapq": rec["mapq"][a:b], "l_qseq": rec["l_qseq"][a:b],
+            "cigar_off": rec["cigar_off"][a:b + 1] - c0, "cigar": rec["cigar"][c0:int(rec["cigar_off"][b])],
+            "seq_off": rec["seq_off"][a:b + 1] - s0, "seq": rec["seq"][s0:int(rec["seq_off"][b])]}
+
+
+def _worker_main(argv):
+    """python -m oracle.pileup_oracle <records.npz> <start> <end> <min seconds>: one single-threaded worker of the CPU baseline (the
+    reference runs one such process per chunk under GNU parallel, scripts/clair3_c_impl.sh): counts its region repeatedly for at
+    least <min seconds> and prints {"bases": ..., "seconds": ...} - bases = sum of the per-column depths, as bench.py counts them."""
+    import json
+    import time
+    path, start, end, min_s = argv[0], int(argv[1]), int(argv[2]), float(argv[3])
+    z = np.load(path)
+    rec = {k: z[k] for k in ("pos", "flag", "mapq", "cigar_off", "cigar", "seq_off", "seq", "l_qseq")}
+    ref, rs = z["ref"].tobytes(), int(z["ref_start"])
+    sub = _reads_overlapping(rec, start, end)
+    bases, reps, t0 = 0, 0, time.perf_counter()
+    while sub is not None:
+        r = clair3_pileup(sub, start, end, ref, rs)
+        bases += int(r["stats"][:, 0].sum())
+        reps += 1
+        if time.perf_counter() - t0 >= min_s:
+            break
+    print(json.dumps({"bases": bases, "seconds": time.perf_counter() - t0, "reps": reps}))
+
+
+if __name__ == "__main__":
+    import sys
+    _worker_main(sys.argv[1:])

@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -42,3 +44,21 @@ def test_workload_selection():
     assert bench.select_workloads(default, False, 1) == default.split(",")
     assert bench.select_workloads(default, False, 8) == ["pileup", "fa", "fa_dwell", "cascade"]
     assert bench.select_workloads("pileup_counts", True, 2) == ["pileup_counts"]
+
+
+def test_counter_cpu_baseline_in_the_reference_deployment_shape():
+    """bench.cpu_counts_all_cores: one single-threaded oracle process per chunk of the region, rates summed; together the workers
+    count exactly the bases the one-process oracle counts."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from clair3_b200 import synth_reads as sr
+    from oracle import pileup_oracle as po
+    rec, ref, rs = sr.random_alignment(6000, depth=20, read_len=700, seed=2)
+    r = bench.cpu_counts_all_cores(rec, ref, rs, 1000, 7000, 3, min_seconds=0.0)
+    assert r["processes"] == 3 and r["value"] > 0 and r["unit"] == "bases/s"
+    sub = po._reads_overlapping(rec, 3000, 5000)
+    whole = po.clair3_pileup(rec, 3000, 5000, ref, rs)
+    part = po.clair3_pileup(sub, 3000, 5000, ref, rs)
+    assert len(sub["pos"]) < len(rec["pos"])
+    for k in ("matrix", "major", "stats", "cand_cols"):
+        assert np.array_equal(whole[k], part[k]), k
