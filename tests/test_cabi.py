@@ -20,10 +20,52 @@ def test_library_exports_every_declared_symbol():
 
 def test_header_has_no_torch_types():
     import re
-    src = open(_ffi.HEADER).read()
-    code = re.sub(r"/\*.*?\*/", "", src, flags=re.S)          # declarations only, comments stripped
-    assert "torch" not in code.lower() and "at::" not in code and "std::" not in code
-    assert 'extern "C"' in code
+    for path in (_ffi.HEADER, _ffi.PILEUP_HEADER, _ffi.DEBUG_HEADER):
+        src = open(path).read()
+        code = re.sub(r"/\*.*?\*/", "", src, flags=re.S)          # declarations only, comments stripped
+        assert "torch" not in code.lower() and "at::" not in code and "std::" not in code, path
+        assert 'extern "C"' in code, path
+
+
+def test_headers_are_plain_c_and_a_c_caller_links(tmp_path):
+    """The drop-in boundary is a C ABI: every header compiles as C99 on its own, and a C translation unit that calls the entry points
+    a maintainer would bind (network forward + pileup feature counter) links against the shared object."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include")
+    for h in ("clair3_b200.h", "clair3_b200_pileup.h", "clair3_b200_debug.h"):
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(inc, h)], capture_output=True, text=True)
+        assert r.returncode == 0, (h, r.stderr)
+    src = tmp_path / "caller.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include "clair3_b200.h"
+#include "clair3_b200_pileup.h"
+int main(void) {
+    c3b_model *m = NULL;
+    c3b_plp *w = NULL;
+    c3b_bam_records recs = {0};
+    c3b_plp_params prm = {2, 0.08f, 0.15f, 5, 0, 0, 0, 0};
+    int64_t n_cols = 0, n_cand = 0;
+    if (c3b_create(&m, C3B_PILEUP, 18, 0, 0) != 0 || c3b_plp_create(&w, 0) != 0) {      /* no GPU here: fails loudly, no fallback */
+        printf("%s\n", c3b_last_error());
+        return 3;
+    }
+    if (c3b_plp_count(w, &recs, 0, 0, 0, "", 0, 0, &prm, NULL) || c3b_plp_sizes(w, &n_cols, &n_cand)) return 4;
+    c3b_plp_destroy(w);
+    c3b_destroy(m);
+    return 0;
+}
+""")
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(_ffi.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-lclair3b200",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        run = subprocess.run([str(exe)], capture_output=True, text=True)
+        assert run.returncode == 3 and "no CUDA device" in run.stdout
 
 
 def test_version_and_error_strings():
