@@ -62,3 +62,11 @@ def test_counter_cpu_baseline_in_the_reference_deployment_shape():
     assert len(sub["pos"]) < len(rec["pos"])
     for k in ("matrix", "major", "stats", "cand_cols"):
         assert np.array_equal(whole[k], part[k]), k
+
+
+def test_summary_tool_renders_the_committed_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_summary.py"), os.path.join(ROOT, "profiles", "r2_bench_line.json")],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-1000:]
+    for needle in ("| pileup |", "| fa |", "| cascade |", "## pileup_counts", "bases/s"):
+        assert needle in r.stdout, needle

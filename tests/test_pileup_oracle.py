@@ -358,3 +358,23 @@ def test_arbitrary_operation_orders(block):
         b = model_pileup(rec, start, end, ref, 0, **kw)
         for k in KEYS:
             assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), (seed, k)
+
+
+def load_counts_golden(tag):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pileup_counts.npz"))
+    rec = {k: z["%s_rec_%s" % (tag, k)] for k in ("pos", "flag", "mapq", "cigar_off", "cigar", "seq_off", "seq", "l_qseq")}
+    start, end, rs, gvcf, call_ht, max_indel = (int(v) for v in z["%s_meta" % tag])
+    want = {k: z["%s_%s" % (tag, k)] for k in ("matrix", "major", "stats", "cand_cols", "cand_ok", "pos_ref_count", "pos_total_count")}
+    want["alt_info"] = [str(x) for x in z["%s_alt_info" % tag]]
+    return rec, z["%s_ref" % tag].tobytes().decode(), rs, start, end, dict(gvcf=bool(gvcf), call_ht=bool(call_ht), max_indel_length=max_indel), want
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_oracle_against_committed_vectors(tag):
+    """tests/golden/pileup_counts.npz (tests/golden/make_pileup_counts_golden.py) freezes the hand-verified oracle: records in,
+    every output array and the all_alt_info strings out."""
+    rec, ref, rs, start, end, kw, want = load_counts_golden(tag)
+    got = po.clair3_pileup(rec, start, end, ref, rs, alt_info=True, **kw)
+    for k in ("matrix", "major", "stats", "cand_cols", "cand_ok") + (("pos_ref_count", "pos_total_count") if kw["gvcf"] else ()):
+        assert np.array_equal(got[k], want[k]), k
+    assert got["alt_info"] == want["alt_info"] and len(want["alt_info"]) > 5
