@@ -208,12 +208,3 @@ def test_pileup_counts_clair3_shape_of_the_reference_caller(counter):
     assert tuples == pc.alt_info_list(want["alt_info"], "chr20") and len(tuples) > 0
     assert np.array_equal(gv[0], want["pos_ref_count"]) and np.array_equal(gv[1], want["pos_total_count"])
 
-
-@pytest.mark.parametrize("tag", ["a", "b"])
-def test_committed_golden_vectors(counter, tag):
-    """The committed fixtures of tests/golden/pileup_counts.npz through the C-ABI: counts, candidates, gVCF arrays, all_alt_info."""
-    from test_pileup_oracle import load_counts_golden
-    rec, ref, rs, start, end, kw, want = load_counts_golden(tag)
-    got = counter.count(rec, start, end, ref, rs, alt_info=True, **kw).fetch()
-    _compare("golden_%s" % tag, got, want, gvcf=kw["gvcf"])
-    assert counter.alt_info_strings(got) == want["alt_info"]
